@@ -1,0 +1,192 @@
+"""Host setup: spectral AMGe restriction operator and Galerkin coarse operator.
+
+Restates the reference's HOST setup path for block agglomerates -- it is not on the hot path; it
+produces the CSR operators (R, A_c) that are uploaded once:
+
+  * block agglomeration             include/mfmg/common/amge.templates.hpp:412-499
+  * agglomerate sub-problems: same bilinear form on the agglomerate's cells, Dirichlet only on
+    faces of the GLOBAL boundary    include/mfmg/common/amge.templates.hpp:645-698
+  * local eigenproblem: diag_agg = diag(K_agg); shift by mean(diag); constrained diagonal parked
+    far away; n_e algebraically smallest eigenpairs, unit 2-norm
+                                     include/mfmg/dealii/amge_host.templates.hpp:378-394,446-467
+  * R[row(a,k), g_j] += diag_agg_a[j] / diag_A[g_j] * v_{a,k}[j], rows agglomerate-major,
+    eigenvector-minor               include/mfmg/common/amge.templates.hpp:300-321
+  * A_c = R (A R^T)                 include/mfmg/common/hierarchy.hpp:225,230
+
+Deviations (documented in SURVEY.md appendix C): agglomerates are visited lexicographically instead
+of in deal.II's z-order (a permutation of coarse rows); the eigenproblem is solved on the
+unconstrained block directly instead of through the (-0.5, 100] window of the `lapack` branch,
+which returns too few pairs when kappa is large.
+"""
+from __future__ import annotations
+
+import itertools
+
+import numpy as np
+
+from .problems import HostCSR, LaplaceProblem, assemble
+
+
+def block_agglomerates(dim: int, cells, block):
+    """List of (origin_cell, size_in_cells) per agglomerate, lexicographic (x fastest)."""
+    ranges = []
+    for d in range(dim):
+        nb = -(-cells[d] // block[d])
+        ranges.append([(b * block[d], min(block[d], cells[d] - b * block[d])) for b in range(nb)])
+    aggs = []
+    if dim == 2:
+        for (oy, sy), (ox, sx) in itertools.product(ranges[1], ranges[0]):
+            aggs.append(((ox, oy), (sx, sy)))
+    else:
+        for (oz, sz), (oy, sy), (ox, sx) in itertools.product(ranges[2], ranges[1], ranges[0]):
+            aggs.append(((ox, oy, oz), (sx, sy, sz)))
+    return aggs
+
+
+def _local_global_nodes(problem: LaplaceProblem, origin, size) -> np.ndarray:
+    p = problem.degree
+    nodes = problem.nodes
+    dim = problem.dim
+    ax = [np.arange(size[d] * p + 1) + origin[d] * p for d in range(dim)]
+    if dim == 2:
+        g = ax[0][None, :] + nodes[0] * ax[1][:, None]
+    else:
+        g = ax[0][None, None, :] + nodes[0] * (ax[1][None, :, None] + nodes[1] * ax[2][:, None, None])
+    return g.reshape(-1)
+
+
+def _local_cells(problem: LaplaceProblem, origin, size) -> np.ndarray:
+    dim = problem.dim
+    cells = problem.cells
+    ax = [np.arange(size[d]) + origin[d] for d in range(dim)]
+    if dim == 2:
+        c = ax[0][None, :] + cells[0] * ax[1][:, None]
+    else:
+        c = ax[0][None, None, :] + cells[0] * (ax[1][None, :, None] + cells[1] * ax[2][:, None, None])
+    return c.reshape(-1)
+
+
+def local_eigenvectors(problem: LaplaceProblem, coef_loc: np.ndarray, constr_loc: np.ndarray,
+                       size, n_eigenvectors: int, mode: str = "free", dense_limit: int = 1500):
+    """(eigvecs[n_e, nloc], diag_agg[nloc]) for one agglomerate class.
+
+    mode:
+      "free"          n_e smallest eigenpairs of the unconstrained block (robust default)
+      "host_lapack"   literal amge_host.templates.hpp:378-394,446-467: shift by mean(diag), constrained
+                      diagonal := 200, dense symmetric solve, eigenvalues in (-0.5, 100], ascending
+      "device_lapack" literal amge_device.templates.cuh:217-323: dense sygvd of the local matrix AS
+                      ASSEMBLED (no shift, constrained rows keep their assembled diagonal), n_e smallest.
+                      Constrained unit vectors can win here; this is what the device golds of
+                      tests/test_hierarchy_device.cu:365-381 were recorded with.
+    """
+    dim, p = problem.dim, problem.degree
+    Aloc, diag_agg = assemble(dim, p, size, problem.G, coef_loc, constr_loc)
+    nloc = Aloc.n_rows
+    vecs = np.zeros((n_eigenvectors, nloc))
+    K = Aloc.to_scipy()
+    if mode == "device_lapack":
+        w, v = np.linalg.eigh(K.toarray())
+        ne = min(n_eigenvectors, nloc)
+        vecs[:ne] = v[:, :ne].T
+        return vecs, diag_agg
+    if mode == "host_lapack":
+        M = K.toarray()
+        M[np.diag_indices(nloc)] += np.mean(diag_agg)
+        cidx = np.flatnonzero(constr_loc != 0)
+        M[cidx, cidx] = 200.0
+        w, v = np.linalg.eigh(M)
+        keep = np.flatnonzero((w > -0.5) & (w <= 100.0))
+        if len(keep) < n_eigenvectors:
+            raise RuntimeError("lapack branch: only %d eigenvalues in (-0.5, 100]" % len(keep))
+        vecs[:] = v[:, keep[:n_eigenvectors]].T
+        return vecs, diag_agg
+    free = np.flatnonzero(constr_loc == 0)
+    if len(free) == 0:
+        return vecs, diag_agg
+    Kff = K[free][:, free]
+    ne = min(n_eigenvectors, len(free))
+    if len(free) <= dense_limit:
+        w, v = np.linalg.eigh(Kff.toarray())
+        v = v[:, :ne]
+    else:
+        import scipy.sparse as sp
+        import scipy.sparse.linalg as spla
+
+        shift = float(np.mean(diag_agg))  # amge_host.templates.hpp:384-388
+        Ks = (Kff + shift * sp.identity(len(free))).tocsc()
+        rng = np.random.default_rng(0)
+        w, v = spla.eigsh(Ks, k=ne, sigma=0.0, which="LM", v0=rng.standard_normal(len(free)),
+                          tol=1e-13)
+        order = np.argsort(w)
+        v = v[:, order]
+    # deterministic sign: make the entry of largest magnitude positive
+    for k in range(ne):
+        j = np.argmax(np.abs(v[:, k]))
+        if v[j, k] < 0:
+            v[:, k] = -v[:, k]
+        vecs[k, free] = v[:, k] / np.linalg.norm(v[:, k])
+    return vecs, diag_agg
+
+
+def build_restrictor(problem: LaplaceProblem, block, n_eigenvectors: int,
+                     eigensolver: str = "free") -> HostCSR:
+    """The restriction matrix R (n_c x n) of AMGe::setup_restrictor for block agglomerates."""
+    dim = problem.dim
+    aggs = block_agglomerates(dim, problem.cells, block)
+    diag_A = problem.diag
+    classes: dict = {}
+    members: dict = {}
+    for ia, (origin, size) in enumerate(aggs):
+        cells_loc = _local_cells(problem, origin, size)
+        g = _local_global_nodes(problem, origin, size)
+        coef_loc = problem.coef[cells_loc]
+        constr_loc = problem.constrained[g]
+        key = (tuple(size), coef_loc.tobytes(), constr_loc.tobytes())
+        if key not in classes:
+            classes[key] = local_eigenvectors(problem, np.ascontiguousarray(coef_loc),
+                                              np.ascontiguousarray(constr_loc), size,
+                                              n_eigenvectors, mode=eigensolver)
+            members[key] = []
+        members[key].append((ia, g))
+
+    n_agg = len(aggs)
+    ne = n_eigenvectors
+    nloc_of = np.zeros(n_agg, dtype=np.int64)
+    for key, lst in members.items():
+        for ia, g in lst:
+            nloc_of[ia] = len(g)
+    # row r = ia*ne + k has nloc_of[ia] entries
+    row_len = np.repeat(nloc_of, ne)
+    rowptr = np.zeros(n_agg * ne + 1, dtype=np.int64)
+    np.cumsum(row_len, out=rowptr[1:])
+    nnz = int(rowptr[-1])
+    col = np.empty(nnz, dtype=np.int32)
+    val = np.empty(nnz, dtype=np.float64)
+    for key, lst in members.items():
+        vecs, diag_agg = classes[key]
+        for ia, g in lst:
+            order = np.argsort(g, kind="stable")
+            gs = g[order]
+            w = diag_agg[order] / diag_A[gs]
+            for k in range(ne):
+                r = ia * ne + k
+                col[rowptr[r]:rowptr[r + 1]] = gs
+                val[rowptr[r]:rowptr[r + 1]] = w * vecs[k, order]
+    return HostCSR(n_agg * ne, problem.n, rowptr, col, val)
+
+
+def galerkin(A: HostCSR, R: HostCSR) -> HostCSR:
+    """A_c = R (A R^T): include/mfmg/common/hierarchy.hpp:225,230 (no dropping)."""
+    a = A.to_scipy()
+    r = R.to_scipy()
+    ap = a @ r.T.tocsr()
+    ac = (r @ ap).tocsr()
+    ac.sort_indices()
+    return HostCSR.from_scipy(ac)
+
+
+def transpose(R: HostCSR) -> HostCSR:
+    """Explicit transpose with ascending column indices (stable counting sort)."""
+    t = R.to_scipy().T.tocsr()
+    t.sort_indices()
+    return HostCSR.from_scipy(t)

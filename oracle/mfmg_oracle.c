@@ -1,0 +1,786 @@
+/*
+ * mfmg_oracle.c -- CPU ORACLE for the mfmg V-cycle-apply hot path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.  The product path
+ * (mfmg_b200/, include/) never links, imports or calls anything in oracle/.
+ *
+ * It is a plain-C restatement of the reference's HOST algorithm for the path; every
+ * function cites the reference file:line it follows (paths relative to the mfmg tree).
+ * The reference itself cannot be built here (needs deal.II, Trilinos, MPI, Boost, LAPACKE,
+ * ARPACK, p4est; its CUDA path needs cuSPARSE entry points removed in CUDA 12), so there is
+ * no oracle/_ref.  Parity pins: the known-answer tests of the reference's own test-suite
+ * (tests/golden/, see tests/test_oracle_kat.py).  PCG iteration counts / residual
+ * histories are "parity unpinned": no reference test asserts a value for them
+ * (tests/hierarchy_driver.cc:211-212), so the oracle's own history is the contract.
+ *
+ * Threading: rows of an SpMV are independent, so "#pragma omp parallel for" over rows
+ * does not change any result bit (each row is still summed left to right).  Reductions
+ * (dot, norm) are summed serially in index order so that results do not depend on the
+ * thread count.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef int64_t i64;
+typedef int32_t i32;
+
+/* ------------------------------------------------------------------------------------------
+ * CSR y = A x.  Follows the host operator apply, source/dealii/dealii_trilinos_matrix_operator.cc:28-35
+ * (Epetra CrsMatrix::Multiply, row sums left to right in stored column order) and is the
+ * semantics the device SparseMatrixDevice::vmult must reproduce
+ * (include/mfmg/cuda/sparse_matrix_device.templates.cuh:351-371, tests/test_sparse_matrix_device.cu:98-107).
+ * ---------------------------------------------------------------------------------------- */
+void orc_spmv(i64 n_rows, const i64 *rowptr, const i32 *col, const double *val,
+              const double *x, double *y)
+{
+#pragma omp parallel for schedule(static)
+  for (i64 i = 0; i < n_rows; ++i)
+  {
+    double s = 0.;
+    for (i64 k = rowptr[i]; k < rowptr[i + 1]; ++k)
+      s += val[k] * x[col[k]];
+    y[i] = s;
+  }
+}
+
+/* y = A^T x with the implicit transpose (Epetra Multiply(TransA=true), used by the host
+ * operator for OperatorMode::TRANS, source/dealii/dealii_trilinos_matrix_operator.cc:33-34;
+ * the V-cycle prolongation, include/mfmg/common/hierarchy.hpp:297-298).  Serial scatter:
+ * contributions to y[c] arrive in ascending row order, which is exactly the order of an
+ * explicitly stored, column-sorted transpose (source/cuda/cuda_matrix_operator.cu:93-123). */
+void orc_spmv_transpose(i64 n_rows, i64 n_cols, const i64 *rowptr, const i32 *col,
+                        const double *val, const double *x, double *y)
+{
+  for (i64 c = 0; c < n_cols; ++c)
+    y[c] = 0.;
+  for (i64 i = 0; i < n_rows; ++i)
+    for (i64 k = rowptr[i]; k < rowptr[i + 1]; ++k)
+      y[col[k]] += val[k] * x[i];
+}
+
+/* Explicit transpose (counting sort, stable in row order => columns of A^T ascending).
+ * Restates what CudaMatrixOperator::transpose builds through EpetraExt on the host
+ * (source/cuda/cuda_matrix_operator.cu:93-123).  Output arrays are caller-allocated:
+ * t_rowptr[n_cols+1], t_col[nnz], t_val[nnz]. */
+void orc_csr_transpose(i64 n_rows, i64 n_cols, const i64 *rowptr, const i32 *col,
+                       const double *val, i64 *t_rowptr, i32 *t_col, double *t_val)
+{
+  for (i64 c = 0; c <= n_cols; ++c)
+    t_rowptr[c] = 0;
+  for (i64 k = 0; k < rowptr[n_rows]; ++k)
+    t_rowptr[col[k] + 1]++;
+  for (i64 c = 0; c < n_cols; ++c)
+    t_rowptr[c + 1] += t_rowptr[c];
+  i64 *next = (i64 *)malloc(sizeof(i64) * (size_t)(n_cols > 0 ? n_cols : 1));
+  memcpy(next, t_rowptr, sizeof(i64) * (size_t)n_cols);
+  for (i64 i = 0; i < n_rows; ++i)
+    for (i64 k = rowptr[i]; k < rowptr[i + 1]; ++k)
+    {
+      i64 p = next[col[k]]++;
+      t_col[p] = (i32)i;
+      t_val[p] = val[k];
+    }
+  free(next);
+}
+
+/* Inverse diagonal: D^-1_ii = 1 / a_ii (kernel extract_inv_diag, source/cuda/cuda_smoother.cu:86-96).
+ * Returns the number of rows without a stored diagonal entry (dinv left at 0 for those). */
+i64 orc_inv_diag(i64 n, const i64 *rowptr, const i32 *col, const double *val, double *dinv)
+{
+  i64 missing = 0;
+  for (i64 i = 0; i < n; ++i)
+  {
+    int found = 0;
+    dinv[i] = 0.;
+    for (i64 k = rowptr[i]; k < rowptr[i + 1]; ++k)
+      if (col[k] == i)
+      {
+        dinv[i] = 1. / val[k];
+        found = 1;
+      }
+    if (!found)
+      ++missing;
+  }
+  return missing;
+}
+
+/* r = A x - b : the NEGATIVE residual of include/mfmg/common/hierarchy.hpp:282-286. */
+void orc_residual_neg(i64 n, const i64 *rowptr, const i32 *col, const double *val,
+                      const double *x, const double *b, double *r)
+{
+  orc_spmv(n, rowptr, col, val, x, r);
+#pragma omp parallel for schedule(static)
+  for (i64 i = 0; i < n; ++i)
+    r[i] = r[i] - b[i];
+}
+
+/* One Jacobi sweep exactly as SmootherOperator::apply, source/cuda/cuda_smoother.cu:49-59
+ * (same algebra on the host: source/dealii/dealii_smoother.cc:72-80):
+ *     r = A x;  r -= b;  t = D^-1 r;  x -= t.
+ * omega is NOT in the reference (it is pinned to 1 by tests/test_smoother_device.cu:71-78);
+ * for omega != 1 the update is x -= omega * t.  work has n entries. */
+void orc_jacobi_apply(i64 n, const i64 *rowptr, const i32 *col, const double *val,
+                      const double *dinv, double omega, const double *b, double *x, double *work)
+{
+  orc_spmv(n, rowptr, col, val, x, work);
+  if (omega == 1.)
+  {
+#pragma omp parallel for schedule(static)
+    for (i64 i = 0; i < n; ++i)
+    {
+      double r = work[i] - b[i];
+      double t = dinv[i] * r;
+      x[i] = x[i] - t;
+    }
+  }
+  else
+  {
+#pragma omp parallel for schedule(static)
+    for (i64 i = 0; i < n; ++i)
+    {
+      double r = work[i] - b[i];
+      double t = dinv[i] * r;
+      x[i] = x[i] - omega * t;
+    }
+  }
+}
+
+/* CSR -> dense row-major (cusparseDcsr2dense at source/cuda/dealii_operator_device_helpers.cu:182,
+ * duplicates summed). */
+void orc_csr_to_dense(i64 n, const i64 *rowptr, const i32 *col, const double *val, double *dense)
+{
+  memset(dense, 0, sizeof(double) * (size_t)n * (size_t)n);
+  for (i64 i = 0; i < n; ++i)
+    for (i64 k = rowptr[i]; k < rowptr[i + 1]; ++k)
+      dense[i * n + col[k]] += val[k];
+}
+
+/* Dense LU with partial (row) pivoting, in place, row-major: P A = L U, unit-diagonal L.
+ * Restates getrf as used by lu_factorization, source/cuda/dealii_operator_device_helpers.cu:169-228
+ * (pivot = first entry of maximal magnitude in the column, as LAPACK idamax).
+ * piv[k] = row swapped with k at step k.  Returns 0, or k+1 if U(k,k) == 0. */
+int orc_lu_factor(i64 n, double *a, i32 *piv)
+{
+  int info = 0;
+  for (i64 k = 0; k < n; ++k)
+  {
+    i64 p = k;
+    double amax = fabs(a[k * n + k]);
+    for (i64 i = k + 1; i < n; ++i)
+    {
+      double v = fabs(a[i * n + k]);
+      if (v > amax)
+      {
+        amax = v;
+        p = i;
+      }
+    }
+    piv[k] = (i32)p;
+    if (amax == 0.)
+    {
+      if (!info)
+        info = (int)(k + 1);
+      continue;
+    }
+    if (p != k)
+      for (i64 j = 0; j < n; ++j)
+      {
+        double t = a[k * n + j];
+        a[k * n + j] = a[p * n + j];
+        a[p * n + j] = t;
+      }
+    double inv = 1. / a[k * n + k];
+#pragma omp parallel for schedule(static) if (n - k > 256)
+    for (i64 i = k + 1; i < n; ++i)
+    {
+      double l = a[i * n + k] * inv;
+      a[i * n + k] = l;
+      if (l != 0.)
+        for (i64 j = k + 1; j < n; ++j)
+          a[i * n + j] -= l * a[k * n + j];
+    }
+  }
+  return info;
+}
+
+/* x = A^-1 b from the factors (getrs, source/cuda/dealii_operator_device_helpers.cu:214):
+ * apply the row interchanges, forward substitution with unit L, back substitution with U. */
+void orc_lu_solve(i64 n, const double *lu, const i32 *piv, const double *b, double *x)
+{
+  if (x != b)
+    memcpy(x, b, sizeof(double) * (size_t)n);
+  for (i64 k = 0; k < n; ++k)
+  {
+    i64 p = piv[k];
+    if (p != k)
+    {
+      double t = x[k];
+      x[k] = x[p];
+      x[p] = t;
+    }
+  }
+  for (i64 i = 0; i < n; ++i)
+  {
+    double s = x[i];
+    const double *row = lu + i * n;
+    for (i64 j = 0; j < i; ++j)
+      s -= row[j] * x[j];
+    x[i] = s;
+  }
+  for (i64 i = n - 1; i >= 0; --i)
+  {
+    double s = x[i];
+    const double *row = lu + i * n;
+    for (i64 j = i + 1; j < n; ++j)
+      s -= row[j] * x[j];
+    x[i] = s / row[i];
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Hierarchy: levels[0] finest ... levels[L-1] coarsest.  Mirrors mfmg::Hierarchy / Level
+ * (include/mfmg/common/hierarchy.hpp:159-309, level.hpp:22-76).  Operators are given, not
+ * built: setup (agglomeration, eigensolves, R assembly, R A R^T) is outside the hot path.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct
+{
+  i64 n;
+  /* A of this level (CSR); on the coarsest level only used to build the dense factors */
+  const i64 *a_rowptr;
+  const i32 *a_col;
+  const double *a_val;
+  /* matrix-free fine operator (level 0 only): if mf != NULL, A x is evaluated by it */
+  void *mf;
+  /* restrictor from the next-finer level to this one: n x n_finer (levels >= 1) */
+  i64 r_ncols;
+  const i64 *r_rowptr;
+  const i32 *r_col;
+  const double *r_val;
+  /* explicit transpose of the restrictor (built at finalize) */
+  i64 *p_rowptr;
+  i32 *p_col;
+  double *p_val;
+  double *dinv;
+  /* coarsest level */
+  double *lu;
+  i32 *piv;
+  /* work vectors */
+  double *res, *work, *bc, *xc;
+} orc_level;
+
+typedef struct
+{
+  int n_levels;
+  int n_smoothing_steps; /* smoother.n_smoothing_steps, hierarchy.hpp:169 */
+  int is_preconditioner; /* "is preconditioner", hierarchy.hpp:168 */
+  double omega;
+  int explicit_transpose; /* 1: prolong with stored R^T; 0: implicit Tvmult */
+  orc_level *lev;
+} orc_hierarchy;
+
+void orc_mf_apply(const void *mf, const double *x, double *y);
+void orc_mf_diag(const void *mf, double *diag);
+i64 orc_mf_n(const void *mf);
+
+orc_hierarchy *orc_hierarchy_new(int n_levels, int n_smoothing_steps, int is_preconditioner,
+                                 double omega)
+{
+  orc_hierarchy *h = (orc_hierarchy *)calloc(1, sizeof(orc_hierarchy));
+  h->n_levels = n_levels;
+  h->n_smoothing_steps = n_smoothing_steps;
+  h->is_preconditioner = is_preconditioner;
+  h->omega = omega;
+  h->explicit_transpose = 1;
+  h->lev = (orc_level *)calloc((size_t)n_levels, sizeof(orc_level));
+  return h;
+}
+
+void orc_hierarchy_set_explicit_transpose(orc_hierarchy *h, int flag) { h->explicit_transpose = flag; }
+
+/* The arrays are borrowed: the caller keeps them alive for the life of the hierarchy. */
+void orc_hierarchy_set_operator(orc_hierarchy *h, int level, i64 n, const i64 *rowptr,
+                                const i32 *col, const double *val)
+{
+  orc_level *l = &h->lev[level];
+  l->n = n;
+  l->a_rowptr = rowptr;
+  l->a_col = col;
+  l->a_val = val;
+}
+
+void orc_hierarchy_set_mf_operator(orc_hierarchy *h, void *mf)
+{
+  h->lev[0].mf = mf;
+  h->lev[0].n = orc_mf_n(mf);
+}
+
+void orc_hierarchy_set_restrictor(orc_hierarchy *h, int level, i64 n_rows, i64 n_cols,
+                                  const i64 *rowptr, const i32 *col, const double *val)
+{
+  orc_level *l = &h->lev[level];
+  (void)n_rows;
+  l->r_ncols = n_cols;
+  l->r_rowptr = rowptr;
+  l->r_col = col;
+  l->r_val = val;
+}
+
+/* Build smoothers (all but last level) and the coarse dense LU (last level):
+ * Hierarchy ctor, include/mfmg/common/hierarchy.hpp:183-234. Returns LU info. */
+int orc_hierarchy_finalize(orc_hierarchy *h)
+{
+  int info = 0;
+  for (int li = 0; li < h->n_levels; ++li)
+  {
+    orc_level *l = &h->lev[li];
+    i64 n = l->n;
+    l->res = (double *)calloc((size_t)n, sizeof(double));
+    l->work = (double *)calloc((size_t)n, sizeof(double));
+    l->bc = (double *)calloc((size_t)n, sizeof(double));
+    l->xc = (double *)calloc((size_t)n, sizeof(double));
+    if (li > 0)
+    {
+      i64 nnz = l->r_rowptr[n];
+      l->p_rowptr = (i64 *)malloc(sizeof(i64) * (size_t)(l->r_ncols + 1));
+      l->p_col = (i32 *)malloc(sizeof(i32) * (size_t)(nnz > 0 ? nnz : 1));
+      l->p_val = (double *)malloc(sizeof(double) * (size_t)(nnz > 0 ? nnz : 1));
+      orc_csr_transpose(n, l->r_ncols, l->r_rowptr, l->r_col, l->r_val, l->p_rowptr, l->p_col,
+                        l->p_val);
+    }
+    if (li < h->n_levels - 1)
+    {
+      l->dinv = (double *)malloc(sizeof(double) * (size_t)n);
+      if (l->mf)
+      {
+        orc_mf_diag(l->mf, l->dinv);
+        for (i64 i = 0; i < n; ++i)
+          l->dinv[i] = 1. / l->dinv[i];
+      }
+      else
+        orc_inv_diag(n, l->a_rowptr, l->a_col, l->a_val, l->dinv);
+    }
+    else
+    {
+      l->lu = (double *)malloc(sizeof(double) * (size_t)n * (size_t)n);
+      l->piv = (i32 *)malloc(sizeof(i32) * (size_t)(n > 0 ? n : 1));
+      orc_csr_to_dense(n, l->a_rowptr, l->a_col, l->a_val, l->lu);
+      info = orc_lu_factor(n, l->lu, l->piv);
+    }
+  }
+  return info;
+}
+
+void orc_hierarchy_free(orc_hierarchy *h)
+{
+  if (!h)
+    return;
+  for (int li = 0; li < h->n_levels; ++li)
+  {
+    orc_level *l = &h->lev[li];
+    free(l->res);
+    free(l->work);
+    free(l->bc);
+    free(l->xc);
+    free(l->p_rowptr);
+    free(l->p_col);
+    free(l->p_val);
+    free(l->dinv);
+    free(l->lu);
+    free(l->piv);
+  }
+  free(h->lev);
+  free(h);
+}
+
+static void level_apply_A(const orc_level *l, const double *x, double *y)
+{
+  if (l->mf)
+    orc_mf_apply(l->mf, x, y);
+  else
+    orc_spmv(l->n, l->a_rowptr, l->a_col, l->a_val, x, y);
+}
+
+static void level_smooth(const orc_hierarchy *h, orc_level *l, const double *b, double *x)
+{
+  /* source/cuda/cuda_smoother.cu:49-59 */
+  i64 n = l->n;
+  level_apply_A(l, x, l->work);
+  const double om = h->omega;
+#pragma omp parallel for schedule(static)
+  for (i64 i = 0; i < n; ++i)
+  {
+    double r = l->work[i] - b[i];
+    double t = l->dinv[i] * r;
+    x[i] = (om == 1.) ? x[i] - t : x[i] - om * t;
+  }
+}
+
+/* Hierarchy::apply, include/mfmg/common/hierarchy.hpp:246-309, line by line. */
+void orc_hierarchy_apply(orc_hierarchy *h, const double *b, double *x, int level_index)
+{
+  orc_level *fine = &h->lev[level_index];
+  i64 n = fine->n;
+  if (level_index > 0 || h->is_preconditioner) /* :253-259 */
+    for (i64 i = 0; i < n; ++i)
+      x[i] = 0.;
+
+  if (level_index == h->n_levels - 1)
+  {
+    orc_lu_solve(n, fine->lu, fine->piv, b, x); /* :261-268 -> cuda_solver.cu:496-515 */
+    return;
+  }
+  orc_level *coarse = &h->lev[level_index + 1];
+  i64 nc = coarse->n;
+
+  for (int s = 0; s < h->n_smoothing_steps; ++s) /* :277-279 */
+    level_smooth(h, fine, b, x);
+
+  level_apply_A(fine, x, fine->res); /* :284-286 */
+#pragma omp parallel for schedule(static)
+  for (i64 i = 0; i < n; ++i)
+    fine->res[i] = fine->res[i] - b[i];
+
+  /* :289-290 b_c = R res */
+  orc_spmv(nc, coarse->r_rowptr, coarse->r_col, coarse->r_val, fine->res, coarse->bc);
+
+  /* :293-294 recurse */
+  orc_hierarchy_apply(h, coarse->bc, coarse->xc, level_index + 1);
+
+  /* :297-298 x_corr = R^T x_c  (reuse fine->work) */
+  if (h->explicit_transpose)
+    orc_spmv(n, coarse->p_rowptr, coarse->p_col, coarse->p_val, coarse->xc, fine->work);
+  else
+    orc_spmv_transpose(nc, n, coarse->r_rowptr, coarse->r_col, coarse->r_val, coarse->xc,
+                       fine->work);
+    /* :302 x -= x_corr */
+#pragma omp parallel for schedule(static)
+  for (i64 i = 0; i < n; ++i)
+    x[i] = x[i] - fine->work[i];
+
+  for (int s = 0; s < h->n_smoothing_steps; ++s) /* :305-306 */
+    level_smooth(h, fine, b, x);
+}
+
+/* Hierarchy::vmult(x, b), hierarchy.hpp:238-244 */
+void orc_hierarchy_vmult(orc_hierarchy *h, double *x, const double *b)
+{
+  orc_hierarchy_apply(h, b, x, 0);
+}
+
+/* serial, index-ordered reductions (thread-count independent) */
+double orc_dot(i64 n, const double *a, const double *b)
+{
+  double s = 0.;
+  for (i64 i = 0; i < n; ++i)
+    s += a[i] * b[i];
+  return s;
+}
+
+/* Preconditioned CG, the recurrence of dealii::SolverCG::solve (deal.II 9.x solver_cg.h, third
+ * party, un-vendored) as called at tests/hierarchy_driver.cc:204-210 with the hierarchy as
+ * preconditioner; stops when the l2 norm of g = A x - b is <= tol (absolute) or after max_it
+ * steps (SolverControl(max_it, tol), hierarchy_driver.cc:202-203).
+ *   g = A x - b; res0 = |g|; h = M^-1 g; d = -h; gh = g.h
+ *   loop: h = A d; alpha = gh / (d.h); g += alpha h; x += alpha d; res = |g|; check;
+ *         h = M^-1 g; beta = gh; gh = g.h; beta = gh / beta; d = beta d - h
+ * res_hist must hold max_it + 1 doubles.  Returns the number of iterations (last_step()),
+ * negative if not converged.  If hier == NULL the preconditioner is the identity. */
+int orc_pcg(orc_hierarchy *hier, i64 n, const i64 *rowptr, const i32 *col, const double *val,
+            const double *b, double *x, double tol, int max_it, double *res_hist)
+{
+  double *g = (double *)malloc(sizeof(double) * (size_t)n);
+  double *hh = (double *)malloc(sizeof(double) * (size_t)n);
+  double *d = (double *)malloc(sizeof(double) * (size_t)n);
+  int it = 0, converged = 0;
+  const orc_level *l0 = hier ? &hier->lev[0] : NULL;
+
+  if (l0 && l0->mf)
+    orc_mf_apply(l0->mf, x, g);
+  else
+    orc_spmv(n, rowptr, col, val, x, g);
+  for (i64 i = 0; i < n; ++i)
+    g[i] = g[i] - b[i];
+  double res = sqrt(orc_dot(n, g, g));
+  res_hist[0] = res;
+  if (res <= tol)
+    converged = 1;
+  else
+  {
+    if (hier)
+      orc_hierarchy_vmult(hier, hh, g);
+    else
+      memcpy(hh, g, sizeof(double) * (size_t)n);
+    for (i64 i = 0; i < n; ++i)
+      d[i] = -hh[i];
+    double gh = orc_dot(n, g, hh);
+    while (!converged && it < max_it)
+    {
+      ++it;
+      if (l0 && l0->mf)
+        orc_mf_apply(l0->mf, d, hh);
+      else
+        orc_spmv(n, rowptr, col, val, d, hh);
+      double alpha = orc_dot(n, d, hh);
+      alpha = gh / alpha;
+      for (i64 i = 0; i < n; ++i)
+        g[i] = g[i] + alpha * hh[i];
+      for (i64 i = 0; i < n; ++i)
+        x[i] = x[i] + alpha * d[i];
+      res = sqrt(orc_dot(n, g, g));
+      res_hist[it] = res;
+      if (res <= tol)
+      {
+        converged = 1;
+        break;
+      }
+      if (hier)
+        orc_hierarchy_vmult(hier, hh, g);
+      else
+        memcpy(hh, g, sizeof(double) * (size_t)n);
+      double beta = gh;
+      gh = orc_dot(n, g, hh);
+      beta = gh / beta;
+      for (i64 i = 0; i < n; ++i)
+        d[i] = beta * d[i] - hh[i];
+    }
+  }
+  free(g);
+  free(hh);
+  free(d);
+  return converged ? it : -it - 1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Matrix-free Laplace/diffusion operator on a uniform Cartesian grid of Q_p hexahedra /
+ * quadrilaterals, lexicographic DoF numbering.  Restates LaplaceOperator::local_apply,
+ * tests/laplace_matrix_free.hpp:129-156, inside deal.II's MatrixFreeOperators::Base::vmult
+ * semantics (constrained DoFs: input treated as 0 in the cell loop, output y_i = x_i), and
+ * compute_diagonal, tests/laplace_matrix_free.hpp:75-98,158-199 (constrained entries := 1).
+ *   per cell: u_loc = gather(x); grad at the (p+1)^d Gauss points; multiply by coef(cell,q);
+ *   integrate against grad(phi_i); scatter-add.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct
+{
+  int dim, degree;
+  i64 cells[3];
+  double h[3];
+  i64 nodes[3];
+  i64 n;
+  int nq1;          /* p+1 */
+  double *shape;    /* [nq1][nq1]  phi_a(x_q) on the unit interval */
+  double *dshape;   /* [nq1][nq1]  phi_a'(x_q) on the unit interval */
+  double *qw;       /* [nq1] Gauss weights on the unit interval */
+  const double *coef;          /* [n_cells][nq1^dim] (borrowed) */
+  const unsigned char *constr; /* [n] (borrowed) */
+} orc_mf;
+
+static void gauss_unit(int nq, double *pts, double *wts)
+{
+  /* Gauss-Legendre on [0,1] (dealii::QGauss<1>(p+1), tests/laplace_matrix_free.hpp:304) */
+  for (int i = 0; i < nq; ++i)
+  {
+    double z = cos(M_PI * (i + 0.75) / (nq + 0.5)), pp = 0.;
+    for (int it = 0; it < 100; ++it)
+    {
+      double p1 = 1., p2 = 0.;
+      for (int j = 0; j < nq; ++j)
+      {
+        double p3 = p2;
+        p2 = p1;
+        p1 = ((2. * j + 1.) * z * p2 - j * p3) / (j + 1.);
+      }
+      pp = nq * (z * p1 - p2) / (z * z - 1.);
+      double z1 = z;
+      z = z1 - p1 / pp;
+      if (fabs(z - z1) < 1e-16)
+        break;
+    }
+    pts[nq - 1 - i] = 0.5 * (z + 1.);
+    wts[nq - 1 - i] = 1. / ((1. - z * z) * pp * pp);
+  }
+}
+
+orc_mf *orc_mf_new(int dim, int degree, const i64 *cells, const double *h, const double *coef,
+                   const unsigned char *constrained)
+{
+  orc_mf *m = (orc_mf *)calloc(1, sizeof(orc_mf));
+  m->dim = dim;
+  m->degree = degree;
+  m->n = 1;
+  for (int d = 0; d < 3; ++d)
+  {
+    m->cells[d] = d < dim ? cells[d] : 1;
+    m->h[d] = d < dim ? h[d] : 1.;
+    m->nodes[d] = d < dim ? cells[d] * degree + 1 : 1;
+    m->n *= m->nodes[d];
+  }
+  int nq = degree + 1;
+  m->nq1 = nq;
+  m->shape = (double *)malloc(sizeof(double) * nq * nq);
+  m->dshape = (double *)malloc(sizeof(double) * nq * nq);
+  m->qw = (double *)malloc(sizeof(double) * nq);
+  double *qp = (double *)malloc(sizeof(double) * nq);
+  gauss_unit(nq, qp, m->qw);
+  /* Lagrange basis on equidistant support points (FE_Q(p) for p <= 2 uses equidistant
+   * Gauss-Lobatto points), a = node index, q = quadrature index. */
+  for (int q = 0; q < nq; ++q)
+    for (int a = 0; a < nq; ++a)
+    {
+      double xa = (double)a / degree, v = 1., dv = 0.;
+      for (int c = 0; c < nq; ++c)
+        if (c != a)
+          v *= (qp[q] - (double)c / degree) / (xa - (double)c / degree);
+      for (int e = 0; e < nq; ++e)
+        if (e != a)
+        {
+          double t = 1. / (xa - (double)e / degree);
+          for (int c = 0; c < nq; ++c)
+            if (c != a && c != e)
+              t *= (qp[q] - (double)c / degree) / (xa - (double)c / degree);
+          dv += t;
+        }
+      m->shape[q * nq + a] = v;
+      m->dshape[q * nq + a] = dv;
+    }
+  free(qp);
+  m->coef = coef;
+  m->constr = constrained;
+  return m;
+}
+
+void orc_mf_free(orc_mf *m)
+{
+  if (!m)
+    return;
+  free(m->shape);
+  free(m->dshape);
+  free(m->qw);
+  free(m);
+}
+
+i64 orc_mf_n(const void *mf) { return ((const orc_mf *)mf)->n; }
+
+/* cell kernel: out_loc = K_cell(coef) u_loc  (dense evaluation, no sum factorisation) */
+static void mf_cell(const orc_mf *m, const double *cq, const double *u, double *out)
+{
+  const int nq = m->nq1, dim = m->dim;
+  const int n3 = dim == 3 ? nq : 1;
+  const int ndof = nq * nq * n3;
+  for (int i = 0; i < ndof; ++i)
+    out[i] = 0.;
+  for (int qz = 0; qz < n3; ++qz)
+    for (int qy = 0; qy < nq; ++qy)
+      for (int qx = 0; qx < nq; ++qx)
+      {
+        const int q = qx + nq * (qy + nq * qz);
+        double g[3] = {0., 0., 0.};
+        for (int az = 0; az < n3; ++az)
+          for (int ay = 0; ay < nq; ++ay)
+            for (int ax = 0; ax < nq; ++ax)
+            {
+              const double uu = u[ax + nq * (ay + nq * az)];
+              const double sx = m->shape[qx * nq + ax], sy = m->shape[qy * nq + ay];
+              const double sz = dim == 3 ? m->shape[qz * nq + az] : 1.;
+              g[0] += uu * m->dshape[qx * nq + ax] / m->h[0] * sy * sz;
+              g[1] += uu * sx * m->dshape[qy * nq + ay] / m->h[1] * sz;
+              if (dim == 3)
+                g[2] += uu * sx * sy * m->dshape[qz * nq + az] / m->h[2];
+            }
+        double jxw = m->qw[qx] * m->qw[qy] * m->h[0] * m->h[1];
+        if (dim == 3)
+          jxw *= m->qw[qz] * m->h[2];
+        const double c = cq[q] * jxw;
+        for (int az = 0; az < n3; ++az)
+          for (int ay = 0; ay < nq; ++ay)
+            for (int ax = 0; ax < nq; ++ax)
+            {
+              const double sx = m->shape[qx * nq + ax], sy = m->shape[qy * nq + ay];
+              const double sz = dim == 3 ? m->shape[qz * nq + az] : 1.;
+              double v = g[0] * m->dshape[qx * nq + ax] / m->h[0] * sy * sz +
+                         g[1] * sx * m->dshape[qy * nq + ay] / m->h[1] * sz;
+              if (dim == 3)
+                v += g[2] * sx * sy * m->dshape[qz * nq + az] / m->h[2];
+              out[ax + nq * (ay + nq * az)] += c * v;
+            }
+      }
+}
+
+static void mf_loop(const orc_mf *m, const double *x, double *y, int diag_mode)
+{
+  const int nq = m->nq1, p = m->degree, dim = m->dim;
+  const int n3 = dim == 3 ? nq : 1;
+  const int ndof = nq * nq * n3;
+  const int nqp = ndof;
+  double u[125], out[125], dg[125];
+  for (i64 i = 0; i < m->n; ++i)
+    y[i] = 0.;
+  for (i64 cz = 0; cz < m->cells[2]; ++cz)
+    for (i64 cy = 0; cy < m->cells[1]; ++cy)
+      for (i64 cx = 0; cx < m->cells[0]; ++cx)
+      {
+        const i64 cell = cx + m->cells[0] * (cy + m->cells[1] * cz);
+        const double *cq = m->coef + cell * nqp;
+        i64 idx[125];
+        for (int az = 0; az < n3; ++az)
+          for (int ay = 0; ay < nq; ++ay)
+            for (int ax = 0; ax < nq; ++ax)
+              idx[ax + nq * (ay + nq * az)] =
+                  (cx * p + ax) + m->nodes[0] * ((cy * p + ay) + m->nodes[1] * (cz * p + az));
+        if (!diag_mode)
+        {
+          for (int a = 0; a < ndof; ++a)
+            u[a] = m->constr[idx[a]] ? 0. : x[idx[a]];
+          mf_cell(m, cq, u, out);
+          for (int a = 0; a < ndof; ++a)
+            if (!m->constr[idx[a]])
+              y[idx[a]] += out[a];
+        }
+        else
+        {
+          for (int i = 0; i < ndof; ++i)
+          {
+            for (int a = 0; a < ndof; ++a)
+              u[a] = 0.;
+            u[i] = 1.;
+            mf_cell(m, cq, u, out);
+            dg[i] = out[i];
+          }
+          for (int a = 0; a < ndof; ++a)
+            if (!m->constr[idx[a]])
+              y[idx[a]] += dg[a];
+        }
+      }
+  for (i64 i = 0; i < m->n; ++i)
+    if (m->constr[i])
+      y[i] = diag_mode ? 1. : x[i];
+}
+
+void orc_mf_apply(const void *mf, const double *x, double *y)
+{
+  mf_loop((const orc_mf *)mf, x, y, 0);
+}
+void orc_mf_diag(const void *mf, double *diag) { mf_loop((const orc_mf *)mf, NULL, diag, 1); }
+
+int orc_num_threads(void)
+{
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+  omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
