@@ -1,0 +1,187 @@
+/*
+ * mfmg_b200.h -- C ABI of the B200-native (sm_100a) multigrid V-cycle apply.
+ *
+ * This is the drop-in boundary for mfmg's device operator path: every entry point names the
+ * reference interface it replaces (paths relative to the ORNL-CEES/mfmg tree).  Plain pointers and
+ * sizes only; opaque handles; every function returns an int status (0 = MFMGB_OK) and never
+ * throws; work is stream-ordered on the context's stream; results are visible to the host after
+ * mfmgb_ctx_synchronize() (the *_host entry points synchronise before returning, matching the
+ * reference's synchronous semantics).  No cuSPARSE / cuSOLVER / AMGX behind any of them.
+ *
+ * Vectors are raw device pointers to double (the storage of
+ * dealii::LinearAlgebra::distributed::Vector<double, MemorySpace::CUDA>::get_values()).
+ * Matrices are CSR with 64-bit row offsets on the host side of the ABI (the reference's int
+ * row_ptr overflows at 513^3 Q1) and int32 local column indices.
+ */
+#ifndef MFMG_B200_H
+#define MFMG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+#if defined(_WIN32)
+#define MFMGB_API
+#else
+#define MFMGB_API __attribute__((visibility("default")))
+#endif
+
+  typedef struct mfmgb_ctx mfmgb_ctx;
+  typedef struct mfmgb_csr mfmgb_csr;
+  typedef struct mfmgb_jacobi mfmgb_jacobi;
+  typedef struct mfmgb_dense mfmgb_dense;
+  typedef struct mfmgb_mf mfmgb_mf;
+  typedef struct mfmgb_hierarchy mfmgb_hierarchy;
+
+  enum
+  {
+    MFMGB_OK = 0,
+    MFMGB_ERR_INVALID = 1,         /* bad argument (reference: ASSERT / ASSERT_THROW, exceptions.hpp:44-63) */
+    MFMGB_ERR_CUDA = 2,            /* a CUDA call failed (reference: ASSERT_CUDA, exceptions.hpp:204-228; checked here in ALL build types) */
+    MFMGB_ERR_NOT_IMPLEMENTED = 3, /* reference: NotImplementedExc, exceptions.hpp:65-84 */
+    MFMGB_ERR_SINGULAR = 4,        /* zero pivot in the dense factorisation / missing diagonal */
+    MFMGB_ERR_NCCL = 5,
+    MFMGB_ERR_NOT_CONVERGED = 6    /* PCG hit max_it (dealii::SolverControl::NoConvergence) */
+  };
+
+  /* ---- context: replaces mfmg::CudaHandle (source/cuda/cuda_handle.cu:17-56), minus the library handles ---- */
+  /* stream: a cudaStream_t to launch on, or NULL to create a private non-blocking stream. */
+  MFMGB_API int mfmgb_ctx_create(int device, void *stream, mfmgb_ctx **out);
+  MFMGB_API int mfmgb_ctx_destroy(mfmgb_ctx *ctx);
+  MFMGB_API int mfmgb_ctx_synchronize(mfmgb_ctx *ctx);
+  MFMGB_API void *mfmgb_ctx_stream(mfmgb_ctx *ctx);
+  /* last error message of this context (or of the calling thread when ctx == NULL) */
+  MFMGB_API const char *mfmgb_last_error(mfmgb_ctx *ctx);
+  /* number of kernels this context has launched so far (bench.py's gpu_launches claim) */
+  MFMGB_API int64_t mfmgb_ctx_launch_count(mfmgb_ctx *ctx);
+  MFMGB_API const char *mfmgb_version(void);
+
+  /* ---- device vectors: replaces cuda_malloc/cuda_free/cuda_mem_copy_to_{dev,host} (include/mfmg/cuda/utils.cuh:66-99)
+   *      and the deal.II CUDA-vector ops used on the path (hierarchy.hpp:258,286,302; cuda_smoother.cu:50-59) ---- */
+  MFMGB_API int mfmgb_vec_alloc(mfmgb_ctx *ctx, int64_t n, double **out);
+  MFMGB_API int mfmgb_vec_free(mfmgb_ctx *ctx, double *v);
+  MFMGB_API int mfmgb_vec_upload(mfmgb_ctx *ctx, double *dst_dev, const double *src_host, int64_t n);
+  MFMGB_API int mfmgb_vec_download(mfmgb_ctx *ctx, const double *src_dev, double *dst_host, int64_t n);
+  MFMGB_API int mfmgb_vec_fill(mfmgb_ctx *ctx, double *v, double value, int64_t n);
+  MFMGB_API int mfmgb_vec_copy(mfmgb_ctx *ctx, double *dst, const double *src, int64_t n);
+  MFMGB_API int mfmgb_vec_axpy(mfmgb_ctx *ctx, double *y, double a, const double *x, int64_t n); /* y += a x  (Vector::add) */
+  MFMGB_API int mfmgb_vec_dot(mfmgb_ctx *ctx, const double *a, const double *b, int64_t n, double *result_host);
+
+  /* ---- CSR matrix: replaces mfmg::SparseMatrixDevice<double> (include/mfmg/cuda/sparse_matrix_device.cuh:28-104)
+   *      and convert_matrix (source/cuda/utils.cu:39-168) ---- */
+  /* copies host arrays to the device; the caller keeps its arrays (convert_matrix semantics). */
+  MFMGB_API int mfmgb_csr_upload(mfmgb_ctx *ctx, int64_t n_rows, int64_t n_cols, const int64_t *rowptr,
+                                 const int32_t *col, const double *val, mfmgb_csr **out);
+  /* same, with the reference's int row_ptr (sparse_matrix_device.cuh:94). */
+  MFMGB_API int mfmgb_csr_upload_i32(mfmgb_ctx *ctx, int64_t n_rows, int64_t n_cols, const int32_t *rowptr,
+                                     const int32_t *col, const double *val, mfmgb_csr **out);
+  /* TAKES OWNERSHIP of three cudaMalloc'ed arrays, exactly like SparseMatrixDevice's ctor
+   * (include/mfmg/cuda/sparse_matrix_device.templates.cuh:244-272); freed in mfmgb_csr_destroy. */
+  MFMGB_API int mfmgb_csr_adopt_device(mfmgb_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz, double *val_dev,
+                                       int32_t *col_dev, int32_t *rowptr_dev, mfmgb_csr **out);
+  MFMGB_API int mfmgb_csr_destroy(mfmgb_ctx *ctx, mfmgb_csr *A);
+  MFMGB_API int mfmgb_csr_info(const mfmgb_csr *A, int64_t *n_rows, int64_t *n_cols, int64_t *nnz);
+  /* raw device arrays (SparseMatrixDevice::val_dev / column_index_dev, public members cuh:92-94) */
+  MFMGB_API int mfmgb_csr_device_arrays(const mfmgb_csr *A, double **val_dev, int32_t **col_dev, void **rowptr_dev,
+                                        int *rowptr_is_64);
+  /* device -> host copy (round-trip check, tests/test_utils_device.cu:221-263) */
+  MFMGB_API int mfmgb_csr_download(mfmgb_ctx *ctx, const mfmgb_csr *A, int64_t *rowptr, int32_t *col, double *val);
+  /* explicit transpose, ascending columns, deterministic; replaces CudaMatrixOperator::transpose
+   * (source/cuda/cuda_matrix_operator.cu:93-130), done once at setup. */
+  MFMGB_API int mfmgb_csr_transpose(mfmgb_ctx *ctx, const mfmgb_csr *A, mfmgb_csr **out);
+  /* lanes-per-row override for the vector-CSR kernels: 0 = choose from the mean row length */
+  MFMGB_API int mfmgb_csr_set_lanes_per_row(mfmgb_csr *A, int lanes);
+  MFMGB_API int mfmgb_csr_get_lanes_per_row(const mfmgb_csr *A);
+
+  /* y = A x : SparseMatrixDevice::vmult (sparse_matrix_device.templates.cuh:351-371), CudaMatrixOperator::apply
+   * NO_TRANS (source/cuda/cuda_matrix_operator.cu:80-91) */
+  MFMGB_API int mfmgb_spmv(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, double *y);
+  /* r = A x - b : the negative residual of Hierarchy::apply (include/mfmg/common/hierarchy.hpp:282-286), fused */
+  MFMGB_API int mfmgb_residual_neg(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const double *b, double *r);
+  /* b_c = R r : restrictor->apply (hierarchy.hpp:289-290) */
+  MFMGB_API int mfmgb_restrict(mfmgb_ctx *ctx, const mfmgb_csr *R, const double *r, double *b_c);
+  /* x -= P x_c with P = R^T stored explicitly: restrictor->apply(TRANS) + x.add(-1, x_corr) (hierarchy.hpp:297-302), fused */
+  MFMGB_API int mfmgb_prolong_correct(mfmgb_ctx *ctx, const mfmgb_csr *P, const double *x_c, double *x);
+
+  /* ---- Jacobi smoother: replaces mfmg::CudaSmoother (source/cuda/cuda_smoother.cu:39-60,99-172) ---- */
+  /* builds D^-1 (kernel extract_inv_diag, cuda_smoother.cu:86-96). omega = 1 is the reference. */
+  MFMGB_API int mfmgb_jacobi_setup(mfmgb_ctx *ctx, const mfmgb_csr *A, double omega, mfmgb_jacobi **out);
+  /* same, from a given diagonal (matrix-free operators: LaplaceOperator::compute_diagonal, tests/laplace_matrix_free.hpp:75-98) */
+  MFMGB_API int mfmgb_jacobi_setup_diag(mfmgb_ctx *ctx, const double *diag_dev, int64_t n, double omega, mfmgb_jacobi **out);
+  MFMGB_API int mfmgb_jacobi_destroy(mfmgb_ctx *ctx, mfmgb_jacobi *J);
+  MFMGB_API const double *mfmgb_jacobi_inv_diag(const mfmgb_jacobi *J);
+  /* x <- x - omega D^-1 (A x - b), one fused kernel; x is updated in place (an internal
+   * ping-pong buffer holds the previous iterate). */
+  MFMGB_API int mfmgb_jacobi_apply(mfmgb_ctx *ctx, const mfmgb_jacobi *J, const mfmgb_csr *A, const double *b, double *x);
+  /* out-of-place form: x_out = x_in - omega D^-1 (A x_in - b); x_out must not alias x_in */
+  MFMGB_API int mfmgb_jacobi_apply_oop(mfmgb_ctx *ctx, const mfmgb_jacobi *J, const mfmgb_csr *A, const double *b,
+                                       const double *x_in, double *x_out);
+  /* x = omega D^-1 b : the sweep when x == 0 on entry (hierarchy.hpp:253-259 then :277-279) */
+  MFMGB_API int mfmgb_jacobi_apply_zero_guess(mfmgb_ctx *ctx, const mfmgb_jacobi *J, const double *b, double *x);
+
+  /* ---- dense coarse solver: replaces mfmg::CudaSolver "lu_dense" (source/cuda/cuda_solver.cu:496-515 ->
+   *      source/cuda/dealii_operator_device_helpers.cu:169-228), factorised ONCE instead of per apply ---- */
+  MFMGB_API int mfmgb_dense_factor(mfmgb_ctx *ctx, const mfmgb_csr *A_c, mfmgb_dense **out);
+  MFMGB_API int mfmgb_dense_destroy(mfmgb_ctx *ctx, mfmgb_dense *D);
+  MFMGB_API int mfmgb_dense_solve(mfmgb_ctx *ctx, const mfmgb_dense *D, const double *b, double *x);
+  MFMGB_API int64_t mfmgb_dense_size(const mfmgb_dense *D);
+  /* number of row interchanges the factorisation performed (diagnostic) */
+  MFMGB_API int64_t mfmgb_dense_num_swaps(const mfmgb_dense *D);
+
+  /* ---- matrix-free Laplace/diffusion operator: fills the CudaMatrixFreeOperator slot
+   *      (source/cuda/cuda_matrix_free_operator.cu:32-37,60-70; the operator itself is defined by
+   *      tests/laplace_matrix_free.hpp:75-199) on a uniform Cartesian grid, lexicographic DoFs ---- */
+  /* coef: host array [n_cells][(degree+1)^dim]; constrained: host uint8[n]; h: cell size per direction */
+  MFMGB_API int mfmgb_mf_laplace_create(mfmgb_ctx *ctx, int dim, int degree, const int64_t *cells, const double *h,
+                                        const double *coef, const uint8_t *constrained, mfmgb_mf **out);
+  MFMGB_API int mfmgb_mf_destroy(mfmgb_ctx *ctx, mfmgb_mf *M);
+  MFMGB_API int64_t mfmgb_mf_size(const mfmgb_mf *M);
+  MFMGB_API int mfmgb_mf_apply(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, double *y);
+  /* diagonal with constrained entries set to 1 (compute_diagonal) into a device vector */
+  MFMGB_API int mfmgb_mf_diagonal(mfmgb_ctx *ctx, const mfmgb_mf *M, double *diag_dev);
+
+  /* ---- hierarchy / V-cycle / PCG: replaces mfmg::Hierarchy<V>::vmult/apply
+   *      (include/mfmg/common/hierarchy.hpp:238-309) and the dealii::SolverCG loop around it
+   *      (tests/hierarchy_driver.cc:200-213) ---- */
+  /* n_smoothing_steps = "smoother.n_smoothing_steps" (hierarchy.hpp:169); is_preconditioner = "is preconditioner" (:168) */
+  MFMGB_API int mfmgb_hierarchy_create(mfmgb_ctx *ctx, int n_levels, int n_smoothing_steps, int is_preconditioner,
+                                       double omega, mfmgb_hierarchy **out);
+  /* level operators are BORROWED (they must outlive the hierarchy). level 0 = finest. */
+  MFMGB_API int mfmgb_hierarchy_set_operator(mfmgb_hierarchy *H, int level, const mfmgb_csr *A);
+  MFMGB_API int mfmgb_hierarchy_set_mf_operator(mfmgb_hierarchy *H, const mfmgb_mf *M); /* level 0 only */
+  /* R maps level-1 -> level (n_level x n_{level-1}); P = R^T explicit (may be NULL: built internally) */
+  MFMGB_API int mfmgb_hierarchy_set_restrictor(mfmgb_hierarchy *H, int level, const mfmgb_csr *R, const mfmgb_csr *P);
+  /* builds smoothers, the coarse factorisation and all level workspaces (no allocation afterwards) */
+  MFMGB_API int mfmgb_hierarchy_finalize(mfmgb_ctx *ctx, mfmgb_hierarchy *H);
+  MFMGB_API int mfmgb_hierarchy_destroy(mfmgb_ctx *ctx, mfmgb_hierarchy *H);
+  /* Hierarchy::vmult(x, b): one V-cycle, device vectors */
+  MFMGB_API int mfmgb_vcycle(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x);
+  /* Hierarchy::apply(b, x, level) */
+  MFMGB_API int mfmgb_hierarchy_apply(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, int level);
+  /* Hierarchy<Vector<double,Host>>::vmult: HOST vectors, H2D + V-cycle + D2H inside, synchronous
+   * (the host-vector specialisations, source/cuda/cuda_matrix_operator.cu:51-70, cuda_smoother.cu:62-84) */
+  MFMGB_API int mfmgb_vcycle_host(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b_host, double *x_host);
+  /* one un-captured V-cycle with CUDA events between the level-0 stages (measurement aid for bench.py):
+   * stage_ms[6] = pre-smoothing, residual, restriction, coarse levels (recursion), prolongation+correction,
+   * post-smoothing -- the "Apply: fine levels" / "Apply: coarsest level" timer sections of hierarchy.hpp:263,271. */
+  MFMGB_API int mfmgb_vcycle_profile(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, double *stage_ms);
+  /* capture the V-cycle into a CUDA graph and replay it on later mfmgb_vcycle calls (1 = on) */
+  MFMGB_API int mfmgb_hierarchy_use_graph(mfmgb_hierarchy *H, int on);
+  /* kernels launched by one V-cycle of this hierarchy */
+  MFMGB_API int mfmgb_hierarchy_launches_per_cycle(const mfmgb_hierarchy *H);
+
+  /* Preconditioned CG with deal.II's SolverCG recurrence; A = level-0 operator of H.  Device vectors.
+   * Stops when |A x - b|_2 <= tol (absolute) or after max_it iterations.  res_hist_host (may be NULL)
+   * receives max_it + 1 residual norms.  H == NULL: unpreconditioned CG on A. */
+  MFMGB_API int mfmgb_pcg(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const mfmgb_csr *A, const double *b, double *x, double tol,
+                          int max_it, int *iterations, double *res_hist_host);
+  MFMGB_API int mfmgb_pcg_host(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const mfmgb_csr *A, const double *b_host,
+                               double *x_host, double tol, int max_it, int *iterations, double *res_hist_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFMG_B200_H */

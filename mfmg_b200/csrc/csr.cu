@@ -1,0 +1,367 @@
+// csr.cu -- CSR upload/transposition and the vector-CSR SpMV kernels with fused epilogues.
+//
+// Kernel: LPR lanes (a power of two, 2..32) cooperate on one row; LPR is chosen per matrix
+// (i.e. per level) from the mean row length.  Column indices and values are streamed once,
+// x is gathered through the read-only path and stays L2/L1 resident; the row sum is reduced
+// with a fixed shuffle tree (no atomics => deterministic) and the epilogue (residual, Jacobi
+// update, prolongation correction) is applied in the same kernel, so no intermediate vector
+// ever goes to HBM.
+#include <algorithm>
+#include <cstring>
+
+#include "csr.cuh"
+
+using namespace mfmgb;
+
+namespace mfmgb
+{
+namespace
+{
+constexpr int kBlock = 256;
+
+template <int EPI>
+__device__ __forceinline__ void epilogue(const EpiArgs &e, int64_t row, double s)
+{
+  if (EPI == (int)Epi::Spmv)
+    e.y[row] = s;
+  else if (EPI == (int)Epi::Resid)
+    e.y[row] = __dsub_rn(s, e.b[row]);
+  else if (EPI == (int)Epi::Jacobi)
+  {
+    const double r = __dsub_rn(s, e.b[row]);
+    double t = __dmul_rn(e.dinv[row], r);
+    if (e.omega != 1.)
+      t = __dmul_rn(e.omega, t);
+    e.y[row] = __dsub_rn(e.xin[row], t);
+  }
+  else
+    e.y[row] = __dsub_rn(e.y[row], s);
+}
+
+template <int LPR, int EPI, typename OffT>
+__global__ void __launch_bounds__(kBlock)
+    csr_vec_kernel(int64_t n_rows, const OffT *__restrict__ rowptr, const int *__restrict__ col,
+                   const double *__restrict__ val, const double *__restrict__ x, EpiArgs e)
+{
+  const int64_t row = ((int64_t)blockIdx.x * kBlock + threadIdx.x) / LPR;
+  const int lane = threadIdx.x & (LPR - 1);
+  double s0 = 0., s1 = 0.;
+  if (row < n_rows)
+  {
+    OffT k = rowptr[row] + lane;
+    const OffT k1 = rowptr[row + 1];
+    for (; k + LPR < k1; k += 2 * LPR)
+    {
+      const int c0 = col[k], c1 = col[k + LPR];
+      const double v0 = val[k], v1 = val[k + LPR];
+      s0 = fma(v0, __ldg(x + c0), s0);
+      s1 = fma(v1, __ldg(x + c1), s1);
+    }
+    if (k < k1)
+      s0 = fma(val[k], __ldg(x + col[k]), s0);
+  }
+  double s = subwarp_sum<LPR>(s0 + s1);
+  if (lane == 0 && row < n_rows)
+    epilogue<EPI>(e, row, s);
+}
+
+template <int LPR, int EPI, typename OffT>
+int launch_vec(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArgs &e)
+{
+  const int64_t threads = A->n_rows * LPR;
+  const int64_t nb = ceil_div(threads, kBlock);
+  if (nb == 0)
+    return MFMGB_OK;
+  csr_vec_kernel<LPR, EPI, OffT><<<(unsigned)nb, kBlock, 0, ctx->stream>>>(
+      A->n_rows, (const OffT *)A->rowptr, A->col, A->val, x, e);
+  MFMGB_LAUNCHED(ctx);
+  return MFMGB_OK;
+}
+
+template <int EPI, typename OffT>
+int dispatch_lanes(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArgs &e)
+{
+  switch (A->lanes)
+  {
+  case 1:
+  case 2:
+    return launch_vec<2, EPI, OffT>(ctx, A, x, e);
+  case 4:
+    return launch_vec<4, EPI, OffT>(ctx, A, x, e);
+  case 8:
+    return launch_vec<8, EPI, OffT>(ctx, A, x, e);
+  case 16:
+    return launch_vec<16, EPI, OffT>(ctx, A, x, e);
+  default:
+    return launch_vec<32, EPI, OffT>(ctx, A, x, e);
+  }
+}
+
+template <typename OffT>
+int dispatch_epi(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &e)
+{
+  switch (epi)
+  {
+  case Epi::Spmv:
+    return dispatch_lanes<(int)Epi::Spmv, OffT>(ctx, A, x, e);
+  case Epi::Resid:
+    return dispatch_lanes<(int)Epi::Resid, OffT>(ctx, A, x, e);
+  case Epi::Jacobi:
+    return dispatch_lanes<(int)Epi::Jacobi, OffT>(ctx, A, x, e);
+  default:
+    return dispatch_lanes<(int)Epi::Sub, OffT>(ctx, A, x, e);
+  }
+}
+} // namespace
+
+int choose_lanes(int64_t n_rows, int64_t nnz)
+{
+  if (n_rows <= 0)
+    return 8;
+  const double mean = (double)nnz / (double)n_rows;
+  int lanes = 2;
+  while (lanes < 32 && lanes * 4 < mean)
+    lanes *= 2;
+  return lanes;
+}
+
+int csr_apply(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args)
+{
+  if (A->n_rows >= ((int64_t)1 << 31) * 8)
+    return fail(ctx, MFMGB_ERR_INVALID, "csr_apply: too many rows");
+  if (A->off64)
+    return dispatch_epi<int64_t>(ctx, A, x, epi, args);
+  return dispatch_epi<int32_t>(ctx, A, x, epi, args);
+}
+
+namespace
+{
+int finish_upload(mfmgb_ctx *ctx, mfmgb_csr *A)
+{
+  A->lanes = A->lanes_override ? A->lanes_override : choose_lanes(A->n_rows, A->nnz);
+  A->device = ctx->device;
+  return MFMGB_OK;
+}
+
+template <typename OffT>
+int upload_impl(mfmgb_ctx *ctx, int64_t n_rows, int64_t n_cols, const OffT *rowptr,
+                const int32_t *col, const double *val, mfmgb_csr **out)
+{
+  MFMGB_REQUIRE(ctx, ctx && out && rowptr && n_rows >= 0 && n_cols >= 0, "csr_upload: bad arguments");
+  *out = nullptr;
+  const int64_t nnz = (int64_t)rowptr[n_rows];
+  MFMGB_REQUIRE(ctx, rowptr[0] == 0 && nnz >= 0, "csr_upload: rowptr must start at 0");
+  MFMGB_REQUIRE(ctx, nnz == 0 || (col && val), "csr_upload: col/val are NULL");
+  for (int64_t i = 0; i < n_rows; ++i)
+    if (rowptr[i + 1] < rowptr[i])
+      return fail(ctx, MFMGB_ERR_INVALID, "csr_upload: rowptr not monotone at row %lld", (long long)i);
+  for (int64_t k = 0; k < nnz; ++k)
+    if (col[k] < 0 || col[k] >= n_cols)
+      return fail(ctx, MFMGB_ERR_INVALID, "csr_upload: column index %d out of range at entry %lld",
+                  col[k], (long long)k);
+  mfmgb_csr *A = new mfmgb_csr();
+  A->n_rows = n_rows;
+  A->n_cols = n_cols;
+  A->nnz = nnz;
+  A->off64 = nnz >= ((int64_t)1 << 31) - 64;
+  const size_t pad = 8;
+  MFMGB_CUDA(ctx, cudaMalloc(&A->val, sizeof(double) * (size_t)(nnz + pad)));
+  MFMGB_CUDA(ctx, cudaMalloc(&A->col, sizeof(int32_t) * (size_t)(nnz + pad)));
+  MFMGB_CUDA(ctx, cudaMemsetAsync(A->val + nnz, 0, sizeof(double) * pad, ctx->stream));
+  MFMGB_CUDA(ctx, cudaMemsetAsync(A->col + nnz, 0, sizeof(int32_t) * pad, ctx->stream));
+  MFMGB_CUDA(ctx, cudaMemcpyAsync(A->val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+  MFMGB_CUDA(ctx, cudaMemcpyAsync(A->col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+  if (A->off64)
+  {
+    std::vector<int64_t> rp(rowptr, rowptr + n_rows + 1);
+    MFMGB_CUDA(ctx, cudaMalloc(&A->rowptr, sizeof(int64_t) * (size_t)(n_rows + 1)));
+    MFMGB_CUDA(ctx, cudaMemcpy(A->rowptr, rp.data(), sizeof(int64_t) * (size_t)(n_rows + 1), cudaMemcpyHostToDevice));
+  }
+  else
+  {
+    std::vector<int32_t> rp((size_t)n_rows + 1);
+    for (int64_t i = 0; i <= n_rows; ++i)
+      rp[i] = (int32_t)rowptr[i];
+    MFMGB_CUDA(ctx, cudaMalloc(&A->rowptr, sizeof(int32_t) * (size_t)(n_rows + 1)));
+    MFMGB_CUDA(ctx, cudaMemcpy(A->rowptr, rp.data(), sizeof(int32_t) * (size_t)(n_rows + 1), cudaMemcpyHostToDevice));
+  }
+  MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  finish_upload(ctx, A);
+  *out = A;
+  return MFMGB_OK;
+}
+} // namespace
+} // namespace mfmgb
+
+extern "C"
+{
+  MFMGB_API int mfmgb_csr_upload(mfmgb_ctx *ctx, int64_t n_rows, int64_t n_cols, const int64_t *rowptr,
+                                 const int32_t *col, const double *val, mfmgb_csr **out)
+  {
+    return upload_impl<int64_t>(ctx, n_rows, n_cols, rowptr, col, val, out);
+  }
+
+  MFMGB_API int mfmgb_csr_upload_i32(mfmgb_ctx *ctx, int64_t n_rows, int64_t n_cols, const int32_t *rowptr,
+                                     const int32_t *col, const double *val, mfmgb_csr **out)
+  {
+    return upload_impl<int32_t>(ctx, n_rows, n_cols, rowptr, col, val, out);
+  }
+
+  MFMGB_API int mfmgb_csr_adopt_device(mfmgb_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                                       double *val_dev, int32_t *col_dev, int32_t *rowptr_dev, mfmgb_csr **out)
+  {
+    MFMGB_REQUIRE(ctx, ctx && out && rowptr_dev && n_rows >= 0 && n_cols >= 0 && nnz >= 0,
+                  "csr_adopt_device: bad arguments");
+    MFMGB_REQUIRE(ctx, nnz == 0 || (val_dev && col_dev), "csr_adopt_device: NULL arrays");
+    mfmgb_csr *A = new mfmgb_csr();
+    A->n_rows = n_rows;
+    A->n_cols = n_cols;
+    A->nnz = nnz;
+    A->val = val_dev;
+    A->col = col_dev;
+    A->rowptr = rowptr_dev;
+    A->off64 = false;
+    A->owns = true;
+    finish_upload(ctx, A);
+    *out = A;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_csr_destroy(mfmgb_ctx *ctx, mfmgb_csr *A)
+  {
+    if (!A)
+      return MFMGB_OK;
+    MFMGB_REQUIRE(ctx, ctx, "ctx is NULL");
+    MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (A->owns)
+    {
+      cudaFree(A->val);
+      cudaFree(A->col);
+      cudaFree(A->rowptr);
+    }
+    delete A;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_csr_info(const mfmgb_csr *A, int64_t *n_rows, int64_t *n_cols, int64_t *nnz)
+  {
+    if (!A)
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_csr_info: A is NULL");
+    if (n_rows)
+      *n_rows = A->n_rows;
+    if (n_cols)
+      *n_cols = A->n_cols;
+    if (nnz)
+      *nnz = A->nnz;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_csr_device_arrays(const mfmgb_csr *A, double **val_dev, int32_t **col_dev, void **rowptr_dev,
+                                        int *rowptr_is_64)
+  {
+    if (!A)
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_csr_device_arrays: A is NULL");
+    if (val_dev)
+      *val_dev = A->val;
+    if (col_dev)
+      *col_dev = A->col;
+    if (rowptr_dev)
+      *rowptr_dev = A->rowptr;
+    if (rowptr_is_64)
+      *rowptr_is_64 = A->off64 ? 1 : 0;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_csr_download(mfmgb_ctx *ctx, const mfmgb_csr *A, int64_t *rowptr, int32_t *col, double *val)
+  {
+    MFMGB_REQUIRE(ctx, ctx && A && rowptr, "csr_download: bad arguments");
+    MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (A->off64)
+      MFMGB_CUDA(ctx, cudaMemcpy(rowptr, A->rowptr, sizeof(int64_t) * (size_t)(A->n_rows + 1), cudaMemcpyDeviceToHost));
+    else
+    {
+      std::vector<int32_t> rp((size_t)A->n_rows + 1);
+      MFMGB_CUDA(ctx, cudaMemcpy(rp.data(), A->rowptr, sizeof(int32_t) * (size_t)(A->n_rows + 1), cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i <= A->n_rows; ++i)
+        rowptr[i] = rp[i];
+    }
+    if (col && A->nnz)
+      MFMGB_CUDA(ctx, cudaMemcpy(col, A->col, sizeof(int32_t) * (size_t)A->nnz, cudaMemcpyDeviceToHost));
+    if (val && A->nnz)
+      MFMGB_CUDA(ctx, cudaMemcpy(val, A->val, sizeof(double) * (size_t)A->nnz, cudaMemcpyDeviceToHost));
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_csr_transpose(mfmgb_ctx *ctx, const mfmgb_csr *A, mfmgb_csr **out)
+  {
+    // Setup-time operation (done once per restrictor); the reference does it on the host too
+    // (EpetraExt::RowMatrix_Transpose, source/cuda/cuda_matrix_operator.cu:102-112).  Stable
+    // counting sort => ascending columns, so P x_c sums in ascending coarse index: the same
+    // order as the implicit Tvmult scatter of the host path.
+    MFMGB_REQUIRE(ctx, ctx && A && out, "csr_transpose: bad arguments");
+    std::vector<int64_t> rp((size_t)A->n_rows + 1);
+    std::vector<int32_t> col((size_t)std::max<int64_t>(A->nnz, 1));
+    std::vector<double> val((size_t)std::max<int64_t>(A->nnz, 1));
+    MFMGB_CHECK(mfmgb_csr_download(ctx, A, rp.data(), col.data(), val.data()));
+    std::vector<int64_t> trp((size_t)A->n_cols + 1, 0);
+    for (int64_t k = 0; k < A->nnz; ++k)
+      trp[col[k] + 1]++;
+    for (int64_t c = 0; c < A->n_cols; ++c)
+      trp[c + 1] += trp[c];
+    std::vector<int64_t> next(trp.begin(), trp.end() - 1);
+    std::vector<int32_t> tcol((size_t)std::max<int64_t>(A->nnz, 1));
+    std::vector<double> tval((size_t)std::max<int64_t>(A->nnz, 1));
+    for (int64_t i = 0; i < A->n_rows; ++i)
+      for (int64_t k = rp[i]; k < rp[i + 1]; ++k)
+      {
+        const int64_t p = next[col[k]]++;
+        tcol[p] = (int32_t)i;
+        tval[p] = val[k];
+      }
+    return mfmgb_csr_upload(ctx, A->n_cols, A->n_rows, trp.data(), tcol.data(), tval.data(), out);
+  }
+
+  MFMGB_API int mfmgb_csr_set_lanes_per_row(mfmgb_csr *A, int lanes)
+  {
+    if (!A || !(lanes == 0 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32))
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_csr_set_lanes_per_row: lanes must be 0,2,4,8,16,32");
+    A->lanes_override = lanes;
+    A->lanes = lanes ? lanes : choose_lanes(A->n_rows, A->nnz);
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_csr_get_lanes_per_row(const mfmgb_csr *A) { return A ? A->lanes : 0; }
+
+  MFMGB_API int mfmgb_spmv(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, double *y)
+  {
+    MFMGB_REQUIRE(ctx, ctx && A && (A->n_cols == 0 || x) && (A->n_rows == 0 || y), "mfmgb_spmv: bad arguments");
+    MFMGB_REQUIRE(ctx, x != y, "mfmgb_spmv: x and y must not alias");
+    EpiArgs e;
+    e.y = y;
+    return csr_apply(ctx, A, x, Epi::Spmv, e);
+  }
+
+  MFMGB_API int mfmgb_residual_neg(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const double *b, double *r)
+  {
+    MFMGB_REQUIRE(ctx, ctx && A && x && b && r, "mfmgb_residual_neg: bad arguments");
+    MFMGB_REQUIRE(ctx, x != r, "mfmgb_residual_neg: x and r must not alias");
+    EpiArgs e;
+    e.y = r;
+    e.b = b;
+    return csr_apply(ctx, A, x, Epi::Resid, e);
+  }
+
+  MFMGB_API int mfmgb_restrict(mfmgb_ctx *ctx, const mfmgb_csr *R, const double *r, double *b_c)
+  {
+    return mfmgb_spmv(ctx, R, r, b_c);
+  }
+
+  MFMGB_API int mfmgb_prolong_correct(mfmgb_ctx *ctx, const mfmgb_csr *P, const double *x_c, double *x)
+  {
+    MFMGB_REQUIRE(ctx, ctx && P && x_c && x, "mfmgb_prolong_correct: bad arguments");
+    MFMGB_REQUIRE(ctx, x != x_c, "mfmgb_prolong_correct: x and x_c must not alias");
+    EpiArgs e;
+    e.y = x;
+    return csr_apply(ctx, P, x_c, Epi::Sub, e);
+  }
+}

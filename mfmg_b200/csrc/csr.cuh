@@ -1,0 +1,40 @@
+// csr.cuh -- device CSR matrix and the SpMV family with fused epilogues (internal C++ API).
+#pragma once
+#include "common.cuh"
+
+struct mfmgb_csr
+{
+  int64_t n_rows = 0, n_cols = 0, nnz = 0;
+  double *val = nullptr;  // [nnz + pad]
+  int32_t *col = nullptr; // [nnz + pad]
+  void *rowptr = nullptr; // int32[n_rows+1] or int64[n_rows+1]
+  bool off64 = false;
+  bool owns = true;
+  int lanes = 8;          // lanes per row used by the vector-CSR kernels
+  int lanes_override = 0; // 0 = automatic
+  int device = 0;
+};
+
+namespace mfmgb
+{
+enum class Epi : int
+{
+  Spmv = 0,   // y = A x
+  Resid = 1,  // y = A x - b                       (hierarchy.hpp:284-286)
+  Jacobi = 2, // y = xin - omega * dinv * (A x - b) (cuda_smoother.cu:49-59)
+  Sub = 3     // y = y - A x                       (hierarchy.hpp:297-302)
+};
+
+struct EpiArgs
+{
+  double *y = nullptr;
+  const double *b = nullptr;
+  const double *dinv = nullptr;
+  const double *xin = nullptr;
+  double omega = 1.;
+};
+
+// one launch: y = epilogue(A x)
+int csr_apply(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args);
+int choose_lanes(int64_t n_rows, int64_t nnz);
+} // namespace mfmgb

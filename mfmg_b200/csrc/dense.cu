@@ -1,0 +1,641 @@
+// dense.cu -- coarsest-level dense FP64 direct solver: factor ONCE, two triangular applies per solve.
+//
+// Replaces mfmg::CudaSolver "lu_dense" (source/cuda/cuda_solver.cu:496-515 -> lu_factorization,
+// source/cuda/dealii_operator_device_helpers.cu:169-228), which runs csr2dense + getrf + getrs and
+// four cudaMalloc/cudaFree on EVERY V-cycle.  Here:
+//   setup  (once):  CSR -> dense, blocked right-looking LU with partial pivoting (P A = L U), then the
+//                   triangular factors are inverted explicitly (recursive block doubling, all GEMM)
+//                   and packed into one n x n array:  strictly-lower = L^-1 (unit diagonal implied),
+//                   upper incl. diagonal = U^-1.
+//   solve  (hot):   y = L^-1 (P b);  x = U^-1 y  -- two bandwidth-bound triangular GEMVs that read
+//                   the packed array exactly once (8 n^2 bytes), with no sequential dependency chain
+//                   (a substitution solve would need n/nb grid-wide steps per triangle).
+// No cuSOLVER / cuBLAS.  Tensor cores are not used (FP64, and the hot part is a GEMV).
+#include <algorithm>
+#include <vector>
+
+#include "csr.cuh"
+#include "dense.cuh"
+
+using namespace mfmgb;
+
+namespace
+{
+constexpr int NB = 32; // panel width == warp size
+
+// ---------------------------------------------------------------------------------------------
+// CSR -> dense row-major (cusparseDcsr2dense at dealii_operator_device_helpers.cu:182)
+// ---------------------------------------------------------------------------------------------
+template <typename OffT>
+__global__ void __launch_bounds__(256) csr_to_dense_kernel(int64_t n, const OffT *__restrict__ rowptr,
+                                                           const int *__restrict__ col,
+                                                           const double *__restrict__ val, double *__restrict__ a,
+                                                           int64_t lda)
+{
+  // one warp per row; duplicates are summed in storage order by lane 0 only when they collide,
+  // so use a serial loop per row chunk: entries of one row are distinct in practice, but keep
+  // it exact for duplicates by letting a single thread own each row.
+  const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (row >= n)
+    return;
+  for (OffT k = rowptr[row]; k < rowptr[row + 1]; ++k)
+    a[row * lda + col[k]] += val[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// panel factorisation: columns [k0, k0+kb), rows [k0, n); one CTA of 1024 threads (32 warps),
+// lane = panel column.  getf2 with partial pivoting (first entry of maximal magnitude).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) lu_panel_kernel(double *__restrict__ a, int64_t lda, int64_t n, int64_t k0,
+                                                        int kb, int *__restrict__ piv, int *__restrict__ info)
+{
+  __shared__ double s_val[32];
+  __shared__ long long s_idx[32];
+  __shared__ long long s_p;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int j = 0; j < kb; ++j)
+  {
+    const int64_t cj = k0 + j;
+    // 1. pivot search in column cj over rows [cj, n)
+    double best = -1.;
+    long long bidx = 0x7fffffffffffffffLL;
+    for (int64_t i = cj + tid; i < n; i += 1024)
+    {
+      const double v = fabs(a[i * lda + cj]);
+      if (v > best)
+      {
+        best = v;
+        bidx = i;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ov > best || (ov == best && oi < bidx))
+      {
+        best = ov;
+        bidx = oi;
+      }
+    }
+    if (lane == 0)
+    {
+      s_val[w] = best;
+      s_idx[w] = bidx;
+    }
+    __syncthreads();
+    if (w == 0)
+    {
+      best = s_val[lane];
+      bidx = s_idx[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+      {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ov > best || (ov == best && oi < bidx))
+        {
+          best = ov;
+          bidx = oi;
+        }
+      }
+      if (lane == 0)
+      {
+        s_p = bidx;
+        piv[cj] = (int)bidx;
+        if (best == 0. && atomicCAS(info, 0, (int)(cj + 1)) == 0)
+        {
+        }
+      }
+      // 2. swap rows cj <-> p inside the panel
+      const int64_t p = __shfl_sync(0xffffffffu, bidx, 0);
+      if (p != cj && lane < kb)
+      {
+        const double t = a[cj * lda + k0 + lane];
+        a[cj * lda + k0 + lane] = a[p * lda + k0 + lane];
+        a[p * lda + k0 + lane] = t;
+      }
+    }
+    __syncthreads();
+    // 3. eliminate below the pivot inside the panel
+    const double prow = lane < kb ? a[cj * lda + k0 + lane] : 0.;
+    const double pivot = __shfl_sync(0xffffffffu, prow, j);
+    if (pivot != 0.)
+    {
+      const double inv = 1. / pivot;
+      for (int64_t i = cj + 1 + w; i < n; i += 32)
+      {
+        double v = lane < kb ? a[i * lda + k0 + lane] : 0.;
+        const double l = __dmul_rn(__shfl_sync(0xffffffffu, v, j), inv);
+        if (lane == j)
+          v = l;
+        else if (lane > j)
+          v = fma(-l, prow, v);
+        if (lane >= j && lane < kb)
+          a[i * lda + k0 + lane] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// apply the panel's row interchanges to the columns outside the panel
+__global__ void __launch_bounds__(256) lu_swap_kernel(double *__restrict__ a, int64_t lda, int64_t n, int64_t k0, int kb,
+                                                      const int *__restrict__ piv)
+{
+  int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (c >= n - kb)
+    return;
+  if (c >= k0)
+    c += kb; // skip the panel's own columns
+  for (int j = 0; j < kb; ++j)
+  {
+    const int64_t r = k0 + j, p = piv[r];
+    if (p != r)
+    {
+      const double t = a[r * lda + c];
+      a[r * lda + c] = a[p * lda + c];
+      a[p * lda + c] = t;
+    }
+  }
+}
+
+// U12 = L11^-1 A12 : one thread per column right of the panel
+__global__ void __launch_bounds__(256) lu_trsm_kernel(double *__restrict__ a, int64_t lda, int64_t n, int64_t k0, int kb)
+{
+  __shared__ double L[NB][NB + 1];
+  for (int e = threadIdx.x; e < kb * kb; e += 256)
+    L[e / kb][e % kb] = a[(k0 + e / kb) * lda + k0 + e % kb];
+  __syncthreads();
+  const int64_t c = k0 + kb + (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (c >= n)
+    return;
+  double u[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i)
+    u[i] = i < kb ? a[(k0 + i) * lda + c] : 0.;
+#pragma unroll
+  for (int j = 0; j < NB; ++j)
+#pragma unroll
+    for (int i = j + 1; i < NB; ++i)
+      if (i < kb)
+        u[i] = fma(-L[i][j], u[j], u[i]);
+#pragma unroll
+  for (int i = 0; i < NB; ++i)
+    if (i < kb)
+      a[(k0 + i) * lda + c] = u[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic FP64 GEMM tile: C[64x64 tile] = alpha * A[M x K] B[K x N] + beta * C, row-major.
+// 256 threads, 4x4 outputs per thread, K in chunks of 16 through shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int TM = 64, TN = 64, TK = 16;
+
+__device__ __forceinline__ void gemm_tile(int64_t M, int64_t N, int64_t K, const double *__restrict__ A, int64_t lda,
+                                          const double *__restrict__ B, int64_t ldb, double *__restrict__ C,
+                                          int64_t ldc, double alpha, double beta, int64_t tile_m, int64_t tile_n)
+{
+  __shared__ double As[TK][TM + 1];
+  __shared__ double Bs[TK][TN];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = tile_m * TM, n0 = tile_n * TN;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      acc[i][j] = 0.;
+  for (int64_t k0 = 0; k0 < K; k0 += TK)
+  {
+    // A tile: 64 rows x 16 k  (each thread loads 4 elements)
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+    {
+      const int idx = tid + e * 256; // 0..1023
+      const int r = idx >> 4, kk = idx & 15;
+      const int64_t gr = m0 + r, gk = k0 + kk;
+      As[kk][r] = (gr < M && gk < K) ? A[gr * lda + gk] : 0.;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+    {
+      const int idx = tid + e * 256;
+      const int kk = idx >> 6, c = idx & 63;
+      const int64_t gk = k0 + kk, gc = n0 + c;
+      Bs[kk][c] = (gk < K && gc < N) ? B[gk * ldb + gc] : 0.;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk)
+    {
+      double av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        bv[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+  {
+    const int64_t gr = m0 + ty * 4 + i;
+    if (gr >= M)
+      continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+    {
+      const int64_t gc = n0 + tx + 16 * j;
+      if (gc < N)
+      {
+        double *p = C + gr * ldc + gc;
+        *p = beta == 0. ? alpha * acc[i][j] : fma(alpha, acc[i][j], beta * *p);
+      }
+    }
+  }
+}
+
+// trailing update A22 -= L21 U12
+__global__ void __launch_bounds__(256) lu_update_kernel(double *__restrict__ a, int64_t lda, int64_t n, int64_t k0, int kb)
+{
+  const int64_t k1 = k0 + kb;
+  const int64_t M = n - k1;
+  gemm_tile(M, M, kb, a + k1 * lda + k0, lda, a + k0 * lda + k1, lda, a + k1 * lda + k1, lda, -1., 1., blockIdx.y,
+            blockIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// triangular inverses
+// ---------------------------------------------------------------------------------------------
+// base case: invert the 32x32 diagonal blocks.  One warp per block, lane = column of the inverse.
+__global__ void __launch_bounds__(32) tri_diag_inverse_kernel(const double *__restrict__ lu, int64_t lda, int64_t n,
+                                                              double *__restrict__ linv, double *__restrict__ uinv)
+{
+  __shared__ double S[NB][NB + 1];
+  const int64_t r0 = (int64_t)blockIdx.x * NB;
+  const int m = (int)min((int64_t)NB, n - r0);
+  const int j = threadIdx.x;
+  for (int i = 0; i < m; ++i)
+    if (j < m)
+      S[i][j] = lu[(r0 + i) * lda + r0 + j];
+  __syncwarp();
+  if (j < m)
+  {
+    double x[NB];
+    // unit lower: X = L^-1, column j
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+      x[i] = 0.;
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+    {
+      if (i == j)
+        x[i] = 1.;
+      else if (i > j && i < m)
+      {
+        double s = 0.;
+#pragma unroll
+        for (int k = 0; k < NB; ++k)
+          if (k >= j && k < i)
+            s = fma(S[i][k], x[k], s);
+        x[i] = -s;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+      if (i < m)
+        linv[(r0 + i) * lda + r0 + j] = i >= j ? x[i] : 0.;
+    // upper: X = U^-1, column j
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+      x[i] = 0.;
+#pragma unroll
+    for (int ii = 0; ii < NB; ++ii)
+    {
+      const int i = NB - 1 - ii;
+      if (i == j)
+        x[i] = 1. / S[i][i];
+      else if (i < j)
+      {
+        double s = 0.;
+#pragma unroll
+        for (int k = 0; k < NB; ++k)
+          if (k > i && k <= j)
+            s = fma(S[i][k], x[k], s);
+        x[i] = -s / S[i][i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+      if (i < m)
+        uinv[(r0 + i) * lda + r0 + j] = i <= j ? x[i] : 0.;
+  }
+}
+
+// level step for block size s: pair p covers [r0, mid) and [mid, r1).
+//   LOWER: T = L21 X11        then X21 = -X22 T        (X = L^-1)
+//   UPPER: T = U12 X22        then X12 = -X11 T        (X = U^-1)
+template <bool LOWER, int STEP>
+__global__ void __launch_bounds__(256) tri_level_kernel(const double *__restrict__ lu, double *__restrict__ X,
+                                                        double *__restrict__ T, int64_t lda, int64_t n, int64_t s)
+{
+  const int64_t p = blockIdx.z;
+  const int64_t r0 = p * 2 * s;
+  const int64_t mid = min(r0 + s, n), r1 = min(r0 + 2 * s, n);
+  const int64_t m1 = mid - r0, m2 = r1 - mid;
+  if (m2 <= 0)
+    return;
+  if (LOWER)
+  {
+    // off-diagonal block lives at rows [mid,r1), cols [r0,mid): m2 x m1
+    if ((int64_t)blockIdx.y * TM >= m2 || (int64_t)blockIdx.x * TN >= m1)
+      return;
+    if (STEP == 1)
+      gemm_tile(m2, m1, m1, lu + mid * lda + r0, lda, X + r0 * lda + r0, lda, T + mid * lda + r0, lda, 1., 0.,
+                blockIdx.y, blockIdx.x);
+    else
+      gemm_tile(m2, m1, m2, X + mid * lda + mid, lda, T + mid * lda + r0, lda, X + mid * lda + r0, lda, -1., 0.,
+                blockIdx.y, blockIdx.x);
+  }
+  else
+  {
+    // off-diagonal block lives at rows [r0,mid), cols [mid,r1): m1 x m2
+    if ((int64_t)blockIdx.y * TM >= m1 || (int64_t)blockIdx.x * TN >= m2)
+      return;
+    if (STEP == 1)
+      gemm_tile(m1, m2, m2, lu + r0 * lda + mid, lda, X + mid * lda + mid, lda, T + r0 * lda + mid, lda, 1., 0.,
+                blockIdx.y, blockIdx.x);
+    else
+      gemm_tile(m1, m2, m1, X + r0 * lda + r0, lda, T + r0 * lda + mid, lda, X + r0 * lda + mid, lda, -1., 0.,
+                blockIdx.y, blockIdx.x);
+  }
+}
+
+__global__ void __launch_bounds__(256) tri_pack_kernel(const double *__restrict__ linv, const double *__restrict__ uinv,
+                                                       double *__restrict__ out, int64_t lda, int64_t n)
+{
+  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t i = blockIdx.y;
+  if (j < lda)
+    out[i * lda + j] = j >= n ? 0. : (j < i ? linv[i * lda + j] : uinv[i * lda + j]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// solve: pb = b[perm];  y = L^-1 pb;  x = U^-1 y
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) permute_kernel(int64_t n, const int *__restrict__ perm,
+                                                      const double *__restrict__ b, double *__restrict__ pb)
+{
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n)
+    pb[i] = b[perm[i]];
+}
+
+// TPR threads cooperate on one row.  LOWER: out[i] = v[i] + sum_{j<i} M[i][j] v[j];
+// UPPER: out[i] = sum_{j>=i} M[i][j] v[j].  Fixed reduction tree => deterministic.
+template <bool LOWER, int TPR>
+__global__ void __launch_bounds__(256) tri_gemv_kernel(int64_t n, const double *__restrict__ M, int64_t lda,
+                                                       const double *__restrict__ v, double *__restrict__ out)
+{
+  __shared__ double sm[8];
+  constexpr int ROWS_PER_BLOCK = 256 / TPR;
+  const int t = threadIdx.x % TPR;
+  const int64_t i = (int64_t)blockIdx.x * ROWS_PER_BLOCK + threadIdx.x / TPR;
+  double s0 = 0., s1 = 0.;
+  if (i < n)
+  {
+    const double *row = M + i * lda;
+    int64_t j0 = LOWER ? 0 : i, j1 = LOWER ? i : n;
+    // scalar head to reach 16-byte alignment (lda is even, so parity of j decides)
+    if ((j0 & 1) && j0 < j1)
+    {
+      if (t == 0)
+        s0 = row[j0] * v[j0];
+      ++j0;
+    }
+    const int64_t npairs = (j1 - j0) >> 1;
+    const double2 *row2 = reinterpret_cast<const double2 *>(row + j0);
+    const double2 *v2 = reinterpret_cast<const double2 *>(v + j0);
+    int64_t q = t;
+    for (; q + TPR < npairs; q += 2 * TPR)
+    {
+      const double2 a = ld_stream_f64x2(reinterpret_cast<const double *>(row2 + q));
+      const double2 c = ld_stream_f64x2(reinterpret_cast<const double *>(row2 + q + TPR));
+      const double2 x = v2[q], z = v2[q + TPR];
+      s0 = fma(a.x, x.x, s0);
+      s1 = fma(a.y, x.y, s1);
+      s0 = fma(c.x, z.x, s0);
+      s1 = fma(c.y, z.y, s1);
+    }
+    if (q < npairs)
+    {
+      const double2 a = ld_stream_f64x2(reinterpret_cast<const double *>(row2 + q));
+      const double2 x = v2[q];
+      s0 = fma(a.x, x.x, s0);
+      s1 = fma(a.y, x.y, s1);
+    }
+    if (((j1 - j0) & 1) && t == 0)
+      s0 = fma(row[j1 - 1], v[j1 - 1], s0);
+  }
+  double s = s0 + s1;
+  if (TPR == 256)
+  {
+    s = block_sum<256>(s, sm);
+    if (threadIdx.x == 0 && i < n)
+      out[i] = LOWER ? s + v[i] : s;
+  }
+  else
+  {
+    s = subwarp_sum<(TPR < 32 ? TPR : 32)>(s);
+    if (t == 0 && i < n)
+      out[i] = LOWER ? s + v[i] : s;
+  }
+}
+} // namespace
+
+namespace mfmgb
+{
+int dense_solve_async(mfmgb_ctx *ctx, const mfmgb_dense *D, const double *b, double *x)
+{
+  const int64_t n = D->n;
+  if (n == 0)
+    return MFMGB_OK;
+  permute_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(n, D->perm, b, D->work0);
+  MFMGB_LAUNCHED(ctx);
+  if (n >= 1024)
+  {
+    tri_gemv_kernel<true, 256><<<(unsigned)n, 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work0, D->work1);
+    MFMGB_LAUNCHED(ctx);
+    tri_gemv_kernel<false, 256><<<(unsigned)n, 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work1, x);
+    MFMGB_LAUNCHED(ctx);
+  }
+  else
+  {
+    tri_gemv_kernel<true, 32><<<(unsigned)ceil_div(n, 8), 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work0, D->work1);
+    MFMGB_LAUNCHED(ctx);
+    tri_gemv_kernel<false, 32><<<(unsigned)ceil_div(n, 8), 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work1, x);
+    MFMGB_LAUNCHED(ctx);
+  }
+  return MFMGB_OK;
+}
+} // namespace mfmgb
+
+extern "C"
+{
+  MFMGB_API int mfmgb_dense_factor(mfmgb_ctx *ctx, const mfmgb_csr *A, mfmgb_dense **out)
+  {
+    MFMGB_REQUIRE(ctx, ctx && A && out, "mfmgb_dense_factor: bad arguments");
+    MFMGB_REQUIRE(ctx, A->n_rows == A->n_cols, "mfmgb_dense_factor: the matrix is not square");
+    *out = nullptr;
+    const int64_t n = A->n_rows;
+    const int64_t lda = (n + 3) & ~(int64_t)3;
+    mfmgb_dense *D = new mfmgb_dense();
+    D->n = n;
+    D->lda = lda;
+    const size_t bytes = sizeof(double) * (size_t)std::max<int64_t>(n * lda, 1);
+    double *lu = nullptr, *linv = nullptr, *uinv = nullptr, *T = nullptr;
+    int *piv = nullptr, *info_dev = nullptr;
+    MFMGB_CUDA(ctx, cudaMalloc(&lu, bytes));
+    MFMGB_CUDA(ctx, cudaMalloc(&linv, bytes));
+    MFMGB_CUDA(ctx, cudaMalloc(&uinv, bytes));
+    MFMGB_CUDA(ctx, cudaMalloc(&T, bytes));
+    MFMGB_CUDA(ctx, cudaMalloc(&piv, sizeof(int) * (size_t)std::max<int64_t>(n, 1)));
+    MFMGB_CUDA(ctx, cudaMalloc(&info_dev, sizeof(int)));
+    MFMGB_CUDA(ctx, cudaMalloc(&D->perm, sizeof(int) * (size_t)std::max<int64_t>(n, 1)));
+    MFMGB_CUDA(ctx, cudaMalloc(&D->work0, sizeof(double) * (size_t)(n + 2)));
+    MFMGB_CUDA(ctx, cudaMalloc(&D->work1, sizeof(double) * (size_t)(n + 2)));
+    MFMGB_CUDA(ctx, cudaMemsetAsync(D->work0, 0, sizeof(double) * (size_t)(n + 2), ctx->stream));
+    MFMGB_CUDA(ctx, cudaMemsetAsync(D->work1, 0, sizeof(double) * (size_t)(n + 2), ctx->stream));
+    MFMGB_CUDA(ctx, cudaMemsetAsync(lu, 0, bytes, ctx->stream));
+    MFMGB_CUDA(ctx, cudaMemsetAsync(linv, 0, bytes, ctx->stream));
+    MFMGB_CUDA(ctx, cudaMemsetAsync(uinv, 0, bytes, ctx->stream));
+    MFMGB_CUDA(ctx, cudaMemsetAsync(T, 0, bytes, ctx->stream));
+    MFMGB_CUDA(ctx, cudaMemsetAsync(info_dev, 0, sizeof(int), ctx->stream));
+    cudaStream_t st = ctx->stream;
+    if (n > 0)
+    {
+      if (A->off64)
+        csr_to_dense_kernel<int64_t><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(n, (const int64_t *)A->rowptr, A->col,
+                                                                                 A->val, lu, lda);
+      else
+        csr_to_dense_kernel<int32_t><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(n, (const int32_t *)A->rowptr, A->col,
+                                                                                 A->val, lu, lda);
+      MFMGB_LAUNCHED(ctx);
+      // blocked right-looking LU
+      for (int64_t k0 = 0; k0 < n; k0 += NB)
+      {
+        const int kb = (int)std::min<int64_t>(NB, n - k0);
+        lu_panel_kernel<<<1, 1024, 0, st>>>(lu, lda, n, k0, kb, piv, info_dev);
+        MFMGB_LAUNCHED(ctx);
+        if (n - kb > 0)
+        {
+          lu_swap_kernel<<<(unsigned)ceil_div(n - kb, 256), 256, 0, st>>>(lu, lda, n, k0, kb, piv);
+          MFMGB_LAUNCHED(ctx);
+        }
+        const int64_t rest = n - k0 - kb;
+        if (rest > 0)
+        {
+          lu_trsm_kernel<<<(unsigned)ceil_div(rest, 256), 256, 0, st>>>(lu, lda, n, k0, kb);
+          MFMGB_LAUNCHED(ctx);
+          dim3 grid((unsigned)ceil_div(rest, TN), (unsigned)ceil_div(rest, TM));
+          lu_update_kernel<<<grid, 256, 0, st>>>(lu, lda, n, k0, kb);
+          MFMGB_LAUNCHED(ctx);
+        }
+      }
+      int info = 0;
+      MFMGB_CUDA(ctx, cudaMemcpyAsync(&info, info_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+      std::vector<int> hpiv((size_t)n);
+      MFMGB_CUDA(ctx, cudaMemcpyAsync(hpiv.data(), piv, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+      MFMGB_CUDA(ctx, cudaStreamSynchronize(st));
+      if (info != 0)
+      {
+        cudaFree(lu);
+        cudaFree(linv);
+        cudaFree(uinv);
+        cudaFree(T);
+        cudaFree(piv);
+        cudaFree(info_dev);
+        cudaFree(D->perm);
+        cudaFree(D->work0);
+        cudaFree(D->work1);
+        delete D;
+        return fail(ctx, MFMGB_ERR_SINGULAR, "mfmgb_dense_factor: zero pivot at column %d", info - 1);
+      }
+      std::vector<int> perm((size_t)n);
+      for (int64_t i = 0; i < n; ++i)
+        perm[i] = (int)i;
+      int64_t swaps = 0;
+      for (int64_t k = 0; k < n; ++k)
+        if (hpiv[k] != k)
+        {
+          std::swap(perm[k], perm[hpiv[k]]);
+          ++swaps;
+        }
+      D->num_swaps = swaps;
+      MFMGB_CUDA(ctx, cudaMemcpyAsync(D->perm, perm.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+      MFMGB_CUDA(ctx, cudaStreamSynchronize(st));
+      // triangular inverses by block doubling
+      const int64_t nblk = ceil_div(n, NB);
+      tri_diag_inverse_kernel<<<(unsigned)nblk, 32, 0, st>>>(lu, lda, n, linv, uinv);
+      MFMGB_LAUNCHED(ctx);
+      for (int64_t s = NB; s < n; s *= 2)
+      {
+        const int64_t npairs = ceil_div(n, 2 * s);
+        dim3 grid((unsigned)ceil_div(s, TN), (unsigned)ceil_div(s, TM), (unsigned)npairs);
+        tri_level_kernel<true, 1><<<grid, 256, 0, st>>>(lu, linv, T, lda, n, s);
+        MFMGB_LAUNCHED(ctx);
+        tri_level_kernel<true, 2><<<grid, 256, 0, st>>>(lu, linv, T, lda, n, s);
+        MFMGB_LAUNCHED(ctx);
+        tri_level_kernel<false, 1><<<grid, 256, 0, st>>>(lu, uinv, T, lda, n, s);
+        MFMGB_LAUNCHED(ctx);
+        tri_level_kernel<false, 2><<<grid, 256, 0, st>>>(lu, uinv, T, lda, n, s);
+        MFMGB_LAUNCHED(ctx);
+      }
+      dim3 pgrid((unsigned)ceil_div(lda, 256), (unsigned)n);
+      tri_pack_kernel<<<pgrid, 256, 0, st>>>(linv, uinv, lu, lda, n);
+      MFMGB_LAUNCHED(ctx);
+      MFMGB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    D->inv = lu;
+    cudaFree(linv);
+    cudaFree(uinv);
+    cudaFree(T);
+    cudaFree(piv);
+    cudaFree(info_dev);
+    *out = D;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_dense_destroy(mfmgb_ctx *ctx, mfmgb_dense *D)
+  {
+    if (!D)
+      return MFMGB_OK;
+    MFMGB_REQUIRE(ctx, ctx, "ctx is NULL");
+    MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(D->inv);
+    cudaFree(D->perm);
+    cudaFree(D->work0);
+    cudaFree(D->work1);
+    delete D;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_dense_solve(mfmgb_ctx *ctx, const mfmgb_dense *D, const double *b, double *x)
+  {
+    MFMGB_REQUIRE(ctx, ctx && D && (D->n == 0 || (b && x)), "mfmgb_dense_solve: bad arguments");
+    return dense_solve_async(ctx, D, b, x);
+  }
+
+  MFMGB_API int64_t mfmgb_dense_size(const mfmgb_dense *D) { return D ? D->n : 0; }
+  MFMGB_API int64_t mfmgb_dense_num_swaps(const mfmgb_dense *D) { return D ? D->num_swaps : 0; }
+}

@@ -1,0 +1,599 @@
+// hierarchy.cu -- level storage, the V-cycle (mfmg::Hierarchy::apply) and the PCG driver loop.
+//
+// V-cycle: include/mfmg/common/hierarchy.hpp:246-309, statement by statement, with
+//   * every level vector preallocated at finalize (the reference allocates 4 vectors per level per
+//     cycle, hierarchy.hpp:284,289,293,297),
+//   * smoother / residual / prolongation-correction fused into SpMV epilogues,
+//   * the "x == 0" pre-smoothing sweep reduced to x = omega D^-1 b,
+//   * optional CUDA-graph replay of the whole cycle (launch-latency bound on small levels).
+// PCG: the recurrence of dealii::SolverCG (tests/hierarchy_driver.cc:200-213), scalars kept on
+// the device, one host read-back per iteration for the reference's stopping test.
+#include <cmath>
+#include <vector>
+
+#include "dense.cuh"
+#include "jacobi.cuh"
+#include "mf.cuh"
+#include "vecops.cuh"
+
+using namespace mfmgb;
+
+struct mfmgb_level
+{
+  int64_t n = 0;
+  const mfmgb_csr *A = nullptr;
+  const mfmgb_mf *M = nullptr;
+  const mfmgb_csr *R = nullptr; // maps level-1 -> this level
+  const mfmgb_csr *P = nullptr; // explicit transpose of R
+  mfmgb_csr *P_owned = nullptr;
+  mfmgb_jacobi *J = nullptr;
+  mfmgb_dense *D = nullptr;
+  double *res = nullptr, *xtmp = nullptr; // fine-side work vectors (size n)
+  double *bc = nullptr, *xc = nullptr;    // this level's rhs / solution when it is the coarse side
+};
+
+struct mfmgb_hierarchy
+{
+  int n_levels = 0;
+  int nu = 1;
+  bool is_preconditioner = true;
+  double omega = 1.;
+  bool finalized = false;
+  std::vector<mfmgb_level> lev;
+  // graph replay
+  bool use_graph = false;
+  cudaGraphExec_t graph_exec = nullptr;
+  const double *graph_b = nullptr;
+  double *graph_x = nullptr;
+  int launches_per_cycle = 0;
+  // device staging for the *_host entry points and PCG work vectors
+  double *b_dev = nullptr, *x_dev = nullptr;
+  double *g = nullptr, *h = nullptr, *d = nullptr;
+  double *scal = nullptr;      // device scalars: [0]=gh_old [1]=gh_new [2]=dh [3]=res2
+  double *scal_host = nullptr; // pinned
+  // stage profiling (mfmgb_vcycle_profile): events between the level-0 stages
+  bool profiling = false;
+  cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace
+{
+constexpr int kBlock = 256;
+
+int level_apply_A(mfmgb_ctx *ctx, const mfmgb_level &l, const double *x, Epi epi, const EpiArgs &e)
+{
+  if (l.M)
+    return mf_apply(ctx, l.M, x, epi, e);
+  return csr_apply(ctx, l.A, x, epi, e);
+}
+
+#define STAGE_MARK(k)                                                                              \
+  do                                                                                                \
+  {                                                                                                 \
+    if (H->profiling && li == 0)                                                                    \
+      MFMGB_CUDA(ctx, cudaEventRecord(H->ev[k], ctx->stream));                                      \
+  } while (0)
+
+int apply_level(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, int li)
+{
+  mfmgb_level &fine = H->lev[li];
+  const int64_t n = fine.n;
+  const bool x_is_zero = li > 0 || H->is_preconditioner; // hierarchy.hpp:253-259
+  if (li == H->n_levels - 1)
+    return dense_solve_async(ctx, fine.D, b, x); // hierarchy.hpp:261-268 (the solve overwrites x)
+
+  mfmgb_level &coarse = H->lev[li + 1];
+  const int nu = H->nu;
+  // sweeps that run as an out-of-place fused SpMV (each flips the buffer the iterate lives in)
+  const int n_oop = (x_is_zero && nu > 0 ? nu - 1 : nu) + nu;
+  double *cur = x, *other = fine.xtmp;
+  STAGE_MARK(0);
+  if (x_is_zero)
+  {
+    if (n_oop & 1)
+      std::swap(cur, other); // start in xtmp so the last sweep lands in x
+    if (nu > 0)
+      MFMGB_CHECK(mfmgb_jacobi_apply_zero_guess(ctx, fine.J, b, cur)); // x = omega D^-1 b
+    else
+      MFMGB_CHECK(vec_fill(ctx, cur, 0., n));
+  }
+  EpiArgs e;
+  for (int s = (x_is_zero && nu > 0 ? 1 : 0); s < nu; ++s) // pre-smoothing, hierarchy.hpp:277-279
+  {
+    e = EpiArgs();
+    e.y = other;
+    e.b = b;
+    e.dinv = fine.J->dinv;
+    e.xin = cur;
+    e.omega = H->omega;
+    MFMGB_CHECK(level_apply_A(ctx, fine, cur, Epi::Jacobi, e));
+    std::swap(cur, other);
+  }
+  STAGE_MARK(1);
+  // negative residual res = A x - b, hierarchy.hpp:282-286
+  e = EpiArgs();
+  e.y = fine.res;
+  e.b = b;
+  MFMGB_CHECK(level_apply_A(ctx, fine, cur, Epi::Resid, e));
+  STAGE_MARK(2);
+  // b_c = R res, hierarchy.hpp:289-290
+  e = EpiArgs();
+  e.y = coarse.bc;
+  MFMGB_CHECK(csr_apply(ctx, coarse.R, fine.res, Epi::Spmv, e));
+  STAGE_MARK(3);
+  // recurse, hierarchy.hpp:293-294
+  MFMGB_CHECK(apply_level(ctx, H, coarse.bc, coarse.xc, li + 1));
+  STAGE_MARK(4);
+  // x -= R^T x_c, hierarchy.hpp:297-302 (explicit transpose, fused subtraction, in place: row-local)
+  e = EpiArgs();
+  e.y = cur;
+  MFMGB_CHECK(csr_apply(ctx, coarse.P, coarse.xc, Epi::Sub, e));
+  STAGE_MARK(5);
+  for (int s = 0; s < nu; ++s) // post-smoothing, hierarchy.hpp:305-306
+  {
+    e = EpiArgs();
+    e.y = other;
+    e.b = b;
+    e.dinv = fine.J->dinv;
+    e.xin = cur;
+    e.omega = H->omega;
+    MFMGB_CHECK(level_apply_A(ctx, fine, cur, Epi::Jacobi, e));
+    std::swap(cur, other);
+  }
+  if (cur != x) // only in solver mode with an odd number of sweeps
+    MFMGB_CUDA(ctx, cudaMemcpyAsync(x, cur, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+  STAGE_MARK(6);
+  return MFMGB_OK;
+}
+
+int run_vcycle(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x)
+{
+  if (!H->use_graph)
+    return apply_level(ctx, H, b, x, 0);
+  if (!H->graph_exec || H->graph_b != b || H->graph_x != x)
+  {
+    if (H->graph_exec)
+    {
+      cudaGraphExecDestroy(H->graph_exec);
+      H->graph_exec = nullptr;
+    }
+    cudaGraph_t graph = nullptr;
+    const int64_t before = ctx->launches;
+    MFMGB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = apply_level(ctx, H, b, x, 0);
+    cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc != MFMGB_OK)
+    {
+      if (graph)
+        cudaGraphDestroy(graph);
+      return rc;
+    }
+    MFMGB_CUDA(ctx, ce);
+    H->launches_per_cycle = (int)(ctx->launches - before);
+    ctx->launches = before;
+    MFMGB_CUDA(ctx, cudaGraphInstantiate(&H->graph_exec, graph, 0));
+    cudaGraphDestroy(graph);
+    H->graph_b = b;
+    H->graph_x = x;
+  }
+  MFMGB_CUDA(ctx, cudaGraphLaunch(H->graph_exec, ctx->stream));
+  ctx->launches += H->launches_per_cycle;
+  return MFMGB_OK;
+}
+
+// ---- PCG kernels (device-resident scalars) ---------------------------------------------------
+// g += alpha h; x += alpha d with alpha = gh / dh; partial sums of g.g
+__global__ void __launch_bounds__(kBlock)
+    pcg_update_kernel(int64_t n, const double *__restrict__ scal, const double *__restrict__ h,
+                      const double *__restrict__ d, double *__restrict__ g, double *__restrict__ x,
+                      double *__restrict__ partials)
+{
+  __shared__ double sm[kBlock / 32];
+  const double alpha = scal[0] / scal[2];
+  double s = 0.;
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+  {
+    const double gi = fma(alpha, h[i], g[i]);
+    g[i] = gi;
+    x[i] = fma(alpha, d[i], x[i]);
+    s = fma(gi, gi, s);
+  }
+  s = block_sum<kBlock>(s, sm);
+  if (threadIdx.x == 0)
+    partials[blockIdx.x] = s;
+}
+
+// d = beta d - h with beta = gh_new / gh_old
+__global__ void __launch_bounds__(kBlock)
+    pcg_direction_kernel(int64_t n, const double *__restrict__ scal, const double *__restrict__ h, double *__restrict__ d)
+{
+  const double beta = scal[1] / scal[0];
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+    d[i] = fma(beta, d[i], -h[i]);
+}
+
+__global__ void negate_kernel(int64_t n, const double *__restrict__ h, double *__restrict__ d)
+{
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+    d[i] = -h[i];
+}
+
+__global__ void rotate_scalar_kernel(double *scal) { scal[0] = scal[1]; }
+
+int ensure_pcg_work(mfmgb_ctx *ctx, mfmgb_hierarchy *H, int64_t n)
+{
+  if (H->g)
+    return MFMGB_OK;
+  MFMGB_CUDA(ctx, cudaMalloc(&H->g, sizeof(double) * (size_t)(n + 2)));
+  MFMGB_CUDA(ctx, cudaMalloc(&H->h, sizeof(double) * (size_t)(n + 2)));
+  MFMGB_CUDA(ctx, cudaMalloc(&H->d, sizeof(double) * (size_t)(n + 2)));
+  MFMGB_CUDA(ctx, cudaMalloc(&H->scal, sizeof(double) * 8));
+  MFMGB_CUDA(ctx, cudaMallocHost(&H->scal_host, sizeof(double) * 8));
+  return MFMGB_OK;
+}
+
+int ensure_host_staging(mfmgb_ctx *ctx, mfmgb_hierarchy *H, int64_t n)
+{
+  if (H->b_dev)
+    return MFMGB_OK;
+  MFMGB_CUDA(ctx, cudaMalloc(&H->b_dev, sizeof(double) * (size_t)(n + 2)));
+  MFMGB_CUDA(ctx, cudaMalloc(&H->x_dev, sizeof(double) * (size_t)(n + 2)));
+  return MFMGB_OK;
+}
+} // namespace
+
+extern "C"
+{
+  MFMGB_API int mfmgb_hierarchy_create(mfmgb_ctx *ctx, int n_levels, int n_smoothing_steps, int is_preconditioner,
+                                       double omega, mfmgb_hierarchy **out)
+  {
+    MFMGB_REQUIRE(ctx, ctx && out && n_levels >= 1 && n_smoothing_steps >= 0, "mfmgb_hierarchy_create: bad arguments");
+    mfmgb_hierarchy *H = new mfmgb_hierarchy();
+    H->n_levels = n_levels;
+    H->nu = n_smoothing_steps;
+    H->is_preconditioner = is_preconditioner != 0;
+    H->omega = omega;
+    H->lev.resize((size_t)n_levels);
+    *out = H;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_hierarchy_set_operator(mfmgb_hierarchy *H, int level, const mfmgb_csr *A)
+  {
+    if (!H || !A || level < 0 || level >= H->n_levels || H->finalized)
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_operator: bad arguments");
+    if (A->n_rows != A->n_cols)
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_operator: level operator must be square");
+    H->lev[level].A = A;
+    H->lev[level].n = A->n_rows;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_hierarchy_set_mf_operator(mfmgb_hierarchy *H, const mfmgb_mf *M)
+  {
+    if (!H || !M || H->finalized)
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_mf_operator: bad arguments");
+    H->lev[0].M = M;
+    H->lev[0].n = M->n;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_hierarchy_set_restrictor(mfmgb_hierarchy *H, int level, const mfmgb_csr *R, const mfmgb_csr *P)
+  {
+    if (!H || !R || level < 1 || level >= H->n_levels || H->finalized)
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_restrictor: bad arguments");
+    if (P && (P->n_rows != R->n_cols || P->n_cols != R->n_rows || P->nnz != R->nnz))
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_restrictor: P is not shaped like R^T");
+    H->lev[level].R = R;
+    H->lev[level].P = P;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_hierarchy_finalize(mfmgb_ctx *ctx, mfmgb_hierarchy *H)
+  {
+    MFMGB_REQUIRE(ctx, ctx && H && !H->finalized, "mfmgb_hierarchy_finalize: bad arguments");
+    for (int li = 0; li < H->n_levels; ++li)
+    {
+      mfmgb_level &l = H->lev[li];
+      if (!l.A && !l.M)
+        return fail(ctx, MFMGB_ERR_INVALID, "mfmgb_hierarchy_finalize: level %d has no operator", li);
+      if (li > 0)
+      {
+        if (!l.R)
+          return fail(ctx, MFMGB_ERR_INVALID, "mfmgb_hierarchy_finalize: level %d has no restrictor", li);
+        if (l.R->n_rows != l.n || l.R->n_cols != H->lev[li - 1].n)
+          return fail(ctx, MFMGB_ERR_INVALID,
+                      "mfmgb_hierarchy_finalize: restrictor of level %d is %lld x %lld, expected %lld x %lld", li,
+                      (long long)l.R->n_rows, (long long)l.R->n_cols, (long long)l.n, (long long)H->lev[li - 1].n);
+        if (!l.P)
+        {
+          MFMGB_CHECK(mfmgb_csr_transpose(ctx, l.R, &l.P_owned));
+          l.P = l.P_owned;
+        }
+        MFMGB_CHECK(mfmgb_vec_alloc(ctx, l.n, &l.bc));
+        MFMGB_CHECK(mfmgb_vec_alloc(ctx, l.n, &l.xc));
+      }
+      if (li < H->n_levels - 1)
+      {
+        // build_smoother, hierarchy.hpp:204
+        if (l.M)
+        {
+          double *diag = nullptr;
+          MFMGB_CHECK(mfmgb_vec_alloc(ctx, l.n, &diag));
+          MFMGB_CHECK(mfmgb_mf_diagonal(ctx, l.M, diag));
+          MFMGB_CHECK(mfmgb_jacobi_setup_diag(ctx, diag, l.n, H->omega, &l.J));
+          MFMGB_CHECK(mfmgb_vec_free(ctx, diag));
+        }
+        else
+          MFMGB_CHECK(mfmgb_jacobi_setup(ctx, l.A, H->omega, &l.J));
+        MFMGB_CHECK(mfmgb_vec_alloc(ctx, l.n, &l.res));
+        MFMGB_CHECK(mfmgb_vec_alloc(ctx, l.n, &l.xtmp));
+      }
+      else
+      {
+        // build_coarse_solver, hierarchy.hpp:194
+        if (!l.A)
+          return fail(ctx, MFMGB_ERR_INVALID, "mfmgb_hierarchy_finalize: the coarsest level needs an assembled operator");
+        MFMGB_CHECK(mfmgb_dense_factor(ctx, l.A, &l.D));
+      }
+    }
+    MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // count the launches of one cycle (dry capture, nothing executes)
+    {
+      double *tb = nullptr, *tx = nullptr;
+      MFMGB_CHECK(mfmgb_vec_alloc(ctx, H->lev[0].n, &tb));
+      MFMGB_CHECK(mfmgb_vec_alloc(ctx, H->lev[0].n, &tx));
+      MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      cudaGraph_t graph = nullptr;
+      const int64_t before = ctx->launches;
+      MFMGB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = apply_level(ctx, H, tb, tx, 0);
+      cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+      if (graph)
+        cudaGraphDestroy(graph);
+      H->launches_per_cycle = (int)(ctx->launches - before);
+      ctx->launches = before;
+      MFMGB_CHECK(rc);
+      MFMGB_CUDA(ctx, ce);
+      MFMGB_CHECK(mfmgb_vec_free(ctx, tb));
+      MFMGB_CHECK(mfmgb_vec_free(ctx, tx));
+    }
+    H->finalized = true;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_hierarchy_destroy(mfmgb_ctx *ctx, mfmgb_hierarchy *H)
+  {
+    if (!H)
+      return MFMGB_OK;
+    MFMGB_REQUIRE(ctx, ctx, "ctx is NULL");
+    MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (H->graph_exec)
+      cudaGraphExecDestroy(H->graph_exec);
+    for (int k = 0; k < 7; ++k)
+      if (H->ev[k])
+        cudaEventDestroy(H->ev[k]);
+    for (auto &l : H->lev)
+    {
+      if (l.P_owned)
+        mfmgb_csr_destroy(ctx, l.P_owned);
+      mfmgb_jacobi_destroy(ctx, l.J);
+      mfmgb_dense_destroy(ctx, l.D);
+      cudaFree(l.res);
+      cudaFree(l.xtmp);
+      cudaFree(l.bc);
+      cudaFree(l.xc);
+    }
+    cudaFree(H->b_dev);
+    cudaFree(H->x_dev);
+    cudaFree(H->g);
+    cudaFree(H->h);
+    cudaFree(H->d);
+    cudaFree(H->scal);
+    if (H->scal_host)
+      cudaFreeHost(H->scal_host);
+    delete H;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_hierarchy_use_graph(mfmgb_hierarchy *H, int on)
+  {
+    if (!H)
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_use_graph: H is NULL");
+    H->use_graph = on != 0;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_hierarchy_launches_per_cycle(const mfmgb_hierarchy *H) { return H ? H->launches_per_cycle : 0; }
+
+  MFMGB_API int mfmgb_hierarchy_apply(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, int level)
+  {
+    MFMGB_REQUIRE(ctx, ctx && H && H->finalized && b && x, "mfmgb_hierarchy_apply: bad arguments");
+    MFMGB_REQUIRE(ctx, level >= 0 && level < H->n_levels, "mfmgb_hierarchy_apply: level out of range");
+    MFMGB_REQUIRE(ctx, b != x, "mfmgb_hierarchy_apply: b and x must not alias");
+    return apply_level(ctx, H, b, x, level);
+  }
+
+  MFMGB_API int mfmgb_vcycle(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x)
+  {
+    MFMGB_REQUIRE(ctx, ctx && H && H->finalized && b && x, "mfmgb_vcycle: bad arguments");
+    MFMGB_REQUIRE(ctx, b != x, "mfmgb_vcycle: b and x must not alias");
+    return run_vcycle(ctx, H, b, x);
+  }
+
+  MFMGB_API int mfmgb_vcycle_profile(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, double *stage_ms)
+  {
+    MFMGB_REQUIRE(ctx, ctx && H && H->finalized && b && x && stage_ms, "mfmgb_vcycle_profile: bad arguments");
+    MFMGB_REQUIRE(ctx, H->n_levels >= 2, "mfmgb_vcycle_profile: needs at least two levels");
+    for (int k = 0; k < 7; ++k)
+      if (!H->ev[k])
+        MFMGB_CUDA(ctx, cudaEventCreate(&H->ev[k]));
+    H->profiling = true;
+    const int rc = apply_level(ctx, H, b, x, 0);
+    H->profiling = false;
+    MFMGB_CHECK(rc);
+    MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 6; ++k)
+    {
+      float ms = 0.f;
+      MFMGB_CUDA(ctx, cudaEventElapsedTime(&ms, H->ev[k], H->ev[k + 1]));
+      stage_ms[k] = (double)ms;
+    }
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_vcycle_host(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b_host, double *x_host)
+  {
+    MFMGB_REQUIRE(ctx, ctx && H && H->finalized && b_host && x_host, "mfmgb_vcycle_host: bad arguments");
+    const int64_t n = H->lev[0].n;
+    MFMGB_CHECK(ensure_host_staging(ctx, H, n));
+    const size_t bytes = sizeof(double) * (size_t)n;
+    MFMGB_CUDA(ctx, cudaMemcpyAsync(H->b_dev, b_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (!H->is_preconditioner) // solver mode: x is an input as well
+      MFMGB_CUDA(ctx, cudaMemcpyAsync(H->x_dev, x_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MFMGB_CHECK(run_vcycle(ctx, H, H->b_dev, H->x_dev));
+    MFMGB_CUDA(ctx, cudaMemcpyAsync(x_host, H->x_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_pcg(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const mfmgb_csr *A, const double *b, double *x, double tol,
+                          int max_it, int *iterations, double *res_hist_host)
+  {
+    MFMGB_REQUIRE(ctx, ctx && b && x && iterations && max_it >= 0, "mfmgb_pcg: bad arguments");
+    MFMGB_REQUIRE(ctx, H || A, "mfmgb_pcg: need a hierarchy or a matrix");
+    MFMGB_REQUIRE(ctx, !H || H->finalized, "mfmgb_pcg: hierarchy not finalized");
+    mfmgb_level op;
+    if (A)
+    {
+      op.A = A;
+      op.n = A->n_rows;
+    }
+    else
+      op = H->lev[0];
+    const int64_t n = op.n;
+    MFMGB_REQUIRE(ctx, !H || H->lev[0].n == n, "mfmgb_pcg: hierarchy and matrix sizes differ");
+    mfmgb_hierarchy local;
+    mfmgb_hierarchy *W = H ? H : &local; // work vectors live in the hierarchy when there is one
+    MFMGB_CHECK(ensure_pcg_work(ctx, W, n));
+    double *g = W->g, *h = W->h, *d = W->d, *scal = W->scal, *sh = W->scal_host;
+    const int nb = reduce_blocks(ctx, n);
+    const int grid_ew = (int)std::min<int64_t>(ceil_div(n, kBlock), (int64_t)ctx->num_sms * 16);
+    cudaStream_t st = ctx->stream;
+    int rc = MFMGB_OK;
+    auto cleanup = [&]() {
+      if (!H)
+      {
+        cudaStreamSynchronize(st);
+        cudaFree(local.g);
+        cudaFree(local.h);
+        cudaFree(local.d);
+        cudaFree(local.scal);
+        cudaFreeHost(local.scal_host);
+      }
+    };
+#define PCG_TRY(call)                                                                               \
+  do                                                                                                \
+  {                                                                                                 \
+    rc = (call);                                                                                    \
+    if (rc != MFMGB_OK)                                                                             \
+    {                                                                                               \
+      cleanup();                                                                                    \
+      return rc;                                                                                    \
+    }                                                                                               \
+  } while (0)
+#define PCG_CUDA(call)                                                                              \
+  do                                                                                                \
+  {                                                                                                 \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+    {                                                                                               \
+      cleanup();                                                                                    \
+      return fail(ctx, MFMGB_ERR_CUDA, "mfmgb_pcg: %s: %s", #call, cudaGetErrorString(e__));        \
+    }                                                                                               \
+  } while (0)
+
+    // g = A x - b ; res0 = |g|
+    EpiArgs e;
+    e.y = g;
+    e.b = b;
+    PCG_TRY(level_apply_A(ctx, op, x, Epi::Resid, e));
+    PCG_TRY(vec_dot_async(ctx, g, g, n, scal + 3));
+    PCG_CUDA(cudaMemcpyAsync(sh, scal + 3, sizeof(double), cudaMemcpyDeviceToHost, st));
+    PCG_CUDA(cudaStreamSynchronize(st));
+    double res = std::sqrt(sh[0]);
+    if (res_hist_host)
+      res_hist_host[0] = res;
+    int it = 0;
+    bool converged = res <= tol;
+    if (!converged)
+    {
+      // h = M^-1 g ; d = -h ; gh = g.h
+      if (H)
+        PCG_TRY(run_vcycle(ctx, H, g, h));
+      else
+        PCG_CUDA(cudaMemcpyAsync(h, g, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+      negate_kernel<<<grid_ew, kBlock, 0, st>>>(n, h, d);
+      ctx->launches++;
+      PCG_TRY(vec_dot_async(ctx, g, h, n, scal + 0));
+      while (!converged && it < max_it)
+      {
+        ++it;
+        e = EpiArgs();
+        e.y = h;
+        PCG_TRY(level_apply_A(ctx, op, d, Epi::Spmv, e)); // h = A d
+        PCG_TRY(vec_dot_async(ctx, d, h, n, scal + 2));   // dh = d.h
+        pcg_update_kernel<<<nb, kBlock, 0, st>>>(n, scal, h, d, g, x, ctx->red_partials);
+        ctx->launches++;
+        PCG_TRY(reduce_finalize(ctx, ctx->red_partials, nb, ctx->red_capacity, 1, scal + 3));
+        PCG_CUDA(cudaMemcpyAsync(sh, scal + 3, sizeof(double), cudaMemcpyDeviceToHost, st));
+        PCG_CUDA(cudaStreamSynchronize(st));
+        res = std::sqrt(sh[0]);
+        if (res_hist_host)
+          res_hist_host[it] = res;
+        if (res <= tol)
+        {
+          converged = true;
+          break;
+        }
+        if (H)
+          PCG_TRY(run_vcycle(ctx, H, g, h)); // h = M^-1 g
+        else
+          PCG_CUDA(cudaMemcpyAsync(h, g, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        PCG_TRY(vec_dot_async(ctx, g, h, n, scal + 1)); // gh_new
+        pcg_direction_kernel<<<grid_ew, kBlock, 0, st>>>(n, scal, h, d);
+        ctx->launches++;
+        rotate_scalar_kernel<<<1, 1, 0, st>>>(scal);
+        ctx->launches++;
+      }
+    }
+    PCG_CUDA(cudaStreamSynchronize(st));
+    PCG_CUDA(cudaGetLastError());
+    cleanup();
+#undef PCG_TRY
+#undef PCG_CUDA
+    *iterations = it;
+    if (!converged)
+      return fail(ctx, MFMGB_ERR_NOT_CONVERGED, "mfmgb_pcg: no convergence after %d iterations (residual %g > %g)", it,
+                  res, tol);
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_pcg_host(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const mfmgb_csr *A, const double *b_host,
+                               double *x_host, double tol, int max_it, int *iterations, double *res_hist_host)
+  {
+    MFMGB_REQUIRE(ctx, ctx && (H || A) && b_host && x_host, "mfmgb_pcg_host: bad arguments");
+    const int64_t n = A ? A->n_rows : H->lev[0].n;
+    double *b = nullptr, *x = nullptr;
+    MFMGB_CHECK(mfmgb_vec_alloc(ctx, n, &b));
+    MFMGB_CHECK(mfmgb_vec_alloc(ctx, n, &x));
+    MFMGB_CHECK(mfmgb_vec_upload(ctx, b, b_host, n));
+    MFMGB_CHECK(mfmgb_vec_upload(ctx, x, x_host, n));
+    const int rc = mfmgb_pcg(ctx, H, A, b, x, tol, max_it, iterations, res_hist_host);
+    if (rc == MFMGB_OK || rc == MFMGB_ERR_NOT_CONVERGED)
+      mfmgb_vec_download(ctx, x, x_host, n);
+    mfmgb_vec_free(ctx, b);
+    mfmgb_vec_free(ctx, x);
+    return rc;
+  }
+}

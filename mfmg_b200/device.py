@@ -1,0 +1,503 @@
+"""Host-side mirror of mfmg's device operator interface on top of the C ABI.
+
+Same names, argument meaning and error behaviour as the reference classes, so the parity tests
+read like the reference's own tests (tests/test_sparse_matrix_device.cu, test_smoother_device.cu,
+test_direct_solver_device.cu, test_hierarchy_device.cu):
+
+  CudaHandle            source/cuda/cuda_handle.cu:17-56       (context; no library handles inside)
+  DeviceVector          dealii::LinearAlgebra::distributed::Vector<double, MemorySpace::CUDA>
+  SparseMatrixDevice    include/mfmg/cuda/sparse_matrix_device.cuh:28-104
+  CudaMatrixOperator    source/cuda/cuda_matrix_operator.cu     (alias SparseMatrixDeviceOperator)
+  CudaSmoother          source/cuda/cuda_smoother.cu            (alias SmootherDevice)
+  CudaSolver            source/cuda/cuda_solver.cu              (alias DirectSolverDevice)
+  Hierarchy             include/mfmg/common/hierarchy.hpp:159-309 (alias HierarchyDevice)
+
+Everything numeric happens in libmfmg_b200.so; this module only holds handles.
+"""
+from __future__ import annotations
+
+import ctypes
+from enum import Enum
+
+import numpy as np
+
+from . import _lib
+from ._lib import MfmgError, NoConvergence, NotImplementedExc, check  # noqa: F401
+
+
+class OperatorMode(Enum):
+    """include/mfmg/common/operator.hpp:19-23"""
+    NO_TRANS = 0
+    TRANS = 1
+
+
+def _get(params, key: str, default=None):
+    """boost::property_tree-style lookup: nested dicts addressed by a dotted path."""
+    if params is None:
+        return default
+    node = params
+    if key in node:
+        return node[key]
+    for part in key.split("."):
+        if not isinstance(node, dict) or part not in node:
+            return default
+        node = node[part]
+    return node
+
+
+class CudaHandle:
+    """Owns the mfmgb context (device + stream)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = _lib.load()
+        p = ctypes.c_void_p()
+        rc = self.lib.mfmgb_ctx_create(device, ctypes.c_void_p(stream) if stream else None, ctypes.byref(p))
+        check(None, rc)
+        self.ctx = p
+        self.device = device
+
+    def synchronize(self) -> None:
+        check(self.ctx, self.lib.mfmgb_ctx_synchronize(self.ctx))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.mfmgb_ctx_launch_count(self.ctx))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.mfmgb_ctx_stream(self.ctx) or 0)
+
+    def close(self) -> None:
+        if getattr(self, "ctx", None):
+            self.lib.mfmgb_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceVector:
+    """A device-resident FP64 vector (raw cudaMalloc storage, like Vector<double, CUDA>::get_values())."""
+
+    def __init__(self, handle: CudaHandle, n: int):
+        self.handle = handle
+        self.size = int(n)
+        p = ctypes.c_void_p()
+        check(handle.ctx, handle.lib.mfmgb_vec_alloc(handle.ctx, self.size, ctypes.byref(p)))
+        self.ptr = p
+
+    @staticmethod
+    def from_host(handle: CudaHandle, a) -> "DeviceVector":
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        v = DeviceVector(handle, a.shape[0])
+        v.upload(a)
+        return v
+
+    def upload(self, a) -> None:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.shape[0] != self.size:
+            raise MfmgError(_lib.ERR_INVALID, "DeviceVector.upload: size mismatch")
+        check(self.handle.ctx, self.handle.lib.mfmgb_vec_upload(self.handle.ctx, self.ptr, a.ctypes.data, self.size))
+
+    def to_host(self) -> np.ndarray:
+        out = np.empty(self.size, dtype=np.float64)
+        check(self.handle.ctx,
+              self.handle.lib.mfmgb_vec_download(self.handle.ctx, self.ptr, out.ctypes.data, self.size))
+        return out
+
+    def fill(self, value: float) -> None:
+        check(self.handle.ctx, self.handle.lib.mfmgb_vec_fill(self.handle.ctx, self.ptr, float(value), self.size))
+
+    def add(self, a: float, other: "DeviceVector") -> None:
+        """Vector::add(a, v): this += a * v"""
+        check(self.handle.ctx,
+              self.handle.lib.mfmgb_vec_axpy(self.handle.ctx, self.ptr, float(a), other.ptr, self.size))
+
+    def dot(self, other: "DeviceVector") -> float:
+        r = ctypes.c_double()
+        check(self.handle.ctx,
+              self.handle.lib.mfmgb_vec_dot(self.handle.ctx, self.ptr, other.ptr, self.size, ctypes.byref(r)))
+        return r.value
+
+    def l2_norm(self) -> float:
+        return float(np.sqrt(self.dot(self)))
+
+    def free(self) -> None:
+        if getattr(self, "ptr", None) and getattr(self.handle, "ctx", None):
+            self.handle.lib.mfmgb_vec_free(self.handle.ctx, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class SparseMatrixDevice:
+    """Device CSR matrix.  Construct from host CSR arrays (convert_matrix semantics: the data is
+    copied, source/cuda/utils.cu:39-168)."""
+
+    def __init__(self, handle: CudaHandle, n_rows: int, n_cols: int, rowptr, col, val, _adopt=None):
+        self.handle = handle
+        lib = handle.lib
+        p = ctypes.c_void_p()
+        if _adopt is not None:
+            self.ptr = _adopt
+        else:
+            rowptr = np.ascontiguousarray(rowptr)
+            col = np.ascontiguousarray(col, dtype=np.int32)
+            val = np.ascontiguousarray(val, dtype=np.float64)
+            if rowptr.dtype == np.int32:
+                rc = lib.mfmgb_csr_upload_i32(handle.ctx, n_rows, n_cols, rowptr.ctypes.data, col.ctypes.data,
+                                              val.ctypes.data, ctypes.byref(p))
+            else:
+                rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+                rc = lib.mfmgb_csr_upload(handle.ctx, n_rows, n_cols, rowptr.ctypes.data, col.ctypes.data,
+                                          val.ctypes.data, ctypes.byref(p))
+            check(handle.ctx, rc)
+            self.ptr = p
+        a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        check(handle.ctx, lib.mfmgb_csr_info(self.ptr, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        self._m, self._n, self._nnz = a.value, b.value, c.value
+
+    @staticmethod
+    def from_host(handle: CudaHandle, A) -> "SparseMatrixDevice":
+        """A: hostsetup.HostCSR or scipy.sparse matrix."""
+        if hasattr(A, "tocsr"):
+            A = A.tocsr()
+            return SparseMatrixDevice(handle, A.shape[0], A.shape[1], A.indptr.astype(np.int64), A.indices, A.data)
+        return SparseMatrixDevice(handle, A.n_rows, A.n_cols, A.rowptr, A.col, A.val)
+
+    # sparse_matrix_device.cuh:61-71
+    def m(self) -> int:
+        return self._m
+
+    def n(self) -> int:
+        return self._n
+
+    def n_local_rows(self) -> int:
+        return self._m
+
+    def local_nnz(self) -> int:
+        return self._nnz
+
+    def n_nonzero_elements(self) -> int:
+        return self._nnz
+
+    def vmult(self, dst: DeviceVector, src: DeviceVector) -> None:
+        """dst = A src (sparse_matrix_device.templates.cuh:351-371)"""
+        if src.size != self._n or dst.size != self._m:
+            raise MfmgError(_lib.ERR_INVALID, "SparseMatrixDevice.vmult: size mismatch")
+        check(self.handle.ctx, self.handle.lib.mfmgb_spmv(self.handle.ctx, self.ptr, src.ptr, dst.ptr))
+
+    def transpose(self) -> "SparseMatrixDevice":
+        p = ctypes.c_void_p()
+        check(self.handle.ctx, self.handle.lib.mfmgb_csr_transpose(self.handle.ctx, self.ptr, ctypes.byref(p)))
+        return SparseMatrixDevice(self.handle, 0, 0, None, None, None, _adopt=p)
+
+    def to_host(self):
+        """(rowptr int64, col int32, val f64): round trip of tests/test_utils_device.cu:221-263."""
+        rowptr = np.empty(self._m + 1, dtype=np.int64)
+        col = np.empty(max(self._nnz, 1), dtype=np.int32)
+        val = np.empty(max(self._nnz, 1), dtype=np.float64)
+        check(self.handle.ctx, self.handle.lib.mfmgb_csr_download(self.handle.ctx, self.ptr, rowptr.ctypes.data,
+                                                                  col.ctypes.data, val.ctypes.data))
+        return rowptr, col[:self._nnz], val[:self._nnz]
+
+    def set_lanes_per_row(self, lanes: int) -> None:
+        check(self.handle.ctx, self.handle.lib.mfmgb_csr_set_lanes_per_row(self.ptr, lanes))
+
+    @property
+    def lanes_per_row(self) -> int:
+        return int(self.handle.lib.mfmgb_csr_get_lanes_per_row(self.ptr))
+
+    def free(self) -> None:
+        if getattr(self, "ptr", None) and getattr(self.handle, "ctx", None):
+            self.handle.lib.mfmgb_csr_destroy(self.handle.ctx, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class CudaMatrixOperator:
+    """mfmg::CudaMatrixOperator (Operator interface, include/mfmg/common/operator.hpp:25-52)."""
+
+    def __init__(self, matrix: SparseMatrixDevice):
+        self._matrix = matrix
+        self._transposed = None
+        self.handle = matrix.handle
+
+    def get_matrix(self) -> SparseMatrixDevice:
+        return self._matrix
+
+    def apply(self, x: DeviceVector, y: DeviceVector, mode: OperatorMode = OperatorMode.NO_TRANS) -> None:
+        if mode == OperatorMode.NO_TRANS:
+            self._matrix.vmult(y, x)
+        else:
+            # explicit transpose built lazily on first use (cuda_matrix_operator.cu:84-88)
+            if self._transposed is None:
+                self._transposed = self._matrix.transpose()
+            self._transposed.vmult(y, x)
+
+    def transpose(self) -> "CudaMatrixOperator":
+        if self._transposed is None:
+            self._transposed = self._matrix.transpose()
+        return CudaMatrixOperator(self._transposed)
+
+    def multiply(self, b: "CudaMatrixOperator") -> "CudaMatrixOperator":
+        """C = this * b.  SETUP operation; like the reference's parallel path it runs on the host
+        (sparse_matrix_device.templates.cuh:417-433) and uploads the product."""
+        import scipy.sparse as sp
+
+        ra, ca, va = self._matrix.to_host()
+        rb, cb, vb = b._matrix.to_host()
+        A = sp.csr_matrix((va, ca, ra), shape=(self._matrix.m(), self._matrix.n()))
+        B = sp.csr_matrix((vb, cb, rb), shape=(b._matrix.m(), b._matrix.n()))
+        C = (A @ B).tocsr()
+        C.sort_indices()
+        return CudaMatrixOperator(SparseMatrixDevice.from_host(self.handle, C))
+
+    def multiply_transpose(self, b: "CudaMatrixOperator") -> "CudaMatrixOperator":
+        """this * b^T (cuda_matrix_operator.cu:151-225); setup, host."""
+        return self.multiply(b.transpose())
+
+    def build_domain_vector(self) -> DeviceVector:
+        return DeviceVector(self.handle, self._matrix.n())
+
+    def build_range_vector(self) -> DeviceVector:
+        return DeviceVector(self.handle, self._matrix.m())
+
+    def grid_complexity(self) -> int:
+        return self._matrix.m()
+
+    def operator_complexity(self) -> int:
+        return self._matrix.n_nonzero_elements()
+
+
+class CudaSmoother:
+    """mfmg::CudaSmoother: Jacobi only (source/cuda/cuda_smoother.cu:99-172)."""
+
+    def __init__(self, op: CudaMatrixOperator, params=None, omega: float = 1.0):
+        prec_type = str(_get(params, "smoother.type", "Jacobi")).lower()
+        if prec_type != "jacobi":
+            raise MfmgError(_lib.ERR_INVALID, "Only Jacobi smoother is implemented.")  # cuda_smoother.cu:110
+        self._operator = op
+        self.handle = op.handle
+        m = op.get_matrix()
+        if m.m() != m.n():
+            raise MfmgError(_lib.ERR_INVALID, f"The matrix is not square. The matrix is a {m.m()} by {m.n()} .")
+        p = ctypes.c_void_p()
+        check(self.handle.ctx, self.handle.lib.mfmgb_jacobi_setup(self.handle.ctx, m.ptr, float(omega), ctypes.byref(p)))
+        self.ptr = p
+
+    def apply(self, b: DeviceVector, x: DeviceVector) -> None:
+        """x <- x - D^-1 (A x - b)"""
+        check(self.handle.ctx, self.handle.lib.mfmgb_jacobi_apply(self.handle.ctx, self.ptr,
+                                                                 self._operator.get_matrix().ptr, b.ptr, x.ptr))
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None) and getattr(self.handle, "ctx", None):
+                self.handle.lib.mfmgb_jacobi_destroy(self.handle.ctx, self.ptr)
+        except Exception:
+            pass
+
+
+class CudaSolver:
+    """mfmg::CudaSolver (source/cuda/cuda_solver.cu:196-515).  `solver.type`: "lu_dense" (default)
+    is the hand-written dense factor-and-solve; "cholesky" and "lu_sparse_host" -- cuSOLVER wrappers
+    in the reference -- are served by the same dense kernel (identical mathematical result);
+    "amgx" is not available (the north star forbids library solvers)."""
+
+    def __init__(self, handle: CudaHandle, op: CudaMatrixOperator, params=None):
+        solver = str(_get(params, "solver.type", "lu_dense"))
+        if solver == "amgx":
+            raise NotImplementedExc(_lib.ERR_NOT_IMPLEMENTED, "solver.type amgx is not available in mfmg_b200")
+        if solver not in ("lu_dense", "cholesky", "lu_sparse_host"):
+            raise MfmgError(_lib.ERR_INVALID, f"The provided solver name {solver} is invalid.")  # cuda_solver.cu:70
+        self.handle = handle
+        self._operator = op
+        p = ctypes.c_void_p()
+        check(handle.ctx, handle.lib.mfmgb_dense_factor(handle.ctx, op.get_matrix().ptr, ctypes.byref(p)))
+        self.ptr = p
+
+    def apply(self, b: DeviceVector, x: DeviceVector) -> None:
+        check(self.handle.ctx, self.handle.lib.mfmgb_dense_solve(self.handle.ctx, self.ptr, b.ptr, x.ptr))
+
+    @property
+    def num_swaps(self) -> int:
+        return int(self.handle.lib.mfmgb_dense_num_swaps(self.ptr))
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None) and getattr(self.handle, "ctx", None):
+                self.handle.lib.mfmgb_dense_destroy(self.handle.ctx, self.ptr)
+        except Exception:
+            pass
+
+
+class MatrixFreeLaplaceDevice:
+    """The matrix-free fine-level operator (CudaMatrixFreeOperator slot)."""
+
+    def __init__(self, handle: CudaHandle, dim, degree, cells, h, coef_per_q, constrained):
+        self.handle = handle
+        cells_a = np.ascontiguousarray(list(cells) + [1] * (3 - dim), dtype=np.int64)
+        h_a = np.ascontiguousarray(list(h) + [1.0] * (3 - dim), dtype=np.float64)
+        coef = np.ascontiguousarray(coef_per_q, dtype=np.float64)
+        constr = np.ascontiguousarray(constrained, dtype=np.uint8)
+        p = ctypes.c_void_p()
+        check(handle.ctx, handle.lib.mfmgb_mf_laplace_create(handle.ctx, dim, degree, cells_a.ctypes.data,
+                                                             h_a.ctypes.data, coef.ctypes.data, constr.ctypes.data,
+                                                             ctypes.byref(p)))
+        self.ptr = p
+        self.size = int(handle.lib.mfmgb_mf_size(p))
+
+    def apply(self, x: DeviceVector, y: DeviceVector, mode: OperatorMode = OperatorMode.NO_TRANS) -> None:
+        # the operator is symmetric: TRANS == NO_TRANS (cuda_matrix_free_operator.cu:60-70)
+        check(self.handle.ctx, self.handle.lib.mfmgb_mf_apply(self.handle.ctx, self.ptr, x.ptr, y.ptr))
+
+    def diagonal(self) -> DeviceVector:
+        d = DeviceVector(self.handle, self.size)
+        check(self.handle.ctx, self.handle.lib.mfmgb_mf_diagonal(self.handle.ctx, self.ptr, d.ptr))
+        return d
+
+    def build_domain_vector(self) -> DeviceVector:
+        return DeviceVector(self.handle, self.size)
+
+    build_range_vector = build_domain_vector
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None) and getattr(self.handle, "ctx", None):
+                self.handle.lib.mfmgb_mf_destroy(self.handle.ctx, self.ptr)
+        except Exception:
+            pass
+
+
+class Hierarchy:
+    """mfmg::Hierarchy on device vectors.  Built from already-assembled level operators
+    (`from_operators`) -- the setup that produces them stays on the host path
+    (mfmg_b200.hostsetup), exactly as the north star prescribes.
+
+    params keys honoured (include/mfmg/common/hierarchy.hpp:168-172): "is preconditioner",
+    "smoother.n_smoothing_steps", "smoother.type", "solver.type"."""
+
+    def __init__(self, handle: CudaHandle, operators, restrictors, params=None, omega: float = 1.0,
+                 prolongators=None):
+        self.handle = handle
+        lib = handle.lib
+        self.params = params or {}
+        if str(_get(params, "smoother.type", "Jacobi")).lower() != "jacobi":
+            raise MfmgError(_lib.ERR_INVALID, "Only Jacobi smoother is implemented.")
+        solver = str(_get(params, "solver.type", "lu_dense"))
+        if solver == "amgx":
+            raise NotImplementedExc(_lib.ERR_NOT_IMPLEMENTED, "solver.type amgx is not available in mfmg_b200")
+        self.is_preconditioner = bool(_get(params, "is preconditioner", True))
+        self.n_smoothing_steps = int(_get(params, "smoother.n_smoothing_steps", 1))
+        self.operators = list(operators)
+        self.restrictors = list(restrictors)
+        self.prolongators = list(prolongators) if prolongators else [None] * len(self.restrictors)
+        n_levels = len(self.operators)
+        if len(self.restrictors) != n_levels - 1:
+            raise MfmgError(_lib.ERR_INVALID, "Hierarchy: need one restrictor per level transition")
+        p = ctypes.c_void_p()
+        check(handle.ctx, lib.mfmgb_hierarchy_create(handle.ctx, n_levels, self.n_smoothing_steps,
+                                                     int(self.is_preconditioner), float(omega), ctypes.byref(p)))
+        self.ptr = p
+        for li, op in enumerate(self.operators):
+            if isinstance(op, MatrixFreeLaplaceDevice):
+                check(handle.ctx, lib.mfmgb_hierarchy_set_mf_operator(self.ptr, op.ptr))
+            else:
+                check(handle.ctx, lib.mfmgb_hierarchy_set_operator(self.ptr, li, op.ptr))
+        for li, r in enumerate(self.restrictors):
+            pr = self.prolongators[li]
+            check(handle.ctx, lib.mfmgb_hierarchy_set_restrictor(self.ptr, li + 1, r.ptr, pr.ptr if pr else None))
+        check(handle.ctx, lib.mfmgb_hierarchy_finalize(handle.ctx, self.ptr))
+        self.n = self.operators[0].size if isinstance(self.operators[0], MatrixFreeLaplaceDevice) \
+            else self.operators[0].m()
+
+    @staticmethod
+    def from_host(handle: CudaHandle, A, R, A_c, params=None, omega: float = 1.0) -> "Hierarchy":
+        """Two-level hierarchy from host CSR operators (A fine, R restrictor, A_c = R A R^T)."""
+        ops = [SparseMatrixDevice.from_host(handle, A), SparseMatrixDevice.from_host(handle, A_c)]
+        res = [SparseMatrixDevice.from_host(handle, R)]
+        return Hierarchy(handle, ops, res, params, omega)
+
+    def use_graph(self, on: bool = True) -> None:
+        check(self.handle.ctx, self.handle.lib.mfmgb_hierarchy_use_graph(self.ptr, int(on)))
+
+    @property
+    def launches_per_cycle(self) -> int:
+        return int(self.handle.lib.mfmgb_hierarchy_launches_per_cycle(self.ptr))
+
+    def vmult(self, x: DeviceVector, b: DeviceVector) -> None:
+        """x = V-cycle(b)  (Hierarchy::vmult, hierarchy.hpp:238-244)"""
+        check(self.handle.ctx, self.handle.lib.mfmgb_vcycle(self.handle.ctx, self.ptr, b.ptr, x.ptr))
+
+    def apply(self, b: DeviceVector, x: DeviceVector, level_index: int = 0) -> None:
+        check(self.handle.ctx, self.handle.lib.mfmgb_hierarchy_apply(self.handle.ctx, self.ptr, b.ptr, x.ptr,
+                                                                    level_index))
+
+    def vmult_host(self, x_host: np.ndarray, b_host: np.ndarray) -> None:
+        """Hierarchy<Vector<double, Host>>::vmult: host arrays in/out (H2D + cycle + D2H)."""
+        assert x_host.dtype == np.float64 and b_host.dtype == np.float64
+        check(self.handle.ctx, self.handle.lib.mfmgb_vcycle_host(self.handle.ctx, self.ptr, b_host.ctypes.data,
+                                                                 x_host.ctypes.data))
+
+    def vmult_host_ptr(self, x_ptr: int, b_ptr: int) -> None:
+        check(self.handle.ctx, self.handle.lib.mfmgb_vcycle_host(self.handle.ctx, self.ptr, ctypes.c_void_p(b_ptr),
+                                                                 ctypes.c_void_p(x_ptr)))
+
+    STAGES = ("pre_smooth", "residual", "restrict", "coarse", "prolong_correct", "post_smooth")
+
+    def profile(self, x: DeviceVector, b: DeviceVector) -> dict:
+        """One un-captured V-cycle with CUDA events between the level-0 stages -> {stage: ms}."""
+        ms = np.zeros(6)
+        check(self.handle.ctx, self.handle.lib.mfmgb_vcycle_profile(self.handle.ctx, self.ptr, b.ptr, x.ptr,
+                                                                    ms.ctypes.data))
+        return dict(zip(self.STAGES, ms.tolist()))
+
+    def grid_complexity(self) -> float:
+        sizes = [op.size if isinstance(op, MatrixFreeLaplaceDevice) else op.m() for op in self.operators]
+        return sum(sizes) / sizes[0]
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None) and getattr(self.handle, "ctx", None):
+                self.handle.lib.mfmgb_hierarchy_destroy(self.handle.ctx, self.ptr)
+        except Exception:
+            pass
+
+
+def solver_cg(handle: CudaHandle, A: SparseMatrixDevice | None, x: DeviceVector, b: DeviceVector,
+              hierarchy: Hierarchy | None, tol: float = 1e-6, max_it: int | None = None):
+    """dealii::SolverCG(SolverControl(max_it, tol)).solve(A, x, b, hierarchy)
+    (tests/hierarchy_driver.cc:200-213).  Returns (last_step, residual_history).  Raises
+    NoConvergence like deal.II when max_it is exhausted."""
+    n = x.size
+    if max_it is None:
+        max_it = n
+    hist = np.zeros(max_it + 1)
+    it = ctypes.c_int(0)
+    rc = handle.lib.mfmgb_pcg(handle.ctx, hierarchy.ptr if hierarchy else None, A.ptr if A else None, b.ptr, x.ptr,
+                              float(tol), int(max_it), ctypes.byref(it), hist.ctypes.data)
+    if rc == _lib.ERR_NOT_CONVERGED:
+        msg = handle.lib.mfmgb_last_error(handle.ctx).decode()
+        raise NoConvergence(rc, msg, it.value, hist[:it.value + 1].copy())
+    check(handle.ctx, rc)
+    return it.value, hist[:it.value + 1].copy()
+
+
+# names used by BASELINE.json / older mfmg snapshots (SURVEY.md section 8b "Name mapping")
+SparseMatrixDeviceOperator = CudaMatrixOperator
+SmootherDevice = CudaSmoother
+DirectSolverDevice = CudaSolver
+HierarchyDevice = Hierarchy

@@ -1,0 +1,349 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Tolerances: bit-exact on the reference's integer-valued KATs; 1e-12 relative (FP64) for
+SpMV / smoother / transfer outputs; 1e-10 relative for PCG residual histories; equal iteration counts
+(BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle
+from helpers import (banded_matrix, csr_arrays, golden, oracle_hierarchy, rel_err, serial_mv_matrix, tridiag_matrix,
+                     two_level_problem)
+
+pytestmark = pytest.mark.gpu
+
+TOL_OP = 1e-12   # per-application outputs
+TOL_PCG = 1e-10  # residual histories
+
+
+def _dev():
+    from mfmg_b200 import device
+
+    return device
+
+
+def test_serial_mv_kat_exact(handle):
+    # tests/test_sparse_matrix_device.cu:24-114
+    d = _dev()
+    g = golden()
+    A = serial_mv_matrix()
+    Ad = d.SparseMatrixDevice.from_host(handle, A)
+    x = d.DeviceVector.from_host(handle, g["serial_mv_x"])
+    y = d.DeviceVector(handle, 10)
+    for lanes in (0, 2, 4, 8, 16, 32):
+        Ad.set_lanes_per_row(lanes)
+        y.fill(-1.0)
+        Ad.vmult(y, x)
+        assert np.array_equal(y.to_host(), g["serial_mv_y"])
+
+
+def test_operator_kat_exact(handle):
+    # tests/test_sparse_matrix_device_operator.cu:31-133 (apply, transpose()->apply, multiply; BOOST_CHECK_EQUAL)
+    d = _dev()
+    A = banded_matrix()
+    op = d.CudaMatrixOperator(d.SparseMatrixDevice.from_host(handle, A))
+    dom, rng = op.build_domain_vector(), op.build_range_vector()
+    assert dom.size == 39 and rng.size == 30
+    dom.upload(np.ones(39))
+    op.apply(dom, rng)
+    dense = np.asarray(A.todense())
+    assert np.array_equal(rng.to_host(), dense @ np.ones(39))
+    top = op.transpose()
+    tdom, trng = top.build_domain_vector(), top.build_range_vector()
+    assert tdom.size == 30 and trng.size == 39
+    tdom.upload(np.ones(30))
+    top.apply(tdom, trng)
+    assert np.array_equal(trng.to_host(), dense.T @ np.ones(30))
+    # OperatorMode.TRANS on the original operator is the same thing
+    trng2 = d.DeviceVector(handle, 39)
+    op.apply(tdom, trng2, d.OperatorMode.TRANS)
+    assert np.array_equal(trng2.to_host(), trng.to_host())
+    mult = op.multiply(top)
+    mult.apply(tdom, rng)
+    assert np.array_equal(rng.to_host(), dense @ (dense.T @ np.ones(30)))
+
+
+def test_upload_roundtrip(handle):
+    # tests/test_utils_device.cu:59-263: upload layout and round trip are bit exact
+    d = _dev()
+    A = sp.random(123, 77, density=0.1, random_state=11, format="csr")
+    n, m, rp, col, val = csr_arrays(A)
+    for rowptr in (rp, rp.astype(np.int32)):
+        Ad = d.SparseMatrixDevice(handle, n, m, rowptr, col, val)
+        rp2, col2, val2 = Ad.to_host()
+        assert np.array_equal(rp2, rp) and np.array_equal(col2, col) and np.array_equal(val2, val)
+        assert (Ad.m(), Ad.n(), Ad.n_local_rows(), Ad.local_nnz(), Ad.n_nonzero_elements()) == (n, m, n, len(val), len(val))
+
+
+def test_transpose_matches_oracle_bitwise(handle):
+    d = _dev()
+    A = sp.random(200, 150, density=0.05, random_state=5, format="csr")
+    n, m, rp, col, val = csr_arrays(A)
+    At = d.SparseMatrixDevice(handle, n, m, rp, col, val).transpose()
+    trp, tcol, tval = oracle.csr_transpose(n, m, rp, col, val)
+    rp2, col2, val2 = At.to_host()
+    assert np.array_equal(rp2, trp) and np.array_equal(col2, tcol) and np.array_equal(val2, tval)
+
+
+def test_smoother_kat(handle):
+    # tests/test_smoother_device.cu:28-119: expected 0.25 to 1e-12 %; we are bit exact
+    d = _dev()
+    A = tridiag_matrix()
+    op = d.CudaMatrixOperator(d.SparseMatrixDevice.from_host(handle, A))
+    sm = d.CudaSmoother(op, {})
+    b = d.DeviceVector.from_host(handle, np.ones(30))
+    x = d.DeviceVector.from_host(handle, np.zeros(30))
+    sm.apply(b, x)
+    assert np.array_equal(x.to_host(), golden()["smoother_expected"])
+    with pytest.raises(d.MfmgError):
+        d.CudaSmoother(op, {"smoother": {"type": "Gauss-Seidel"}})
+
+
+def test_direct_solver_kat(handle):
+    # tests/test_direct_solver_device.cu:23-110: all three solver names within 1e-12 %
+    d = _dev()
+    A = tridiag_matrix()
+    n, m, rp, col, val = csr_arrays(A)
+    xref = golden()["direct_solver_xref"]
+    rhs = oracle.spmv(n, rp, col, val, xref)
+    op = d.CudaMatrixOperator(d.SparseMatrixDevice.from_host(handle, A))
+    for solver in ("cholesky", "lu_dense", "lu_sparse_host"):
+        s = d.CudaSolver(handle, op, {"solver": {"type": solver}})
+        b = d.DeviceVector.from_host(handle, rhs)
+        x = d.DeviceVector(handle, n)
+        s.apply(b, x)
+        assert np.max(np.abs(x.to_host() - xref) / np.abs(xref)) < 1e-14
+    with pytest.raises(d.NotImplementedExc):
+        d.CudaSolver(handle, op, {"solver": {"type": "amgx"}})
+    with pytest.raises(d.MfmgError):
+        d.CudaSolver(handle, op, {"solver": {"type": "bogus"}})
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 100, 257, 700, 1500])
+def test_dense_solver_with_pivoting_vs_oracle(handle, n):
+    d = _dev()
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal((n, n)) + 0.1 * np.eye(n)   # forces row interchanges
+    n_, m, rp, col, val = csr_arrays(sp.csr_matrix(a))
+    b_h = rng.standard_normal(n)
+    lu, piv, info = oracle.lu_factor_csr(n, rp, col, val)
+    x_ref = oracle.lu_solve(lu, piv, b_h)
+    op = d.CudaMatrixOperator(d.SparseMatrixDevice(handle, n, n, rp, col, val))
+    s = d.CudaSolver(handle, op, {})
+    if n > 2:
+        assert s.num_swaps > 0
+    x = d.DeviceVector(handle, n)
+    s.apply(d.DeviceVector.from_host(handle, b_h), x)
+    cond = np.linalg.cond(a)
+    assert rel_err(x.to_host(), x_ref) < 1e-15 * cond * 50 + 1e-13
+
+
+def test_dense_solver_singular_reports_error(handle):
+    d = _dev()
+    a = np.ones((8, 8))
+    n, m, rp, col, val = csr_arrays(sp.csr_matrix(a))
+    op = d.CudaMatrixOperator(d.SparseMatrixDevice(handle, n, n, rp, col, val))
+    with pytest.raises(d.MfmgError) as e:
+        d.CudaSolver(handle, op, {})
+    assert e.value.code == 4
+
+
+CASES = [(2, 1, 16, 2, 2, "constant"), (2, 1, 24, 4, 1, "discontinuous"), (3, 1, 8, 2, 1, "constant"),
+         (3, 1, 12, 4, 2, "linear"), (3, 2, 4, 2, 2, "linear_x"), (2, 2, 8, 2, 2, "discontinuous")]
+
+
+@pytest.mark.parametrize("dim,degree,cells,block,ne,mat", CASES)
+def test_kernels_vs_oracle(handle, dim, degree, cells, block, ne, mat):
+    """spmv, residual_neg, jacobi (in place / out of place / zero guess), restrict, prolong_correct."""
+    d = _dev()
+    P, R, Ac = two_level_problem(dim, degree, cells, block, ne, mat)
+    n, nc = P.n, R.n_rows
+    A = (P.A.rowptr, P.A.col, P.A.val)
+    rng = np.random.default_rng(42)
+    x_h, b_h, xc_h = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(nc)
+    Ad = d.SparseMatrixDevice.from_host(handle, P.A)
+    Rd = d.SparseMatrixDevice.from_host(handle, R)
+    Pd = Rd.transpose()
+    x, b = d.DeviceVector.from_host(handle, x_h), d.DeviceVector.from_host(handle, b_h)
+    y = d.DeviceVector(handle, n)
+    lib, ctx = handle.lib, handle.ctx
+    for lanes in (0, 2, 8, 32):
+        Ad.set_lanes_per_row(lanes)
+        Ad.vmult(y, x)
+        assert rel_err(y.to_host(), oracle.spmv(n, *A, x_h)) < TOL_OP
+    Ad.set_lanes_per_row(0)
+    d.check(ctx, lib.mfmgb_residual_neg(ctx, Ad.ptr, x.ptr, b.ptr, y.ptr))
+    assert rel_err(y.to_host(), oracle.residual_neg(n, *A, x_h, b_h)) < TOL_OP
+    sm = d.CudaSmoother(d.CudaMatrixOperator(Ad), {})
+    xs = d.DeviceVector.from_host(handle, x_h)
+    sm.apply(b, xs)
+    x_ref = oracle.jacobi_apply(n, *A, b_h, x_h)
+    assert rel_err(xs.to_host(), x_ref) < TOL_OP
+    d.check(ctx, lib.mfmgb_jacobi_apply_oop(ctx, sm.ptr, Ad.ptr, b.ptr, x.ptr, y.ptr))
+    assert rel_err(y.to_host(), x_ref) < TOL_OP
+    d.check(ctx, lib.mfmgb_jacobi_apply_zero_guess(ctx, sm.ptr, b.ptr, y.ptr))
+    assert np.array_equal(y.to_host(), oracle.jacobi_apply(n, *A, b_h, np.zeros(n)))
+    # transfers
+    bc = d.DeviceVector(handle, nc)
+    d.check(ctx, lib.mfmgb_restrict(ctx, Rd.ptr, x.ptr, bc.ptr))
+    assert rel_err(bc.to_host(), oracle.spmv(nc, R.rowptr, R.col, R.val, x_h)) < TOL_OP
+    xc = d.DeviceVector.from_host(handle, xc_h)
+    xp = d.DeviceVector.from_host(handle, x_h)
+    d.check(ctx, lib.mfmgb_prolong_correct(ctx, Pd.ptr, xc.ptr, xp.ptr))
+    ref = x_h - oracle.spmv_transpose(nc, n, R.rowptr, R.col, R.val, xc_h)
+    assert rel_err(xp.to_host(), ref) < TOL_OP
+
+
+@pytest.mark.parametrize("dim,degree,cells,block,ne,mat", CASES)
+@pytest.mark.parametrize("nu,precond,graph", [(1, True, False), (1, True, True), (2, True, False), (1, False, False),
+                                              (2, False, True), (0, True, False)])
+def test_vcycle_vs_oracle(handle, dim, degree, cells, block, ne, mat, nu, precond, graph):
+    d = _dev()
+    P, R, Ac = two_level_problem(dim, degree, cells, block, ne, mat)
+    params = {"is preconditioner": precond, "smoother": {"n_smoothing_steps": nu, "type": "Jacobi"}}
+    H = d.Hierarchy.from_host(handle, P.A, R, Ac, params)
+    H.use_graph(graph)
+    Ho = oracle_hierarchy(P, R, Ac, nu, precond)
+    rng = np.random.default_rng(7)
+    b_h = rng.standard_normal(P.n)
+    x_h = rng.standard_normal(P.n)
+    b, x = d.DeviceVector.from_host(handle, b_h), d.DeviceVector.from_host(handle, x_h)
+    for rep in range(2):  # second call replays the graph
+        x.upload(x_h)
+        H.vmult(x, b)
+        assert rel_err(x.to_host(), Ho.vmult(b_h, x_h)) < TOL_OP
+    # host-vector entry point (Hierarchy<Vector<double,Host>>)
+    xh = x_h.copy()
+    H.vmult_host(xh, b_h)
+    assert rel_err(xh, Ho.vmult(b_h, x_h)) < TOL_OP
+    assert H.launches_per_cycle > 0
+
+
+def test_two_grid_gold_rate_on_device(handle):
+    # tests/test_hierarchy_device.cu:359-420, gold 0.14933479171507894 (1e-6 %): the whole device path
+    d = _dev()
+    P, R, Ac = two_level_problem(3, 1, 4, 2, 2, "constant", "device_lapack")
+    params = {"is preconditioner": False, "smoother": {"type": "Jacobi"}, "solver": {"type": "lu_dense"}}
+    H = d.Hierarchy.from_host(handle, P.A, R, Ac, params)
+    Ad = d.SparseMatrixDevice.from_host(handle, P.A)
+    x = d.DeviceVector.from_host(handle, oracle.std_uniform01(P.n))
+    b = d.DeviceVector.from_host(handle, np.zeros(P.n))
+    r = d.DeviceVector(handle, P.n)
+    res = []
+    for _ in range(20):
+        H.apply(b, x)
+        Ad.vmult(r, x)
+        res.append(r.l2_norm())
+    gold = float(golden()["gold_rate_device_cube"])
+    assert abs(res[-1] / res[-2] - gold) / gold < 1e-8
+
+
+@pytest.mark.parametrize("dim,degree,cells,block,ne,mat,tol", [(2, 1, 64, 2, 2, "constant", 1e-6),
+                                                               (2, 1, 64, 2, 2, "constant", 1e-8),
+                                                               (3, 1, 16, 4, 2, "constant", 1e-8),
+                                                               (3, 2, 6, 3, 2, "discontinuous", 1e-8)])
+def test_pcg_iterations_and_history_vs_oracle(handle, dim, degree, cells, block, ne, mat, tol):
+    """configs[0] (2D Q1, hyper_cube refined 6x, eigenvector agglomerates, CG preconditioner) and friends:
+    equal iteration counts, residual histories within 1e-10 relative."""
+    d = _dev()
+    P, R, Ac = two_level_problem(dim, degree, cells, block, ne, mat)
+    H = d.Hierarchy.from_host(handle, P.A, R, Ac, {"is preconditioner": True})
+    Ho = oracle_hierarchy(P, R, Ac, 1, True)
+    x0 = oracle.std_uniform01(P.n, skip=P.constrained)   # tests/hierarchy_driver.cc:153-164
+    b_h = np.zeros(P.n)                                  # Source::value == 0
+    x_ref, it_ref, hist_ref = Ho.pcg(b_h, x0, tol, P.n)
+    Ad = H.operators[0]
+    x, b = d.DeviceVector.from_host(handle, x0), d.DeviceVector.from_host(handle, b_h)
+    it, hist = d.solver_cg(handle, Ad, x, b, H, tol, P.n)
+    assert it == it_ref and it > 2
+    assert np.max(np.abs(hist - hist_ref) / hist_ref) < TOL_PCG
+    assert rel_err(x.to_host(), x_ref) < 1e-9 or np.linalg.norm(x_ref) < 1e-6
+    # graph replay gives the same answer
+    H.use_graph(True)
+    x.upload(x0)
+    it2, hist2 = d.solver_cg(handle, Ad, x, b, H, tol, P.n)
+    assert it2 == it and np.array_equal(hist2, hist)
+
+
+def test_pcg_no_convergence_raises(handle):
+    d = _dev()
+    P, R, Ac = two_level_problem(2, 1, 16, 2, 2)
+    H = d.Hierarchy.from_host(handle, P.A, R, Ac, {})
+    x = d.DeviceVector.from_host(handle, oracle.std_uniform01(P.n, skip=P.constrained))
+    b = d.DeviceVector.from_host(handle, np.zeros(P.n))
+    with pytest.raises(d.NoConvergence) as e:
+        d.solver_cg(handle, H.operators[0], x, b, H, 1e-30, 3)
+    assert e.value.iterations == 3
+
+
+def test_unpreconditioned_cg_vs_oracle(handle):
+    d = _dev()
+    P, R, Ac = two_level_problem(2, 1, 16, 2, 2)
+    A = (P.n, P.A.rowptr, P.A.col, P.A.val)
+    x0 = oracle.std_uniform01(P.n, skip=P.constrained)
+    x_ref, it_ref, hist_ref = oracle.cg_unpreconditioned(A, np.zeros(P.n), x0, 1e-8, 500)
+    Ad = d.SparseMatrixDevice.from_host(handle, P.A)
+    x, b = d.DeviceVector.from_host(handle, x0), d.DeviceVector.from_host(handle, np.zeros(P.n))
+    it, hist = d.solver_cg(handle, Ad, x, b, None, 1e-8, 500)
+    assert it == it_ref
+    assert np.max(np.abs(hist - hist_ref) / hist_ref) < 1e-9
+
+
+def test_edge_cases(handle):
+    d = _dev()
+    # empty rows, a ragged matrix, a 1x1 matrix
+    A = sp.csr_matrix(np.array([[0, 0, 0, 0], [1, 0, 2, 0], [0, 0, 0, 0], [0, 3, 0, 4.0]]))
+    Ad = d.SparseMatrixDevice.from_host(handle, A)
+    x = d.DeviceVector.from_host(handle, np.array([1.0, 2, 3, 4]))
+    y = d.DeviceVector(handle, 4)
+    for lanes in (2, 4, 32):
+        Ad.set_lanes_per_row(lanes)
+        Ad.vmult(y, x)
+        assert np.array_equal(y.to_host(), np.array([0.0, 7, 0, 22]))
+    # missing diagonal -> error, not garbage
+    with pytest.raises(d.MfmgError):
+        d.CudaSmoother(d.CudaMatrixOperator(Ad), {})
+    # column index out of range rejected at upload
+    with pytest.raises(d.MfmgError):
+        d.SparseMatrixDevice(handle, 1, 1, np.array([0, 1]), np.array([3], dtype=np.int32), np.array([1.0]))
+    # size mismatch
+    with pytest.raises(d.MfmgError):
+        Ad.vmult(d.DeviceVector(handle, 3), x)
+    # long ragged rows (R-like: 729 entries) with every lane width
+    rng = np.random.default_rng(0)
+    B = sp.random(37, 5000, density=0.15, random_state=3, format="csr")
+    n, m, rp, col, val = csr_arrays(B)
+    xb = rng.standard_normal(m)
+    Bd = d.SparseMatrixDevice(handle, n, m, rp, col, val)
+    yb = d.DeviceVector(handle, n)
+    for lanes in (0, 2, 4, 8, 16, 32):
+        Bd.set_lanes_per_row(lanes)
+        Bd.vmult(yb, d.DeviceVector.from_host(handle, xb))
+        assert rel_err(yb.to_host(), oracle.spmv(n, rp, col, val, xb)) < TOL_OP
+
+
+def test_full_size_properties_cfg1_like(handle):
+    """Size-independent properties at a size the oracle is not run on (3D Q1, 64^3 cells, 274 625 DoFs):
+    linearity of the V-cycle, symmetry of the preconditioner, SpMV of the constant vector vanishes on
+    interior rows, and PCG drives the true residual below tol."""
+    d = _dev()
+    P, R, Ac = two_level_problem(3, 1, 64, 8, 1)
+    H = d.Hierarchy.from_host(handle, P.A, R, Ac, {})
+    H.use_graph(True)
+    n = P.n
+    rng = np.random.default_rng(1)
+    u_h, v_h = rng.standard_normal(n), rng.standard_normal(n)
+    u, v = d.DeviceVector.from_host(handle, u_h), d.DeviceVector.from_host(handle, v_h)
+    w = d.DeviceVector.from_host(handle, 2.0 * u_h - 3.0 * v_h)
+    Mu, Mv, Mw = d.DeviceVector(handle, n), d.DeviceVector(handle, n), d.DeviceVector(handle, n)
+    H.vmult(Mu, u)
+    H.vmult(Mv, v)
+    H.vmult(Mw, w)
+    assert rel_err(Mw.to_host(), 2.0 * Mu.to_host() - 3.0 * Mv.to_host()) < 1e-12
+    assert abs(v.dot(Mu) - u.dot(Mv)) < 1e-11 * abs(v.dot(Mu))
+    x = d.DeviceVector.from_host(handle, oracle.std_uniform01(n, skip=P.constrained))
+    b = d.DeviceVector.from_host(handle, np.zeros(n))
+    it, hist = d.solver_cg(handle, H.operators[0], x, b, H, 1e-8, 200)
+    r = d.DeviceVector(handle, n)
+    H.operators[0].vmult(r, x)
+    assert r.l2_norm() <= 1e-8 * 1.0001 and it < 60

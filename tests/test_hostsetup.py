@@ -1,0 +1,77 @@
+"""CPU-only checks of the host setup path (problem generation, AMGe restrictor, Galerkin product)
+against the oracle's independent restatement."""
+import numpy as np
+import pytest
+
+import oracle
+from mfmg_b200 import hostsetup as hs
+from mfmg_b200.hostsetup import amge
+
+
+@pytest.mark.parametrize("dim,degree,cells,mat", [(2, 1, 4, "constant"), (2, 2, 3, "linear"),
+                                                  (3, 1, 3, "discontinuous"), (3, 2, 2, "linear_x")])
+def test_assembly_matches_independent_cell_loop(dim, degree, cells, mat):
+    P = hs.LaplaceProblem.create(dim, degree, cells, mat)
+    dense = P.A.to_scipy().toarray()
+    ref = oracle.assemble_laplace_py(dim, degree, list(P.cells), P.coef_per_q(), P.constrained)
+    assert np.abs(dense - ref).max() <= 1e-14 * np.abs(ref).max()
+    assert np.abs(dense - dense.T).max() == 0.0
+
+
+def test_pattern_sizes_match_survey_appendix_a():
+    # nnz = (3N-2)^d for Q1, (8c+1)^d for Q2: constrained rows/columns stay in the pattern
+    P = hs.LaplaceProblem.create(2, 1, 32)
+    assert (P.n, P.A.nnz) == (1089, 9409)
+    P = hs.LaplaceProblem.create(2, 1, 64)
+    assert (P.n, P.A.nnz) == (4225, 37249)
+    P = hs.LaplaceProblem.create(3, 2, 3)
+    assert P.A.nnz == (8 * 3 + 1) ** 3
+    P = hs.LaplaceProblem.create(3, 1, 16)
+    assert P.A.nnz == (3 * 17 - 2) ** 3
+
+
+def test_row_range_assembly_equals_slices_of_global():
+    P = hs.LaplaceProblem.create(3, 1, 6, "linear")
+    n = P.n
+    a, _ = hs.assemble(3, 1, P.cells, P.G, P.coef, P.constrained, 100, 250)
+    full = P.A.to_scipy()
+    assert np.array_equal(a.to_scipy().toarray(), full[100:250].toarray())
+    assert a.n_cols == n
+
+
+def test_block_agglomerates_cover_all_cells_once():
+    aggs = amge.block_agglomerates(3, (6, 6, 4), (2, 3, 4))
+    seen = np.zeros((4, 6, 6), dtype=int)
+    for (ox, oy, oz), (sx, sy, sz) in aggs:
+        seen[oz:oz + sz, oy:oy + sy, ox:ox + sx] += 1
+    assert np.all(seen == 1) and len(aggs) == 3 * 2 * 1
+
+
+def test_restrictor_entries_follow_the_formula():
+    # tests/test_restriction_matrix.cc:157-167: R entries = diag_agg / diag_glob * eigvec
+    P = hs.LaplaceProblem.create(2, 1, 8)
+    R = hs.build_restrictor(P, (4, 4), 2)
+    assert R.n_rows == 4 * 2 and R.n_cols == P.n and R.nnz == 8 * 25
+    aggs = amge.block_agglomerates(2, P.cells, (4, 4))
+    origin, size = aggs[3]
+    g = amge._local_global_nodes(P, origin, size)
+    cl = amge._local_cells(P, origin, size)
+    vecs, d = amge.local_eigenvectors(P, P.coef[cl], P.constrained[g], size, 2)
+    Rd = R.to_scipy().toarray()
+    for k in range(2):
+        assert np.allclose(Rd[3 * 2 + k, g], d / P.diag[g] * vecs[k], rtol=1e-14, atol=0)
+
+
+def test_galerkin_operator_is_spd():
+    P = hs.LaplaceProblem.create(3, 1, 8)
+    R = hs.build_restrictor(P, (4, 4, 4), 2)
+    Ac = hs.galerkin(P.A, R).to_scipy().toarray()
+    assert np.allclose(Ac, Ac.T, atol=1e-13)
+    assert np.linalg.eigvalsh(Ac).min() > 0
+
+
+def test_partial_blocks_and_eigensolver_modes():
+    P = hs.LaplaceProblem.create(2, 1, 10)
+    for mode in ("free", "host_lapack", "device_lapack"):
+        R = hs.build_restrictor(P, (4, 4), 1, eigensolver=mode)
+        assert R.n_rows == 9 and np.all(np.isfinite(R.val))

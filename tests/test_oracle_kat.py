@@ -1,0 +1,219 @@
+"""Pins the CPU oracle against the reference test-suite's known-answer tests.
+CPU only."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle
+from helpers import (banded_matrix, csr_arrays, golden, oracle_hierarchy, rel_err, serial_mv_matrix, tridiag_matrix,
+                     two_level_problem)
+
+
+def test_rng_restatement_matches_libstdcxx():
+    # tests/hierarchy_driver.cc:153-164: std::default_random_engine + uniform_real_distribution(0,1)
+    g = golden()
+    assert np.array_equal(oracle.std_uniform01(32), g["uniform01_first32"])
+    assert np.array_equal(oracle.minstd_uniform01_py(32), g["uniform01_first32"])
+
+
+def test_masked_stream_skips_constrained():
+    skip = np.array([0, 1, 0, 0, 1, 0], dtype=np.uint8)
+    v = oracle.std_uniform01(6, skip=skip)
+    ref = oracle.std_uniform01(4)
+    assert np.array_equal(v[skip == 0], ref) and np.all(v[skip == 1] == 0)
+
+
+def test_serial_mv_exact():
+    # tests/test_sparse_matrix_device.cu:24-114 (values i+j, x = i): integer arithmetic, exact
+    g = golden()
+    n, m, rp, col, val = csr_arrays(serial_mv_matrix())
+    y = oracle.spmv(n, rp, col, val, g["serial_mv_x"])
+    assert np.array_equal(y, g["serial_mv_y"])
+
+
+def test_operator_apply_transpose_multiply_exact():
+    # tests/test_sparse_matrix_device_operator.cu:75-133: BOOST_CHECK_EQUAL (bit exact)
+    A = banded_matrix()
+    n, m, rp, col, val = csr_arrays(A)
+    ones_c, ones_r = np.ones(m), np.ones(n)
+    y = oracle.spmv(n, rp, col, val, ones_c)
+    assert np.array_equal(y, np.asarray(A.todense()) @ ones_c)
+    yt = oracle.spmv_transpose(n, m, rp, col, val, ones_r)
+    assert np.array_equal(yt, np.asarray(A.todense()).T @ ones_r)
+    trp, tcol, tval = oracle.csr_transpose(n, m, rp, col, val)
+    yt2 = oracle.spmv(m, trp, tcol, tval, ones_r)
+    assert np.array_equal(yt2, yt)
+    # multiply: A * A^T applied to ones
+    z = oracle.spmv(n, rp, col, val, yt)
+    assert np.array_equal(z, np.asarray(A.todense()) @ (np.asarray(A.todense()).T @ ones_r))
+
+
+def test_explicit_and_implicit_transpose_bitwise_equal():
+    rng = np.random.default_rng(3)
+    A = sp.random(57, 91, density=0.2, random_state=7, format="csr")
+    n, m, rp, col, val = csr_arrays(A)
+    x = rng.standard_normal(n)
+    trp, tcol, tval = oracle.csr_transpose(n, m, rp, col, val)
+    assert np.array_equal(oracle.spmv(m, trp, tcol, tval, x), oracle.spmv_transpose(n, m, rp, col, val, x))
+
+
+def test_smoother_kat():
+    # tests/test_smoother_device.cu:28-119: b = 1, x0 = 0 -> x = 0.25 (checked to 1e-12 %)
+    n, m, rp, col, val = csr_arrays(tridiag_matrix())
+    x = oracle.jacobi_apply(n, rp, col, val, np.ones(n), np.zeros(n))
+    assert np.array_equal(x, golden()["smoother_expected"])
+
+
+def test_direct_solver_kat():
+    # tests/test_direct_solver_device.cu:23-110: x_ref ~ N(10,2), b = A x_ref, solve within 1e-12 %
+    A = tridiag_matrix()
+    n, m, rp, col, val = csr_arrays(A)
+    xref = golden()["direct_solver_xref"]
+    b = oracle.spmv(n, rp, col, val, xref)
+    lu, piv, info = oracle.lu_factor_csr(n, rp, col, val)
+    assert info == 0
+    x = oracle.lu_solve(lu, piv, b)
+    assert np.max(np.abs(x - xref) / np.abs(xref)) < 1e-14
+
+
+def test_lu_matches_scipy_with_pivoting():
+    import scipy.linalg as sla
+
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((40, 40))
+    n, m, rp, col, val = csr_arrays(sp.csr_matrix(a))
+    lu, piv, info = oracle.lu_factor_csr(n, rp, col, val)
+    lu_ref, piv_ref = sla.lu_factor(a)
+    assert np.array_equal(piv, piv_ref)
+    assert np.allclose(lu, lu_ref, rtol=1e-12, atol=1e-13)
+
+
+def test_two_grid_gold_rate_device():
+    # tests/test_hierarchy_device.cu:359-420: 3D Q1 refine 2, 2x2x2 agglomerates, 2 eigenvectors,
+    # lapack(sygvd), Jacobi, lu_dense, solver mode, x0 ~ U(0,1) on ALL dofs, rhs 0; rate = res20/res19.
+    # Gold 0.14933479171507894 is asserted by the reference to 1e-6 %.
+    P, R, Ac = two_level_problem(3, 1, 4, 2, 2, "constant", "device_lapack")
+    H = oracle_hierarchy(P, R, Ac, 1, False)
+    x = oracle.std_uniform01(P.n)
+    b = np.zeros(P.n)
+    res = []
+    for _ in range(20):
+        x = H.vmult(b, x)
+        res.append(np.linalg.norm(oracle.spmv(P.n, P.A.rowptr, P.A.col, P.A.val, x)))
+    rate = res[-1] / res[-2]
+    gold = float(golden()["gold_rate_device_cube"])
+    # our DoF numbering is lexicographic (a permutation of deal.II's), so x0 differs as a vector:
+    # the asymptotic rate agrees to ~2e-9 relative, inside the reference's own 1e-8 relative window
+    assert abs(rate - gold) / gold < 1e-8
+
+
+def test_mf_operator_equals_assembled_matrix():
+    # tests/test_hierarchy.cc:644-695: matrix-free == assembled, ||.||_2 < 1e-9, all four materials (2D Q1 there)
+    from mfmg_b200 import hostsetup as hs
+
+    for dim, degree, cells in [(2, 1, 8), (3, 1, 4), (2, 2, 4), (3, 2, 2)]:
+        for mat in ["constant", "linear_x", "linear", "discontinuous"]:
+            P = hs.LaplaceProblem.create(dim, degree, cells, mat)
+            mf = oracle.MatrixFreeLaplace(dim, degree, P.cells, P.h, P.coef_per_q(), P.constrained)
+            x = oracle.std_uniform01(P.n, skip=P.constrained)
+            y_mf = mf.apply(x)
+            y_mat = oracle.spmv(P.n, P.A.rowptr, P.A.col, P.A.val, x)
+            free = P.constrained == 0
+            assert np.linalg.norm((y_mf - y_mat)[free]) < 1e-9
+            d = mf.diag()
+            assert np.allclose(d[free], P.diag[free], rtol=1e-12)
+            assert np.all(d[~free] == 1.0)
+
+
+def test_laplace_discretisation_exact_for_quadratic():
+    # tests/test_laplace.cc: Q2 reproduces a quadratic solution to 1e-14: -Lap u = f with u = x(1-x) in 1D sense.
+    # Here: A u_h = b assembled from f = 2 (u = x(1-x) extended constant in y is not zero on the y-boundaries), so
+    # use the product-free check on the unconstrained block: A_ff u_f equals the load vector of f = -Lap u.
+    from mfmg_b200 import hostsetup as hs
+
+    P = hs.LaplaceProblem.create(2, 2, 4, "constant")
+    N = P.nodes[0]
+    xs = np.arange(N) / (N - 1)
+    X, Y = np.meshgrid(xs, xs, indexing="xy")
+    u = (X * (1 - X) * Y * (1 - Y)).reshape(-1)  # zero on the boundary
+    # f = -Lap u = 2 y(1-y) + 2 x(1-x): a quadratic, integrated exactly against Q2 by 3-point Gauss
+    qp, qw = hs.problems.gauss_unit(3)
+    S, _ = hs.problems.lagrange_1d(2, qp)
+    b = np.zeros(P.n)
+    h = P.h[0]
+    for cy in range(4):
+        for cx in range(4):
+            for qy in range(3):
+                for qx in range(3):
+                    x, y = (cx + qp[qx]) * h, (cy + qp[qy]) * h
+                    f = 2 * y * (1 - y) + 2 * x * (1 - x)
+                    w = qw[qx] * qw[qy] * h * h
+                    for ay in range(3):
+                        for ax in range(3):
+                            g = (cx * 2 + ax) + N * (cy * 2 + ay)
+                            b[g] += f * S[qx, ax] * S[qy, ay] * w
+    free = P.constrained == 0
+    r = oracle.spmv(P.n, P.A.rowptr, P.A.col, P.A.val, u) - b
+    # u is in the Q2 x Q2 tensor space (degree 2 per variable) => Galerkin reproduces it exactly
+    assert np.max(np.abs(r[free])) < 1e-14
+
+
+def test_restriction_weights_sum_to_one():
+    # include/mfmg/common/utils.hpp:117-146 (debug check), tests/test_restriction_matrix.cc:293-354
+    from mfmg_b200 import hostsetup as hs
+    from mfmg_b200.hostsetup import amge
+
+    P = hs.LaplaceProblem.create(2, 1, 8, "constant")
+    aggs = amge.block_agglomerates(2, P.cells, (2, 2))
+    wsum = np.zeros(P.n)
+    for origin, size in aggs:
+        g = amge._local_global_nodes(P, origin, size)
+        cl = amge._local_cells(P, origin, size)
+        _, d = hs.assemble(2, 1, size, P.G, P.coef[cl], P.constrained[g])
+        wsum[g] += d / P.diag[g]
+    assert np.allclose(wsum, 1.0, atol=1e-14)
+
+
+def test_pcg_matches_independent_python_restatement():
+    # deal.II SolverCG recurrence restated independently in numpy with the same V-cycle
+    P, R, Ac = two_level_problem(2, 1, 16, 2, 2)
+    H = oracle_hierarchy(P, R, Ac, 1, True)
+    A = P.A.to_scipy()
+    x0 = oracle.std_uniform01(P.n, skip=P.constrained)
+    b = np.zeros(P.n)
+    x, it, hist = H.pcg(b, x0, 1e-8, 200)
+    assert it > 0
+    # numpy restatement
+    xx = x0.copy()
+    g = A @ xx - b
+    res = [np.linalg.norm(g)]
+    h = H.vmult(g)
+    d = -h
+    gh = g @ h
+    k = 0
+    while True:
+        k += 1
+        h = A @ d
+        alpha = gh / (d @ h)
+        g = g + alpha * h
+        xx = xx + alpha * d
+        res.append(np.linalg.norm(g))
+        if res[-1] <= 1e-8:
+            break
+        h = H.vmult(g)
+        beta = gh
+        gh = g @ h
+        beta = gh / beta
+        d = beta * d - h
+    assert k == it
+    assert np.allclose(hist, res, rtol=1e-9)
+
+
+def test_vcycle_is_spd_preconditioner_and_reduces_error():
+    P, R, Ac = two_level_problem(3, 1, 8, 2, 1)
+    H = oracle_hierarchy(P, R, Ac, 1, True)
+    rng = np.random.default_rng(0)
+    u, v = rng.standard_normal(P.n), rng.standard_normal(P.n)
+    Mu, Mv = H.vmult(u), H.vmult(v)
+    assert abs(v @ Mu - u @ Mv) < 1e-10 * abs(v @ Mu)  # symmetric (nu pre == nu post, Jacobi)
+    assert u @ Mu > 0
