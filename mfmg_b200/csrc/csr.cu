@@ -50,6 +50,8 @@ __global__ void __launch_bounds__(kBlock)
   {
     OffT k = rowptr[row] + lane;
     const OffT k1 = rowptr[row + 1];
+    // two independent (col, val, x) chains per lane; a 4-way unroll measured 13 % slower on B200
+    // (profiles/r01_lanes_sweep.md)
     for (; k + LPR < k1; k += 2 * LPR)
     {
       const int c0 = col[k], c1 = col[k + LPR];
@@ -84,6 +86,7 @@ int dispatch_lanes(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const Ep
   switch (A->lanes)
   {
   case 1:
+    return launch_vec<1, EPI, OffT>(ctx, A, x, e);
   case 2:
     return launch_vec<2, EPI, OffT>(ctx, A, x, e);
   case 4:
@@ -118,9 +121,11 @@ int choose_lanes(int64_t n_rows, int64_t nnz)
 {
   if (n_rows <= 0)
     return 8;
+  // Measured on B200 (profiles/r01_lanes_sweep.md): about 6-7 entries per lane is the sweet spot
+  // (27-nnz rows: 4 lanes reach 88 % of the copy bandwidth, 8 lanes 65 %, 32 lanes 28 %).
   const double mean = (double)nnz / (double)n_rows;
-  int lanes = 2;
-  while (lanes < 32 && lanes * 4 < mean)
+  int lanes = 1;
+  while (lanes < 32 && lanes * 2 * 6 <= mean)
     lanes *= 2;
   return lanes;
 }
@@ -323,8 +328,8 @@ extern "C"
 
   MFMGB_API int mfmgb_csr_set_lanes_per_row(mfmgb_csr *A, int lanes)
   {
-    if (!A || !(lanes == 0 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32))
-      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_csr_set_lanes_per_row: lanes must be 0,2,4,8,16,32");
+    if (!A || !(lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32))
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_csr_set_lanes_per_row: lanes must be 0,1,2,4,8,16,32");
     A->lanes_override = lanes;
     A->lanes = lanes ? lanes : choose_lanes(A->n_rows, A->nnz);
     return MFMGB_OK;

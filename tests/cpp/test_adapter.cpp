@@ -1,0 +1,263 @@
+// test_adapter.cpp -- the reference's device unit tests, restated against the C++ adapter (include/mfmg_b200/mfmg.hpp):
+//   tests/test_smoother_device.cu:28-119          tridiag(-1,4,-1), b = 1, x0 = 0 -> x = 0.25
+//   tests/test_direct_solver_device.cu:23-110     x_ref ~ N(10,2), b = A x_ref, all solver names within 1e-12 %
+//   tests/test_sparse_matrix_device_operator.cu   30x39 banded matrix, apply / transpose, exact
+//   Hierarchy::apply (fused) == the same algorithm composed from the abstract objects == dense host algebra
+// Build: g++ -std=c++17 -Iinclude tests/cpp/test_adapter.cpp -Lmfmg_b200/csrc -lmfmg_b200 (+rpath).  Needs a GPU to run.
+#include <cmath>
+#include <cstdio>
+#include <random>
+
+#include "mfmg_b200/mfmg.hpp"
+
+using V = mfmg::DeviceVector;
+
+static int failures = 0;
+#define CHECK(cond)                                                                                 \
+  do                                                                                                \
+  {                                                                                                 \
+    if (!(cond))                                                                                    \
+    {                                                                                               \
+      std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);                                 \
+      ++failures;                                                                                   \
+    }                                                                                               \
+  } while (0)
+
+struct HostCsr
+{
+  unsigned n_rows, n_cols;
+  std::vector<int64_t> rp;
+  std::vector<int> col;
+  std::vector<double> val;
+};
+
+static HostCsr tridiag(unsigned size)
+{
+  HostCsr a{size, size, {0}, {}, {}};
+  for (unsigned i = 0; i < size; ++i)
+  {
+    for (unsigned j = (i == 0 ? 0 : i - 1); j < std::min(size, i + 2); ++j)
+    {
+      a.col.push_back((int)j);
+      a.val.push_back(i == j ? 4. : -1.);
+    }
+    a.rp.push_back((int64_t)a.col.size());
+  }
+  return a;
+}
+
+static std::vector<double> host_spmv(HostCsr const &a, std::vector<double> const &x)
+{
+  std::vector<double> y(a.n_rows, 0.);
+  for (unsigned i = 0; i < a.n_rows; ++i)
+    for (int64_t k = a.rp[i]; k < a.rp[i + 1]; ++k)
+      y[i] += a.val[k] * x[a.col[k]];
+  return y;
+}
+
+int main()
+{
+  auto handle = std::make_shared<mfmg::CudaHandle>(0);
+  auto params = std::make_shared<mfmg::ParameterTree>();
+
+  // ---- smoother ----
+  {
+    auto a = tridiag(30);
+    auto m = std::make_shared<mfmg::SparseMatrixDevice<double>>(handle, a.n_rows, a.n_cols, a.rp, a.col, a.val);
+    std::shared_ptr<mfmg::Operator<V>> op = std::make_shared<mfmg::CudaMatrixOperator<V>>(m);
+    mfmg::CudaSmoother<V> smoother(op, params);
+    auto b = op->build_domain_vector();
+    auto x = op->build_range_vector();
+    *b = 1.;
+    *x = 0.;
+    smoother.apply(*b, *x);
+    for (double v : x->export_to_host())
+      CHECK(v == 0.25);
+    auto bad = std::make_shared<mfmg::ParameterTree>();
+    bad->put("smoother.type", "Gauss-Seidel");
+    bool threw = false;
+    try
+    {
+      mfmg::CudaSmoother<V> s2(op, bad);
+    }
+    catch (std::runtime_error const &)
+    {
+      threw = true;
+    }
+    CHECK(threw);
+  }
+
+  // ---- direct solver ----
+  {
+    auto a = tridiag(30);
+    auto m = std::make_shared<mfmg::SparseMatrixDevice<double>>(handle, a.n_rows, a.n_cols, a.rp, a.col, a.val);
+    std::shared_ptr<mfmg::Operator<V>> op = std::make_shared<mfmg::CudaMatrixOperator<V>>(m);
+    std::vector<double> sol_ref(30);
+    std::default_random_engine generator;
+    std::normal_distribution<> distribution(10., 2.);
+    for (auto &v : sol_ref)
+      v = distribution(generator);
+    auto rhs = host_spmv(a, sol_ref);
+    for (auto solver : {"cholesky", "lu_dense", "lu_sparse_host"})
+    {
+      auto p = std::make_shared<mfmg::ParameterTree>();
+      p->put("solver.type", solver);
+      mfmg::CudaSolver<V> direct(*handle, op, p);
+      V b(handle, 30), x(handle, 30);
+      b.import_from_host(rhs);
+      direct.apply(b, x);
+      auto xh = x.export_to_host();
+      for (unsigned i = 0; i < 30; ++i)
+        CHECK(std::abs(xh[i] - sol_ref[i]) <= 1e-14 * std::abs(sol_ref[i]));
+    }
+    bool threw = false;
+    try
+    {
+      auto p = std::make_shared<mfmg::ParameterTree>();
+      p->put("solver.type", "amgx");
+      mfmg::CudaSolver<V> s(*handle, op, p);
+    }
+    catch (mfmg::NotImplementedExc const &)
+    {
+      threw = true;
+    }
+    CHECK(threw);
+  }
+
+  // ---- operator apply / transpose (exact) ----
+  {
+    unsigned const n_rows = 30, nnz_per_row = 10, n_cols = n_rows + nnz_per_row - 1;
+    HostCsr a{n_rows, n_cols, {0}, {}, {}};
+    for (unsigned i = 0; i < n_rows; ++i)
+    {
+      for (unsigned j = 0; j < nnz_per_row; ++j)
+      {
+        a.col.push_back((int)(i + j));
+        a.val.push_back((double)(i + i + j));
+      }
+      a.rp.push_back((int64_t)a.col.size());
+    }
+    auto m = std::make_shared<mfmg::SparseMatrixDevice<double>>(handle, a.n_rows, a.n_cols, a.rp, a.col, a.val);
+    mfmg::CudaMatrixOperator<V> op(m);
+    auto dom = op.build_domain_vector();
+    auto rng = op.build_range_vector();
+    CHECK(dom->size() == n_cols && rng->size() == n_rows);
+    *dom = 1.;
+    op.apply(*dom, *rng);
+    auto ref = host_spmv(a, std::vector<double>(n_cols, 1.));
+    auto got = rng->export_to_host();
+    for (unsigned i = 0; i < n_rows; ++i)
+      CHECK(got[i] == ref[i]);
+    auto top = op.transpose();
+    auto tdom = top->build_domain_vector();
+    auto trng = top->build_range_vector();
+    CHECK(tdom->size() == n_rows && trng->size() == n_cols);
+    *tdom = 1.;
+    top->apply(*tdom, *trng);
+    std::vector<double> tref(n_cols, 0.);
+    for (unsigned i = 0; i < n_rows; ++i)
+      for (int64_t k = a.rp[i]; k < a.rp[i + 1]; ++k)
+        tref[a.col[k]] += a.val[k];
+    auto tgot = trng->export_to_host();
+    for (unsigned i = 0; i < n_cols; ++i)
+      CHECK(tgot[i] == tref[i]);
+    V t2(handle, n_cols);
+    op.apply(*tdom, t2, mfmg::OperatorMode::TRANS);
+    auto t2h = t2.export_to_host();
+    for (unsigned i = 0; i < n_cols; ++i)
+      CHECK(t2h[i] == tref[i]);
+  }
+
+  // ---- two-level hierarchy: fused == generic composition ----
+  {
+    unsigned const n = 255, nc = 127;
+    auto a = tridiag(n);
+    // linear-interpolation restrictor (full weighting): R[i, 2i..2i+2] = (0.5, 1, 0.5)
+    HostCsr r{nc, n, {0}, {}, {}};
+    for (unsigned i = 0; i < nc; ++i)
+    {
+      for (unsigned j = 0; j < 3; ++j)
+      {
+        r.col.push_back((int)(2 * i + j));
+        r.val.push_back(j == 1 ? 1. : 0.5);
+      }
+      r.rp.push_back((int64_t)r.col.size());
+    }
+    // A_c = R A R^T (dense on the host, then CSR with the tridiagonal pattern it has)
+    std::vector<double> ac(nc * nc, 0.);
+    for (unsigned i = 0; i < nc; ++i)
+      for (unsigned j = 0; j < nc; ++j)
+      {
+        double s = 0.;
+        for (int64_t ki = r.rp[i]; ki < r.rp[i + 1]; ++ki)
+          for (int64_t kj = r.rp[j]; kj < r.rp[j + 1]; ++kj)
+          {
+            int const p = r.col[ki], q = r.col[kj];
+            double apq = p == q ? 4. : (std::abs(p - q) == 1 ? -1. : 0.);
+            s += r.val[ki] * apq * r.val[kj];
+          }
+        ac[i * nc + j] = s;
+      }
+    HostCsr c{nc, nc, {0}, {}, {}};
+    for (unsigned i = 0; i < nc; ++i)
+    {
+      for (unsigned j = 0; j < nc; ++j)
+        if (ac[i * nc + j] != 0.)
+        {
+          c.col.push_back((int)j);
+          c.val.push_back(ac[i * nc + j]);
+        }
+      c.rp.push_back((int64_t)c.col.size());
+    }
+    auto mk = [&](HostCsr const &h) {
+      return std::make_shared<mfmg::CudaMatrixOperator<V>>(
+          std::make_shared<mfmg::SparseMatrixDevice<double>>(handle, h.n_rows, h.n_cols, h.rp, h.col, h.val));
+    };
+    for (bool precond : {true, false})
+      for (unsigned nu : {1u, 2u})
+      {
+        auto p = std::make_shared<mfmg::ParameterTree>();
+        p->put("is preconditioner", precond);
+        p->put("smoother.n_smoothing_steps", nu);
+        mfmg::Hierarchy<V> hierarchy(handle, {mk(a), mk(c)}, {mk(r)}, p);
+        std::vector<double> bh(n), xh(n);
+        std::default_random_engine gen(7);
+        std::uniform_real_distribution<double> dist(0., 1.);
+        for (auto &v : bh)
+          v = dist(gen);
+        for (auto &v : xh)
+          v = dist(gen);
+        V b(handle, n), x1(handle, n), x2(handle, n);
+        b.import_from_host(bh);
+        x1.import_from_host(xh);
+        x2.import_from_host(xh);
+        hierarchy.vmult(x1, b);
+        hierarchy.apply_generic(b, x2);
+        auto h1 = x1.export_to_host(), h2 = x2.export_to_host();
+        double num = 0., den = 0.;
+        for (unsigned i = 0; i < n; ++i)
+        {
+          num += (h1[i] - h2[i]) * (h1[i] - h2[i]);
+          den += h2[i] * h2[i];
+        }
+        CHECK(std::sqrt(num / den) < 1e-13);
+        CHECK(hierarchy.grid_complexity() > 1.0 && hierarchy.operator_complexity() > 1.0);
+        // the cycle contracts the error of A x = b: |b - A x_new| < |b - A x_old| in solver mode
+        if (!precond)
+        {
+          auto r0 = host_spmv(a, xh), r1 = host_spmv(a, h1);
+          double n0 = 0., n1 = 0.;
+          for (unsigned i = 0; i < n; ++i)
+          {
+            n0 += (r0[i] - bh[i]) * (r0[i] - bh[i]);
+            n1 += (r1[i] - bh[i]) * (r1[i] - bh[i]);
+          }
+          CHECK(n1 < 0.05 * n0);
+        }
+      }
+  }
+
+  if (failures == 0)
+    std::printf("test_adapter: ALL OK\n");
+  return failures == 0 ? 0 : 1;
+}

@@ -30,7 +30,7 @@ def test_serial_mv_kat_exact(handle):
     Ad = d.SparseMatrixDevice.from_host(handle, A)
     x = d.DeviceVector.from_host(handle, g["serial_mv_x"])
     y = d.DeviceVector(handle, 10)
-    for lanes in (0, 2, 4, 8, 16, 32):
+    for lanes in (0, 1, 2, 4, 8, 16, 32):
         Ad.set_lanes_per_row(lanes)
         y.fill(-1.0)
         Ad.vmult(y, x)
@@ -167,7 +167,7 @@ def test_kernels_vs_oracle(handle, dim, degree, cells, block, ne, mat):
     x, b = d.DeviceVector.from_host(handle, x_h), d.DeviceVector.from_host(handle, b_h)
     y = d.DeviceVector(handle, n)
     lib, ctx = handle.lib, handle.ctx
-    for lanes in (0, 2, 8, 32):
+    for lanes in (0, 1, 2, 4, 8, 32):
         Ad.set_lanes_per_row(lanes)
         Ad.vmult(y, x)
         assert rel_err(y.to_host(), oracle.spmv(n, *A, x_h)) < TOL_OP
@@ -296,7 +296,7 @@ def test_edge_cases(handle):
     Ad = d.SparseMatrixDevice.from_host(handle, A)
     x = d.DeviceVector.from_host(handle, np.array([1.0, 2, 3, 4]))
     y = d.DeviceVector(handle, 4)
-    for lanes in (2, 4, 32):
+    for lanes in (1, 2, 4, 32):
         Ad.set_lanes_per_row(lanes)
         Ad.vmult(y, x)
         assert np.array_equal(y.to_host(), np.array([0.0, 7, 0, 22]))
@@ -316,7 +316,7 @@ def test_edge_cases(handle):
     xb = rng.standard_normal(m)
     Bd = d.SparseMatrixDevice(handle, n, m, rp, col, val)
     yb = d.DeviceVector(handle, n)
-    for lanes in (0, 2, 4, 8, 16, 32):
+    for lanes in (0, 1, 2, 4, 8, 16, 32):
         Bd.set_lanes_per_row(lanes)
         Bd.vmult(yb, d.DeviceVector.from_host(handle, xb))
         assert rel_err(yb.to_host(), oracle.spmv(n, rp, col, val, xb)) < TOL_OP

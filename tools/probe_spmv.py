@@ -52,7 +52,7 @@ out = {"n": n, "nnz": P.A.nnz, "nc": nc, "nnzR": R.nnz}
 bA = 12 * P.A.nnz + 4 * (n + 1) + 16 * n
 bR = 12 * R.nnz + 4 * (nc + 1) + 8 * n + 8 * nc
 bP = 12 * R.nnz + 4 * (n + 1) + 8 * nc + 16 * n
-for lanes in (2, 4, 8, 16, 32):
+for lanes in (1, 2, 4, 8, 16, 32):
     Ad.set_lanes_per_row(lanes)
     ms = timeit(lambda: Ad.vmult(y, x))
     out[f"A_lanes{lanes}"] = {"ms": ms, "gbs": bA / ms / 1e6}
