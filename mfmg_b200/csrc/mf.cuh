@@ -12,7 +12,8 @@ struct mfmgb_mf
   int nq = 0;                 // (degree+1)^dim quadrature points per cell
   double *coef = nullptr;     // device [n_cells][nq]
   uint8_t *constr = nullptr;  // device [n]
-  double *work = nullptr;     // device [n] (row sums before the epilogue)
+  // host copies of the 1D tables of this degree: S[q][a], D[q][a], Gauss weights (unit interval)
+  double S[9] = {0}, D[9] = {0}, W[3] = {0};
 };
 
 namespace mfmgb
