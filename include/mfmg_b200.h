@@ -181,6 +181,35 @@ extern "C"
   MFMGB_API int mfmgb_pcg_host(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const mfmgb_csr *A, const double *b_host,
                                double *x_host, double tol, int max_it, int *iterations, double *res_hist_host);
 
+  /* ---- multi-GPU (one process per GPU, NCCL over NVLink): replaces the per-SpMV host MPI_Allgatherv of the whole
+   *      source vector (include/mfmg/cuda/sparse_matrix_device.templates.cuh:104-138, source/cuda/utils.cu:305-482)
+   *      by a halo exchange of boundary entries, and deal.II's MPI reductions in SolverCG by ncclAllReduce ---- */
+  typedef struct mfmgb_halo mfmgb_halo;
+  /* rank 0 creates the 128-byte NCCL id; the launcher (MPI_Bcast / torch.distributed) hands it to every rank */
+  MFMGB_API int mfmgb_comm_unique_id(char *out128);
+  MFMGB_API int mfmgb_comm_init(mfmgb_ctx *ctx, const char *id128, int nranks, int rank);
+  MFMGB_API int mfmgb_comm_finalize(mfmgb_ctx *ctx);
+  MFMGB_API int mfmgb_comm_rank(mfmgb_ctx *ctx);
+  MFMGB_API int mfmgb_comm_size(mfmgb_ctx *ctx);
+  /* Halo plan of a row-partitioned level.  Vectors that are gathered from have n_owned + n_ghost entries; the ghost
+   * tail is ordered by neighbour (neighbor_ranks order, recv_counts entries each).  send_indices: concatenated LOCAL
+   * owned indices sent to each neighbour (send_counts each), in the order the receiver stores them. */
+  MFMGB_API int mfmgb_halo_create(mfmgb_ctx *ctx, int64_t n_owned, int64_t n_ghost, int n_neighbors,
+                                  const int *neighbor_ranks, const int64_t *send_counts, const int32_t *send_indices,
+                                  const int64_t *recv_counts, mfmgb_halo **out);
+  MFMGB_API int mfmgb_halo_destroy(mfmgb_ctx *ctx, mfmgb_halo *halo);
+  /* fill the ghost tail of v (blocking form, on the context stream) */
+  MFMGB_API int mfmgb_halo_exchange(mfmgb_ctx *ctx, const mfmgb_halo *halo, double *v);
+  MFMGB_API int mfmgb_allreduce_sum(mfmgb_ctx *ctx, double *dev, int n);
+  /* attach the plan to a (non-coarsest) level whose operator is n_owned x (n_owned + n_ghost); rows
+   * [boundary_lo, boundary_hi) reference owned columns only and overlap the exchange */
+  MFMGB_API int mfmgb_hierarchy_set_halo(mfmgb_hierarchy *H, int level, const mfmgb_halo *halo, int64_t boundary_lo,
+                                         int64_t boundary_hi);
+  /* offsets (nranks + 1) of the rank-owned rows of the replicated coarsest level */
+  MFMGB_API int mfmgb_hierarchy_set_coarse_offsets(mfmgb_hierarchy *H, const int64_t *offsets, int nranks);
+  /* length device vectors of this level must have (n_owned + n_ghost) */
+  MFMGB_API int64_t mfmgb_hierarchy_vector_size(const mfmgb_hierarchy *H, int level);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,6 +102,18 @@ SIGNATURES = {
     "mfmgb_hierarchy_launches_per_cycle": (_int, [_vp]),
     "mfmgb_pcg": (_int, [_vp, _vp, _vp, _vp, _vp, _dbl, _int, ctypes.POINTER(_int), _vp]),
     "mfmgb_pcg_host": (_int, [_vp, _vp, _vp, _vp, _vp, _dbl, _int, ctypes.POINTER(_int), _vp]),
+    "mfmgb_comm_unique_id": (_int, [ctypes.c_char_p]),
+    "mfmgb_comm_init": (_int, [_vp, ctypes.c_char_p, _int, _int]),
+    "mfmgb_comm_finalize": (_int, [_vp]),
+    "mfmgb_comm_rank": (_int, [_vp]),
+    "mfmgb_comm_size": (_int, [_vp]),
+    "mfmgb_halo_create": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _pp]),
+    "mfmgb_halo_destroy": (_int, [_vp, _vp]),
+    "mfmgb_halo_exchange": (_int, [_vp, _vp, _vp]),
+    "mfmgb_allreduce_sum": (_int, [_vp, _vp, _int]),
+    "mfmgb_hierarchy_set_halo": (_int, [_vp, _int, _vp, _i64, _i64]),
+    "mfmgb_hierarchy_set_coarse_offsets": (_int, [_vp, _vp, _int]),
+    "mfmgb_hierarchy_vector_size": (_i64, [_vp, _int]),
 }
 
 _LIB = None

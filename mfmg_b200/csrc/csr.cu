@@ -40,10 +40,11 @@ __device__ __forceinline__ void epilogue(const EpiArgs &e, int64_t row, double s
 
 template <int LPR, int EPI, typename OffT>
 __global__ void __launch_bounds__(kBlock)
-    csr_vec_kernel(int64_t n_rows, const OffT *__restrict__ rowptr, const int *__restrict__ col,
+    csr_vec_kernel(int64_t row_begin, int64_t n_rows, const OffT *__restrict__ rowptr, const int *__restrict__ col,
                    const double *__restrict__ val, const double *__restrict__ x, EpiArgs e)
 {
-  const int64_t row = ((int64_t)blockIdx.x * kBlock + threadIdx.x) / LPR;
+  // rows [row_begin, n_rows) are processed by this launch
+  const int64_t row = row_begin + ((int64_t)blockIdx.x * kBlock + threadIdx.x) / LPR;
   const int lane = threadIdx.x & (LPR - 1);
   double s0 = 0., s1 = 0.;
   if (row < n_rows)
@@ -68,51 +69,52 @@ __global__ void __launch_bounds__(kBlock)
 }
 
 template <int LPR, int EPI, typename OffT>
-int launch_vec(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArgs &e)
+int launch_vec(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArgs &e, int64_t r0, int64_t r1)
 {
-  const int64_t threads = A->n_rows * LPR;
+  const int64_t threads = (r1 - r0) * LPR;
   const int64_t nb = ceil_div(threads, kBlock);
-  if (nb == 0)
+  if (nb <= 0)
     return MFMGB_OK;
   csr_vec_kernel<LPR, EPI, OffT><<<(unsigned)nb, kBlock, 0, ctx->stream>>>(
-      A->n_rows, (const OffT *)A->rowptr, A->col, A->val, x, e);
+      r0, r1, (const OffT *)A->rowptr, A->col, A->val, x, e);
   MFMGB_LAUNCHED(ctx);
   return MFMGB_OK;
 }
 
 template <int EPI, typename OffT>
-int dispatch_lanes(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArgs &e)
+int dispatch_lanes(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArgs &e, int64_t r0, int64_t r1)
 {
   switch (A->lanes)
   {
   case 1:
-    return launch_vec<1, EPI, OffT>(ctx, A, x, e);
+    return launch_vec<1, EPI, OffT>(ctx, A, x, e, r0, r1);
   case 2:
-    return launch_vec<2, EPI, OffT>(ctx, A, x, e);
+    return launch_vec<2, EPI, OffT>(ctx, A, x, e, r0, r1);
   case 4:
-    return launch_vec<4, EPI, OffT>(ctx, A, x, e);
+    return launch_vec<4, EPI, OffT>(ctx, A, x, e, r0, r1);
   case 8:
-    return launch_vec<8, EPI, OffT>(ctx, A, x, e);
+    return launch_vec<8, EPI, OffT>(ctx, A, x, e, r0, r1);
   case 16:
-    return launch_vec<16, EPI, OffT>(ctx, A, x, e);
+    return launch_vec<16, EPI, OffT>(ctx, A, x, e, r0, r1);
   default:
-    return launch_vec<32, EPI, OffT>(ctx, A, x, e);
+    return launch_vec<32, EPI, OffT>(ctx, A, x, e, r0, r1);
   }
 }
 
 template <typename OffT>
-int dispatch_epi(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &e)
+int dispatch_epi(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &e, int64_t r0,
+                 int64_t r1)
 {
   switch (epi)
   {
   case Epi::Spmv:
-    return dispatch_lanes<(int)Epi::Spmv, OffT>(ctx, A, x, e);
+    return dispatch_lanes<(int)Epi::Spmv, OffT>(ctx, A, x, e, r0, r1);
   case Epi::Resid:
-    return dispatch_lanes<(int)Epi::Resid, OffT>(ctx, A, x, e);
+    return dispatch_lanes<(int)Epi::Resid, OffT>(ctx, A, x, e, r0, r1);
   case Epi::Jacobi:
-    return dispatch_lanes<(int)Epi::Jacobi, OffT>(ctx, A, x, e);
+    return dispatch_lanes<(int)Epi::Jacobi, OffT>(ctx, A, x, e, r0, r1);
   default:
-    return dispatch_lanes<(int)Epi::Sub, OffT>(ctx, A, x, e);
+    return dispatch_lanes<(int)Epi::Sub, OffT>(ctx, A, x, e, r0, r1);
   }
 }
 } // namespace
@@ -130,13 +132,18 @@ int choose_lanes(int64_t n_rows, int64_t nnz)
   return lanes;
 }
 
-int csr_apply(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args)
+int csr_apply(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args, int64_t row_begin,
+              int64_t row_end)
 {
   if (A->n_rows >= ((int64_t)1 << 31) * 8)
     return fail(ctx, MFMGB_ERR_INVALID, "csr_apply: too many rows");
+  if (row_end < 0)
+    row_end = A->n_rows;
+  if (row_begin < 0 || row_end > A->n_rows)
+    return fail(ctx, MFMGB_ERR_INVALID, "csr_apply: row range out of bounds");
   if (A->off64)
-    return dispatch_epi<int64_t>(ctx, A, x, epi, args);
-  return dispatch_epi<int32_t>(ctx, A, x, epi, args);
+    return dispatch_epi<int64_t>(ctx, A, x, epi, args, row_begin, row_end);
+  return dispatch_epi<int32_t>(ctx, A, x, epi, args, row_begin, row_end);
 }
 
 namespace

@@ -34,7 +34,8 @@ struct EpiArgs
   double omega = 1.;
 };
 
-// one launch: y = epilogue(A x)
-int csr_apply(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args);
+// one launch: y = epilogue(A x) on rows [row_begin, row_end) (row_end < 0: all rows)
+int csr_apply(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args,
+              int64_t row_begin = 0, int64_t row_end = -1);
 int choose_lanes(int64_t n_rows, int64_t nnz);
 } // namespace mfmgb

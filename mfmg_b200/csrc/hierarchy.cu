@@ -11,6 +11,7 @@
 #include <cmath>
 #include <vector>
 
+#include "comm.cuh"
 #include "dense.cuh"
 #include "jacobi.cuh"
 #include "mf.cuh"
@@ -28,8 +29,11 @@ struct mfmgb_level
   mfmgb_csr *P_owned = nullptr;
   mfmgb_jacobi *J = nullptr;
   mfmgb_dense *D = nullptr;
-  double *res = nullptr, *xtmp = nullptr; // fine-side work vectors (size n)
+  double *res = nullptr, *xtmp = nullptr; // fine-side work vectors (size n + ghosts)
   double *bc = nullptr, *xc = nullptr;    // this level's rhs / solution when it is the coarse side
+  // row-partitioned (multi-GPU) level: ghost entries live in the tail [n, n + n_ghost) of every gathered vector
+  const mfmgb_halo *halo = nullptr;
+  int64_t blo = 0, bhi = 0; // rows [0, blo) and [bhi, n) reference ghost columns, [blo, bhi) is the interior
 };
 
 struct mfmgb_hierarchy
@@ -51,6 +55,9 @@ struct mfmgb_hierarchy
   double *g = nullptr, *h = nullptr, *d = nullptr;
   double *scal = nullptr;      // device scalars: [0]=gh_old [1]=gh_new [2]=dh [3]=res2
   double *scal_host = nullptr; // pinned
+  // multi-GPU: offsets of the rank-owned slices of the (replicated) coarsest-level vectors
+  std::vector<int64_t> coarse_offsets;
+  bool distributed = false;
   // stage profiling (mfmgb_vcycle_profile): events between the level-0 stages
   bool profiling = false;
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -60,11 +67,22 @@ namespace
 {
 constexpr int kBlock = 256;
 
-int level_apply_A(mfmgb_ctx *ctx, const mfmgb_level &l, const double *x, Epi epi, const EpiArgs &e)
+int level_apply_A(mfmgb_ctx *ctx, const mfmgb_level &l, double *x, Epi epi, const EpiArgs &e)
 {
   if (l.M)
     return mf_apply(ctx, l.M, x, epi, e);
-  return csr_apply(ctx, l.A, x, epi, e);
+  if (!l.halo)
+    return csr_apply(ctx, l.A, x, epi, e);
+  // row-partitioned level: the halo exchange of x runs on the communication stream while the interior rows
+  // are computed; the rows that reference ghost columns follow once the ghosts have landed
+  MFMGB_CHECK(halo_start(ctx, l.halo, x));
+  MFMGB_CHECK(csr_apply(ctx, l.A, x, epi, e, l.blo, l.bhi));
+  MFMGB_CHECK(halo_wait(ctx));
+  if (l.blo > 0)
+    MFMGB_CHECK(csr_apply(ctx, l.A, x, epi, e, 0, l.blo));
+  if (l.bhi < l.n)
+    MFMGB_CHECK(csr_apply(ctx, l.A, x, epi, e, l.bhi, l.n));
+  return MFMGB_OK;
 }
 
 #define STAGE_MARK(k)                                                                              \
@@ -118,8 +136,22 @@ int apply_level(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, 
   STAGE_MARK(2);
   // b_c = R res, hierarchy.hpp:289-290
   e = EpiArgs();
-  e.y = coarse.bc;
-  MFMGB_CHECK(csr_apply(ctx, coarse.R, fine.res, Epi::Spmv, e));
+  if (fine.halo)
+  {
+    // R's columns include the ghost plane of the residual; owned coarse rows go to this rank's slice of b_c,
+    // then every rank gathers the whole (small) coarse right-hand side: the dense solve is replicated
+    MFMGB_CHECK(halo_start(ctx, fine.halo, fine.res));
+    MFMGB_CHECK(halo_wait(ctx));
+    mfmgb_comm *c = ctx_comm(ctx);
+    e.y = coarse.bc + H->coarse_offsets[c->rank];
+    MFMGB_CHECK(csr_apply(ctx, coarse.R, fine.res, Epi::Spmv, e));
+    MFMGB_CHECK(allgather_slices(ctx, coarse.bc, H->coarse_offsets));
+  }
+  else
+  {
+    e.y = coarse.bc;
+    MFMGB_CHECK(csr_apply(ctx, coarse.R, fine.res, Epi::Spmv, e));
+  }
   STAGE_MARK(3);
   // recurse, hierarchy.hpp:293-294
   MFMGB_CHECK(apply_level(ctx, H, coarse.bc, coarse.xc, li + 1));
@@ -148,7 +180,7 @@ int apply_level(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, 
 
 int run_vcycle(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x)
 {
-  if (!H->use_graph)
+  if (!H->use_graph || H->distributed) // (NCCL + two streams are launched eagerly in the partitioned mode)
     return apply_level(ctx, H, b, x, 0);
   if (!H->graph_exec || H->graph_b != b || H->graph_x != x)
   {
@@ -224,6 +256,8 @@ int ensure_pcg_work(mfmgb_ctx *ctx, mfmgb_hierarchy *H, int64_t n)
 {
   if (H->g)
     return MFMGB_OK;
+  if (!H->lev.empty() && H->lev[0].halo)
+    n += H->lev[0].halo->n_ghost; // gathered vectors carry their ghost tail
   MFMGB_CUDA(ctx, cudaMalloc(&H->g, sizeof(double) * (size_t)(n + 2)));
   MFMGB_CUDA(ctx, cudaMalloc(&H->h, sizeof(double) * (size_t)(n + 2)));
   MFMGB_CUDA(ctx, cudaMalloc(&H->d, sizeof(double) * (size_t)(n + 2)));
@@ -236,6 +270,8 @@ int ensure_host_staging(mfmgb_ctx *ctx, mfmgb_hierarchy *H, int64_t n)
 {
   if (H->b_dev)
     return MFMGB_OK;
+  if (H->lev[0].halo)
+    n += H->lev[0].halo->n_ghost;
   MFMGB_CUDA(ctx, cudaMalloc(&H->b_dev, sizeof(double) * (size_t)(n + 2)));
   MFMGB_CUDA(ctx, cudaMalloc(&H->x_dev, sizeof(double) * (size_t)(n + 2)));
   return MFMGB_OK;
@@ -262,8 +298,9 @@ extern "C"
   {
     if (!H || !A || level < 0 || level >= H->n_levels || H->finalized)
       return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_operator: bad arguments");
-    if (A->n_rows != A->n_cols)
-      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_operator: level operator must be square");
+    if (A->n_cols < A->n_rows)
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_operator: level operator must be square "
+                                                "(or n_rows x (n_rows + ghosts) for a row-partitioned level)");
     H->lev[level].A = A;
     H->lev[level].n = A->n_rows;
     return MFMGB_OK;
@@ -282,11 +319,44 @@ extern "C"
   {
     if (!H || !R || level < 1 || level >= H->n_levels || H->finalized)
       return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_restrictor: bad arguments");
-    if (P && (P->n_rows != R->n_cols || P->n_cols != R->n_rows || P->nnz != R->nnz))
+    if (P && !H->distributed && (P->n_rows != R->n_cols || P->n_cols != R->n_rows || P->nnz != R->nnz))
       return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_restrictor: P is not shaped like R^T");
     H->lev[level].R = R;
     H->lev[level].P = P;
     return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_hierarchy_set_halo(mfmgb_hierarchy *H, int level, const mfmgb_halo *halo, int64_t boundary_lo,
+                                         int64_t boundary_hi)
+  {
+    if (!H || !halo || level < 0 || level >= H->n_levels - 1 || H->finalized)
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_halo: bad arguments");
+    mfmgb_level &l = H->lev[level];
+    if (!l.A || halo->n_owned != l.n || l.A->n_cols != halo->n_owned + halo->n_ghost || boundary_lo < 0 ||
+        boundary_hi > l.n || boundary_lo > boundary_hi)
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_halo: plan does not match the level operator");
+    l.halo = halo;
+    l.blo = boundary_lo;
+    l.bhi = boundary_hi;
+    H->distributed = true;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_hierarchy_set_coarse_offsets(mfmgb_hierarchy *H, const int64_t *offsets, int nranks)
+  {
+    if (!H || !offsets || nranks < 1 || H->finalized)
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_coarse_offsets: bad arguments");
+    H->coarse_offsets.assign(offsets, offsets + nranks + 1);
+    H->distributed = true;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int64_t mfmgb_hierarchy_vector_size(const mfmgb_hierarchy *H, int level)
+  {
+    if (!H || level < 0 || level >= H->n_levels)
+      return 0;
+    const mfmgb_level &l = H->lev[level];
+    return l.n + (l.halo ? l.halo->n_ghost : 0);
   }
 
   MFMGB_API int mfmgb_hierarchy_finalize(mfmgb_ctx *ctx, mfmgb_hierarchy *H)
@@ -301,7 +371,23 @@ extern "C"
       {
         if (!l.R)
           return fail(ctx, MFMGB_ERR_INVALID, "mfmgb_hierarchy_finalize: level %d has no restrictor", li);
-        if (l.R->n_rows != l.n || l.R->n_cols != H->lev[li - 1].n)
+        const mfmgb_level &lf = H->lev[li - 1];
+        const int64_t fine_cols = lf.n + (lf.halo ? lf.halo->n_ghost : 0);
+        if (H->distributed)
+        {
+          mfmgb_comm *c = ctx_comm(ctx);
+          if (!c || (int)H->coarse_offsets.size() != c->nranks + 1)
+            return fail(ctx, MFMGB_ERR_INVALID, "mfmgb_hierarchy_finalize: partitioned hierarchy needs mfmgb_comm_init "
+                                                "and mfmgb_hierarchy_set_coarse_offsets");
+          if (li != H->n_levels - 1 || !l.P)
+            return fail(ctx, MFMGB_ERR_INVALID, "mfmgb_hierarchy_finalize: partitioned mode supports a replicated "
+                                                "coarsest level right below the partitioned one, with an explicit P");
+          const int64_t nc_own = H->coarse_offsets[c->rank + 1] - H->coarse_offsets[c->rank];
+          if (l.R->n_rows != nc_own || l.R->n_cols != fine_cols || l.P->n_rows != lf.n || l.P->n_cols != l.n ||
+              H->coarse_offsets.back() != l.n)
+            return fail(ctx, MFMGB_ERR_INVALID, "mfmgb_hierarchy_finalize: partitioned R / P shapes are inconsistent");
+        }
+        else if (l.R->n_rows != l.n || l.R->n_cols != H->lev[li - 1].n)
           return fail(ctx, MFMGB_ERR_INVALID,
                       "mfmgb_hierarchy_finalize: restrictor of level %d is %lld x %lld, expected %lld x %lld", li,
                       (long long)l.R->n_rows, (long long)l.R->n_cols, (long long)l.n, (long long)H->lev[li - 1].n);
@@ -326,8 +412,11 @@ extern "C"
         }
         else
           MFMGB_CHECK(mfmgb_jacobi_setup(ctx, l.A, H->omega, &l.J));
-        MFMGB_CHECK(mfmgb_vec_alloc(ctx, l.n, &l.res));
-        MFMGB_CHECK(mfmgb_vec_alloc(ctx, l.n, &l.xtmp));
+        if (l.halo && l.M)
+          return fail(ctx, MFMGB_ERR_NOT_IMPLEMENTED, "matrix-free level in partitioned mode is not implemented");
+        const int64_t ng = l.halo ? l.halo->n_ghost : 0;
+        MFMGB_CHECK(mfmgb_vec_alloc(ctx, l.n + ng, &l.res));
+        MFMGB_CHECK(mfmgb_vec_alloc(ctx, l.n + ng, &l.xtmp));
       }
       else
       {
@@ -339,6 +428,7 @@ extern "C"
     }
     MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     // count the launches of one cycle (dry capture, nothing executes)
+    if (!H->distributed)
     {
       double *tb = nullptr, *tx = nullptr;
       MFMGB_CHECK(mfmgb_vec_alloc(ctx, H->lev[0].n, &tb));
@@ -468,6 +558,8 @@ extern "C"
     {
       op.A = A;
       op.n = A->n_rows;
+      if (H && H->lev[0].halo && H->lev[0].A == A)
+        op = H->lev[0]; // row-partitioned operator: reuse the level's halo plan
     }
     else
       op = H->lev[0];
@@ -519,6 +611,7 @@ extern "C"
     e.b = b;
     PCG_TRY(level_apply_A(ctx, op, x, Epi::Resid, e));
     PCG_TRY(vec_dot_async(ctx, g, g, n, scal + 3));
+    PCG_TRY(allreduce_sum(ctx, scal + 3, 1));
     PCG_CUDA(cudaMemcpyAsync(sh, scal + 3, sizeof(double), cudaMemcpyDeviceToHost, st));
     PCG_CUDA(cudaStreamSynchronize(st));
     double res = std::sqrt(sh[0]);
@@ -536,6 +629,7 @@ extern "C"
       negate_kernel<<<grid_ew, kBlock, 0, st>>>(n, h, d);
       ctx->launches++;
       PCG_TRY(vec_dot_async(ctx, g, h, n, scal + 0));
+      PCG_TRY(allreduce_sum(ctx, scal + 0, 1));
       while (!converged && it < max_it)
       {
         ++it;
@@ -543,9 +637,11 @@ extern "C"
         e.y = h;
         PCG_TRY(level_apply_A(ctx, op, d, Epi::Spmv, e)); // h = A d
         PCG_TRY(vec_dot_async(ctx, d, h, n, scal + 2));   // dh = d.h
+        PCG_TRY(allreduce_sum(ctx, scal + 2, 1));
         pcg_update_kernel<<<nb, kBlock, 0, st>>>(n, scal, h, d, g, x, ctx->red_partials);
         ctx->launches++;
         PCG_TRY(reduce_finalize(ctx, ctx->red_partials, nb, ctx->red_capacity, 1, scal + 3));
+        PCG_TRY(allreduce_sum(ctx, scal + 3, 1));
         PCG_CUDA(cudaMemcpyAsync(sh, scal + 3, sizeof(double), cudaMemcpyDeviceToHost, st));
         PCG_CUDA(cudaStreamSynchronize(st));
         res = std::sqrt(sh[0]);
@@ -561,6 +657,7 @@ extern "C"
         else
           PCG_CUDA(cudaMemcpyAsync(h, g, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
         PCG_TRY(vec_dot_async(ctx, g, h, n, scal + 1)); // gh_new
+        PCG_TRY(allreduce_sum(ctx, scal + 1, 1));
         pcg_direction_kernel<<<grid_ew, kBlock, 0, st>>>(n, scal, h, d);
         ctx->launches++;
         rotate_scalar_kernel<<<1, 1, 0, st>>>(scal);

@@ -67,8 +67,29 @@ class CudaHandle:
     def stream(self) -> int:
         return int(self.lib.mfmgb_ctx_stream(self.ctx) or 0)
 
+    # ---- multi-GPU: one process per GPU, NCCL communicator owned by the context ----
+    def unique_id(self) -> bytes:
+        """128-byte NCCL id (create on rank 0, broadcast with the launcher's own transport)."""
+        buf = ctypes.create_string_buffer(128)
+        check(self.ctx, self.lib.mfmgb_comm_unique_id(buf))
+        return buf.raw
+
+    def init_comm(self, unique_id: bytes, nranks: int, rank: int) -> None:
+        check(self.ctx, self.lib.mfmgb_comm_init(self.ctx, unique_id, nranks, rank))
+        self.nranks, self.rank = nranks, rank
+
+    def init_comm_from_torch(self) -> None:
+        """Rendezvous through an initialised torch.distributed process group (any backend)."""
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        obj = [self.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        self.init_comm(obj[0], world, rank)
+
     def close(self) -> None:
         if getattr(self, "ctx", None):
+            self.lib.mfmgb_comm_finalize(self.ctx)
             self.lib.mfmgb_ctx_destroy(self.ctx)
             self.ctx = None
 
@@ -382,6 +403,35 @@ class MatrixFreeLaplaceDevice:
             pass
 
 
+class HaloPlan:
+    """Halo plan of a row-partitioned level (hostsetup.partition.LocalPart -> mfmgb_halo)."""
+
+    def __init__(self, handle: CudaHandle, part):
+        self.handle = handle
+        nb = np.ascontiguousarray(part.neighbors, dtype=np.int32)
+        sc = np.ascontiguousarray([len(s) for s in part.send_indices], dtype=np.int64)
+        si = np.ascontiguousarray(np.concatenate(part.send_indices) if len(part.send_indices) else np.zeros(0),
+                                  dtype=np.int32)
+        rc = np.ascontiguousarray(part.recv_counts, dtype=np.int64)
+        p = ctypes.c_void_p()
+        check(handle.ctx, handle.lib.mfmgb_halo_create(handle.ctx, part.n_owned, part.n_ghost, len(nb),
+                                                       nb.ctypes.data, sc.ctypes.data, si.ctypes.data, rc.ctypes.data,
+                                                       ctypes.byref(p)))
+        self.ptr = p
+        self.n_owned, self.n_ghost = part.n_owned, part.n_ghost
+
+    def exchange(self, v: DeviceVector) -> None:
+        assert v.size >= self.n_owned + self.n_ghost
+        check(self.handle.ctx, self.handle.lib.mfmgb_halo_exchange(self.handle.ctx, self.ptr, v.ptr))
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None) and getattr(self.handle, "ctx", None):
+                self.handle.lib.mfmgb_halo_destroy(self.handle.ctx, self.ptr)
+        except Exception:
+            pass
+
+
 class Hierarchy:
     """mfmg::Hierarchy on device vectors.  Built from already-assembled level operators
     (`from_operators`) -- the setup that produces them stays on the host path
@@ -391,8 +441,9 @@ class Hierarchy:
     "smoother.n_smoothing_steps", "smoother.type", "solver.type"."""
 
     def __init__(self, handle: CudaHandle, operators, restrictors, params=None, omega: float = 1.0,
-                 prolongators=None):
+                 prolongators=None, halo: "HaloPlan | None" = None, boundary=(0, 0), coarse_offsets=None):
         self.handle = handle
+        self.halo = halo
         lib = handle.lib
         self.params = params or {}
         if str(_get(params, "smoother.type", "Jacobi")).lower() != "jacobi":
@@ -417,12 +468,19 @@ class Hierarchy:
                 check(handle.ctx, lib.mfmgb_hierarchy_set_mf_operator(self.ptr, op.ptr))
             else:
                 check(handle.ctx, lib.mfmgb_hierarchy_set_operator(self.ptr, li, op.ptr))
+        if coarse_offsets is not None:  # (marks the hierarchy as row-partitioned before R / P are checked)
+            co = np.ascontiguousarray(coarse_offsets, dtype=np.int64)
+            check(handle.ctx, lib.mfmgb_hierarchy_set_coarse_offsets(self.ptr, co.ctypes.data, len(co) - 1))
         for li, r in enumerate(self.restrictors):
             pr = self.prolongators[li]
             check(handle.ctx, lib.mfmgb_hierarchy_set_restrictor(self.ptr, li + 1, r.ptr, pr.ptr if pr else None))
+        if halo is not None:
+            check(handle.ctx, lib.mfmgb_hierarchy_set_halo(self.ptr, 0, halo.ptr, int(boundary[0]), int(boundary[1])))
         check(handle.ctx, lib.mfmgb_hierarchy_finalize(handle.ctx, self.ptr))
         self.n = self.operators[0].size if isinstance(self.operators[0], MatrixFreeLaplaceDevice) \
             else self.operators[0].m()
+        # length of gathered vectors (owned + ghost tail); == n on a single GPU
+        self.vector_size = int(lib.mfmgb_hierarchy_vector_size(self.ptr, 0))
 
     @staticmethod
     def from_host(handle: CudaHandle, A, R, A_c, params=None, omega: float = 1.0) -> "Hierarchy":
@@ -430,6 +488,21 @@ class Hierarchy:
         ops = [SparseMatrixDevice.from_host(handle, A), SparseMatrixDevice.from_host(handle, A_c)]
         res = [SparseMatrixDevice.from_host(handle, R)]
         return Hierarchy(handle, ops, res, params, omega)
+
+    @staticmethod
+    def from_partition(handle: CudaHandle, part, params=None, omega: float = 1.0) -> "Hierarchy":
+        """Row-partitioned two-level hierarchy of one rank (hostsetup.partition.LocalPart); the context must have
+        an initialised communicator (CudaHandle.init_comm*)."""
+        ops = [SparseMatrixDevice.from_host(handle, part.A), SparseMatrixDevice.from_host(handle, part.Ac)]
+        res = [SparseMatrixDevice.from_host(handle, part.R)]
+        pro = [SparseMatrixDevice.from_host(handle, part.P)]
+        plan = HaloPlan(handle, part)
+        return Hierarchy(handle, ops, res, params, omega, prolongators=pro, halo=plan,
+                         boundary=(part.boundary_lo, part.boundary_hi), coarse_offsets=part.coarse_offsets)
+
+    def build_vector(self) -> DeviceVector:
+        """A level-0 vector with room for the ghost tail (Level::build_vector, level.hpp:63-70)."""
+        return DeviceVector(self.handle, self.vector_size)
 
     def use_graph(self, on: bool = True) -> None:
         check(self.handle.ctx, self.handle.lib.mfmgb_hierarchy_use_graph(self.ptr, int(on)))

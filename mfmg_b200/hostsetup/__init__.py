@@ -5,3 +5,5 @@ fallback for it."""
 from .amge import block_agglomerates, build_restrictor, galerkin, transpose  # noqa: F401
 from .problems import (HostCSR, LaplaceProblem, assemble, boundary_mask,  # noqa: F401
                        coefficient_table, material_value, reference_matrices)
+from .partition import LocalPart, make_parts, partition_two_level, slab_row_ranges  # noqa: F401,E402
+from .slab import build_slab_part  # noqa: F401,E402

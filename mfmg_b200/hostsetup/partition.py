@@ -1,0 +1,159 @@
+"""Host setup: row partition of the level operators for the multi-GPU V-cycle.
+
+The reference partitions rows through deal.II's distributed triangulation (`locally_owned_dofs`, agglomerates never
+cross ranks, include/mfmg/common/amge.templates.hpp:453-478) and keeps GLOBAL column indices with a full-length
+source vector that is all-gathered on every SpMV (include/mfmg/cuda/sparse_matrix_device.templates.cuh:104-138).
+Here every level is partitioned in contiguous row blocks (z-slabs of the lexicographic numbering, aligned with the
+agglomerate layers), columns are renumbered `[owned | ghost]`, and a halo plan lists exactly the entries that cross
+rank boundaries (the information cuda_solver.cu:306-426 derives for AMGX's one-ring maps).
+
+Pure host code (numpy); used once at setup.  Nothing here runs in the V-cycle.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .problems import HostCSR
+
+
+@dataclass
+class LocalPart:
+    rank: int
+    world: int
+    row_begin: int          # first owned fine row (global numbering)
+    row_end: int
+    n_owned: int
+    n_ghost: int
+    ghost_global: np.ndarray  # global fine index of every ghost slot, ascending (hence grouped by owner)
+    A: HostCSR                # n_owned x (n_owned + n_ghost), local columns
+    R: HostCSR                # nc_owned x (n_owned + n_ghost), local columns
+    P: HostCSR                # n_owned x n_c (GLOBAL coarse columns: x_c is replicated on every rank)
+    Ac: HostCSR               # the full coarse operator (replicated dense solve)
+    coarse_offsets: np.ndarray  # world + 1 offsets of the owned coarse rows
+    neighbors: list = field(default_factory=list)      # ranks exchanged with, ascending
+    recv_counts: list = field(default_factory=list)    # ghost entries received from each neighbour (ghost order)
+    send_indices: list = field(default_factory=list)   # per neighbour: LOCAL owned indices to send, ascending
+    # rows [0, n_owned) whose columns are all owned form the interior; with a slab partition the rows that
+    # touch ghosts are a prefix and a suffix of the owned range:
+    boundary_lo: int = 0     # rows [0, boundary_lo) reference ghosts below
+    boundary_hi: int = 0     # rows [boundary_hi, n_owned) reference ghosts above
+
+
+def slab_row_ranges(nodes, degree: int, cells_z: int, block_z: int, world: int):
+    """Split the cell layers along z into `world` contiguous slabs aligned with the agglomerate layers.
+    Returns (cell_layer_offsets[world+1], row_offsets[world+1])."""
+    n_blocks = -(-cells_z // block_z)
+    if n_blocks < world:
+        raise ValueError(f"cannot give each of {world} ranks an agglomerate layer ({n_blocks} layers)")
+    base, rem = divmod(n_blocks, world)
+    layers = [0]
+    for r in range(world):
+        nb = base + (1 if r < rem else 0)
+        layers.append(min(cells_z, layers[-1] + nb * block_z))
+    layers[-1] = cells_z
+    plane = int(np.prod(nodes[:-1]))
+    rows = [layers[r] * degree * plane for r in range(world)]
+    rows.append(int(np.prod(nodes)))
+    return np.array(layers, dtype=np.int64), np.array(rows, dtype=np.int64)
+
+
+def _localise(M: HostCSR, rows: slice, row_begin: int, row_end: int, ghost_global: np.ndarray) -> HostCSR:
+    """Rows `rows` of M with columns renumbered [owned | ghost]."""
+    rp = M.rowptr[rows.start:rows.stop + 1]
+    k0, k1 = int(rp[0]), int(rp[-1])
+    col = M.col[k0:k1].astype(np.int64)
+    owned = (col >= row_begin) & (col < row_end)
+    loc = np.empty_like(col)
+    loc[owned] = col[owned] - row_begin
+    gpos = np.searchsorted(ghost_global, col[~owned])
+    assert np.all(ghost_global[gpos] == col[~owned])
+    loc[~owned] = (row_end - row_begin) + gpos
+    return HostCSR(rows.stop - rows.start, (row_end - row_begin) + len(ghost_global),
+                   np.ascontiguousarray(rp - k0), loc.astype(np.int32), np.ascontiguousarray(M.val[k0:k1]))
+
+
+def partition_two_level(A: HostCSR, R: HostCSR, Ac: HostCSR, row_offsets, coarse_offsets, rank: int) -> LocalPart:
+    """Local operators of `rank` from the global ones (the global-redundant setup mode: every rank runs the host
+    setup and slices; a slab-local setup is the next step)."""
+    world = len(row_offsets) - 1
+    rb, re_ = int(row_offsets[rank]), int(row_offsets[rank + 1])
+    cb, ce = int(coarse_offsets[rank]), int(coarse_offsets[rank + 1])
+    n_owned = re_ - rb
+    # ghosts: every column of the owned rows of A and of the owned rows of R that is not owned
+    ka0, ka1 = int(A.rowptr[rb]), int(A.rowptr[re_])
+    kr0, kr1 = int(R.rowptr[cb]), int(R.rowptr[ce])
+    cols = np.concatenate([A.col[ka0:ka1], R.col[kr0:kr1]]).astype(np.int64)
+    ghost_global = np.unique(cols[(cols < rb) | (cols >= re_)])
+    A_loc = _localise(A, slice(rb, re_), rb, re_, ghost_global)
+    R_loc = _localise(R, slice(cb, ce), rb, re_, ghost_global)
+    # P = R^T rows of the owned fine nodes, global coarse columns
+    Rt = R.to_scipy().T.tocsr()
+    Rt.sort_indices()
+    P_loc = HostCSR.from_scipy(Rt[rb:re_])
+    part = LocalPart(rank, world, rb, re_, n_owned, len(ghost_global), ghost_global, A_loc, R_loc, P_loc, Ac,
+                     np.asarray(coarse_offsets, dtype=np.int64))
+    owner = np.searchsorted(np.asarray(row_offsets), ghost_global, side="right") - 1
+    for q in np.unique(owner):
+        part.neighbors.append(int(q))
+        part.recv_counts.append(int(np.sum(owner == q)))
+    # boundary row ranges (rows referencing ghost columns)
+    has_ghost = np.zeros(n_owned, dtype=bool)
+    gmask = A_loc.col >= n_owned
+    if gmask.any():
+        row_of = np.repeat(np.arange(n_owned), np.diff(A_loc.rowptr))
+        has_ghost[np.unique(row_of[gmask])] = True
+    idx = np.flatnonzero(has_ghost)
+    lo_rows = idx[idx < n_owned // 2]
+    hi_rows = idx[idx >= n_owned // 2]
+    part.boundary_lo = int(lo_rows.max() + 1) if len(lo_rows) else 0
+    part.boundary_hi = int(hi_rows.min()) if len(hi_rows) else n_owned
+    return part
+
+
+def wire_send_lists(parts_or_ghost_lists, row_offsets, rank: int):
+    """Send lists of `rank`: for every other rank q, the owned entries q has as ghosts (ascending global order,
+    which is the order of q's ghost slots).  `parts_or_ghost_lists[q]` is q's ghost_global array (gathered at setup
+    with torch.distributed.all_gather_object, or computed redundantly)."""
+    rb, re_ = int(row_offsets[rank]), int(row_offsets[rank + 1])
+    neighbors, send_indices = [], []
+    for q, gl in enumerate(parts_or_ghost_lists):
+        if q == rank:
+            continue
+        gl = np.asarray(gl, dtype=np.int64)
+        mine = gl[(gl >= rb) & (gl < re_)]
+        if len(mine):
+            neighbors.append(q)
+            send_indices.append((mine - rb).astype(np.int32))
+    return neighbors, send_indices
+
+
+def finalize_plan(part: LocalPart, all_ghost_lists, row_offsets) -> LocalPart:
+    nb_send, send_idx = wire_send_lists(all_ghost_lists, row_offsets, part.rank)
+    # one neighbour list for both directions (a rank may only send to or only receive from a neighbour)
+    nbs = sorted(set(part.neighbors) | set(nb_send))
+    recv = {q: c for q, c in zip(part.neighbors, part.recv_counts)}
+    send = {q: s for q, s in zip(nb_send, send_idx)}
+    part.neighbors = nbs
+    part.recv_counts = [recv.get(q, 0) for q in nbs]
+    part.send_indices = [send.get(q, np.zeros(0, dtype=np.int32)) for q in nbs]
+    return part
+
+
+def make_parts(problem, R: HostCSR, Ac: HostCSR, block, n_eigenvectors: int, world: int, ranks=None):
+    """LocalParts (wired halo plans) of the slab partition of a two-level hierarchy.  `ranks`: which ranks to
+    build (default all); the ghost lists of all ranks are derived from the global operators, so no setup-time
+    communication is needed in this global-redundant mode."""
+    dim = problem.dim
+    layers, row_off = slab_row_ranges(problem.nodes, problem.degree, problem.cells[dim - 1], block[dim - 1], world)
+    aggs_per_layer = 1
+    for d in range(dim - 1):
+        aggs_per_layer *= -(-problem.cells[d] // block[d])
+    coarse_off = np.array([(-(-int(l) // block[dim - 1])) * aggs_per_layer * n_eigenvectors for l in layers],
+                          dtype=np.int64)
+    coarse_off[-1] = R.n_rows
+    parts = [partition_two_level(problem.A, R, Ac, row_off, coarse_off, r) for r in range(world)]
+    ghost_lists = [p.ghost_global for p in parts]
+    wanted = range(world) if ranks is None else ranks
+    return [finalize_plan(parts[r], ghost_lists, row_off) for r in wanted], row_off, coarse_off

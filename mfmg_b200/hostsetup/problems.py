@@ -103,13 +103,14 @@ def reference_matrices(dim: int, degree: int, h) -> np.ndarray:
     return np.ascontiguousarray(G)
 
 
-def quadrature_points(dim: int, degree: int, cells, h) -> np.ndarray:
+def quadrature_points(dim: int, degree: int, cells, h, origin=None) -> np.ndarray:
     """Physical quadrature points, shape (n_cells, nq, dim), cells and points lexicographic."""
     n1 = degree + 1
     qp, _ = gauss_unit(n1)
     axes = []
     for d in range(dim):
-        c = np.arange(cells[d])[:, None] * h[d] + qp[None, :] * h[d]  # (cells_d, n1)
+        o = 0.0 if origin is None else origin[d]
+        c = o + np.arange(cells[d])[:, None] * h[d] + qp[None, :] * h[d]  # (cells_d, n1)
         axes.append(c)
     if dim == 2:
         X = np.broadcast_to(axes[0][None, :, None, :], (cells[1], cells[0], n1, n1))
@@ -147,14 +148,14 @@ def material_value(kind: str, pts: np.ndarray) -> np.ndarray:
     raise NotImplementedError(kind)
 
 
-def coefficient_table(kind: str, dim: int, degree: int, cells, h=None, chunk_cells: int = 1 << 18):
+def coefficient_table(kind: str, dim: int, degree: int, cells, h=None, origin=None):
     """coef[cell, q] for the whole grid.  Returns a (n_cells, 1) array when the coefficient is
     the same at every quadrature point of every cell (detected, not assumed)."""
     cells = [int(c) for c in cells]
     h = [1.0 / c for c in cells] if h is None else list(h)
     if kind == "constant":
         return np.ones((int(np.prod(cells)), 1))
-    pts = quadrature_points(dim, degree, cells, h)
+    pts = quadrature_points(dim, degree, cells, h, origin)
     coef = material_value(kind, pts)
     if np.all(coef == coef[:, :1]):
         return np.ascontiguousarray(coef[:, :1])
@@ -276,6 +277,23 @@ class LaplaceProblem:
         p.G = reference_matrices(dim, degree, p.h)
         p.coef = coefficient_table(material, dim, degree, cells, p.h)
         p.constrained = boundary_mask(dim, degree, cells)
+        if assemble_matrix:
+            p.A, p.diag = assemble(dim, degree, cells, p.G, p.coef, p.constrained)
+        return p
+
+    @staticmethod
+    def create_box(dim: int, degree: int, cells, h, material: str = "constant",
+                   assemble_matrix: bool = True, origin=None, faces=None) -> "LaplaceProblem":
+        """Same problem on a box of `cells` (per direction) cells of size `h`: the weak-scaling domains
+        (cubes stacked along z) and the slab-local sub-boxes of the multi-GPU setup (`origin`: physical position
+        of the box corner, for the material; `faces[d] = (low, high)`: which faces are Dirichlet -- cut planes
+        of a slab are not)."""
+        cells = tuple(int(c) for c in cells)
+        p = LaplaceProblem(dim, degree, cells, material)
+        p.h = tuple(float(x) for x in h)
+        p.G = reference_matrices(dim, degree, p.h)
+        p.coef = coefficient_table(material, dim, degree, cells, p.h, origin)
+        p.constrained = boundary_mask(dim, degree, cells, faces)
         if assemble_matrix:
             p.A, p.diag = assemble(dim, degree, cells, p.G, p.coef, p.constrained)
         return p

@@ -1,0 +1,111 @@
+"""Host setup, slab-local: each rank builds ONLY its z-slab of a two-level hierarchy (plus one agglomerate layer
+on each side), so the multi-GPU configurations never materialise the global operators on one host process.
+
+Rank r owns the cell layers [cz0, cz1) (aligned with the agglomerate layers) and the node planes [cz0 p, cz1 p)
+(the last rank also owns the top plane).  It assembles the sub-box of cell layers [cz0 - bz, cz1 + bz) -- cut planes
+are NOT Dirichlet; rows on the cut planes are incomplete and never used -- builds the restrictor rows of the
+agglomerates in that sub-box, and extracts
+
+  A_loc  rows of the owned nodes, columns [owned | ghost]
+  R_loc  rows of the owned agglomerates
+  P_loc  rows of R^T for the owned nodes (global coarse columns; nodes on the bottom shared plane pick up the
+         agglomerate layer below, which is why that layer is built too)
+  A_c    rows of R A R^T for the owned agglomerates (exact because every node within reach of an owned
+         agglomerate lies strictly inside the sub-box when the agglomerates are >= 2 cells thick); the row blocks
+         are gathered so that every rank holds the whole coarse operator (replicated dense solve).
+
+`gather(obj) -> [obj of rank 0, ..., obj of rank world-1]` is the only setup-time communication
+(torch.distributed.all_gather_object in bench.py; a list comprehension in the single-process tests).
+The result is identical to slicing the global operators (tests/test_distributed_cpu.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+from .amge import build_restrictor
+from .partition import LocalPart, _localise, finalize_plan, slab_row_ranges
+from .problems import HostCSR, LaplaceProblem
+
+
+def build_slab_part(degree: int, cells, h, material: str, block, n_eigenvectors: int, world: int, rank: int, gather,
+                    eigensolver: str = "free") -> LocalPart:
+    dim = 3
+    cells = tuple(int(c) for c in cells)
+    block = tuple(int(b) for b in block)
+    p = degree
+    if block[2] < 2 and world > 1:
+        raise ValueError("slab-local setup needs agglomerates at least 2 cells thick in z")
+    nodes = tuple(c * p + 1 for c in cells)
+    plane = nodes[0] * nodes[1]
+    layers, row_off = slab_row_ranges(nodes, p, cells[2], block[2], world)
+    aggs_per_layer = (-(-cells[0] // block[0])) * (-(-cells[1] // block[1]))
+    coarse_off = np.array([(-(-int(l) // block[2])) * aggs_per_layer * n_eigenvectors for l in layers], dtype=np.int64)
+    cz0, cz1 = int(layers[rank]), int(layers[rank + 1])
+    e0, e1 = max(0, cz0 - block[2]), min(cells[2], cz1 + block[2])
+    ext = LaplaceProblem.create_box(dim, p, (cells[0], cells[1], e1 - e0), h, material,
+                                    origin=(0.0, 0.0, e0 * h[2]),
+                                    faces=[(True, True), (True, True), (e0 == 0, e1 == cells[2])])
+    R_ext = build_restrictor(ext, block, n_eigenvectors, eigensolver=eigensolver)
+    off = e0 * p * plane                                  # ext node index + off = global node index
+    coff = (e0 // block[2]) * aggs_per_layer * n_eigenvectors   # ext coarse index + coff = global coarse index
+    rb, re_ = int(row_off[rank]), int(row_off[rank + 1])
+    cb, ce = int(coarse_off[rank]), int(coarse_off[rank + 1])
+    n_global = int(np.prod(nodes))
+    nc_global = int(coarse_off[-1])
+
+    # global-column views of the ext operators
+    A_g = HostCSR(ext.A.n_rows, n_global, ext.A.rowptr, (ext.A.col.astype(np.int64) + off), ext.A.val)
+    R_g = HostCSR(R_ext.n_rows, n_global, R_ext.rowptr, (R_ext.col.astype(np.int64) + off), R_ext.val)
+    ka0, ka1 = int(A_g.rowptr[rb - off]), int(A_g.rowptr[re_ - off])
+    kr0, kr1 = int(R_g.rowptr[cb - coff]), int(R_g.rowptr[ce - coff])
+    cols = np.concatenate([A_g.col[ka0:ka1], R_g.col[kr0:kr1]])
+    ghost_global = np.unique(cols[(cols < rb) | (cols >= re_)])
+    A_loc = _localise(A_g, slice(rb - off, re_ - off), rb, re_, ghost_global)
+    R_loc = _localise(R_g, slice(cb - coff, ce - coff), rb, re_, ghost_global)
+
+    # P rows of the owned nodes, global coarse columns
+    Rs = R_ext.to_scipy()
+    Rt = Rs.T.tocsr()
+    Rt.sort_indices()
+    Pl = Rt[rb - off:re_ - off].tocsr()
+    P_loc = HostCSR(Pl.shape[0], nc_global, np.ascontiguousarray(Pl.indptr, dtype=np.int64),
+                    np.ascontiguousarray(Pl.indices + coff, dtype=np.int32), np.ascontiguousarray(Pl.data))
+
+    # owned rows of A_c = R A R^T
+    As = ext.A.to_scipy()
+    rows = Rs[cb - coff:ce - coff]
+    ac_rows = (rows @ (As @ Rt)).tocsr()
+    ac_rows.sort_indices()
+    blocks = gather((ac_rows.indptr.astype(np.int64), (ac_rows.indices.astype(np.int64) + coff), ac_rows.data))
+    rp = [np.zeros(1, dtype=np.int64)]
+    cols_all, vals_all = [], []
+    for indptr, indices, data in blocks:
+        rp.append(indptr[1:] + rp[-1][-1])
+        cols_all.append(indices)
+        vals_all.append(data)
+    Ac = HostCSR(nc_global, nc_global, np.concatenate(rp), np.concatenate(cols_all).astype(np.int32),
+                 np.concatenate(vals_all))
+
+    part = LocalPart(rank, world, rb, re_, re_ - rb, len(ghost_global), ghost_global, A_loc, R_loc, P_loc, Ac, coarse_off)
+    row_offsets = np.asarray(row_off)
+    owner = np.searchsorted(row_offsets, ghost_global, side="right") - 1
+    for q in np.unique(owner):
+        part.neighbors.append(int(q))
+        part.recv_counts.append(int(np.sum(owner == q)))
+    n_owned = re_ - rb
+    gmask = A_loc.col >= n_owned
+    has_ghost = np.zeros(n_owned, dtype=bool)
+    if gmask.any():
+        row_of = np.repeat(np.arange(n_owned), np.diff(A_loc.rowptr))
+        has_ghost[np.unique(row_of[gmask])] = True
+    idx = np.flatnonzero(has_ghost)
+    lo_rows, hi_rows = idx[idx < n_owned // 2], idx[idx >= n_owned // 2]
+    part.boundary_lo = int(lo_rows.max() + 1) if len(lo_rows) else 0
+    part.boundary_hi = int(hi_rows.min()) if len(hi_rows) else n_owned
+    ghost_lists = gather(ghost_global)
+    finalize_plan(part, ghost_lists, row_offsets)
+    # extras for the driver
+    part.constrained = ext.constrained[rb - off:re_ - off]
+    part.n_global = n_global
+    return part

@@ -1,0 +1,28 @@
+"""Multi-GPU parity (-m gpu, needs >= 2 GPUs; skipped otherwise): runs tests/dist_gpu_worker.py with one rank per GPU."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _n_gpus():
+    import torch
+
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_partitioned_hierarchy_on_gpus(world):
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world),
+           os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-4000:]
+    for r in range(world):
+        assert f"RANK {r} OK" in res.stdout, res.stdout[-4000:]
