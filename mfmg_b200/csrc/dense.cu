@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "comm.cuh"
 #include "csr.cuh"
 #include "dense.cuh"
 
@@ -403,16 +404,25 @@ __global__ void __launch_bounds__(256) permute_kernel(int64_t n, const int *__re
 
 // TPR threads cooperate on one row.  LOWER: out[i] = v[i] + sum_{j<i} M[i][j] v[j];
 // UPPER: out[i] = sum_{j>=i} M[i][j] v[j].  Fixed reduction tree => deterministic.
+// row split of the multi-GPU solve: slot b of rank r is row r*h + b (b < h) or row n - (r+1)*h + (b - h)
+__device__ __host__ __forceinline__ int64_t split_row(int64_t n, int64_t h, int r, int64_t b)
+{
+  return b < h ? (int64_t)r * h + b : n - (int64_t)(r + 1) * h + (b - h);
+}
+
 template <bool LOWER, int TPR>
 __global__ void __launch_bounds__(256) tri_gemv_kernel(int64_t n, const double *__restrict__ M, int64_t lda,
-                                                       const double *__restrict__ v, double *__restrict__ out)
+                                                       const double *__restrict__ v, double *__restrict__ out,
+                                                       int64_t n_slots, int64_t half, int rank)
 {
   __shared__ double sm[8];
   constexpr int ROWS_PER_BLOCK = 256 / TPR;
   const int t = threadIdx.x % TPR;
-  const int64_t i = (int64_t)blockIdx.x * ROWS_PER_BLOCK + threadIdx.x / TPR;
+  // slot = output index; on one GPU slot == row, in the row-split form the rank's slots map to its two row ranges
+  const int64_t slot = (int64_t)blockIdx.x * ROWS_PER_BLOCK + threadIdx.x / TPR;
+  const int64_t i = half > 0 ? (slot < n_slots ? split_row(n, half, rank, slot) : -1) : (slot < n_slots ? slot : -1);
   double s0 = 0., s1 = 0.;
-  if (i < n)
+  if (i >= 0 && i < n)
   {
     const double *row = M + i * lda;
     int64_t j0 = LOWER ? 0 : i, j1 = LOWER ? i : n;
@@ -448,18 +458,32 @@ __global__ void __launch_bounds__(256) tri_gemv_kernel(int64_t n, const double *
       s0 = fma(row[j1 - 1], v[j1 - 1], s0);
   }
   double s = s0 + s1;
+  const bool valid = i >= 0 && i < n;
   if (TPR == 256)
   {
     s = block_sum<256>(s, sm);
-    if (threadIdx.x == 0 && i < n)
-      out[i] = LOWER ? s + v[i] : s;
+    if (threadIdx.x == 0 && slot < n_slots)
+      out[slot] = valid ? (LOWER ? s + v[i] : s) : 0.;
   }
   else
   {
     s = subwarp_sum<(TPR < 32 ? TPR : 32)>(s);
-    if (t == 0 && i < n)
-      out[i] = LOWER ? s + v[i] : s;
+    if (t == 0 && slot < n_slots)
+      out[slot] = valid ? (LOWER ? s + v[i] : s) : 0.;
   }
+}
+
+// gathered (rank-major chunks of 2h slots) -> natural row order; rows covered twice carry identical values
+__global__ void __launch_bounds__(256) unshuffle_kernel(int64_t n, int64_t half, int nranks,
+                                                        const double *__restrict__ gathered, double *__restrict__ out)
+{
+  const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (g >= 2 * half * nranks)
+    return;
+  const int r = (int)(g / (2 * half));
+  const int64_t i = split_row(n, half, r, g % (2 * half));
+  if (i >= 0 && i < n)
+    out[i] = gathered[g];
 }
 } // namespace
 
@@ -472,20 +496,56 @@ int dense_solve_async(mfmgb_ctx *ctx, const mfmgb_dense *D, const double *b, dou
     return MFMGB_OK;
   permute_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(n, D->perm, b, D->work0);
   MFMGB_LAUNCHED(ctx);
+  if (D->distributed)
+  {
+    // every rank: its 2h rows of y = L^-1 (P b); all-gather; its 2h rows of x = U^-1 y; all-gather
+    mfmgb_comm *c = ctx_comm(ctx);
+    const int64_t slots = 2 * D->half;
+    const unsigned ug = (unsigned)ceil_div(slots * D->nranks, 256);
+    tri_gemv_kernel<true, 256><<<(unsigned)slots, 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work0, D->chunk, slots,
+                                                                         D->half, D->rank);
+    MFMGB_LAUNCHED(ctx);
+    MFMGB_NCCL(ctx, ncclAllGather(D->chunk, D->gathered, (size_t)slots, ncclDouble, c->nccl, ctx->stream));
+    unshuffle_kernel<<<ug, 256, 0, ctx->stream>>>(n, D->half, D->nranks, D->gathered, D->work1);
+    MFMGB_LAUNCHED(ctx);
+    tri_gemv_kernel<false, 256><<<(unsigned)slots, 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work1, D->chunk, slots,
+                                                                          D->half, D->rank);
+    MFMGB_LAUNCHED(ctx);
+    MFMGB_NCCL(ctx, ncclAllGather(D->chunk, D->gathered, (size_t)slots, ncclDouble, c->nccl, ctx->stream));
+    unshuffle_kernel<<<ug, 256, 0, ctx->stream>>>(n, D->half, D->nranks, D->gathered, x);
+    MFMGB_LAUNCHED(ctx);
+    return MFMGB_OK;
+  }
   if (n >= 1024)
   {
-    tri_gemv_kernel<true, 256><<<(unsigned)n, 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work0, D->work1);
+    tri_gemv_kernel<true, 256><<<(unsigned)n, 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work0, D->work1, n, 0, 0);
     MFMGB_LAUNCHED(ctx);
-    tri_gemv_kernel<false, 256><<<(unsigned)n, 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work1, x);
+    tri_gemv_kernel<false, 256><<<(unsigned)n, 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work1, x, n, 0, 0);
     MFMGB_LAUNCHED(ctx);
   }
   else
   {
-    tri_gemv_kernel<true, 32><<<(unsigned)ceil_div(n, 8), 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work0, D->work1);
+    tri_gemv_kernel<true, 32><<<(unsigned)ceil_div(n, 8), 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work0, D->work1,
+                                                                                n, 0, 0);
     MFMGB_LAUNCHED(ctx);
-    tri_gemv_kernel<false, 32><<<(unsigned)ceil_div(n, 8), 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work1, x);
+    tri_gemv_kernel<false, 32><<<(unsigned)ceil_div(n, 8), 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work1, x, n, 0,
+                                                                                 0);
     MFMGB_LAUNCHED(ctx);
   }
+  return MFMGB_OK;
+}
+
+int dense_enable_distributed(mfmgb_ctx *ctx, mfmgb_dense *D)
+{
+  mfmgb_comm *c = ctx_comm(ctx);
+  if (!c || c->nranks < 2 || D->n == 0)
+    return MFMGB_OK;
+  D->nranks = c->nranks;
+  D->rank = c->rank;
+  D->half = ceil_div(D->n, 2 * (int64_t)c->nranks);
+  MFMGB_CUDA(ctx, cudaMalloc(&D->chunk, sizeof(double) * (size_t)(2 * D->half)));
+  MFMGB_CUDA(ctx, cudaMalloc(&D->gathered, sizeof(double) * (size_t)(2 * D->half * c->nranks)));
+  D->distributed = true;
   return MFMGB_OK;
 }
 } // namespace mfmgb
@@ -626,6 +686,8 @@ extern "C"
     cudaFree(D->perm);
     cudaFree(D->work0);
     cudaFree(D->work1);
+    cudaFree(D->chunk);
+    cudaFree(D->gathered);
     delete D;
     return MFMGB_OK;
   }

@@ -9,6 +9,7 @@
 // PCG: the recurrence of dealii::SolverCG (tests/hierarchy_driver.cc:200-213), scalars kept on
 // the device, one host read-back per iteration for the reference's stopping test.
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "comm.cuh"
@@ -424,6 +425,16 @@ extern "C"
         if (!l.A)
           return fail(ctx, MFMGB_ERR_INVALID, "mfmgb_hierarchy_finalize: the coarsest level needs an assembled operator");
         MFMGB_CHECK(mfmgb_dense_factor(ctx, l.A, &l.D));
+        // partitioned hierarchy: from n_c = 8192 on, splitting the two triangular GEMVs by rows across the ranks
+        // (2 small all-gathers) beats every rank streaming the whole factor (MFMGB_DENSE_SPLIT_MIN overrides)
+        if (H->distributed)
+        {
+          int64_t split_min = 8192;
+          if (const char *env = getenv("MFMGB_DENSE_SPLIT_MIN"))
+            split_min = atoll(env);
+          if (l.n >= split_min)
+            MFMGB_CHECK(dense_enable_distributed(ctx, l.D));
+        }
       }
     }
     MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -28,7 +28,10 @@ def main():
     handle.init_comm_from_torch()
     cases = [(3, 1, 16, 2, 2, "constant", 1), (3, 1, 24, 4, 1, "discontinuous", 2), (3, 2, 8, 2, 2, "linear", 1),
              (2, 1, 64, 2, 2, "constant", 1)]
-    for dim, degree, cells, block, ne, mat, nu in cases:
+    # second pass: force the row-split (multi-GPU) dense coarse solve, which is normally used from n_c = 8192 on
+    cases = [c + (False,) for c in cases] + [c + (True,) for c in cases[:2]]
+    for dim, degree, cells, block, ne, mat, nu, split_dense in cases:
+        os.environ["MFMGB_DENSE_SPLIT_MIN"] = "1" if split_dense else "8192"
         P, R, Ac = two_level_problem(dim, degree, cells, block, ne, mat)
         (part,), row_off, coarse_off = hs.make_parts(P, R, Ac, (block,) * dim, ne, world, ranks=[rank])
         H = d.Hierarchy.from_partition(handle, part, {"is preconditioner": True, "smoother": {"n_smoothing_steps": nu}})
@@ -74,7 +77,7 @@ def main():
         err = np.linalg.norm(x.to_host()[:part.n_owned] - x_o[sl]) / max(np.linalg.norm(x_o[sl]), 1e-300)
         assert err < 1e-8 or np.linalg.norm(x_o[sl]) < 1e-6, (rank, "pcg x", err)
         if rank == 0:
-            print(f"case {dim}D Q{degree} {cells}^{dim} {mat}: vcycle OK, PCG {it.value} its (oracle {it_ref})", flush=True)
+            print(f"case {dim}D Q{degree} {cells}^{dim} {mat} split_dense={split_dense}: vcycle OK, PCG {it.value} its (oracle {it_ref})", flush=True)
     dist.barrier()
     print(f"RANK {rank} OK", flush=True)
     handle.close()
