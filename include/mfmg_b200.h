@@ -95,6 +95,10 @@ extern "C"
   /* lanes-per-row override for the vector-CSR kernels: 0 = choose from the mean row length */
   MFMGB_API int mfmgb_csr_set_lanes_per_row(mfmgb_csr *A, int lanes);
   MFMGB_API int mfmgb_csr_get_lanes_per_row(const mfmgb_csr *A);
+  /* kernel family behind mfmgb_spmv & co.: -1 = automatic, 0 = vector-CSR with direct global loads, 1 = tile-streamed
+   * (col/val/rowptr staged in shared memory by TMA bulk copies, csrc/csr_tile.cu); both give bit-identical results */
+  MFMGB_API int mfmgb_csr_set_kernel(mfmgb_csr *A, int kernel);
+  MFMGB_API int mfmgb_csr_get_kernel(const mfmgb_csr *A);
 
   /* y = A x : SparseMatrixDevice::vmult (sparse_matrix_device.templates.cuh:351-371), CudaMatrixOperator::apply
    * NO_TRANS (source/cuda/cuda_matrix_operator.cu:80-91) */

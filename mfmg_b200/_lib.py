@@ -67,6 +67,8 @@ SIGNATURES = {
     "mfmgb_csr_transpose": (_int, [_vp, _vp, _pp]),
     "mfmgb_csr_set_lanes_per_row": (_int, [_vp, _int]),
     "mfmgb_csr_get_lanes_per_row": (_int, [_vp]),
+    "mfmgb_csr_set_kernel": (_int, [_vp, _int]),
+    "mfmgb_csr_get_kernel": (_int, [_vp]),
     "mfmgb_spmv": (_int, [_vp, _vp, _vp, _vp]),
     "mfmgb_residual_neg": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "mfmgb_restrict": (_int, [_vp, _vp, _vp, _vp]),
@@ -119,6 +121,23 @@ SIGNATURES = {
 _LIB = None
 
 
+def _preload_bundled_nccl() -> None:
+    """libmfmg_b200.so needs libnccl.so.2.  When this module is loaded before torch, the dynamic linker would pick
+    the system NCCL, and torch (which needs the newer NCCL bundled with its wheel) would then fail to import in the
+    same process.  Loading the bundled copy first makes both share it; without one, the system NCCL serves."""
+    import importlib.util
+
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for base in (spec.submodule_search_locations if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            ctypes.CDLL(cand, mode=ctypes.RTLD_GLOBAL)
+            return
+
+
 def load() -> ctypes.CDLL:
     """Load the CUDA library.  Raises if it has not been built (python -m mfmg_b200.build)."""
     global _LIB
@@ -127,6 +146,7 @@ def load() -> ctypes.CDLL:
             raise ImportError(
                 f"{LIB_PATH} is missing: the sm_100a extension has not been built "
                 "(run `python -m mfmg_b200.build` or __graft_entry__.build()); there is no CPU fallback")
+        _preload_bundled_nccl()
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the symbol is not exported

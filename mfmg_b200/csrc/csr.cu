@@ -7,6 +7,7 @@
 // update, prolongation correction) is applied in the same kernel, so no intermediate vector
 // ever goes to HBM.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "csr.cuh"
@@ -18,24 +19,47 @@ namespace mfmgb
 namespace
 {
 constexpr int kBlock = 256;
+constexpr size_t kRowptrPad = 264; // >= rows per tile (256) + 4, see csr_tile.cu
+
+// epilogue operands of one row; requested before the dot-product loop so that their latency overlaps it
+struct EpiRegs
+{
+  double b = 0., dinv = 0., x = 0.;
+};
 
 template <int EPI>
-__device__ __forceinline__ void epilogue(const EpiArgs &e, int64_t row, double s)
+__device__ __forceinline__ EpiRegs epilogue_load(const EpiArgs &e, int64_t row)
+{
+  EpiRegs r;
+  if (EPI == (int)Epi::Resid || EPI == (int)Epi::Jacobi)
+    r.b = e.b[row];
+  if (EPI == (int)Epi::Jacobi)
+  {
+    r.dinv = e.dinv[row];
+    r.x = e.xin[row];
+  }
+  if (EPI == (int)Epi::Sub)
+    r.x = e.y[row];
+  return r;
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue(const EpiArgs &e, const EpiRegs &g, int64_t row, double s)
 {
   if (EPI == (int)Epi::Spmv)
     e.y[row] = s;
   else if (EPI == (int)Epi::Resid)
-    e.y[row] = __dsub_rn(s, e.b[row]);
+    e.y[row] = __dsub_rn(s, g.b);
   else if (EPI == (int)Epi::Jacobi)
   {
-    const double r = __dsub_rn(s, e.b[row]);
-    double t = __dmul_rn(e.dinv[row], r);
+    const double r = __dsub_rn(s, g.b);
+    double t = __dmul_rn(g.dinv, r);
     if (e.omega != 1.)
       t = __dmul_rn(e.omega, t);
-    e.y[row] = __dsub_rn(e.xin[row], t);
+    e.y[row] = __dsub_rn(g.x, t);
   }
   else
-    e.y[row] = __dsub_rn(e.y[row], s);
+    e.y[row] = __dsub_rn(g.x, s);
 }
 
 template <int LPR, int EPI, typename OffT>
@@ -47,10 +71,13 @@ __global__ void __launch_bounds__(kBlock)
   const int64_t row = row_begin + ((int64_t)blockIdx.x * kBlock + threadIdx.x) / LPR;
   const int lane = threadIdx.x & (LPR - 1);
   double s0 = 0., s1 = 0.;
+  EpiRegs g;
   if (row < n_rows)
   {
     OffT k = rowptr[row] + lane;
     const OffT k1 = rowptr[row + 1];
+    if (lane == 0)
+      g = epilogue_load<EPI>(e, row);
     // two independent (col, val, x) chains per lane; a 4-way unroll measured 13 % slower on B200
     // (profiles/r01_lanes_sweep.md)
     for (; k + LPR < k1; k += 2 * LPR)
@@ -65,7 +92,7 @@ __global__ void __launch_bounds__(kBlock)
   }
   double s = subwarp_sum<LPR>(s0 + s1);
   if (lane == 0 && row < n_rows)
-    epilogue<EPI>(e, row, s);
+    epilogue<EPI>(e, g, row, s);
 }
 
 template <int LPR, int EPI, typename OffT>
@@ -132,6 +159,22 @@ int choose_lanes(int64_t n_rows, int64_t nnz)
   return lanes;
 }
 
+bool csr_uses_tile_kernel(const mfmgb_csr *A)
+{
+  if (!A->tile_ok || A->kernel_override == 0)
+    return false;
+  if (A->kernel_override == 1)
+    return true;
+  static const int env_kernel = [] {
+    const char *v = getenv("MFMGB_CSR_KERNEL");
+    return !v ? -1 : (!strcmp(v, "vec") ? 0 : (!strcmp(v, "tile") ? 1 : -1));
+  }();
+  if (env_kernel >= 0)
+    return env_kernel == 1;
+  // automatic: the TMA ring pays off on long streams; tiny operators stay on the direct-load kernel
+  return A->n_rows >= 32768 && A->nnz >= 8 * A->n_rows;
+}
+
 int csr_apply(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args, int64_t row_begin,
               int64_t row_end)
 {
@@ -141,6 +184,8 @@ int csr_apply(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, cons
     row_end = A->n_rows;
   if (row_begin < 0 || row_end > A->n_rows)
     return fail(ctx, MFMGB_ERR_INVALID, "csr_apply: row range out of bounds");
+  if (csr_uses_tile_kernel(A))
+    return csr_apply_tile(ctx, A, x, epi, args, row_begin, row_end);
   if (A->off64)
     return dispatch_epi<int64_t>(ctx, A, x, epi, args, row_begin, row_end);
   return dispatch_epi<int32_t>(ctx, A, x, epi, args, row_begin, row_end);
@@ -152,6 +197,8 @@ int finish_upload(mfmgb_ctx *ctx, mfmgb_csr *A)
 {
   A->lanes = A->lanes_override ? A->lanes_override : choose_lanes(A->n_rows, A->nnz);
   A->device = ctx->device;
+  MFMGB_CHECK(csr_measure_tiles(ctx, A));
+  csr_plan_tile(A);
   return MFMGB_OK;
 }
 
@@ -183,22 +230,26 @@ int upload_impl(mfmgb_ctx *ctx, int64_t n_rows, int64_t n_cols, const OffT *rowp
   MFMGB_CUDA(ctx, cudaMemsetAsync(A->col + nnz, 0, sizeof(int32_t) * pad, ctx->stream));
   MFMGB_CUDA(ctx, cudaMemcpyAsync(A->val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
   MFMGB_CUDA(ctx, cudaMemcpyAsync(A->col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+  // row offsets carry kRowptrPad entries of slack (the tile kernel copies whole 16-byte-granular chunks of them)
+  const size_t rp_len = (size_t)n_rows + 1 + kRowptrPad;
   if (A->off64)
   {
-    std::vector<int64_t> rp(rowptr, rowptr + n_rows + 1);
-    MFMGB_CUDA(ctx, cudaMalloc(&A->rowptr, sizeof(int64_t) * (size_t)(n_rows + 1)));
-    MFMGB_CUDA(ctx, cudaMemcpy(A->rowptr, rp.data(), sizeof(int64_t) * (size_t)(n_rows + 1), cudaMemcpyHostToDevice));
+    std::vector<int64_t> rp(rp_len, nnz);
+    std::copy(rowptr, rowptr + n_rows + 1, rp.begin());
+    MFMGB_CUDA(ctx, cudaMalloc(&A->rowptr, sizeof(int64_t) * rp_len));
+    MFMGB_CUDA(ctx, cudaMemcpy(A->rowptr, rp.data(), sizeof(int64_t) * rp_len, cudaMemcpyHostToDevice));
   }
   else
   {
-    std::vector<int32_t> rp((size_t)n_rows + 1);
+    std::vector<int32_t> rp(rp_len, (int32_t)nnz);
     for (int64_t i = 0; i <= n_rows; ++i)
       rp[i] = (int32_t)rowptr[i];
-    MFMGB_CUDA(ctx, cudaMalloc(&A->rowptr, sizeof(int32_t) * (size_t)(n_rows + 1)));
-    MFMGB_CUDA(ctx, cudaMemcpy(A->rowptr, rp.data(), sizeof(int32_t) * (size_t)(n_rows + 1), cudaMemcpyHostToDevice));
+    MFMGB_CUDA(ctx, cudaMalloc(&A->rowptr, sizeof(int32_t) * rp_len));
+    MFMGB_CUDA(ctx, cudaMemcpy(A->rowptr, rp.data(), sizeof(int32_t) * rp_len, cudaMemcpyHostToDevice));
   }
   MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  finish_upload(ctx, A);
+  A->padded = true;
+  MFMGB_CHECK(finish_upload(ctx, A));
   *out = A;
   return MFMGB_OK;
 }
@@ -234,7 +285,8 @@ extern "C"
     A->rowptr = rowptr_dev;
     A->off64 = false;
     A->owns = true;
-    finish_upload(ctx, A);
+    A->padded = false; // the caller's allocations have no slack: served by the direct-load kernel
+    MFMGB_CHECK(finish_upload(ctx, A));
     *out = A;
     return MFMGB_OK;
   }
@@ -339,8 +391,22 @@ extern "C"
       return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_csr_set_lanes_per_row: lanes must be 0,1,2,4,8,16,32");
     A->lanes_override = lanes;
     A->lanes = lanes ? lanes : choose_lanes(A->n_rows, A->nnz);
+    csr_plan_tile(A);
     return MFMGB_OK;
   }
+
+  MFMGB_API int mfmgb_csr_set_kernel(mfmgb_csr *A, int kernel)
+  {
+    if (!A || kernel < -1 || kernel > 1)
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_csr_set_kernel: kernel must be -1 (auto), 0 (vector) or 1 (tile)");
+    if (kernel == 1 && !A->tile_ok)
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_csr_set_kernel: the tile-streamed kernel cannot serve this matrix "
+                                                "(adopted arrays without slack, or rows too long for shared memory)");
+    A->kernel_override = kernel;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_csr_get_kernel(const mfmgb_csr *A) { return A && csr_uses_tile_kernel(A) ? 1 : 0; }
 
   MFMGB_API int mfmgb_csr_get_lanes_per_row(const mfmgb_csr *A) { return A ? A->lanes : 0; }
 

@@ -13,6 +13,12 @@ struct mfmgb_csr
   int lanes = 8;          // lanes per row used by the vector-CSR kernels
   int lanes_override = 0; // 0 = automatic
   int device = 0;
+  // tile-streamed kernel (csr_tile.cu)
+  bool padded = false;        // arrays carry slack for 16-byte-granular bulk copies (uploads do; adopted arrays do not)
+  int64_t tile_cap[6] = {0, 0, 0, 0, 0, 0}; // widest aligned nnz span of a tile, per lanes = 1, 2, 4, 8, 16, 32
+  bool tile_ok = false;       // the tile kernel can serve this matrix with the current lanes
+  int tile_stages = 0, tile_ctas = 0;
+  int kernel_override = -1;   // -1 = automatic, 0 = vector-CSR (csr.cu), 1 = tile-streamed (csr_tile.cu)
 };
 
 namespace mfmgb
@@ -38,4 +44,11 @@ struct EpiArgs
 int csr_apply(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args,
               int64_t row_begin = 0, int64_t row_end = -1);
 int choose_lanes(int64_t n_rows, int64_t nnz);
+// tile-streamed variant (csr_tile.cu): same contract as csr_apply; requires A->tile_ok
+int csr_apply_tile(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args, int64_t row_begin,
+                   int64_t row_end);
+int csr_measure_tiles(mfmgb_ctx *ctx, mfmgb_csr *A); // fills tile_cap (setup time, synchronises)
+void csr_plan_tile(mfmgb_csr *A);                    // sets tile_ok / tile_stages / tile_ctas for the current lanes
+int tile_cap_slot(int lanes);
+bool csr_uses_tile_kernel(const mfmgb_csr *A);
 } // namespace mfmgb

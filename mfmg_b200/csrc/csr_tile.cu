@@ -1,0 +1,433 @@
+// csr_tile.cu -- tile-streamed CSR SpMV family: col/val/rowptr staged into shared memory by TMA bulk copies.
+//
+// Why: the plain vector-CSR kernel (csr.cu) moves exactly the algorithmic bytes but is latency bound -- every
+// byte in flight needs a resident warp waiting on it (ncu, round 1: issue slots 23 % busy, 92 % occupancy, DRAM
+// 60 %).  Here the matrix stream does not occupy warps at all:
+//   * a tile is RPT = 256 / LPR consecutive rows; its col / val / rowptr ranges are contiguous in the CSR arrays,
+//     so ONE elected producer thread moves them with three cp.async.bulk copies (1-D TMA, 16-byte aligned ranges,
+//     L2 evict-first: the stream is read once and must not push x out of L2) into a ring of S stages, each
+//     guarded by a full/empty mbarrier pair;
+//   * 8 consumer warps wait on the full barrier, compute their rows out of shared memory with the same
+//     LPR-lanes-per-row mapping and shuffle tree as the vector-CSR kernel (so the x gather of a warp-level load
+//     stays within a few 128-byte lines), gather x through the read-only path, apply the fused epilogue and
+//     release the stage; the epilogue operands (b, D^-1, x_old) are requested before the wait;
+//   * CTAs are persistent (contiguous runs of tiles per CTA, so the j+-1 neighbour lines of x are re-used from L1).
+// Bytes in flight per SM = CTAs/SM x S x tile bytes (~170 KB by default) instead of 64 warps x 2 loads x 12 B.
+// Summation order depends only on (LPR, row length): deterministic, and graph replay == eager launch.
+#include <algorithm>
+#include <cstdlib>
+
+#include "csr.cuh"
+
+using namespace mfmgb;
+
+namespace mfmgb
+{
+namespace
+{
+constexpr int kConsumerWarps = 8;
+constexpr int kTileThreads = (kConsumerWarps + 1) * 32;
+constexpr int kUnroll = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  uint32_t done;
+  do
+  {
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                 "selp.u32 %0, 1, 0, p;\n"
+                 "}"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               :
+               : "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+
+template <typename OffT>
+struct TileArgs
+{
+  int64_t n_rows;             // rows of the matrix
+  int64_t row_begin, row_end; // rows this launch computes
+  int64_t tile_begin, n_tiles;
+  const OffT *rowptr;
+  const int *col;
+  const double *val;
+  const double *x;
+  int cap;    // elements per stage (multiple of 4)
+  int stages; // ring depth
+};
+
+__host__ __device__ constexpr size_t round_up_sz(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+template <int LPR, typename OffT>
+__host__ __device__ constexpr size_t tile_stage_bytes(int cap)
+{
+  return round_up_sz((size_t)cap * 12 + (size_t)(kConsumerWarps * 32 / LPR + 4) * sizeof(OffT), 128);
+}
+
+template <int LPR, int EPI, typename OffT>
+__global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArgs<OffT> a, const EpiArgs e)
+{
+  constexpr int RPT = kConsumerWarps * 32 / LPR; // rows per tile
+  constexpr int RP_ELEMS = RPT + 4;              // staged row offsets (a multiple of 4 => 16-byte multiple)
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int S = a.stages;
+  const size_t stage_bytes = tile_stage_bytes<LPR, OffT>(a.cap);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)S * stage_bytes);
+  uint64_t *empty = full + S;
+  if (threadIdx.x == 0)
+  {
+    for (int s = 0; s < S; ++s)
+    {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, kConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t tpc = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t t_begin = a.tile_begin + (int64_t)blockIdx.x * tpc;
+  const int64_t t_last = a.tile_begin + a.n_tiles;
+  const int64_t t_end = t_begin + tpc < t_last ? t_begin + tpc : t_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == kConsumerWarps)
+  {
+    // ---- producer: one elected thread streams the tiles of this CTA through the ring ----
+    if (lane != 0 || t_begin >= t_end)
+      return;
+    const uint64_t policy = policy_evict_first();
+    auto row_off = [&](int64_t r) { return a.rowptr[r < a.n_rows ? r : a.n_rows]; };
+    OffT k_lo = row_off(t_begin * RPT), k_hi = row_off((t_begin + 1) * RPT);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t t = t_begin; t < t_end; ++t)
+    {
+      const OffT k_next = t + 1 < t_end ? row_off((t + 2) * RPT) : k_hi; // requested one tile ahead of its use
+      mbar_wait(empty + s, ph ^ 1u);
+      const OffT a0 = k_lo & ~(OffT)3, a1 = (k_hi + 3) & ~(OffT)3;
+      const uint32_t span = (uint32_t)(a1 - a0);
+      unsigned char *st = smem + (size_t)s * stage_bytes;
+      mbar_expect_tx(full + s, span * 12u + (uint32_t)(RP_ELEMS * sizeof(OffT)));
+      bulk_g2s(st + (size_t)a.cap * 12, a.rowptr + t * RPT, (uint32_t)(RP_ELEMS * sizeof(OffT)), full + s, policy);
+      if (span)
+      {
+        bulk_g2s(st, a.val + a0, span * 8u, full + s, policy);
+        bulk_g2s(st + (size_t)a.cap * 8, a.col + a0, span * 4u, full + s, policy);
+      }
+      k_lo = k_hi;
+      k_hi = k_next;
+      if (++s == S)
+      {
+        s = 0;
+        ph ^= 1u;
+      }
+    }
+    return;
+  }
+
+  // ---- consumers: LPR lanes per row, one row per lane group and tile ----
+  const int lr = warp * (32 / LPR) + lane / LPR;
+  const int sub = lane % LPR;
+  int s = 0;
+  uint32_t ph = 0;
+  for (int64_t t = t_begin; t < t_end; ++t)
+  {
+    const int64_t row = t * RPT + lr;
+    const bool active = row >= a.row_begin && row < a.row_end;
+    const bool writer = active && sub == 0;
+    // epilogue operands are requested before the wait so that their latency overlaps it
+    double eb = 0., ed = 0., ex = 0.;
+    if (writer)
+    {
+      if (EPI == (int)Epi::Resid || EPI == (int)Epi::Jacobi)
+        eb = e.b[row];
+      if (EPI == (int)Epi::Jacobi)
+      {
+        ed = e.dinv[row];
+        ex = e.xin[row];
+      }
+      if (EPI == (int)Epi::Sub)
+        ex = e.y[row];
+    }
+    mbar_wait(full + s, ph);
+    const unsigned char *st = smem + (size_t)s * stage_bytes;
+    const double *sval = reinterpret_cast<const double *>(st);
+    const int *scol = reinterpret_cast<const int *>(st + (size_t)a.cap * 8);
+    const OffT *srp = reinterpret_cast<const OffT *>(st + (size_t)a.cap * 12);
+    double s0 = 0., s1 = 0.;
+    if (active)
+    {
+      const OffT base = srp[0] & ~(OffT)3;
+      int k = (int)(srp[lr] - base) + sub;
+      const int ke = (int)(srp[lr + 1] - base);
+      // kUnroll gathers of x in flight per lane (the gather latency under load is what the consumers wait on);
+      // even multiples of LPR go to s0, odd ones to s1, ascending: the vector-CSR kernel's summation order
+      for (; k < ke; k += kUnroll * LPR)
+      {
+        // No predicated memory operation in this block: lanes past the row end re-read the row's last entry and
+        // get their product zeroed afterwards.  (With predicated loads ptxas paired every gather with its FMA --
+        // one gather in flight per lane; unconditional, the kUnroll gathers issue back to back.)
+        int kk[kUnroll], c[kUnroll];
+        double v[kUnroll], xv[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+        {
+          kk[u] = min(k + u * LPR, ke - 1);
+          c[u] = scol[kk[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+          xv[u] = __ldg(a.x + c[u]);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+          v[u] = sval[kk[u]];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+          if (k + u * LPR >= ke)
+            v[u] = 0., xv[u] = 0.;
+#pragma unroll
+        for (int u = 0; u < kUnroll; u += 2)
+        {
+          s0 = fma(v[u], xv[u], s0);
+          s1 = fma(v[u + 1], xv[u + 1], s1);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0)
+      mbar_arrive(empty + s); // every lane of this warp has its col/val in registers: the stage may be refilled
+    const double sum = subwarp_sum<LPR>(s0 + s1);
+    if (writer)
+    {
+      if (EPI == (int)Epi::Spmv)
+        e.y[row] = sum;
+      else if (EPI == (int)Epi::Resid)
+        e.y[row] = __dsub_rn(sum, eb);
+      else if (EPI == (int)Epi::Jacobi)
+      {
+        const double r = __dsub_rn(sum, eb);
+        double tt = __dmul_rn(ed, r);
+        if (e.omega != 1.)
+          tt = __dmul_rn(e.omega, tt);
+        e.y[row] = __dsub_rn(ex, tt);
+      }
+      else
+        e.y[row] = __dsub_rn(ex, sum);
+    }
+    if (++s == S)
+    {
+      s = 0;
+      ph ^= 1u;
+    }
+  }
+}
+
+int env_int(const char *name, int dflt)
+{
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+template <int LPR, int EPI, typename OffT>
+int launch_tile(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArgs &e, int64_t r0, int64_t r1)
+{
+  constexpr int RPT = kConsumerWarps * 32 / LPR;
+  if (r1 <= r0)
+    return MFMGB_OK;
+  TileArgs<OffT> a;
+  a.n_rows = A->n_rows;
+  a.row_begin = r0;
+  a.row_end = r1;
+  a.tile_begin = r0 / RPT;
+  a.n_tiles = ceil_div(r1, RPT) - a.tile_begin;
+  a.rowptr = (const OffT *)A->rowptr;
+  a.col = A->col;
+  a.val = A->val;
+  a.x = x;
+  a.cap = A->tile_cap[tile_cap_slot(LPR)];
+  a.stages = A->tile_stages;
+  const size_t smem = (size_t)a.stages * tile_stage_bytes<LPR, OffT>(a.cap) + (size_t)a.stages * 16;
+  // per instantiation: opt in to large dynamic shared memory once, and ask how many CTAs are really co-resident
+  // (registers can allow fewer than the planned number; the grid must not spill into a second wave)
+  static bool attr_set = false;
+  static size_t occ_smem = 0;
+  static int occ_ctas = 0;
+  if (!attr_set)
+  {
+    MFMGB_CUDA(ctx, cudaFuncSetAttribute(csr_tile_kernel<LPR, EPI, OffT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(227 * 1024)));
+    attr_set = true;
+  }
+  if (occ_smem != smem)
+  {
+    MFMGB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ctas, csr_tile_kernel<LPR, EPI, OffT>,
+                                                                  kTileThreads, smem));
+    occ_smem = smem;
+  }
+  if (occ_ctas < 1)
+    return fail(ctx, MFMGB_ERR_CUDA, "csr_tile_kernel: %zu bytes of shared memory do not fit an SM", smem);
+  const int64_t grid = std::min<int64_t>(a.n_tiles, (int64_t)ctx->num_sms * std::min(A->tile_ctas, occ_ctas));
+  csr_tile_kernel<LPR, EPI, OffT><<<(unsigned)grid, kTileThreads, smem, ctx->stream>>>(a, e);
+  MFMGB_LAUNCHED(ctx);
+  return MFMGB_OK;
+}
+
+template <int EPI, typename OffT>
+int dispatch_lanes(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArgs &e, int64_t r0, int64_t r1)
+{
+  switch (A->lanes)
+  {
+  case 1:
+    return launch_tile<1, EPI, OffT>(ctx, A, x, e, r0, r1);
+  case 2:
+    return launch_tile<2, EPI, OffT>(ctx, A, x, e, r0, r1);
+  case 4:
+    return launch_tile<4, EPI, OffT>(ctx, A, x, e, r0, r1);
+  case 8:
+    return launch_tile<8, EPI, OffT>(ctx, A, x, e, r0, r1);
+  case 16:
+    return launch_tile<16, EPI, OffT>(ctx, A, x, e, r0, r1);
+  default:
+    return launch_tile<32, EPI, OffT>(ctx, A, x, e, r0, r1);
+  }
+}
+
+template <typename OffT>
+int dispatch_epi(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &e, int64_t r0, int64_t r1)
+{
+  switch (epi)
+  {
+  case Epi::Spmv:
+    return dispatch_lanes<(int)Epi::Spmv, OffT>(ctx, A, x, e, r0, r1);
+  case Epi::Resid:
+    return dispatch_lanes<(int)Epi::Resid, OffT>(ctx, A, x, e, r0, r1);
+  case Epi::Jacobi:
+    return dispatch_lanes<(int)Epi::Jacobi, OffT>(ctx, A, x, e, r0, r1);
+  default:
+    return dispatch_lanes<(int)Epi::Sub, OffT>(ctx, A, x, e, r0, r1);
+  }
+}
+
+// widest aligned nnz span of any tile of `rpt` rows (what one stage must hold)
+template <typename OffT>
+__global__ void __launch_bounds__(256) tile_span_kernel(int64_t n_rows, const OffT *__restrict__ rowptr, int rpt,
+                                                        unsigned long long *__restrict__ out_max)
+{
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t r0 = t * rpt;
+  if (r0 >= n_rows)
+    return;
+  const int64_t r1 = r0 + rpt < n_rows ? r0 + rpt : n_rows;
+  const int64_t span = (((int64_t)rowptr[r1] + 3) & ~(int64_t)3) - ((int64_t)rowptr[r0] & ~(int64_t)3);
+  atomicMax(out_max, (unsigned long long)span);
+}
+} // namespace
+
+int tile_cap_slot(int lanes)
+{
+  int slot = 0;
+  while ((1 << slot) < lanes)
+    ++slot;
+  return slot;
+}
+
+// Decide whether the tile-streamed kernel serves this matrix with its current lanes-per-row, and with which ring.
+void csr_plan_tile(mfmgb_csr *A)
+{
+  A->tile_ok = false;
+  if (!A->padded || A->n_rows == 0 || A->nnz == 0)
+    return;
+  const int rpt = kConsumerWarps * 32 / A->lanes;
+  const int64_t cap = A->tile_cap[tile_cap_slot(A->lanes)];
+  if (cap <= 0 || cap > (1 << 20))
+    return;
+  const size_t stage = round_up_sz((size_t)cap * 12 + (size_t)(rpt + 4) * (A->off64 ? 8 : 4), 128);
+  // Measured on B200 (profiles/r01_tile_sweep.md): what counts is the number of co-resident consumer warps (the x
+  // gather is their critical path), a ring of 2 already keeps HBM busy.  Take the largest CTA count <= 4 whose
+  // ring still has >= 2 stages (Q1 stencils: 4 CTAs x 2 stages x 21 KB; Q2: 2 CTAs x 2 stages x 49 KB).
+  const int want_stages = env_int("MFMGB_TILE_STAGES", 3);
+  const int want_ctas = std::max(1, std::min(env_int("MFMGB_TILE_CTAS", 4), 7));
+  int stages = 0, ctas = want_ctas;
+  for (; ctas >= 1; --ctas)
+  {
+    const size_t budget = (size_t)224 * 1024 / (size_t)ctas - 1024; // shared memory per CTA (1 KB reserved each)
+    stages = (int)std::min<size_t>((size_t)want_stages, budget / (stage + 16));
+    if (stages >= 2)
+      break;
+  }
+  if (ctas < 1)
+    return;
+  A->tile_stages = stages;
+  A->tile_ctas = ctas;
+  A->tile_ok = true;
+}
+
+int csr_measure_tiles(mfmgb_ctx *ctx, mfmgb_csr *A)
+{
+  for (int s = 0; s < 6; ++s)
+    A->tile_cap[s] = 0;
+  if (!A->padded || A->n_rows == 0)
+    return MFMGB_OK;
+  unsigned long long *dmax = nullptr;
+  MFMGB_CUDA(ctx, cudaMalloc(&dmax, sizeof(unsigned long long) * 6));
+  MFMGB_CUDA(ctx, cudaMemsetAsync(dmax, 0, sizeof(unsigned long long) * 6, ctx->stream));
+  for (int s = 0; s < 6; ++s)
+  {
+    const int rpt = kConsumerWarps * 32 / (1 << s);
+    const int64_t n_tiles = ceil_div(A->n_rows, rpt);
+    const unsigned nb = (unsigned)ceil_div(n_tiles, 256);
+    if (A->off64)
+      tile_span_kernel<int64_t><<<nb, 256, 0, ctx->stream>>>(A->n_rows, (const int64_t *)A->rowptr, rpt, dmax + s);
+    else
+      tile_span_kernel<int32_t><<<nb, 256, 0, ctx->stream>>>(A->n_rows, (const int32_t *)A->rowptr, rpt, dmax + s);
+    MFMGB_LAUNCHED(ctx);
+  }
+  unsigned long long hmax[6];
+  MFMGB_CUDA(ctx, cudaMemcpyAsync(hmax, dmax, sizeof(hmax), cudaMemcpyDeviceToHost, ctx->stream));
+  MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(dmax);
+  for (int s = 0; s < 6; ++s)
+    A->tile_cap[s] = (int64_t)hmax[s];
+  return MFMGB_OK;
+}
+
+int csr_apply_tile(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args, int64_t row_begin,
+                   int64_t row_end)
+{
+  if (A->off64)
+    return dispatch_epi<int64_t>(ctx, A, x, epi, args, row_begin, row_end);
+  return dispatch_epi<int32_t>(ctx, A, x, epi, args, row_begin, row_end);
+}
+} // namespace mfmgb

@@ -236,6 +236,16 @@ class SparseMatrixDevice:
     def lanes_per_row(self) -> int:
         return int(self.handle.lib.mfmgb_csr_get_lanes_per_row(self.ptr))
 
+    KERNEL_AUTO, KERNEL_VECTOR, KERNEL_TILE = -1, 0, 1
+
+    def set_kernel(self, kernel: int) -> None:
+        """Kernel family behind vmult & the fused epilogues: KERNEL_AUTO / KERNEL_VECTOR / KERNEL_TILE."""
+        check(self.handle.ctx, self.handle.lib.mfmgb_csr_set_kernel(self.ptr, kernel))
+
+    @property
+    def kernel(self) -> str:
+        return "tile" if int(self.handle.lib.mfmgb_csr_get_kernel(self.ptr)) == 1 else "vector"
+
     def free(self) -> None:
         if getattr(self, "ptr", None) and getattr(self.handle, "ctx", None):
             self.handle.lib.mfmgb_csr_destroy(self.handle.ctx, self.ptr)

@@ -15,14 +15,16 @@ def _n_gpus():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["auto", "tile"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_partitioned_hierarchy_on_gpus(world):
+def test_partitioned_hierarchy_on_gpus(world, kernel):
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world),
            os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    env = dict(os.environ, MFMGB_CSR_KERNEL=kernel)  # "tile": interior/boundary row ranges through csr_tile.cu
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, env=env)
     assert res.returncode == 0, res.stdout[-4000:]
     for r in range(world):
         assert f"RANK {r} OK" in res.stdout, res.stdout[-4000:]

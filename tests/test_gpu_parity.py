@@ -347,3 +347,78 @@ def test_full_size_properties_cfg1_like(handle):
     r = d.DeviceVector(handle, n)
     H.operators[0].vmult(r, x)
     assert r.l2_norm() <= 1e-8 * 1.0001 and it < 60
+
+
+def _ragged_matrix(rng, n_rows, n_cols, max_len, empty_frac=0.1):
+    """Random CSR with empty rows, very short and long rows (the tile kernel's staging must cope with all)."""
+    lens = rng.integers(0, max_len + 1, n_rows)
+    lens[rng.random(n_rows) < empty_frac] = 0
+    lens[rng.integers(0, n_rows, 3)] = max_len  # a few full-length rows
+    rowptr = np.zeros(n_rows + 1, dtype=np.int64)
+    np.cumsum(lens, out=rowptr[1:])
+    col = np.concatenate([np.sort(rng.choice(n_cols, int(k), replace=False)) for k in lens] + [np.zeros(0, int)])
+    val = rng.standard_normal(int(rowptr[-1]))
+    return rowptr, col.astype(np.int32), val
+
+
+@pytest.mark.parametrize("n_rows,n_cols,max_len", [(1000, 1000, 40), (4099, 4099, 9), (777, 1500, 130), (5, 5, 3),
+                                                   (2500, 2500, 300)])
+def test_tile_kernel_matches_vector_kernel_bitwise(handle, n_rows, n_cols, max_len):
+    """csr_tile.cu (TMA-staged tiles) against csr.cu (direct loads): same summation order => identical bits, for
+    every lanes-per-row choice and every fused epilogue; both against the oracle at 1e-12."""
+    d = _dev()
+    rng = np.random.default_rng(n_rows + max_len)
+    rowptr, col, val = _ragged_matrix(rng, n_rows, n_cols, max_len)
+    A = d.SparseMatrixDevice(handle, n_rows, n_cols, rowptr, col, val)
+    lib, ctx = handle.lib, handle.ctx
+    x_h, b_h, y0_h = rng.standard_normal(n_cols), rng.standard_normal(n_rows), rng.standard_normal(n_rows)
+    dinv_h = rng.standard_normal(n_rows)
+    x, b = d.DeviceVector.from_host(handle, x_h), d.DeviceVector.from_host(handle, b_h)
+    ref = oracle.spmv(n_rows, rowptr, col, val, x_h)
+    scale = np.abs(oracle.spmv(n_rows, rowptr, col, np.abs(val), np.abs(x_h))).max() + 1.0
+    n_tile = 0
+    for lanes in (1, 2, 4, 8, 16, 32):
+        A.set_lanes_per_row(lanes)
+        out = {}
+        for kern in (d.SparseMatrixDevice.KERNEL_VECTOR, d.SparseMatrixDevice.KERNEL_TILE):
+            try:
+                A.set_kernel(kern)
+            except d.MfmgError:
+                assert kern == d.SparseMatrixDevice.KERNEL_TILE  # rows too long for the ring at this lanes value
+                continue
+            assert A.kernel == ("tile" if kern else "vector")
+            y = d.DeviceVector(handle, n_rows)
+            A.vmult(y, x)
+            r = d.DeviceVector(handle, n_rows)
+            d.check(ctx, lib.mfmgb_residual_neg(ctx, A.ptr, x.ptr, b.ptr, r.ptr))
+            z = d.DeviceVector.from_host(handle, y0_h)
+            d.check(ctx, lib.mfmgb_prolong_correct(ctx, A.ptr, x.ptr, z.ptr))
+            res = [y.to_host(), r.to_host(), z.to_host()]
+            if n_rows == n_cols:
+                J = ctypes_jacobi(d, handle, dinv_h)
+                w = d.DeviceVector(handle, n_rows)
+                d.check(ctx, lib.mfmgb_jacobi_apply_oop(ctx, J, A.ptr, b.ptr, x.ptr, w.ptr))
+                res.append(w.to_host())
+                d.check(ctx, lib.mfmgb_jacobi_destroy(ctx, J))
+            out[kern] = res
+        v = out[d.SparseMatrixDevice.KERNEL_VECTOR]
+        assert np.max(np.abs(v[0] - ref)) <= TOL_OP * scale
+        assert np.max(np.abs(v[1] - (ref - b_h))) <= TOL_OP * scale
+        assert np.max(np.abs(v[2] - (y0_h - ref))) <= TOL_OP * scale
+        if d.SparseMatrixDevice.KERNEL_TILE in out:
+            n_tile += 1
+            for a_, b_ in zip(v, out[d.SparseMatrixDevice.KERNEL_TILE]):
+                assert np.array_equal(a_, b_), f"lanes={lanes}"
+    assert n_tile >= 2
+    A.set_kernel(d.SparseMatrixDevice.KERNEL_AUTO)
+
+
+def ctypes_jacobi(d, handle, dinv_h):
+    """A Jacobi object with a prescribed D^-1 (from the diagonal 1/dinv)."""
+    import ctypes
+
+    diag = d.DeviceVector.from_host(handle, 1.0 / dinv_h)
+    J = ctypes.c_void_p()
+    d.check(handle.ctx, handle.lib.mfmgb_jacobi_setup_diag(handle.ctx, diag.ptr, len(dinv_h), 1.0, ctypes.byref(J)))
+    handle.synchronize()
+    return J
