@@ -222,7 +222,9 @@ int upload_impl(mfmgb_ctx *ctx, int64_t n_rows, int64_t n_cols, const OffT *rowp
   A->n_rows = n_rows;
   A->n_cols = n_cols;
   A->nnz = nnz;
-  A->off64 = nnz >= ((int64_t)1 << 31) - 64;
+  // 64-bit row offsets from 2^31 non-zeros on (MFMGB_FORCE_OFF64=1 forces them: lets small tests cover that path)
+  const char *force64 = getenv("MFMGB_FORCE_OFF64");
+  A->off64 = nnz >= ((int64_t)1 << 31) - 64 || (force64 && force64[0] == '1');
   const size_t pad = 8;
   MFMGB_CUDA(ctx, cudaMalloc(&A->val, sizeof(double) * (size_t)(nnz + pad)));
   MFMGB_CUDA(ctx, cudaMalloc(&A->col, sizeof(int32_t) * (size_t)(nnz + pad)));

@@ -181,7 +181,13 @@ int apply_level(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, 
 
 int run_vcycle(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x)
 {
-  if (!H->use_graph || H->distributed) // (NCCL + two streams are launched eagerly in the partitioned mode)
+  // Partitioned mode launches eagerly (NCCL + two streams).  MFMGB_DIST_GRAPH=1 captures that cycle as well
+  // (experimental: the first attempt hung on 2 GPUs, profiles/r01_summary.md).
+  static const bool dist_graph = [] {
+    const char *v = getenv("MFMGB_DIST_GRAPH");
+    return v && v[0] == '1';
+  }();
+  if (!H->use_graph || (H->distributed && !dist_graph))
     return apply_level(ctx, H, b, x, 0);
   if (!H->graph_exec || H->graph_b != b || H->graph_x != x)
   {

@@ -4,6 +4,7 @@ operators that are uploaded once; nothing here is on the V-cycle hot path and no
 fallback for it."""
 from .amge import block_agglomerates, build_restrictor, galerkin, transpose  # noqa: F401
 from .problems import (HostCSR, LaplaceProblem, assemble, boundary_mask,  # noqa: F401
-                       coefficient_table, material_value, reference_matrices)
+                       coefficient_table, material_value, num_threads, reference_matrices,
+                       set_num_threads)
 from .partition import LocalPart, make_parts, partition_two_level, slab_row_ranges  # noqa: F401,E402
 from .slab import build_slab_part  # noqa: F401,E402

@@ -175,14 +175,57 @@ def build_restrictor(problem: LaplaceProblem, block, n_eigenvectors: int,
     return HostCSR(n_agg * ne, problem.n, rowptr, col, val)
 
 
-def galerkin(A: HostCSR, R: HostCSR) -> HostCSR:
-    """A_c = R (A R^T): include/mfmg/common/hierarchy.hpp:225,230 (no dropping)."""
-    a = A.to_scipy()
+def galerkin(A: HostCSR, R: HostCSR, max_chunk_nnz: int = 400_000_000) -> HostCSR:
+    """A_c = R (A R^T): include/mfmg/common/hierarchy.hpp:225,230 (no dropping).
+
+    Small operators: two sparse products.  Large ones (cfg3: 3.6e9 non-zeros, past scipy's int32 index range and
+    ~100 GB of temporaries) are processed in blocks of coarse rows: a block of R only touches a contiguous range
+    of fine rows, so it is multiplied with a zero-copy row slice of A and then with R^T."""
+    import scipy.sparse as sp
+
     r = R.to_scipy()
-    ap = a @ r.T.tocsr()
-    ac = (r @ ap).tocsr()
-    ac.sort_indices()
+    if A.nnz <= max_chunk_nnz:
+        a = A.to_scipy()
+        ap = a @ r.T.tocsr()
+        ac = (r @ ap).tocsr()
+        ac.sort_indices()
+        return HostCSR.from_scipy(ac)
+    rt = r.T.tocsr()
+    ac = galerkin_rows(A, R, rt, 0, R.n_rows, max_chunk_nnz)
     return HostCSR.from_scipy(ac)
+
+
+def galerkin_rows(A: HostCSR, R: HostCSR, rt, c0: int, c1: int, max_chunk_nnz: int = 400_000_000):
+    """Rows [c0, c1) of R (A R^T) as a scipy CSR matrix (sorted columns); `rt` = R^T in CSR form.  Works in blocks
+    of coarse rows on zero-copy row slices of A, so A may hold more than 2^31 non-zeros."""
+    import scipy.sparse as sp
+
+    n_c = R.n_rows
+    span_nnz = int(A.rowptr[-1])
+    n_chunks = int(min(max(c1 - c0, 1), max(1, -(-span_nnz // (max_chunk_nnz // 4)))))
+    bounds = np.linspace(c0, c1, n_chunks + 1).astype(np.int64)
+    blocks = []
+    for b0, b1 in zip(bounds[:-1], bounds[1:]):
+        if b1 <= b0:
+            continue
+        k0, k1 = int(R.rowptr[b0]), int(R.rowptr[b1])
+        if k1 == k0:
+            blocks.append(sp.csr_matrix((int(b1 - b0), n_c)))
+            continue
+        cols = R.col[k0:k1]
+        p0, p1 = int(cols.min()), int(cols.max()) + 1
+        a0, a1 = int(A.rowptr[p0]), int(A.rowptr[p1])
+        if a1 - a0 >= 2 ** 31 - 1:
+            raise MemoryError("galerkin: a block of coarse rows spans more than 2^31 non-zeros of A; "
+                              "lower max_chunk_nnz")
+        a_sub = sp.csr_matrix((A.val[a0:a1], A.col[a0:a1], (A.rowptr[p0:p1 + 1] - a0).astype(np.int32)),
+                              shape=(p1 - p0, A.n_cols), copy=False)
+        r_sub = sp.csr_matrix((R.val[k0:k1], (cols - p0).astype(np.int32),
+                               (R.rowptr[b0:b1 + 1] - k0).astype(np.int32)), shape=(int(b1 - b0), p1 - p0))
+        blocks.append((r_sub @ (a_sub @ rt)).tocsr())  # the reference's association: R (A R^T)
+    ac = sp.vstack(blocks, format="csr") if blocks else sp.csr_matrix((0, n_c))
+    ac.sort_indices()
+    return ac
 
 
 def transpose(R: HostCSR) -> HostCSR:

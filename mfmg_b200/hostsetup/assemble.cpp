@@ -14,6 +14,9 @@
 // what makes nnz = (3N-2)^d for Q1.
 //
 // Built with plain g++ -fopenmp into libmfmg_b200_host.so; no CUDA here.
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -67,6 +70,25 @@ inline void range_1d(const Grid &g, int d, int64_t i, int64_t &lo, int64_t &hi, 
 
 extern "C"
 {
+  // launchers such as torchrun export OMP_NUM_THREADS=1; the setup path sets its own thread count
+  void hs_set_num_threads(int n)
+  {
+#ifdef _OPENMP
+    if (n > 0)
+      omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+  }
+  int hs_get_max_threads(void)
+  {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+  }
+
   // Row offsets of the rows [row_begin, row_end) of the global matrix (lexicographic numbering).
   // rowptr has row_end - row_begin + 1 entries and starts at 0.  Returns nnz of those rows.
   int64_t hs_assemble_count(int dim, int degree, const int64_t *cells, int64_t row_begin,

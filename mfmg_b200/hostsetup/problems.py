@@ -38,8 +38,19 @@ def _lib():
                                          ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_void_p]
+        lib.hs_set_num_threads.argtypes = [ctypes.c_int]
+        lib.hs_get_max_threads.restype = ctypes.c_int
         _LIB = lib
     return _LIB
+
+
+def set_num_threads(n: int) -> None:
+    """OpenMP threads of the assembly loops (launchers like torchrun export OMP_NUM_THREADS=1)."""
+    _lib().hs_set_num_threads(int(n))
+
+
+def num_threads() -> int:
+    return int(_lib().hs_get_max_threads())
 
 
 # ----------------------------------------------------------------------------------------------

@@ -21,11 +21,51 @@ The result is identical to slicing the global operators (tests/test_distributed_
 from __future__ import annotations
 
 import numpy as np
-import scipy.sparse as sp
-
-from .amge import build_restrictor
-from .partition import LocalPart, _localise, finalize_plan, slab_row_ranges
+from .amge import build_restrictor, galerkin_rows
+from .partition import LocalPart, finalize_plan, slab_row_ranges
 from .problems import HostCSR, LaplaceProblem
+
+
+_BLOCK = 1 << 26  # non-zeros per block of the streaming helpers below
+
+
+def _outside(col: np.ndarray, k0: int, k1: int, lo: int, hi: int) -> np.ndarray:
+    """Sorted unique column indices in col[k0:k1] that are not in [lo, hi)."""
+    found = [np.zeros(0, dtype=col.dtype)]
+    for b0 in range(k0, k1, _BLOCK):
+        c = col[b0:min(k1, b0 + _BLOCK)]
+        found.append(np.unique(c[(c < lo) | (c >= hi)]))
+    return np.unique(np.concatenate(found))
+
+
+def _localise_ext(M: HostCSR, r0: int, r1: int, lo: int, hi: int, ghost: np.ndarray) -> HostCSR:
+    """Rows [r0, r1) of M; column c becomes c - lo when lo <= c < hi (owned), else (hi - lo) + position in `ghost`."""
+    rp = M.rowptr[r0:r1 + 1]
+    k0, k1 = int(rp[0]), int(rp[-1])
+    loc = np.empty(k1 - k0, dtype=np.int32)
+    for b0 in range(k0, k1, _BLOCK):
+        b1 = min(k1, b0 + _BLOCK)
+        c = M.col[b0:b1]
+        owned = (c >= lo) & (c < hi)
+        out = (c - lo).astype(np.int32)
+        if not owned.all():
+            g = c[~owned]
+            pos = np.searchsorted(ghost, g)
+            assert np.all(ghost[np.minimum(pos, len(ghost) - 1)] == g)
+            out[~owned] = (hi - lo) + pos
+        loc[b0 - k0:b1 - k0] = out
+    return HostCSR(r1 - r0, (hi - lo) + len(ghost), np.ascontiguousarray(rp - k0), loc, M.val[k0:k1])
+
+
+def _rows_with_ghosts(A_loc: HostCSR, n_owned: int) -> np.ndarray:
+    """Sorted rows of A_loc that reference a ghost column (>= n_owned)."""
+    rows = [np.zeros(0, dtype=np.int64)]
+    nnz = A_loc.nnz
+    for b0 in range(0, nnz, _BLOCK):
+        k = np.flatnonzero(A_loc.col[b0:min(nnz, b0 + _BLOCK)] >= n_owned) + b0
+        if len(k):
+            rows.append(np.unique(np.searchsorted(A_loc.rowptr, k, side="right") - 1))
+    return np.unique(np.concatenate(rows))
 
 
 def build_slab_part(degree: int, cells, h, material: str, block, n_eigenvectors: int, world: int, rank: int, gather,
@@ -54,15 +94,16 @@ def build_slab_part(degree: int, cells, h, material: str, block, n_eigenvectors:
     n_global = int(np.prod(nodes))
     nc_global = int(coarse_off[-1])
 
-    # global-column views of the ext operators
-    A_g = HostCSR(ext.A.n_rows, n_global, ext.A.rowptr, (ext.A.col.astype(np.int64) + off), ext.A.val)
-    R_g = HostCSR(R_ext.n_rows, n_global, R_ext.rowptr, (R_ext.col.astype(np.int64) + off), R_ext.val)
-    ka0, ka1 = int(A_g.rowptr[rb - off]), int(A_g.rowptr[re_ - off])
-    kr0, kr1 = int(R_g.rowptr[cb - coff]), int(R_g.rowptr[ce - coff])
-    cols = np.concatenate([A_g.col[ka0:ka1], R_g.col[kr0:kr1]])
-    ghost_global = np.unique(cols[(cols < rb) | (cols >= re_)])
-    A_loc = _localise(A_g, slice(rb - off, re_ - off), rb, re_, ghost_global)
-    R_loc = _localise(R_g, slice(cb - coff, ce - coff), rb, re_, ghost_global)
+    # Owned rows of the sub-box operators with columns renumbered [owned | ghost].  Everything works on the sub-box's
+    # own int32 columns, in bounded blocks of non-zeros: at 2 ranks of cfg3 the sub-box operator has 2e9 non-zeros
+    # and whole-array int64 temporaries would cost tens of GB per rank.
+    lo, hi = rb - off, re_ - off            # owned node range in sub-box numbering
+    ka0, ka1 = int(ext.A.rowptr[lo]), int(ext.A.rowptr[hi])
+    kr0, kr1 = int(R_ext.rowptr[cb - coff]), int(R_ext.rowptr[ce - coff])
+    ghost_ext = np.union1d(_outside(ext.A.col, ka0, ka1, lo, hi), _outside(R_ext.col, kr0, kr1, lo, hi))
+    ghost_global = ghost_ext.astype(np.int64) + off
+    A_loc = _localise_ext(ext.A, lo, hi, lo, hi, ghost_ext)
+    R_loc = _localise_ext(R_ext, cb - coff, ce - coff, lo, hi, ghost_ext)
 
     # P rows of the owned nodes, global coarse columns
     Rs = R_ext.to_scipy()
@@ -72,11 +113,8 @@ def build_slab_part(degree: int, cells, h, material: str, block, n_eigenvectors:
     P_loc = HostCSR(Pl.shape[0], nc_global, np.ascontiguousarray(Pl.indptr, dtype=np.int64),
                     np.ascontiguousarray(Pl.indices + coff, dtype=np.int32), np.ascontiguousarray(Pl.data))
 
-    # owned rows of A_c = R A R^T
-    As = ext.A.to_scipy()
-    rows = Rs[cb - coff:ce - coff]
-    ac_rows = (rows @ (As @ Rt)).tocsr()
-    ac_rows.sort_indices()
+    # owned rows of A_c = R (A R^T), in blocks of coarse rows (the sub-box operator can exceed 2^31 non-zeros)
+    ac_rows = galerkin_rows(ext.A, R_ext, Rt, cb - coff, ce - coff)
     blocks = gather((ac_rows.indptr.astype(np.int64), (ac_rows.indices.astype(np.int64) + coff), ac_rows.data))
     rp = [np.zeros(1, dtype=np.int64)]
     cols_all, vals_all = [], []
@@ -94,12 +132,7 @@ def build_slab_part(degree: int, cells, h, material: str, block, n_eigenvectors:
         part.neighbors.append(int(q))
         part.recv_counts.append(int(np.sum(owner == q)))
     n_owned = re_ - rb
-    gmask = A_loc.col >= n_owned
-    has_ghost = np.zeros(n_owned, dtype=bool)
-    if gmask.any():
-        row_of = np.repeat(np.arange(n_owned), np.diff(A_loc.rowptr))
-        has_ghost[np.unique(row_of[gmask])] = True
-    idx = np.flatnonzero(has_ghost)
+    idx = _rows_with_ghosts(A_loc, n_owned)
     lo_rows, hi_rows = idx[idx < n_owned // 2], idx[idx >= n_owned // 2]
     part.boundary_lo = int(lo_rows.max() + 1) if len(lo_rows) else 0
     part.boundary_hi = int(hi_rows.min()) if len(hi_rows) else n_owned

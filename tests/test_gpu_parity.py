@@ -422,3 +422,34 @@ def ctypes_jacobi(d, handle, dinv_h):
     d.check(handle.ctx, handle.lib.mfmgb_jacobi_setup_diag(handle.ctx, diag.ptr, len(dinv_h), 1.0, ctypes.byref(J)))
     handle.synchronize()
     return J
+
+
+def test_int64_row_offsets_path(handle, monkeypatch):
+    """Operators past 2^31 non-zeros (cfg3: 3.6e9) use 64-bit row offsets; MFMGB_FORCE_OFF64 puts a small problem on
+    that code path: both kernel families, the Jacobi setup, the transpose, the dense factorisation and a V-cycle."""
+    import ctypes
+
+    d = _dev()
+    monkeypatch.setenv("MFMGB_FORCE_OFF64", "1")
+    P, R, Ac = two_level_problem(3, 1, 12, 4, 2, "linear")
+    n = P.n
+    A = (P.A.rowptr, P.A.col, P.A.val)
+    rng = np.random.default_rng(3)
+    x_h, b_h = rng.standard_normal(n), rng.standard_normal(n)
+    Ad = d.SparseMatrixDevice.from_host(handle, P.A)
+    is64 = ctypes.c_int(0)
+    d.check(handle.ctx, handle.lib.mfmgb_csr_device_arrays(Ad.ptr, None, None, None, ctypes.byref(is64)))
+    assert is64.value == 1
+    x, b = d.DeviceVector.from_host(handle, x_h), d.DeviceVector.from_host(handle, b_h)
+    y = d.DeviceVector(handle, n)
+    for kern in (d.SparseMatrixDevice.KERNEL_VECTOR, d.SparseMatrixDevice.KERNEL_TILE):
+        Ad.set_kernel(kern)
+        Ad.vmult(y, x)
+        assert rel_err(y.to_host(), oracle.spmv(n, *A, x_h)) < TOL_OP
+        sm = d.CudaSmoother(d.CudaMatrixOperator(Ad), {})
+        d.check(handle.ctx, handle.lib.mfmgb_jacobi_apply_oop(handle.ctx, sm.ptr, Ad.ptr, b.ptr, x.ptr, y.ptr))
+        assert rel_err(y.to_host(), oracle.jacobi_apply(n, *A, b_h, x_h)) < TOL_OP
+    H = d.Hierarchy.from_host(handle, P.A, R, Ac, {"is preconditioner": True})
+    Ho = oracle_hierarchy(P, R, Ac, 1, True)
+    H.vmult(y, b)
+    assert rel_err(y.to_host(), Ho.vmult(b_h)) < TOL_OP

@@ -75,3 +75,12 @@ def test_partial_blocks_and_eigensolver_modes():
     for mode in ("free", "host_lapack", "device_lapack"):
         R = hs.build_restrictor(P, (4, 4), 1, eigensolver=mode)
         assert R.n_rows == 9 and np.all(np.isfinite(R.val))
+
+
+def test_chunked_galerkin_is_bitwise_the_plain_product():
+    """The blocked R (A R^T) used past scipy's int32 range (cfg3) equals the two-product form bit for bit."""
+    P = hs.LaplaceProblem.create(3, 1, 16, "discontinuous")
+    R = hs.build_restrictor(P, (4, 4, 4), 2)
+    a = hs.galerkin(P.A, R)
+    b = hs.galerkin(P.A, R, max_chunk_nnz=20000)
+    assert np.array_equal(a.rowptr, b.rowptr) and np.array_equal(a.col, b.col) and np.array_equal(a.val, b.val)
