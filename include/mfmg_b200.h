@@ -141,8 +141,19 @@ extern "C"
   /* coef: host array [n_cells][(degree+1)^dim]; constrained: host uint8[n]; h: cell size per direction */
   MFMGB_API int mfmgb_mf_laplace_create(mfmgb_ctx *ctx, int dim, int degree, const int64_t *cells, const double *h,
                                         const double *coef, const uint8_t *constrained, mfmgb_mf **out);
+  /* the same operator on one z-slab of a row-partitioned grid (3D Q1): `cells` is the local box (the owned cell layers
+   * plus one layer below when there is a lower neighbour), node planes [own_plane_begin, own_plane_end) of the box are
+   * owned, the others are ghost planes; vectors, `constrained` and the Jacobi data use the layout
+   * [owned planes | ghost planes below | ghost planes above] -- the [owned | ghost] layout of mfmgb_halo_create */
+  MFMGB_API int mfmgb_mf_laplace_create_slab(mfmgb_ctx *ctx, int dim, int degree, const int64_t *cells, const double *h,
+                                             const double *coef, const uint8_t *constrained, int64_t own_plane_begin,
+                                             int64_t own_plane_end, mfmgb_mf **out);
   MFMGB_API int mfmgb_mf_destroy(mfmgb_ctx *ctx, mfmgb_mf *M);
-  MFMGB_API int64_t mfmgb_mf_size(const mfmgb_mf *M);
+  MFMGB_API int64_t mfmgb_mf_size(const mfmgb_mf *M);        /* rows = owned nodes */
+  MFMGB_API int64_t mfmgb_mf_vector_size(const mfmgb_mf *M); /* owned + ghost nodes */
+  /* which kernel serves the operator: 0 = generic colour-phase cell kernel (2D, Q2), 1 = 3D Q1 node-owner z-sweep with a
+   * per-cell coefficient, 2 = the same with the per-quadrature-point table */
+  MFMGB_API int mfmgb_mf_kernel(const mfmgb_mf *M);
   MFMGB_API int mfmgb_mf_apply(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, double *y);
   /* diagonal with constrained entries set to 1 (compute_diagonal) into a device vector */
   MFMGB_API int mfmgb_mf_diagonal(mfmgb_ctx *ctx, const mfmgb_mf *M, double *diag_dev);

@@ -86,6 +86,9 @@ SIGNATURES = {
     "mfmgb_dense_size": (_i64, [_vp]),
     "mfmgb_dense_num_swaps": (_i64, [_vp]),
     "mfmgb_mf_laplace_create": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _pp]),
+    "mfmgb_mf_laplace_create_slab": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _i64, _i64, _pp]),
+    "mfmgb_mf_vector_size": (_i64, [_vp]),
+    "mfmgb_mf_kernel": (_int, [_vp]),
     "mfmgb_mf_destroy": (_int, [_vp, _vp]),
     "mfmgb_mf_size": (_i64, [_vp]),
     "mfmgb_mf_apply": (_int, [_vp, _vp, _vp, _vp]),

@@ -3,13 +3,15 @@
 // Replaces mfmg::CudaSolver "lu_dense" (source/cuda/cuda_solver.cu:496-515 -> lu_factorization,
 // source/cuda/dealii_operator_device_helpers.cu:169-228), which runs csr2dense + getrf + getrs and
 // four cudaMalloc/cudaFree on EVERY V-cycle.  Here:
-//   setup  (once):  CSR -> dense, blocked right-looking LU with partial pivoting (P A = L U), then the
-//                   triangular factors are inverted explicitly (recursive block doubling, all GEMM)
-//                   and packed into one n x n array:  strictly-lower = L^-1 (unit diagonal implied),
-//                   upper incl. diagonal = U^-1.
-//   solve  (hot):   y = L^-1 (P b);  x = U^-1 y  -- two bandwidth-bound triangular GEMVs that read
-//                   the packed array exactly once (8 n^2 bytes), with no sequential dependency chain
-//                   (a substitution solve would need n/nb grid-wide steps per triangle).
+//   setup  (once):  CSR -> dense, blocked right-looking LU with partial pivoting (P A = L U), the triangular
+//                   factors are inverted explicitly (recursive block doubling, all GEMM), multiplied
+//                   (U^-1 L^-1, only the k >= max(i,j) part of the product) and the row permutation is folded
+//                   into the columns:  M = U^-1 L^-1 P  (= A^-1), one n x n row-major array.
+//   solve  (hot):   x = M b  -- ONE bandwidth-bound GEMV that reads 8 n^2 bytes (the same bytes a pair of
+//                   triangular applies reads) with perfectly balanced rows and no sequential dependency chain
+//                   (a substitution solve needs n/nb grid-wide steps per triangle; two triangular GEMVs need
+//                   three launches and have triangular load imbalance: measured 0.044 ms vs 0.022 ms at n = 4096).
+//                   Multi-GPU: every rank holds M, computes a contiguous block of rows, one all-gather.
 // No cuSOLVER / cuBLAS.  Tensor cores are not used (FP64, and the hot part is a GEMV).
 #include <algorithm>
 #include <vector>
@@ -196,7 +198,8 @@ constexpr int TM = 64, TN = 64, TK = 16;
 
 __device__ __forceinline__ void gemm_tile(int64_t M, int64_t N, int64_t K, const double *__restrict__ A, int64_t lda,
                                           const double *__restrict__ B, int64_t ldb, double *__restrict__ C,
-                                          int64_t ldc, double alpha, double beta, int64_t tile_m, int64_t tile_n)
+                                          int64_t ldc, double alpha, double beta, int64_t tile_m, int64_t tile_n,
+                                          int64_t k_begin = 0)
 {
   __shared__ double As[TK][TM + 1];
   __shared__ double Bs[TK][TN];
@@ -209,7 +212,7 @@ __device__ __forceinline__ void gemm_tile(int64_t M, int64_t N, int64_t K, const
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       acc[i][j] = 0.;
-  for (int64_t k0 = 0; k0 < K; k0 += TK)
+  for (int64_t k0 = k_begin; k0 < K; k0 += TK)
   {
     // A tile: 64 rows x 16 k  (each thread loads 4 elements)
 #pragma unroll
@@ -382,108 +385,96 @@ __global__ void __launch_bounds__(256) tri_level_kernel(const double *__restrict
   }
 }
 
-__global__ void __launch_bounds__(256) tri_pack_kernel(const double *__restrict__ linv, const double *__restrict__ uinv,
-                                                       double *__restrict__ out, int64_t lda, int64_t n)
+// Inv = U^-1 L^-1: entry (i, j) only sums over k >= max(i, j) (U^-1 is upper, L^-1 lower triangular)
+__global__ void __launch_bounds__(256) inv_product_kernel(const double *__restrict__ uinv,
+                                                          const double *__restrict__ linv, double *__restrict__ out,
+                                                          int64_t lda, int64_t n)
 {
-  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.y * TM, n0 = (int64_t)blockIdx.x * TN;
+  const int64_t kb = (m0 > n0 ? m0 : n0) / TK * TK;
+  gemm_tile(n, n, n, uinv, lda, linv, lda, out, lda, 1., 0., blockIdx.y, blockIdx.x, kb);
+}
+
+// M[i][perm[k]] = Inv[i][k]  (x = Inv (P b) with (P b)[k] = b[perm[k]]); padding columns are zeroed
+__global__ void __launch_bounds__(256) fold_perm_kernel(const double *__restrict__ inv, const int *__restrict__ perm,
+                                                        double *__restrict__ out, int64_t lda, int64_t n)
+{
+  const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const int64_t i = blockIdx.y;
-  if (j < lda)
-    out[i * lda + j] = j >= n ? 0. : (j < i ? linv[i * lda + j] : uinv[i * lda + j]);
+  if (k < n)
+    out[i * lda + perm[k]] = inv[i * lda + k];
+  else if (k < lda)
+    out[i * lda + k] = 0.;
 }
 
 // ---------------------------------------------------------------------------------------------
-// solve: pb = b[perm];  y = L^-1 pb;  x = U^-1 y
+// solve: x = M b.  TPR threads per row, 128-bit loads, four independent accumulators per thread and a fixed
+// reduction tree (deterministic).  Rows [row0, row0 + n_out) go to out[0 .. n_out); rows >= n give 0.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) permute_kernel(int64_t n, const int *__restrict__ perm,
-                                                      const double *__restrict__ b, double *__restrict__ pb)
-{
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i < n)
-    pb[i] = b[perm[i]];
-}
-
-// TPR threads cooperate on one row.  LOWER: out[i] = v[i] + sum_{j<i} M[i][j] v[j];
-// UPPER: out[i] = sum_{j>=i} M[i][j] v[j].  Fixed reduction tree => deterministic.
-// row split of the multi-GPU solve: slot b of rank r is row r*h + b (b < h) or row n - (r+1)*h + (b - h)
-__device__ __host__ __forceinline__ int64_t split_row(int64_t n, int64_t h, int r, int64_t b)
-{
-  return b < h ? (int64_t)r * h + b : n - (int64_t)(r + 1) * h + (b - h);
-}
-
-template <bool LOWER, int TPR>
-__global__ void __launch_bounds__(256) tri_gemv_kernel(int64_t n, const double *__restrict__ M, int64_t lda,
-                                                       const double *__restrict__ v, double *__restrict__ out,
-                                                       int64_t n_slots, int64_t half, int rank)
+template <int TPR>
+__global__ void __launch_bounds__(256) gemv_kernel(int64_t n, const double *__restrict__ M, int64_t lda,
+                                                   const double *__restrict__ v, double *__restrict__ out,
+                                                   int64_t row0, int64_t n_out)
 {
   __shared__ double sm[8];
   constexpr int ROWS_PER_BLOCK = 256 / TPR;
   const int t = threadIdx.x % TPR;
-  // slot = output index; on one GPU slot == row, in the row-split form the rank's slots map to its two row ranges
   const int64_t slot = (int64_t)blockIdx.x * ROWS_PER_BLOCK + threadIdx.x / TPR;
-  const int64_t i = half > 0 ? (slot < n_slots ? split_row(n, half, rank, slot) : -1) : (slot < n_slots ? slot : -1);
-  double s0 = 0., s1 = 0.;
-  if (i >= 0 && i < n)
+  const int64_t i = row0 + slot;
+  double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
+  if (slot < n_out && i < n)
   {
-    const double *row = M + i * lda;
-    int64_t j0 = LOWER ? 0 : i, j1 = LOWER ? i : n;
-    // scalar head to reach 16-byte alignment (lda is even, so parity of j decides)
-    if ((j0 & 1) && j0 < j1)
-    {
-      if (t == 0)
-        s0 = row[j0] * v[j0];
-      ++j0;
-    }
-    const int64_t npairs = (j1 - j0) >> 1;
-    const double2 *row2 = reinterpret_cast<const double2 *>(row + j0);
-    const double2 *v2 = reinterpret_cast<const double2 *>(v + j0);
+    // lda is a multiple of 4 and the padding columns of M are zero: whole rows in 128-bit pieces
+    const double2 *row2 = reinterpret_cast<const double2 *>(M + i * lda);
+    const double2 *v2 = reinterpret_cast<const double2 *>(v);
+    const int64_t npairs = n >> 1;
     int64_t q = t;
-    for (; q + TPR < npairs; q += 2 * TPR)
+    for (; q + 3 * TPR < npairs; q += 4 * TPR)
     {
-      const double2 a = ld_stream_f64x2(reinterpret_cast<const double *>(row2 + q));
-      const double2 c = ld_stream_f64x2(reinterpret_cast<const double *>(row2 + q + TPR));
-      const double2 x = v2[q], z = v2[q + TPR];
-      s0 = fma(a.x, x.x, s0);
-      s1 = fma(a.y, x.y, s1);
-      s0 = fma(c.x, z.x, s0);
-      s1 = fma(c.y, z.y, s1);
+      const double2 a0 = ld_stream_f64x2(reinterpret_cast<const double *>(row2 + q));
+      const double2 a1 = ld_stream_f64x2(reinterpret_cast<const double *>(row2 + q + TPR));
+      const double2 a2 = ld_stream_f64x2(reinterpret_cast<const double *>(row2 + q + 2 * TPR));
+      const double2 a3 = ld_stream_f64x2(reinterpret_cast<const double *>(row2 + q + 3 * TPR));
+      const double2 b0 = v2[q], b1 = v2[q + TPR], b2 = v2[q + 2 * TPR], b3 = v2[q + 3 * TPR];
+      s0 = fma(a0.y, b0.y, fma(a0.x, b0.x, s0));
+      s1 = fma(a1.y, b1.y, fma(a1.x, b1.x, s1));
+      s2 = fma(a2.y, b2.y, fma(a2.x, b2.x, s2));
+      s3 = fma(a3.y, b3.y, fma(a3.x, b3.x, s3));
     }
-    if (q < npairs)
+    for (; q < npairs; q += TPR)
     {
-      const double2 a = ld_stream_f64x2(reinterpret_cast<const double *>(row2 + q));
-      const double2 x = v2[q];
-      s0 = fma(a.x, x.x, s0);
-      s1 = fma(a.y, x.y, s1);
+      const double2 a0 = ld_stream_f64x2(reinterpret_cast<const double *>(row2 + q));
+      const double2 b0 = v2[q];
+      s0 = fma(a0.y, b0.y, fma(a0.x, b0.x, s0));
     }
-    if (((j1 - j0) & 1) && t == 0)
-      s0 = fma(row[j1 - 1], v[j1 - 1], s0);
+    if ((n & 1) && t == 0)
+      s1 = fma(M[i * lda + n - 1], v[n - 1], s1);
   }
-  double s = s0 + s1;
-  const bool valid = i >= 0 && i < n;
+  double s = (s0 + s1) + (s2 + s3);
   if (TPR == 256)
   {
     s = block_sum<256>(s, sm);
-    if (threadIdx.x == 0 && slot < n_slots)
-      out[slot] = valid ? (LOWER ? s + v[i] : s) : 0.;
+    if (threadIdx.x == 0 && slot < n_out)
+      out[slot] = s;
   }
   else
   {
     s = subwarp_sum<(TPR < 32 ? TPR : 32)>(s);
-    if (t == 0 && slot < n_slots)
-      out[slot] = valid ? (LOWER ? s + v[i] : s) : 0.;
+    if (t == 0 && slot < n_out)
+      out[slot] = s;
   }
 }
 
-// gathered (rank-major chunks of 2h slots) -> natural row order; rows covered twice carry identical values
-__global__ void __launch_bounds__(256) unshuffle_kernel(int64_t n, int64_t half, int nranks,
-                                                        const double *__restrict__ gathered, double *__restrict__ out)
+int launch_gemv(mfmgb_ctx *ctx, const mfmgb_dense *D, const double *b, double *out, int64_t row0, int64_t n_out)
 {
-  const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (g >= 2 * half * nranks)
-    return;
-  const int r = (int)(g / (2 * half));
-  const int64_t i = split_row(n, half, r, g % (2 * half));
-  if (i >= 0 && i < n)
-    out[i] = gathered[g];
+  if (n_out <= 0)
+    return MFMGB_OK;
+  if (D->n >= 2048)
+    gemv_kernel<256><<<(unsigned)n_out, 256, 0, ctx->stream>>>(D->n, D->inv, D->lda, b, out, row0, n_out);
+  else
+    gemv_kernel<32><<<(unsigned)ceil_div(n_out, 8), 256, 0, ctx->stream>>>(D->n, D->inv, D->lda, b, out, row0, n_out);
+  MFMGB_LAUNCHED(ctx);
+  return MFMGB_OK;
 }
 } // namespace
 
@@ -494,44 +485,19 @@ int dense_solve_async(mfmgb_ctx *ctx, const mfmgb_dense *D, const double *b, dou
   const int64_t n = D->n;
   if (n == 0)
     return MFMGB_OK;
-  permute_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(n, D->perm, b, D->work0);
-  MFMGB_LAUNCHED(ctx);
-  if (D->distributed)
+  if (b == x || (reinterpret_cast<uintptr_t>(b) & 15))
   {
-    // every rank: its 2h rows of y = L^-1 (P b); all-gather; its 2h rows of x = U^-1 y; all-gather
-    mfmgb_comm *c = ctx_comm(ctx);
-    const int64_t slots = 2 * D->half;
-    const unsigned ug = (unsigned)ceil_div(slots * D->nranks, 256);
-    tri_gemv_kernel<true, 256><<<(unsigned)slots, 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work0, D->chunk, slots,
-                                                                         D->half, D->rank);
-    MFMGB_LAUNCHED(ctx);
-    MFMGB_NCCL(ctx, ncclAllGather(D->chunk, D->gathered, (size_t)slots, ncclDouble, c->nccl, ctx->stream));
-    unshuffle_kernel<<<ug, 256, 0, ctx->stream>>>(n, D->half, D->nranks, D->gathered, D->work1);
-    MFMGB_LAUNCHED(ctx);
-    tri_gemv_kernel<false, 256><<<(unsigned)slots, 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work1, D->chunk, slots,
-                                                                          D->half, D->rank);
-    MFMGB_LAUNCHED(ctx);
-    MFMGB_NCCL(ctx, ncclAllGather(D->chunk, D->gathered, (size_t)slots, ncclDouble, c->nccl, ctx->stream));
-    unshuffle_kernel<<<ug, 256, 0, ctx->stream>>>(n, D->half, D->nranks, D->gathered, x);
-    MFMGB_LAUNCHED(ctx);
-    return MFMGB_OK;
+    // in-place solve, or a right-hand side that is not 16-byte aligned: stage it (the GEMV reads b with 128-bit loads)
+    MFMGB_CUDA(ctx, cudaMemcpyAsync(D->work0, b, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    b = D->work0;
   }
-  if (n >= 1024)
-  {
-    tri_gemv_kernel<true, 256><<<(unsigned)n, 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work0, D->work1, n, 0, 0);
-    MFMGB_LAUNCHED(ctx);
-    tri_gemv_kernel<false, 256><<<(unsigned)n, 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work1, x, n, 0, 0);
-    MFMGB_LAUNCHED(ctx);
-  }
-  else
-  {
-    tri_gemv_kernel<true, 32><<<(unsigned)ceil_div(n, 8), 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work0, D->work1,
-                                                                                n, 0, 0);
-    MFMGB_LAUNCHED(ctx);
-    tri_gemv_kernel<false, 32><<<(unsigned)ceil_div(n, 8), 256, 0, ctx->stream>>>(n, D->inv, D->lda, D->work1, x, n, 0,
-                                                                                 0);
-    MFMGB_LAUNCHED(ctx);
-  }
+  if (!D->distributed)
+    return launch_gemv(ctx, D, b, x, 0, n);
+  // every rank: its block of rows of x = M b, then one all-gather (b and M are replicated)
+  mfmgb_comm *c = ctx_comm(ctx);
+  MFMGB_CHECK(launch_gemv(ctx, D, b, D->chunk, (int64_t)D->rank * D->rows_per_rank, D->rows_per_rank));
+  MFMGB_NCCL(ctx, ncclAllGather(D->chunk, D->gathered, (size_t)D->rows_per_rank, ncclDouble, c->nccl, ctx->stream));
+  MFMGB_CUDA(ctx, cudaMemcpyAsync(x, D->gathered, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
   return MFMGB_OK;
 }
 
@@ -542,9 +508,9 @@ int dense_enable_distributed(mfmgb_ctx *ctx, mfmgb_dense *D)
     return MFMGB_OK;
   D->nranks = c->nranks;
   D->rank = c->rank;
-  D->half = ceil_div(D->n, 2 * (int64_t)c->nranks);
-  MFMGB_CUDA(ctx, cudaMalloc(&D->chunk, sizeof(double) * (size_t)(2 * D->half)));
-  MFMGB_CUDA(ctx, cudaMalloc(&D->gathered, sizeof(double) * (size_t)(2 * D->half * c->nranks)));
+  D->rows_per_rank = ceil_div(D->n, (int64_t)c->nranks);
+  MFMGB_CUDA(ctx, cudaMalloc(&D->chunk, sizeof(double) * (size_t)D->rows_per_rank));
+  MFMGB_CUDA(ctx, cudaMalloc(&D->gathered, sizeof(double) * (size_t)(D->rows_per_rank * c->nranks)));
   D->distributed = true;
   return MFMGB_OK;
 }
@@ -661,8 +627,12 @@ extern "C"
         tri_level_kernel<false, 2><<<grid, 256, 0, st>>>(lu, uinv, T, lda, n, s);
         MFMGB_LAUNCHED(ctx);
       }
+      // M = U^-1 L^-1 P into `lu` (the factors themselves are not needed any more)
+      dim3 ggrid((unsigned)ceil_div(n, TN), (unsigned)ceil_div(n, TM));
+      inv_product_kernel<<<ggrid, 256, 0, st>>>(uinv, linv, T, lda, n);
+      MFMGB_LAUNCHED(ctx);
       dim3 pgrid((unsigned)ceil_div(lda, 256), (unsigned)n);
-      tri_pack_kernel<<<pgrid, 256, 0, st>>>(linv, uinv, lu, lda, n);
+      fold_perm_kernel<<<pgrid, 256, 0, st>>>(T, D->perm, lu, lda, n);
       MFMGB_LAUNCHED(ctx);
       MFMGB_CUDA(ctx, cudaStreamSynchronize(st));
     }

@@ -5,16 +5,15 @@
 struct mfmgb_dense
 {
   int64_t n = 0, lda = 0;
-  double *inv = nullptr; // packed [n][lda]: strictly lower = L^-1, upper incl. diagonal = U^-1
+  double *inv = nullptr; // M = U^-1 L^-1 P (= A^-1), row-major [n][lda], padding columns zero
   int *perm = nullptr;   // composed row permutation: (P b)[i] = b[perm[i]]
   double *work0 = nullptr, *work1 = nullptr;
   int64_t num_swaps = 0;
-  // multi-GPU: the two triangular GEMVs are split by rows across the ranks (every rank holds the factors and the
-  // full right-hand side); rank r takes h rows from the top and h mirrored rows from the bottom so that both the
-  // lower and the upper sweep are balanced.  chunk = this rank's 2h results, gathered = all ranks' chunks.
+  // multi-GPU: the GEMV is split by rows across the ranks (every rank holds M and the full right-hand side);
+  // chunk = this rank's rows_per_rank results, gathered = all ranks' chunks.
   bool distributed = false;
   int nranks = 1, rank = 0;
-  int64_t half = 0;
+  int64_t rows_per_rank = 0;
   double *chunk = nullptr, *gathered = nullptr;
 };
 

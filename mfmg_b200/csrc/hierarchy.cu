@@ -71,7 +71,14 @@ constexpr int kBlock = 256;
 int level_apply_A(mfmgb_ctx *ctx, const mfmgb_level &l, double *x, Epi epi, const EpiArgs &e)
 {
   if (l.M)
+  {
+    if (l.halo) // (the z-sweep kernel needs its ghost planes up front: exchange, then apply)
+    {
+      MFMGB_CHECK(halo_start(ctx, l.halo, x));
+      MFMGB_CHECK(halo_wait(ctx));
+    }
     return mf_apply(ctx, l.M, x, epi, e);
+  }
   if (!l.halo)
     return csr_apply(ctx, l.A, x, epi, e);
   // row-partitioned level: the halo exchange of x runs on the communication stream while the interior rows
@@ -339,8 +346,9 @@ extern "C"
     if (!H || !halo || level < 0 || level >= H->n_levels - 1 || H->finalized)
       return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_halo: bad arguments");
     mfmgb_level &l = H->lev[level];
-    if (!l.A || halo->n_owned != l.n || l.A->n_cols != halo->n_owned + halo->n_ghost || boundary_lo < 0 ||
-        boundary_hi > l.n || boundary_lo > boundary_hi)
+    const int64_t n_vec = l.A ? l.A->n_cols : (l.M ? l.M->n_local : -1);
+    if (halo->n_owned != l.n || n_vec != halo->n_owned + halo->n_ghost || boundary_lo < 0 || boundary_hi > l.n ||
+        boundary_lo > boundary_hi)
       return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_halo: plan does not match the level operator");
     l.halo = halo;
     l.blo = boundary_lo;
@@ -419,8 +427,6 @@ extern "C"
         }
         else
           MFMGB_CHECK(mfmgb_jacobi_setup(ctx, l.A, H->omega, &l.J));
-        if (l.halo && l.M)
-          return fail(ctx, MFMGB_ERR_NOT_IMPLEMENTED, "matrix-free level in partitioned mode is not implemented");
         const int64_t ng = l.halo ? l.halo->n_ghost : 0;
         MFMGB_CHECK(mfmgb_vec_alloc(ctx, l.n + ng, &l.res));
         MFMGB_CHECK(mfmgb_vec_alloc(ctx, l.n + ng, &l.xtmp));

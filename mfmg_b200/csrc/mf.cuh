@@ -8,10 +8,19 @@ struct mfmgb_mf
   int64_t cells[3] = {1, 1, 1};
   int64_t nodes[3] = {1, 1, 1};
   double h[3] = {1., 1., 1.};
-  int64_t n = 0, n_cells = 0;
+  int64_t n = 0, n_cells = 0; // rows (owned nodes), cells of the local box
+  int64_t n_local = 0;        // nodes of the local box = length of the vectors it reads (owned + ghost planes)
   int nq = 0;                 // (degree+1)^dim quadrature points per cell
   double *coef = nullptr;     // device [n_cells][nq]
   uint8_t *constr = nullptr;  // device [n]
+  // 3D Q1 fast path (mf_q1.cuh)
+  bool q1_cell_constant = false;  // every cell's (cell, q) entries are equal: coef_cell + Kref are used
+  double *coef_cell = nullptr;    // device [n_cells]
+  double Kref[64] = {0};          // sum_q G[q][a][b]: reference cell matrix with the Jacobian folded in
+  bool force_generic = false;     // tests: run the generic colour-phase kernel instead
+  // slab layout of the row-partitioned hierarchy: vectors are [owned planes | ghost planes below | ghost planes
+  // above]; owned node planes are [own0, own1) of the local box (single GPU: all of them)
+  int64_t own0 = 0, own1 = 0;
   // host copies of the 1D tables of this degree: S[q][a], D[q][a], Gauss weights (unit interval)
   double S[9] = {0}, D[9] = {0}, W[3] = {0};
 };

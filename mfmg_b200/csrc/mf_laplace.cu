@@ -20,6 +20,7 @@
 //   * the coefficient table is stored SoA on the device ([q][cell]) so each warp-level load is contiguous.
 // Algorithmic bytes per apply: 16 n + 8 n_cells (p+1)^d + n.
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "mf.cuh"
@@ -504,10 +505,16 @@ int dispatch_mf_epi(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, Epi epi,
 }
 } // namespace
 
+#include "mf_q1.cuh"
+
 namespace mfmgb
 {
 int mf_apply(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, Epi epi, const EpiArgs &args)
 {
+  if (M->dim == 3 && M->degree == 1 && !M->force_generic)
+    return mf_q1_apply(ctx, M, x, epi, args); // node-owner z-sweep (mf_q1.cuh)
+  if (M->own0 != 0 || M->own1 != M->nodes[M->dim - 1])
+    return fail(ctx, MFMGB_ERR_NOT_IMPLEMENTED, "mf_apply: slab layouts are implemented for 3D Q1 only");
   if (M->dim == 3 && M->degree == 1)
     return dispatch_mf_epi<3, 1, 32, 16>(ctx, M, x, epi, args);
   if (M->dim == 3 && M->degree == 2)
@@ -525,6 +532,15 @@ extern "C"
   MFMGB_API int mfmgb_mf_laplace_create(mfmgb_ctx *ctx, int dim, int degree, const int64_t *cells, const double *h,
                                         const double *coef, const uint8_t *constrained, mfmgb_mf **out)
   {
+    MFMGB_REQUIRE(ctx, ctx && cells, "mfmgb_mf_laplace_create: bad arguments");
+    const int64_t top = (dim == 2 || dim == 3) ? cells[dim - 1] * degree + 1 : 0;
+    return mfmgb_mf_laplace_create_slab(ctx, dim, degree, cells, h, coef, constrained, 0, top, out);
+  }
+
+  MFMGB_API int mfmgb_mf_laplace_create_slab(mfmgb_ctx *ctx, int dim, int degree, const int64_t *cells, const double *h,
+                                             const double *coef, const uint8_t *constrained, int64_t own_plane_begin,
+                                             int64_t own_plane_end, mfmgb_mf **out)
+  {
     MFMGB_REQUIRE(ctx, ctx && cells && h && coef && constrained && out, "mfmgb_mf_laplace_create: bad arguments");
     if (!((dim == 2 || dim == 3) && (degree == 1 || degree == 2)))
       return fail(ctx, MFMGB_ERR_NOT_IMPLEMENTED, "mfmgb_mf_laplace_create: dim %d degree %d not implemented (2D/3D, Q1/Q2)",
@@ -532,28 +548,64 @@ extern "C"
     mfmgb_mf *M = new mfmgb_mf();
     M->dim = dim;
     M->degree = degree;
-    M->n = 1;
+    int64_t n_local = 1;
     M->n_cells = 1;
     for (int d = 0; d < 3; ++d)
     {
       M->cells[d] = d < dim ? cells[d] : 1;
       M->h[d] = d < dim ? h[d] : 1.;
       M->nodes[d] = d < dim ? cells[d] * degree + 1 : 1;
-      M->n *= M->nodes[d];
+      n_local *= M->nodes[d];
       M->n_cells *= M->cells[d];
       MFMGB_REQUIRE(ctx, M->cells[d] >= 1 && M->h[d] > 0., "mfmgb_mf_laplace_create: bad grid");
     }
+    M->n_local = n_local;
+    M->own0 = own_plane_begin;
+    M->own1 = own_plane_end;
+    MFMGB_REQUIRE(ctx, own_plane_begin >= 0 && own_plane_begin < own_plane_end && own_plane_end <= M->nodes[dim - 1],
+                  "mfmgb_mf_laplace_create_slab: owned planes out of range");
+    const bool slab = own_plane_begin != 0 || own_plane_end != M->nodes[dim - 1];
+    if (slab && !(dim == 3 && degree == 1))
+    {
+      delete M;
+      return fail(ctx, MFMGB_ERR_NOT_IMPLEMENTED, "mfmgb_mf_laplace_create_slab: slab layouts are implemented for 3D Q1");
+    }
+    M->n = (own_plane_end - own_plane_begin) * (n_local / M->nodes[dim - 1]); // rows = owned nodes
     const int n1 = degree + 1;
     M->nq = dim == 3 ? n1 * n1 * n1 : n1 * n1;
-    // transpose the (cell, q) table of tests/laplace_matrix_free.hpp:100-119 to SoA [q][cell]
-    std::vector<double> soa((size_t)M->nq * (size_t)M->n_cells);
-    for (int64_t c = 0; c < M->n_cells; ++c)
-      for (int q = 0; q < M->nq; ++q)
-        soa[(size_t)q * M->n_cells + c] = coef[(size_t)c * M->nq + q];
-    MFMGB_CUDA(ctx, cudaMalloc(&M->coef, sizeof(double) * soa.size()));
-    MFMGB_CUDA(ctx, cudaMemcpy(M->coef, soa.data(), sizeof(double) * soa.size(), cudaMemcpyHostToDevice));
-    MFMGB_CUDA(ctx, cudaMalloc(&M->constr, (size_t)M->n + 16));
-    MFMGB_CUDA(ctx, cudaMemcpy(M->constr, constrained, (size_t)M->n, cudaMemcpyHostToDevice));
+    // 3D Q1 fast path: a table whose entries are equal within every cell (any piecewise-constant material) is
+    // stored once per cell and applied through the reference cell matrix
+    const char *gen = getenv("MFMGB_MF_GENERIC");
+    M->force_generic = gen && gen[0] == '1';
+    bool cell_constant = dim == 3 && degree == 1 && !M->force_generic;
+    for (int64_t c = 0; c < M->n_cells && cell_constant; ++c)
+      for (int q = 1; q < M->nq; ++q)
+        if (coef[(size_t)c * M->nq + q] != coef[(size_t)c * M->nq])
+        {
+          cell_constant = false;
+          break;
+        }
+    M->q1_cell_constant = cell_constant;
+    if (cell_constant)
+    {
+      std::vector<double> cc((size_t)M->n_cells);
+      for (int64_t c = 0; c < M->n_cells; ++c)
+        cc[(size_t)c] = coef[(size_t)c * M->nq];
+      MFMGB_CUDA(ctx, cudaMalloc(&M->coef_cell, sizeof(double) * cc.size()));
+      MFMGB_CUDA(ctx, cudaMemcpy(M->coef_cell, cc.data(), sizeof(double) * cc.size(), cudaMemcpyHostToDevice));
+    }
+    else
+    {
+      // transpose the (cell, q) table of tests/laplace_matrix_free.hpp:100-119 to SoA [q][cell]
+      std::vector<double> soa((size_t)M->nq * (size_t)M->n_cells);
+      for (int64_t c = 0; c < M->n_cells; ++c)
+        for (int q = 0; q < M->nq; ++q)
+          soa[(size_t)q * M->n_cells + c] = coef[(size_t)c * M->nq + q];
+      MFMGB_CUDA(ctx, cudaMalloc(&M->coef, sizeof(double) * soa.size()));
+      MFMGB_CUDA(ctx, cudaMemcpy(M->coef, soa.data(), sizeof(double) * soa.size(), cudaMemcpyHostToDevice));
+    }
+    MFMGB_CUDA(ctx, cudaMalloc(&M->constr, (size_t)M->n_local + 16));
+    MFMGB_CUDA(ctx, cudaMemcpy(M->constr, constrained, (size_t)M->n_local, cudaMemcpyHostToDevice));
     // 1D tables: Lagrange basis on equidistant nodes at the Gauss points of the unit interval, for p = 1 and 2
     double Sall[2][9] = {{0}}, Dall[2][9] = {{0}}, Wall[2][3] = {{0}};
     for (int deg = 1; deg <= 2; ++deg)
@@ -592,6 +644,32 @@ extern "C"
     }
     for (int i = 0; i < 3; ++i)
       M->W[i] = Wall[degree - 1][i];
+    if (dim == 3 && degree == 1)
+    {
+      // K_ref[a][b] = sum_q (grad phi_a . grad phi_b)(x_q) JxW_q on a cell of size h
+      for (int a = 0; a < 8; ++a)
+        for (int b = 0; b < 8; ++b)
+        {
+          double s = 0.;
+          for (int q = 0; q < 8; ++q)
+          {
+            const int qx = q & 1, qy = (q >> 1) & 1, qz = q >> 2;
+            const double jxw = M->W[qx] * M->W[qy] * M->W[qz] * h[0] * h[1] * h[2];
+            double g[2][3];
+            const int ab[2] = {a, b};
+            for (int t = 0; t < 2; ++t)
+            {
+              const int ax = ab[t] & 1, ay = (ab[t] >> 1) & 1, az = ab[t] >> 2;
+              const double sx = M->S[qx * 2 + ax], sy = M->S[qy * 2 + ay], sz = M->S[qz * 2 + az];
+              g[t][0] = M->D[qx * 2 + ax] / h[0] * sy * sz;
+              g[t][1] = sx * M->D[qy * 2 + ay] / h[1] * sz;
+              g[t][2] = sx * sy * M->D[qz * 2 + az] / h[2];
+            }
+            s += (g[0][0] * g[1][0] + g[0][1] * g[1][1] + g[0][2] * g[1][2]) * jxw;
+          }
+          M->Kref[a * 8 + b] = s;
+        }
+    }
     *out = M;
     return MFMGB_OK;
   }
@@ -603,12 +681,18 @@ extern "C"
     MFMGB_REQUIRE(ctx, ctx, "ctx is NULL");
     MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(M->coef);
+    cudaFree(M->coef_cell);
     cudaFree(M->constr);
     delete M;
     return MFMGB_OK;
   }
 
   MFMGB_API int64_t mfmgb_mf_size(const mfmgb_mf *M) { return M ? M->n : 0; }
+  MFMGB_API int64_t mfmgb_mf_vector_size(const mfmgb_mf *M) { return M ? M->n_local : 0; }
+  MFMGB_API int mfmgb_mf_kernel(const mfmgb_mf *M)
+  {
+    return !M ? -1 : (M->dim == 3 && M->degree == 1 && !M->force_generic ? (M->q1_cell_constant ? 1 : 2) : 0);
+  }
 
   MFMGB_API int mfmgb_mf_apply(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, double *y)
   {
@@ -649,9 +733,14 @@ extern "C"
     double *gd_dev = nullptr;
     MFMGB_CUDA(ctx, cudaMalloc(&gd_dev, sizeof(double) * gd.size()));
     MFMGB_CUDA(ctx, cudaMemcpyAsync(gd_dev, gd.data(), sizeof(double) * gd.size(), cudaMemcpyHostToDevice, ctx->stream));
-    MfParams prm = make_params(M);
-    mf_diag_kernel<<<(unsigned)ceil_div(M->n, 256), 256, 0, ctx->stream>>>(dim, M->degree, prm, gd_dev, M->n, diag_dev);
-    MFMGB_LAUNCHED(ctx);
+    if (dim == 3 && M->degree == 1 && !M->force_generic)
+      MFMGB_CHECK(mf_q1_diagonal(ctx, M, gd_dev, diag_dev));
+    else
+    {
+      MfParams prm = make_params(M);
+      mf_diag_kernel<<<(unsigned)ceil_div(M->n, 256), 256, 0, ctx->stream>>>(dim, M->degree, prm, gd_dev, M->n, diag_dev);
+      MFMGB_LAUNCHED(ctx);
+    }
     MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(gd_dev);
     return MFMGB_OK;

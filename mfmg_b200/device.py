@@ -378,18 +378,30 @@ class CudaSolver:
 class MatrixFreeLaplaceDevice:
     """The matrix-free fine-level operator (CudaMatrixFreeOperator slot)."""
 
-    def __init__(self, handle: CudaHandle, dim, degree, cells, h, coef_per_q, constrained):
+    KERNELS = {0: "generic colour-phase cell kernel", 1: "Q1 node-owner z-sweep, per-cell coefficient",
+               2: "Q1 node-owner z-sweep, per-quadrature-point coefficient"}
+
+    def __init__(self, handle: CudaHandle, dim, degree, cells, h, coef_per_q, constrained, own_planes=None):
+        """own_planes = (begin, end): the z-slab form of a row-partitioned grid -- `cells` is the local box, node
+        planes [begin, end) are owned, vectors / `constrained` are laid out [owned | ghost below | ghost above]."""
         self.handle = handle
         cells_a = np.ascontiguousarray(list(cells) + [1] * (3 - dim), dtype=np.int64)
         h_a = np.ascontiguousarray(list(h) + [1.0] * (3 - dim), dtype=np.float64)
         coef = np.ascontiguousarray(coef_per_q, dtype=np.float64)
         constr = np.ascontiguousarray(constrained, dtype=np.uint8)
         p = ctypes.c_void_p()
-        check(handle.ctx, handle.lib.mfmgb_mf_laplace_create(handle.ctx, dim, degree, cells_a.ctypes.data,
-                                                             h_a.ctypes.data, coef.ctypes.data, constr.ctypes.data,
-                                                             ctypes.byref(p)))
+        if own_planes is None:
+            check(handle.ctx, handle.lib.mfmgb_mf_laplace_create(handle.ctx, dim, degree, cells_a.ctypes.data,
+                                                                 h_a.ctypes.data, coef.ctypes.data, constr.ctypes.data,
+                                                                 ctypes.byref(p)))
+        else:
+            check(handle.ctx, handle.lib.mfmgb_mf_laplace_create_slab(
+                handle.ctx, dim, degree, cells_a.ctypes.data, h_a.ctypes.data, coef.ctypes.data, constr.ctypes.data,
+                int(own_planes[0]), int(own_planes[1]), ctypes.byref(p)))
         self.ptr = p
         self.size = int(handle.lib.mfmgb_mf_size(p))
+        self.vector_size = int(handle.lib.mfmgb_mf_vector_size(p))
+        self.kernel = self.KERNELS[int(handle.lib.mfmgb_mf_kernel(p))]
 
     def apply(self, x: DeviceVector, y: DeviceVector, mode: OperatorMode = OperatorMode.NO_TRANS) -> None:
         # the operator is symmetric: TRANS == NO_TRANS (cuda_matrix_free_operator.cu:60-70)
@@ -500,10 +512,18 @@ class Hierarchy:
         return Hierarchy(handle, ops, res, params, omega)
 
     @staticmethod
-    def from_partition(handle: CudaHandle, part, params=None, omega: float = 1.0) -> "Hierarchy":
+    def from_partition(handle: CudaHandle, part, params=None, omega: float = 1.0,
+                       matrix_free: bool = False) -> "Hierarchy":
         """Row-partitioned two-level hierarchy of one rank (hostsetup.partition.LocalPart); the context must have
-        an initialised communicator (CudaHandle.init_comm*)."""
-        ops = [SparseMatrixDevice.from_host(handle, part.A), SparseMatrixDevice.from_host(handle, part.Ac)]
+        an initialised communicator (CudaHandle.init_comm*).  matrix_free: level 0 is the matrix-free slab operator
+        (part.mf, hostsetup.slab) instead of the assembled rows; R, P and A_c stay assembled."""
+        if matrix_free:
+            mf = part.mf
+            fine = MatrixFreeLaplaceDevice(handle, 3, mf["degree"], mf["cells"], mf["h"], mf["coef"],
+                                           mf["constrained"], own_planes=mf["own_planes"])
+        else:
+            fine = SparseMatrixDevice.from_host(handle, part.A)
+        ops = [fine, SparseMatrixDevice.from_host(handle, part.Ac)]
         res = [SparseMatrixDevice.from_host(handle, part.R)]
         pro = [SparseMatrixDevice.from_host(handle, part.P)]
         plan = HaloPlan(handle, part)

@@ -141,4 +141,33 @@ def build_slab_part(degree: int, cells, h, material: str, block, n_eigenvectors:
     # extras for the driver
     part.constrained = ext.constrained[rb - off:re_ - off]
     part.n_global = n_global
+    part.mf = _matrix_free_slab(ext, p, cells, h, e0, cz0, cz1, rank, world, plane, ghost_global, rb, re_)
     return part
+
+
+def _matrix_free_slab(ext, p, cells, h, e0, cz0, cz1, rank, world, plane, ghost_global, rb, re_):
+    """Data of the matrix-free level-0 operator on this rank's slab (3D Q1): the local box is the owned cell layers
+    plus the layer below (its contributions complete the bottom owned plane); node planes of the box are ordered
+    [owned | ghost below | ghost above] like every vector of the partitioned level.  None when the ghost set of the
+    assembled rows is not exactly those planes (then the halo plan could not serve both)."""
+    if p != 1:
+        return None
+    l0 = cz0 - 1 if rank > 0 else cz0            # first cell layer of the local box (global numbering)
+    l1 = cz1
+    g_lo, g_hi = l0, l1                          # node planes l0 .. l1 (inclusive) of the local box
+    own_lo = cz0
+    own_hi = cz1 + 1 if rank == world - 1 else cz1   # owned planes [own_lo, own_hi)
+    expect = np.concatenate([np.arange(g * plane, (g + 1) * plane, dtype=np.int64)
+                             for g in list(range(g_lo, own_lo)) + list(range(own_hi, g_hi + 1))] + [np.zeros(0, np.int64)])
+    if not np.array_equal(expect, ghost_global):
+        return None
+    cxy = cells[0] * cells[1]
+    coef = ext.coef[(l0 - e0) * cxy:(l1 - e0) * cxy]
+    nq = (p + 1) ** 3
+    if coef.shape[1] != nq:
+        coef = np.repeat(coef, nq, axis=1)
+    c_ext = ext.constrained.reshape(-1, plane)       # [ext plane][node in plane]
+    order = list(range(own_lo, own_hi)) + list(range(g_lo, own_lo)) + list(range(own_hi, g_hi + 1))
+    constrained = np.concatenate([c_ext[g - e0] for g in order])
+    return {"degree": p, "cells": (cells[0], cells[1], l1 - l0), "h": tuple(h), "coef": np.ascontiguousarray(coef),
+            "constrained": np.ascontiguousarray(constrained), "own_planes": (own_lo - g_lo, own_hi - g_lo)}

@@ -81,3 +81,33 @@ def rel_err(a, b):
     b = np.asarray(b, dtype=np.float64)
     d = np.linalg.norm(b)
     return np.linalg.norm(a - b) / (d if d > 0 else 1.0)
+
+
+def slab_parts(world, cells, h, block, n_eig, degree=1, material="constant"):
+    """All ranks' hostsetup.build_slab_part results in one process (the setup-time gathers are emulated by two
+    passes: the first records what every rank contributes)."""
+    from mfmg_b200 import hostsetup as hs
+
+    contributions = {}
+
+    def run(rank, record):
+        calls = [0]
+
+        def gather(obj):
+            k = calls[0]
+            calls[0] += 1
+            if record:
+                contributions.setdefault(k, {})[rank] = obj
+                return [obj] * world
+            return [contributions[k][r] for r in range(world)]
+
+        return hs.build_slab_part(degree, cells, h, material, block, n_eig, world, rank, gather)
+
+    for r in range(world):
+        run(r, True)
+    return [run(r, False) for r in range(world)]
+
+
+def slab_vector(part, v_global):
+    """[owned | ghost] local copy of a global vector."""
+    return np.concatenate([v_global[part.row_begin:part.row_end], v_global[part.ghost_global]])

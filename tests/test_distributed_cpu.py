@@ -145,3 +145,40 @@ def test_slab_local_setup_equals_sliced_global(world, cells, block, ne, degree, 
         for s1, s2 in zip(part.send_indices, ref.send_indices):
             assert np.array_equal(s1, s2)
         assert (part.boundary_lo, part.boundary_hi) == (ref.boundary_lo, ref.boundary_hi)
+
+
+@pytest.mark.parametrize("world,cells,block,mat", [(2, (6, 5, 8), (2, 2, 2), "linear"), (3, (4, 6, 12), (2, 3, 2), "discontinuous"),
+                                                   (1, (4, 4, 4), (2, 2, 2), "constant")])
+def test_matrix_free_slab_data(world, cells, block, mat):
+    """hostsetup.slab attaches the matrix-free level-0 data of each rank (local box, coefficient rows, constraint flags
+    in [owned | ghost below | ghost above] order).  Checked with the oracle's cell loop on the local box: its rows
+    for the owned nodes, fed with the rank's [owned | ghost] copy of a global vector, equal the global operator's."""
+    import oracle
+    from helpers import slab_parts, slab_vector
+    from mfmg_b200 import hostsetup as hs
+
+    h = (0.05, 0.04, 0.03)
+    P = hs.LaplaceProblem.create_box(3, 1, cells, h, mat)
+    Mo = oracle.MatrixFreeLaplace(3, 1, P.cells, P.h, P.coef_per_q(), P.constrained)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(P.n)
+    y_ref = Mo.apply(x)
+    plane = (cells[0] + 1) * (cells[1] + 1)
+    for part in slab_parts(world, cells, h, block, 1, 1, mat):
+        mf = part.mf
+        assert mf is not None
+        own0, own1 = mf["own_planes"]
+        nz = mf["cells"][2] + 1
+        assert (own1 - own0) * plane == part.n_owned and nz * plane == part.n_owned + part.n_ghost
+        # vector layout -> natural plane order of the local box
+        order = list(range(own0, own1)) + list(range(0, own0)) + list(range(own1, nz))
+        nat = np.empty(nz * plane, dtype=np.int64)   # nat[natural index] = vector index
+        for pos, g in enumerate(order):
+            nat[g * plane:(g + 1) * plane] = np.arange(pos * plane, (pos + 1) * plane)
+        Ml = oracle.MatrixFreeLaplace(3, 1, mf["cells"], mf["h"], mf["coef"], mf["constrained"][nat])
+        xl = slab_vector(part, x)
+        yl = Ml.apply(xl[nat])
+        got = yl[own0 * plane:own1 * plane]
+        assert np.max(np.abs(got - y_ref[part.row_begin:part.row_end])) <= 1e-12 * np.abs(y_ref).max()
+        dl = Ml.diag()[own0 * plane:own1 * plane]
+        assert np.max(np.abs(dl - Mo.diag()[part.row_begin:part.row_end])) <= 1e-12 * np.abs(Mo.diag()).max()

@@ -100,3 +100,49 @@ def test_mf_unsupported_degree_raises(handle):
 
     with pytest.raises(d.NotImplementedExc):
         d.MatrixFreeLaplaceDevice(handle, 3, 3, (2, 2, 2), (0.5, 0.5, 0.5), np.ones((8, 64)), np.zeros(343, dtype=np.uint8))
+
+
+@pytest.mark.parametrize("world,cells,block,mat", [(3, (33, 9, 12), (3, 3, 2), "linear"),
+                                                   (2, (40, 20, 16), (4, 4, 4), "discontinuous")])
+def test_mf_slab_operator_on_one_gpu(handle, world, cells, block, mat):
+    """The z-slab form of the 3D Q1 operator (row-partitioned hierarchy): every rank's slab operator, fed with its
+    [owned | ghost] copy of a global vector, reproduces the owned rows of the global operator and of its diagonal."""
+    from helpers import slab_parts, slab_vector
+    from mfmg_b200 import device as d
+    from mfmg_b200 import hostsetup as hs
+
+    h = (0.05, 0.04, 0.03)
+    P = hs.LaplaceProblem.create_box(3, 1, cells, h, mat)
+    Mo = oracle.MatrixFreeLaplace(3, 1, P.cells, P.h, P.coef_per_q(), P.constrained)
+    rng = np.random.default_rng(1)
+    x_h = rng.standard_normal(P.n)
+    y_ref, d_ref = Mo.apply(x_h), Mo.diag()
+    for part in slab_parts(world, cells, h, block, 1, 1, mat):
+        mf = part.mf
+        M = d.MatrixFreeLaplaceDevice(handle, 3, 1, mf["cells"], mf["h"], mf["coef"], mf["constrained"],
+                                      own_planes=mf["own_planes"])
+        assert M.size == part.n_owned and M.vector_size == part.n_owned + part.n_ghost
+        x = d.DeviceVector.from_host(handle, slab_vector(part, x_h))
+        y = d.DeviceVector(handle, part.n_owned)
+        M.apply(x, y)
+        sl = slice(part.row_begin, part.row_end)
+        assert np.max(np.abs(y.to_host() - y_ref[sl])) <= 1e-12 * np.abs(y_ref).max()
+        assert np.max(np.abs(M.diagonal().to_host() - d_ref[sl])) <= 1e-12 * np.abs(d_ref).max()
+
+
+def test_generic_kernel_still_serves_3d_q1(handle, monkeypatch):
+    """MFMGB_MF_GENERIC=1 keeps the colour-phase cell kernel reachable for 3D Q1 (it serves 2D and Q2 by default)."""
+    from mfmg_b200 import device as d
+    from mfmg_b200 import hostsetup as hs
+
+    P = hs.LaplaceProblem.create(3, 1, 20, "discontinuous")
+    fast = _mf(handle, P)
+    monkeypatch.setenv("MFMGB_MF_GENERIC", "1")
+    slow = _mf(handle, P)
+    assert fast.kernel.startswith("Q1 node-owner") and slow.kernel.startswith("generic")
+    rng = np.random.default_rng(0)
+    x = d.DeviceVector.from_host(handle, rng.standard_normal(P.n))
+    y1, y2 = d.DeviceVector(handle, P.n), d.DeviceVector(handle, P.n)
+    fast.apply(x, y1)
+    slow.apply(x, y2)
+    assert rel_err(y1.to_host(), y2.to_host()) < 1e-13
