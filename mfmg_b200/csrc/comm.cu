@@ -152,6 +152,8 @@ extern "C"
       return MFMGB_OK;
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(c->stream);
+    for (auto &o : ctx->graph_owners) // captured V-cycles reference the communicator
+      o.second(o.first);
     ncclCommDestroy(c->nccl);
     cudaEventDestroy(c->ev_ready);
     cudaEventDestroy(c->ev_done);

@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "mfmg_b200.h"
@@ -38,6 +39,9 @@ struct mfmgb_ctx
   // pinned staging for *_host entry points
   double *pinned = nullptr;
   size_t pinned_bytes = 0;
+  // objects holding instantiated CUDA graphs with NCCL nodes: they must be dropped before the communicator is
+  // destroyed (ncclCommDestroy otherwise waits forever).  (owner, drop function)
+  std::vector<std::pair<void *, void (*)(void *)>> graph_owners;
 };
 
 namespace mfmgb

@@ -68,6 +68,16 @@ namespace
 {
 constexpr int kBlock = 256;
 
+void drop_graph(void *h)
+{
+  mfmgb_hierarchy *H = static_cast<mfmgb_hierarchy *>(h);
+  if (H->graph_exec)
+  {
+    cudaGraphExecDestroy(H->graph_exec);
+    H->graph_exec = nullptr;
+  }
+}
+
 int level_apply_A(mfmgb_ctx *ctx, const mfmgb_level &l, double *x, Epi epi, const EpiArgs &e)
 {
   if (l.M)
@@ -188,11 +198,13 @@ int apply_level(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, 
 
 int run_vcycle(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x)
 {
-  // Partitioned mode launches eagerly (NCCL + two streams).  MFMGB_DIST_GRAPH=1 captures that cycle as well
-  // (experimental: the first attempt hung on 2 GPUs, profiles/r01_summary.md).
+  // The partitioned cycle is captured too: NCCL operations and the fork/join onto the communication stream (events)
+  // are capturable, every rank replays the same sequence, and ~25 eager launches per cycle are most of the
+  // multi-GPU overhead at 2 M DoFs per GPU.  (The graph must be dropped before ncclCommDestroy: ctx->graph_owners.)
+  // MFMGB_DIST_GRAPH=0 falls back to eager launches.
   static const bool dist_graph = [] {
     const char *v = getenv("MFMGB_DIST_GRAPH");
-    return v && v[0] == '1';
+    return !(v && v[0] == '0');
   }();
   if (!H->use_graph || (H->distributed && !dist_graph))
     return apply_level(ctx, H, b, x, 0);
@@ -304,6 +316,7 @@ extern "C"
     H->is_preconditioner = is_preconditioner != 0;
     H->omega = omega;
     H->lev.resize((size_t)n_levels);
+    ctx->graph_owners.emplace_back(H, &drop_graph);
     *out = H;
     return MFMGB_OK;
   }
@@ -483,6 +496,12 @@ extern "C"
     MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (H->graph_exec)
       cudaGraphExecDestroy(H->graph_exec);
+    for (size_t k = 0; k < ctx->graph_owners.size(); ++k)
+      if (ctx->graph_owners[k].first == H)
+      {
+        ctx->graph_owners.erase(ctx->graph_owners.begin() + (long)k);
+        break;
+      }
     for (int k = 0; k < 7; ++k)
       if (H->ev[k])
         cudaEventDestroy(H->ev[k]);

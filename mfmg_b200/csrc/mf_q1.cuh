@@ -332,6 +332,16 @@ __global__ void __launch_bounds__(TX *TY, MINB) mf_q1_kernel(const Q1Params p, c
     const bool cell_ok = cell_xy && L >= 0 && L < p.cz;
     if (PERQ)
       load_coef_q(L + 1, coef_next);
+    // epilogue operands of plane L: requested before the cell work so that their latency overlaps it
+    const bool emit = owner && L >= P0 && L < P1;
+    const int64_t row = (L - p.own0) * (p.nx * p.ny) + node_xy; // owned planes: vector offset == row
+    double eb = 0., ed = 0.;
+    if (emit && EPI != (int)Epi::Spmv)
+    {
+      eb = e.b[row];
+      if (EPI == (int)Epi::Jacobi)
+        ed = e.dinv[row];
+    }
     double out[8];
     if (cell_ok)
     {
@@ -368,20 +378,19 @@ __global__ void __launch_bounds__(TX *TY, MINB) mf_q1_kernel(const Q1Params p, c
       const double up = (o[4 * NT] + o[5 * NT - 1]) + (o[6 * NT - TX] + o[7 * NT - TX - 1]);
       const double total = carry + lo;
       carry = up;
-      if (L >= P0 && L < P1)
+      if (emit)
       {
-        const int64_t row = (L - p.own0) * (p.nx * p.ny) + node_xy;
         const bool constrained = fs[l * XS + sx] != 0;
-        const double xraw = constrained ? x[row] : xr[l * XS + sx]; // owned planes: vector offset == row
+        const double xraw = constrained ? x[row] : xr[l * XS + sx];
         const double s = constrained ? xraw : total;
         if (EPI == (int)Epi::Spmv)
           e.y[row] = s;
         else if (EPI == (int)Epi::Resid)
-          e.y[row] = __dsub_rn(s, e.b[row]);
+          e.y[row] = __dsub_rn(s, eb);
         else
         {
-          const double r = __dsub_rn(s, e.b[row]);
-          double t = __dmul_rn(e.dinv[row], r);
+          const double r = __dsub_rn(s, eb);
+          double t = __dmul_rn(ed, r);
           if (e.omega != 1.)
             t = __dmul_rn(e.omega, t);
           e.y[row] = __dsub_rn(e.xin == x ? xraw : e.xin[row], t);

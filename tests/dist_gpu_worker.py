@@ -48,8 +48,8 @@ def main():
         x_ref = Ho.vmult(b_h)[sl]
         err = np.linalg.norm(x.to_host()[:part.n_owned] - x_ref) / np.linalg.norm(x_ref)
         assert err < 1e-12, (rank, "vcycle", err)
-        # (opt-in) CUDA-graph replay of the partitioned cycle == eager launches, bit for bit
-        if os.environ.get("MFMGB_DIST_GRAPH") == "1":
+        # CUDA-graph replay of the partitioned cycle (NCCL + two streams captured) == eager launches, bit for bit
+        if os.environ.get("MFMGB_DIST_GRAPH", "1") != "0":
             x_eager = x.to_host()[:part.n_owned].copy()
             H.use_graph(True)
             for _ in range(3):
