@@ -222,6 +222,25 @@ extern "C"
                                          int64_t boundary_hi);
   /* offsets (nranks + 1) of the rank-owned rows of the replicated coarsest level */
   MFMGB_API int mfmgb_hierarchy_set_coarse_offsets(mfmgb_hierarchy *H, const int64_t *offsets, int nranks);
+  /* Domain-decomposed form of the dense coarse solve for a row-partitioned hierarchy whose coarse operator is block
+   * tridiagonal in the ranks' row blocks (z-slab partitions are): one level of nested dissection with the last
+   * agglomerate layer of every rank but the last as separator.  Exactly the reference's direct solve
+   * (source/cuda/cuda_solver.cu:496-515) reorganised so that a rank reads 8 n_I^2 bytes per cycle instead of
+   * 8 n_c^2 / N, with one all-reduce of n_S doubles as the only communication (csrc/coarse_dd.cu).
+   * Index conventions: this rank's interior = coarse rows [own_begin, own_begin + A_II.n_rows); separators are numbered
+   * globally 0..n_S-1 (sep_index[k] = coarse row of separator k); A_IS / A_SI couple the interior with the adjacent
+   * separators [adj_begin, adj_begin + A_IS.n_cols); the rank's own separator is [own_sep_begin, +own_sep_n).
+   * A_SI is BORROWED (must outlive the solver); the others are only read during creation.  Collective call. */
+  typedef struct mfmgb_coarse_dd mfmgb_coarse_dd;
+  MFMGB_API int mfmgb_coarse_dd_create(mfmgb_ctx *ctx, int64_t n_c, int64_t own_begin, int64_t n_S, int64_t adj_begin,
+                                       int64_t own_sep_begin, int64_t own_sep_n, const mfmgb_csr *A_II,
+                                       const mfmgb_csr *A_IS, const mfmgb_csr *A_SI, const mfmgb_csr *A_SS,
+                                       const int32_t *sep_index, mfmgb_coarse_dd **out);
+  MFMGB_API int mfmgb_coarse_dd_destroy(mfmgb_ctx *ctx, mfmgb_coarse_dd *dd);
+  /* b_c: valid on this rank's coarse rows; x_c: valid on return on this rank's rows and on all separator rows */
+  MFMGB_API int mfmgb_coarse_dd_solve(mfmgb_ctx *ctx, const mfmgb_coarse_dd *dd, const double *b_c, double *x_c);
+  /* use it as the coarsest-level solver of a partitioned hierarchy (before finalize; borrowed) */
+  MFMGB_API int mfmgb_hierarchy_set_coarse_dd(mfmgb_hierarchy *H, const mfmgb_coarse_dd *dd);
   /* length device vectors of this level must have (n_owned + n_ghost) */
   MFMGB_API int64_t mfmgb_hierarchy_vector_size(const mfmgb_hierarchy *H, int level);
 

@@ -1,0 +1,255 @@
+// coarse_dd.cu -- domain-decomposed dense direct solve of the coarsest level of a row-partitioned hierarchy.
+//
+// The reference solves the coarsest level with one dense LU (source/cuda/cuda_solver.cu:496-515).  Replicating (or
+// row-splitting) the dense inverse across the ranks reads 8 n_c^2 / N bytes per GPU and cycle, and in weak scaling
+// n_c grows with N: the coarse solve ends up dominating the cycle.  The coarse operator of a z-slab partition is block
+// tridiagonal in the agglomerate layers, so the SAME direct solve can be organised by one level of nested dissection:
+//
+//   coarse rows of rank r = [ interior I_r | separator S_r ]   (S_r = its last agglomerate layer; none on the last rank)
+//   interiors of different ranks are coupled only through the separators, hence with S = union of the S_r
+//
+//     y_r   = A_II,r^-1 b_I,r                                     local dense GEMV      (8 n_I^2 bytes, constant in N)
+//     t     = b_S - sum_r A_SI,r y_r                              ONE all-reduce of n_S doubles (the only communication)
+//     x_S   = (A_SS - sum_r A_SI,r A_II,r^-1 A_IS,r)^-1 t         replicated dense GEMV (Schur complement, n_S = (N-1) L)
+//     x_I,r = y_r - (A_II,r^-1 A_IS,r) x_S|adjacent               rectangular dense GEMV (n_I x 2L)
+//
+// This is block Gaussian elimination, i.e. the exact solve (rounding differs from the monolithic LU at the 1e-15 cond
+// level).  Each rank ends up with x_c on its own rows and on ALL separators, which is what its prolongation rows read
+// (own agglomerates + the layer below, a separator), so neither the right-hand side nor the solution is all-gathered.
+// Setup (once): A_II^-1 by the dense factorisation of dense.cu, E_r = A_II^-1 A_IS and A_SI E_r by GEMM, the Schur
+// matrix summed over the ranks by an all-reduce and inverted redundantly.
+#include <algorithm>
+
+#include "comm.cuh"
+#include "dense.cuh"
+
+using namespace mfmgb;
+
+struct mfmgb_coarse_dd
+{
+  int64_t n_c = 0;       // size of the coarse level
+  int64_t own_begin = 0; // first coarse row of this rank; the interior is [own_begin, own_begin + n_I)
+  int64_t n_I = 0, n_S = 0;
+  int64_t adj_begin = 0, n_adj = 0;         // separators adjacent to this rank's interior, in S numbering
+  int64_t own_sep_begin = 0, own_sep_n = 0; // this rank's own separator in S numbering (n = 0 on the last rank)
+  mfmgb_dense *D_II = nullptr, *D_S = nullptr;
+  const mfmgb_csr *A_SI = nullptr; // n_adj x n_I (borrowed)
+  double *E = nullptr;             // n_I x ldE: A_II^-1 A_IS
+  int64_t ldE = 0;
+  int32_t *sep_index = nullptr; // [n_S] global coarse index of every separator row
+  double *y = nullptr, *t = nullptr, *xs = nullptr, *g = nullptr;
+};
+
+namespace
+{
+// t[k] = (k adjacent ? -g[k - adj_begin] : 0) + (k in own separator ? b_c[sep_index[k]] : 0)
+__global__ void __launch_bounds__(256) dd_rhs_kernel(int64_t n_S, int64_t adj_begin, int64_t n_adj, int64_t own_begin,
+                                                     int64_t own_n, const double *__restrict__ g,
+                                                     const int32_t *__restrict__ sep_index,
+                                                     const double *__restrict__ b_c, double *__restrict__ t)
+{
+  const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (k >= n_S)
+    return;
+  double v = 0.;
+  if (k >= adj_begin && k < adj_begin + n_adj)
+    v = -g[k - adj_begin];
+  if (k >= own_begin && k < own_begin + own_n)
+    v += b_c[sep_index[k]];
+  t[k] = v;
+}
+
+// x_I[i] = y[i] - sum_j E[i][j] xs[j]   (one warp per row, fixed shuffle tree)
+__global__ void __launch_bounds__(256) dd_interior_kernel(int64_t n_I, int64_t n_adj, const double *__restrict__ E,
+                                                          int64_t ldE, const double *__restrict__ xs,
+                                                          const double *__restrict__ y, double *__restrict__ x_I)
+{
+  const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  double s0 = 0., s1 = 0.;
+  if (i < n_I)
+  {
+    const double *row = E + i * ldE;
+    int64_t j = lane;
+    for (; j + 32 < n_adj; j += 64)
+    {
+      s0 = fma(row[j], xs[j], s0);
+      s1 = fma(row[j + 32], xs[j + 32], s1);
+    }
+    if (j < n_adj)
+      s0 = fma(row[j], xs[j], s0);
+  }
+  const double s = subwarp_sum<32>(s0 + s1);
+  if (lane == 0 && i < n_I)
+    x_I[i] = y[i] - s;
+}
+
+// x_c[sep_index[k]] = xs[k]
+__global__ void __launch_bounds__(256) dd_scatter_kernel(int64_t n_S, const int32_t *__restrict__ sep_index,
+                                                         const double *__restrict__ xs, double *__restrict__ x_c)
+{
+  const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (k < n_S)
+    x_c[sep_index[k]] = xs[k];
+}
+
+// S[(adj_begin + i) * ldS + adj_begin + j] -= C[i * ldC + j]
+__global__ void __launch_bounds__(256) dd_sub_block_kernel(int64_t n_adj, const double *__restrict__ C, int64_t ldC,
+                                                           double *__restrict__ S, int64_t ldS, int64_t adj_begin)
+{
+  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t i = blockIdx.y;
+  if (j < n_adj)
+    S[(adj_begin + i) * ldS + adj_begin + j] -= C[i * ldC + j];
+}
+} // namespace
+
+namespace mfmgb
+{
+int coarse_dd_solve_async(mfmgb_ctx *ctx, const mfmgb_coarse_dd *d, const double *b_c, double *x_c)
+{
+  mfmgb_comm *c = ctx_comm(ctx);
+  cudaStream_t st = ctx->stream;
+  // y = A_II^-1 b_I
+  if (d->n_I > 0)
+    MFMGB_CHECK(dense_solve_async(ctx, d->D_II, b_c + d->own_begin, d->y));
+  if (d->n_S > 0)
+  {
+    // t = (own part of b_S) - A_SI y, summed over the ranks
+    if (d->n_adj > 0 && d->n_I > 0)
+    {
+      EpiArgs e;
+      e.y = d->g;
+      MFMGB_CHECK(csr_apply(ctx, d->A_SI, d->y, Epi::Spmv, e));
+    }
+    dd_rhs_kernel<<<(unsigned)ceil_div(d->n_S, 256), 256, 0, st>>>(d->n_S, d->adj_begin, d->n_I > 0 ? d->n_adj : 0,
+                                                                   d->own_sep_begin, d->own_sep_n, d->g, d->sep_index,
+                                                                   b_c, d->t);
+    MFMGB_LAUNCHED(ctx);
+    MFMGB_NCCL(ctx, ncclAllReduce(d->t, d->t, (size_t)d->n_S, ncclDouble, ncclSum, c->nccl, st));
+    // x_S = Schur^-1 t (replicated)
+    MFMGB_CHECK(dense_solve_async(ctx, d->D_S, d->t, d->xs));
+    dd_scatter_kernel<<<(unsigned)ceil_div(d->n_S, 256), 256, 0, st>>>(d->n_S, d->sep_index, d->xs, x_c);
+    MFMGB_LAUNCHED(ctx);
+  }
+  // x_I = y - E x_S|adjacent
+  if (d->n_I > 0)
+  {
+    dd_interior_kernel<<<(unsigned)ceil_div(d->n_I, 8), 256, 0, st>>>(d->n_I, d->n_adj, d->E, d->ldE,
+                                                                      d->xs + d->adj_begin, d->y, x_c + d->own_begin);
+    MFMGB_LAUNCHED(ctx);
+  }
+  return MFMGB_OK;
+}
+} // namespace mfmgb
+
+extern "C"
+{
+  MFMGB_API int mfmgb_coarse_dd_create(mfmgb_ctx *ctx, int64_t n_c, int64_t own_begin, int64_t n_S, int64_t adj_begin,
+                                       int64_t own_sep_begin, int64_t own_sep_n, const mfmgb_csr *A_II,
+                                       const mfmgb_csr *A_IS, const mfmgb_csr *A_SI, const mfmgb_csr *A_SS,
+                                       const int32_t *sep_index, mfmgb_coarse_dd **out)
+  {
+    MFMGB_REQUIRE(ctx, ctx && out && A_II && A_IS && A_SI && A_SS && (n_S == 0 || sep_index),
+                  "mfmgb_coarse_dd_create: bad arguments");
+    mfmgb_comm *c = ctx_comm(ctx);
+    MFMGB_REQUIRE(ctx, c != nullptr, "mfmgb_coarse_dd_create: needs an initialised communicator (mfmgb_comm_init)");
+    const int64_t n_I = A_II->n_rows, n_adj = A_IS->n_cols;
+    MFMGB_REQUIRE(ctx, A_II->n_cols == n_I && A_IS->n_rows == n_I && A_SI->n_rows == n_adj && A_SI->n_cols == n_I &&
+                           A_SS->n_rows == n_S && A_SS->n_cols == n_S,
+                  "mfmgb_coarse_dd_create: block shapes are inconsistent");
+    MFMGB_REQUIRE(ctx, own_begin >= 0 && own_begin + n_I <= n_c && adj_begin >= 0 && adj_begin + n_adj <= n_S &&
+                           own_sep_begin >= 0 && own_sep_begin + own_sep_n <= n_S,
+                  "mfmgb_coarse_dd_create: index ranges out of bounds");
+    *out = nullptr;
+    mfmgb_coarse_dd *d = new mfmgb_coarse_dd();
+    d->n_c = n_c;
+    d->own_begin = own_begin;
+    d->n_I = n_I;
+    d->n_S = n_S;
+    d->adj_begin = adj_begin;
+    d->n_adj = n_adj;
+    d->own_sep_begin = own_sep_begin;
+    d->own_sep_n = own_sep_n;
+    d->A_SI = A_SI;
+    cudaStream_t st = ctx->stream;
+    const int64_t ldE = (std::max<int64_t>(n_adj, 1) + 3) & ~(int64_t)3;
+    d->ldE = ldE;
+    MFMGB_CUDA(ctx, cudaMalloc(&d->y, sizeof(double) * (size_t)(n_I + 2)));
+    MFMGB_CUDA(ctx, cudaMalloc(&d->t, sizeof(double) * (size_t)(n_S + 2)));
+    MFMGB_CUDA(ctx, cudaMalloc(&d->xs, sizeof(double) * (size_t)(n_S + 2)));
+    MFMGB_CUDA(ctx, cudaMalloc(&d->g, sizeof(double) * (size_t)(n_adj + 2)));
+    MFMGB_CUDA(ctx, cudaMemsetAsync(d->g, 0, sizeof(double) * (size_t)(n_adj + 2), st));
+    MFMGB_CUDA(ctx, cudaMemsetAsync(d->xs, 0, sizeof(double) * (size_t)(n_S + 2), st));
+    if (n_S > 0)
+    {
+      MFMGB_CUDA(ctx, cudaMalloc(&d->sep_index, sizeof(int32_t) * (size_t)n_S));
+      MFMGB_CUDA(ctx, cudaMemcpy(d->sep_index, sep_index, sizeof(int32_t) * (size_t)n_S, cudaMemcpyHostToDevice));
+    }
+    // interior block: A_II^-1
+    if (n_I > 0)
+      MFMGB_CHECK(mfmgb_dense_factor(ctx, A_II, &d->D_II));
+    if (n_S > 0)
+    {
+      const int64_t ldS = (n_S + 3) & ~(int64_t)3;
+      double *S = nullptr;
+      // rank 0 contributes A_SS, every rank subtracts its A_SI A_II^-1 A_IS block; the sum is the Schur complement
+      if (c->rank == 0)
+        MFMGB_CHECK(csr_to_dense_device(ctx, A_SS, ldS, &S));
+      else
+      {
+        MFMGB_CUDA(ctx, cudaMalloc(&S, sizeof(double) * (size_t)(n_S * ldS)));
+        MFMGB_CUDA(ctx, cudaMemsetAsync(S, 0, sizeof(double) * (size_t)(n_S * ldS), st));
+      }
+      if (n_I > 0 && n_adj > 0)
+      {
+        double *Ais = nullptr, *Asi = nullptr, *C = nullptr;
+        const int64_t ldI = (n_I + 3) & ~(int64_t)3;
+        MFMGB_CHECK(csr_to_dense_device(ctx, A_IS, ldE, &Ais)); // n_I x ldE
+        MFMGB_CHECK(csr_to_dense_device(ctx, A_SI, ldI, &Asi)); // n_adj x ldI
+        MFMGB_CUDA(ctx, cudaMalloc(&d->E, sizeof(double) * (size_t)(n_I * ldE)));
+        MFMGB_CUDA(ctx, cudaMemsetAsync(d->E, 0, sizeof(double) * (size_t)(n_I * ldE), st));
+        MFMGB_CUDA(ctx, cudaMalloc(&C, sizeof(double) * (size_t)(n_adj * ldE)));
+        // E = A_II^-1 A_IS ; C = A_SI E
+        MFMGB_CHECK(dense_gemm(ctx, n_I, n_adj, n_I, d->D_II->inv, d->D_II->lda, Ais, ldE, d->E, ldE, 1., 0.));
+        MFMGB_CHECK(dense_gemm(ctx, n_adj, n_adj, n_I, Asi, ldI, d->E, ldE, C, ldE, 1., 0.));
+        dim3 grid((unsigned)ceil_div(n_adj, 256), (unsigned)n_adj);
+        dd_sub_block_kernel<<<grid, 256, 0, st>>>(n_adj, C, ldE, S, ldS, adj_begin);
+        MFMGB_LAUNCHED(ctx);
+        MFMGB_CUDA(ctx, cudaStreamSynchronize(st));
+        cudaFree(Ais);
+        cudaFree(Asi);
+        cudaFree(C);
+      }
+      MFMGB_NCCL(ctx, ncclAllReduce(S, S, (size_t)(n_S * ldS), ncclDouble, ncclSum, c->nccl, st));
+      MFMGB_CHECK(dense_factor_device(ctx, S, n_S, &d->D_S)); // takes ownership of S
+    }
+    MFMGB_CUDA(ctx, cudaStreamSynchronize(st));
+    *out = d;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_coarse_dd_destroy(mfmgb_ctx *ctx, mfmgb_coarse_dd *d)
+  {
+    if (!d)
+      return MFMGB_OK;
+    MFMGB_REQUIRE(ctx, ctx, "ctx is NULL");
+    MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    mfmgb_dense_destroy(ctx, d->D_II);
+    mfmgb_dense_destroy(ctx, d->D_S);
+    cudaFree(d->E);
+    cudaFree(d->sep_index);
+    cudaFree(d->y);
+    cudaFree(d->t);
+    cudaFree(d->xs);
+    cudaFree(d->g);
+    delete d;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_coarse_dd_solve(mfmgb_ctx *ctx, const mfmgb_coarse_dd *d, const double *b_c, double *x_c)
+  {
+    MFMGB_REQUIRE(ctx, ctx && d && b_c && x_c && b_c != x_c, "mfmgb_coarse_dd_solve: bad arguments");
+    return coarse_dd_solve_async(ctx, d, b_c, x_c);
+  }
+}

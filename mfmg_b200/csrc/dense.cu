@@ -269,6 +269,14 @@ __device__ __forceinline__ void gemm_tile(int64_t M, int64_t N, int64_t K, const
   }
 }
 
+// C = alpha A B + beta C (row-major, any sizes)
+__global__ void __launch_bounds__(256) gemm_kernel(int64_t M, int64_t N, int64_t K, const double *__restrict__ A,
+                                                   int64_t lda, const double *__restrict__ B, int64_t ldb,
+                                                   double *__restrict__ C, int64_t ldc, double alpha, double beta)
+{
+  gemm_tile(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, blockIdx.y, blockIdx.x);
+}
+
 // trailing update A22 -= L21 U12
 __global__ void __launch_bounds__(256) lu_update_kernel(double *__restrict__ a, int64_t lda, int64_t n, int64_t k0, int kb)
 {
@@ -516,22 +524,56 @@ int dense_enable_distributed(mfmgb_ctx *ctx, mfmgb_dense *D)
 }
 } // namespace mfmgb
 
-extern "C"
+namespace mfmgb
 {
-  MFMGB_API int mfmgb_dense_factor(mfmgb_ctx *ctx, const mfmgb_csr *A, mfmgb_dense **out)
+int dense_gemm(mfmgb_ctx *ctx, int64_t M, int64_t N, int64_t K, const double *A, int64_t lda, const double *B,
+               int64_t ldb, double *C, int64_t ldc, double alpha, double beta)
+{
+  if (M <= 0 || N <= 0)
+    return MFMGB_OK;
+  dim3 grid((unsigned)ceil_div(N, TN), (unsigned)ceil_div(M, TM));
+  gemm_kernel<<<grid, 256, 0, ctx->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
+  MFMGB_LAUNCHED(ctx);
+  return MFMGB_OK;
+}
+
+int dense_apply_rows(mfmgb_ctx *ctx, const mfmgb_dense *D, const double *b, double *out, int64_t row0, int64_t n_out)
+{
+  return launch_gemv(ctx, D, b, out, row0, n_out);
+}
+
+// dense row-major copy (n_rows x lda, zero padded) of a CSR matrix; duplicates are summed
+int csr_to_dense_device(mfmgb_ctx *ctx, const mfmgb_csr *A, int64_t lda, double **out)
+{
+  const size_t bytes = sizeof(double) * (size_t)std::max<int64_t>(A->n_rows * lda, 1);
+  double *a = nullptr;
+  MFMGB_CUDA(ctx, cudaMalloc(&a, bytes));
+  MFMGB_CUDA(ctx, cudaMemsetAsync(a, 0, bytes, ctx->stream));
+  if (A->n_rows > 0)
   {
-    MFMGB_REQUIRE(ctx, ctx && A && out, "mfmgb_dense_factor: bad arguments");
-    MFMGB_REQUIRE(ctx, A->n_rows == A->n_cols, "mfmgb_dense_factor: the matrix is not square");
+    const unsigned nb = (unsigned)ceil_div(A->n_rows, 256);
+    if (A->off64)
+      csr_to_dense_kernel<int64_t><<<nb, 256, 0, ctx->stream>>>(A->n_rows, (const int64_t *)A->rowptr, A->col, A->val, a, lda);
+    else
+      csr_to_dense_kernel<int32_t><<<nb, 256, 0, ctx->stream>>>(A->n_rows, (const int32_t *)A->rowptr, A->col, A->val, a, lda);
+    MFMGB_LAUNCHED(ctx);
+  }
+  *out = a;
+  return MFMGB_OK;
+}
+
+// factorise / invert the dense row-major matrix `lu` (n x lda, lda = n rounded up to 4, padding columns zero) in place;
+// takes ownership of `lu` (it becomes D->inv)
+int dense_factor_device(mfmgb_ctx *ctx, double *lu, int64_t n, mfmgb_dense **out)
+{
     *out = nullptr;
-    const int64_t n = A->n_rows;
     const int64_t lda = (n + 3) & ~(int64_t)3;
     mfmgb_dense *D = new mfmgb_dense();
     D->n = n;
     D->lda = lda;
     const size_t bytes = sizeof(double) * (size_t)std::max<int64_t>(n * lda, 1);
-    double *lu = nullptr, *linv = nullptr, *uinv = nullptr, *T = nullptr;
+    double *linv = nullptr, *uinv = nullptr, *T = nullptr;
     int *piv = nullptr, *info_dev = nullptr;
-    MFMGB_CUDA(ctx, cudaMalloc(&lu, bytes));
     MFMGB_CUDA(ctx, cudaMalloc(&linv, bytes));
     MFMGB_CUDA(ctx, cudaMalloc(&uinv, bytes));
     MFMGB_CUDA(ctx, cudaMalloc(&T, bytes));
@@ -542,7 +584,6 @@ extern "C"
     MFMGB_CUDA(ctx, cudaMalloc(&D->work1, sizeof(double) * (size_t)(n + 2)));
     MFMGB_CUDA(ctx, cudaMemsetAsync(D->work0, 0, sizeof(double) * (size_t)(n + 2), ctx->stream));
     MFMGB_CUDA(ctx, cudaMemsetAsync(D->work1, 0, sizeof(double) * (size_t)(n + 2), ctx->stream));
-    MFMGB_CUDA(ctx, cudaMemsetAsync(lu, 0, bytes, ctx->stream));
     MFMGB_CUDA(ctx, cudaMemsetAsync(linv, 0, bytes, ctx->stream));
     MFMGB_CUDA(ctx, cudaMemsetAsync(uinv, 0, bytes, ctx->stream));
     MFMGB_CUDA(ctx, cudaMemsetAsync(T, 0, bytes, ctx->stream));
@@ -550,13 +591,6 @@ extern "C"
     cudaStream_t st = ctx->stream;
     if (n > 0)
     {
-      if (A->off64)
-        csr_to_dense_kernel<int64_t><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(n, (const int64_t *)A->rowptr, A->col,
-                                                                                 A->val, lu, lda);
-      else
-        csr_to_dense_kernel<int32_t><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(n, (const int32_t *)A->rowptr, A->col,
-                                                                                 A->val, lu, lda);
-      MFMGB_LAUNCHED(ctx);
       // blocked right-looking LU
       for (int64_t k0 = 0; k0 < n; k0 += NB)
       {
@@ -644,6 +678,22 @@ extern "C"
     cudaFree(info_dev);
     *out = D;
     return MFMGB_OK;
+  }
+
+} // namespace mfmgb
+
+extern "C"
+{
+  MFMGB_API int mfmgb_dense_factor(mfmgb_ctx *ctx, const mfmgb_csr *A, mfmgb_dense **out)
+  {
+    MFMGB_REQUIRE(ctx, ctx && A && out, "mfmgb_dense_factor: bad arguments");
+    MFMGB_REQUIRE(ctx, A->n_rows == A->n_cols, "mfmgb_dense_factor: the matrix is not square");
+    *out = nullptr;
+    const int64_t n = A->n_rows;
+    const int64_t lda = (n + 3) & ~(int64_t)3;
+    double *lu = nullptr;
+    MFMGB_CHECK(csr_to_dense_device(ctx, A, lda, &lu));
+    return dense_factor_device(ctx, lu, n, out);
   }
 
   MFMGB_API int mfmgb_dense_destroy(mfmgb_ctx *ctx, mfmgb_dense *D)

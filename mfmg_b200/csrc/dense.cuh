@@ -1,5 +1,6 @@
 // dense.cuh -- dense coarse solver state (internal).
 #pragma once
+#include "csr.cuh"
 #include "common.cuh"
 
 struct mfmgb_dense
@@ -17,9 +18,20 @@ struct mfmgb_dense
   double *chunk = nullptr, *gathered = nullptr;
 };
 
+struct mfmgb_coarse_dd;
+
 namespace mfmgb
 {
 int dense_solve_async(mfmgb_ctx *ctx, const mfmgb_dense *D, const double *b, double *x);
 // switch the solve of D to the row-split multi-GPU form (needs an initialised communicator)
 int dense_enable_distributed(mfmgb_ctx *ctx, mfmgb_dense *D);
+// domain-decomposed coarse solve of a row-partitioned hierarchy (coarse_dd.cu): on return x_c is valid on this
+// rank's coarse rows and on all separator rows
+int coarse_dd_solve_async(mfmgb_ctx *ctx, const mfmgb_coarse_dd *d, const double *b_c, double *x_c);
+// building blocks shared with the domain-decomposed coarse solver (coarse_dd.cu)
+int csr_to_dense_device(mfmgb_ctx *ctx, const mfmgb_csr *A, int64_t lda, double **out); // n_rows x lda, zero padded
+int dense_factor_device(mfmgb_ctx *ctx, double *lu, int64_t n, mfmgb_dense **out);     // takes ownership of lu
+int dense_apply_rows(mfmgb_ctx *ctx, const mfmgb_dense *D, const double *b, double *out, int64_t row0, int64_t n_out);
+int dense_gemm(mfmgb_ctx *ctx, int64_t M, int64_t N, int64_t K, const double *A, int64_t lda, const double *B,
+               int64_t ldb, double *C, int64_t ldc, double alpha, double beta);
 }

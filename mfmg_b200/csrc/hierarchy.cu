@@ -59,6 +59,7 @@ struct mfmgb_hierarchy
   // multi-GPU: offsets of the rank-owned slices of the (replicated) coarsest-level vectors
   std::vector<int64_t> coarse_offsets;
   bool distributed = false;
+  const mfmgb_coarse_dd *dd = nullptr; // domain-decomposed coarse solve (coarse_dd.cu) instead of the dense inverse
   // stage profiling (mfmgb_vcycle_profile): events between the level-0 stages
   bool profiling = false;
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -115,8 +116,8 @@ int apply_level(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, 
   mfmgb_level &fine = H->lev[li];
   const int64_t n = fine.n;
   const bool x_is_zero = li > 0 || H->is_preconditioner; // hierarchy.hpp:253-259
-  if (li == H->n_levels - 1)
-    return dense_solve_async(ctx, fine.D, b, x); // hierarchy.hpp:261-268 (the solve overwrites x)
+  if (li == H->n_levels - 1) // hierarchy.hpp:261-268 (the solve overwrites x)
+    return H->dd ? coarse_dd_solve_async(ctx, H->dd, b, x) : dense_solve_async(ctx, fine.D, b, x);
 
   mfmgb_level &coarse = H->lev[li + 1];
   const int nu = H->nu;
@@ -163,7 +164,8 @@ int apply_level(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, 
     mfmgb_comm *c = ctx_comm(ctx);
     e.y = coarse.bc + H->coarse_offsets[c->rank];
     MFMGB_CHECK(csr_apply(ctx, coarse.R, fine.res, Epi::Spmv, e));
-    MFMGB_CHECK(allgather_slices(ctx, coarse.bc, H->coarse_offsets));
+    if (!H->dd) // (the domain-decomposed coarse solve reads only this rank's slice)
+      MFMGB_CHECK(allgather_slices(ctx, coarse.bc, H->coarse_offsets));
   }
   else
   {
@@ -379,6 +381,14 @@ extern "C"
     return MFMGB_OK;
   }
 
+  MFMGB_API int mfmgb_hierarchy_set_coarse_dd(mfmgb_hierarchy *H, const mfmgb_coarse_dd *dd)
+  {
+    if (!H || !dd || H->finalized)
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_coarse_dd: bad arguments");
+    H->dd = dd;
+    return MFMGB_OK;
+  }
+
   MFMGB_API int64_t mfmgb_hierarchy_vector_size(const mfmgb_hierarchy *H, int level)
   {
     if (!H || level < 0 || level >= H->n_levels)
@@ -449,6 +459,8 @@ extern "C"
         // build_coarse_solver, hierarchy.hpp:194
         if (!l.A)
           return fail(ctx, MFMGB_ERR_INVALID, "mfmgb_hierarchy_finalize: the coarsest level needs an assembled operator");
+        if (H->dd)
+          continue;
         MFMGB_CHECK(mfmgb_dense_factor(ctx, l.A, &l.D));
         // partitioned hierarchy: from n_c = 8192 on, splitting the two triangular GEMVs by rows across the ranks
         // (2 small all-gathers) beats every rank streaming the whole factor (MFMGB_DENSE_SPLIT_MIN overrides)

@@ -17,6 +17,7 @@ Everything numeric happens in libmfmg_b200.so; this module only holds handles.
 from __future__ import annotations
 
 import ctypes
+import os
 from enum import Enum
 
 import numpy as np
@@ -454,6 +455,36 @@ class HaloPlan:
             pass
 
 
+class CoarseDD:
+    """Domain-decomposed dense coarse solve of a row-partitioned hierarchy (csrc/coarse_dd.cu) from a
+    hostsetup.coarse_dd_plan; a collective constructor (every rank of the communicator must call it)."""
+
+    def __init__(self, handle: CudaHandle, plan):
+        self.handle = handle
+        self.blocks = [SparseMatrixDevice.from_host(handle, plan[k]) for k in ("A_II", "A_IS", "A_SI", "A_SS")]
+        sep = np.ascontiguousarray(plan["sep_index"], dtype=np.int32)
+        p = ctypes.c_void_p()
+        check(handle.ctx, handle.lib.mfmgb_coarse_dd_create(
+            handle.ctx, int(plan["n_c"]), int(plan["own_begin"]), int(plan["n_S"]), int(plan["adj_begin"]),
+            int(plan["own_sep_begin"]), int(plan["own_sep_n"]), self.blocks[0].ptr, self.blocks[1].ptr,
+            self.blocks[2].ptr, self.blocks[3].ptr, sep.ctypes.data, ctypes.byref(p)))
+        self.ptr = p
+        self.n_interior, self.n_separator = int(plan["n_I"]), int(plan["n_S"])
+        self.n_adjacent = int(plan["A_IS"].n_cols)
+        # bytes one solve reads on this rank: A_II^-1, the Schur inverse, E = A_II^-1 A_IS
+        self.bytes_per_solve = 8 * (self.n_interior ** 2 + self.n_separator ** 2 + self.n_interior * self.n_adjacent)
+
+    def solve(self, b_c: DeviceVector, x_c: DeviceVector) -> None:
+        check(self.handle.ctx, self.handle.lib.mfmgb_coarse_dd_solve(self.handle.ctx, self.ptr, b_c.ptr, x_c.ptr))
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None) and getattr(self.handle, "ctx", None):
+                self.handle.lib.mfmgb_coarse_dd_destroy(self.handle.ctx, self.ptr)
+        except Exception:
+            pass
+
+
 class Hierarchy:
     """mfmg::Hierarchy on device vectors.  Built from already-assembled level operators
     (`from_operators`) -- the setup that produces them stays on the host path
@@ -463,9 +494,11 @@ class Hierarchy:
     "smoother.n_smoothing_steps", "smoother.type", "solver.type"."""
 
     def __init__(self, handle: CudaHandle, operators, restrictors, params=None, omega: float = 1.0,
-                 prolongators=None, halo: "HaloPlan | None" = None, boundary=(0, 0), coarse_offsets=None):
+                 prolongators=None, halo: "HaloPlan | None" = None, boundary=(0, 0), coarse_offsets=None,
+                 coarse_dd: "CoarseDD | None" = None):
         self.handle = handle
         self.halo = halo
+        self.coarse_dd = coarse_dd
         lib = handle.lib
         self.params = params or {}
         if str(_get(params, "smoother.type", "Jacobi")).lower() != "jacobi":
@@ -498,6 +531,8 @@ class Hierarchy:
             check(handle.ctx, lib.mfmgb_hierarchy_set_restrictor(self.ptr, li + 1, r.ptr, pr.ptr if pr else None))
         if halo is not None:
             check(handle.ctx, lib.mfmgb_hierarchy_set_halo(self.ptr, 0, halo.ptr, int(boundary[0]), int(boundary[1])))
+        if coarse_dd is not None:
+            check(handle.ctx, lib.mfmgb_hierarchy_set_coarse_dd(self.ptr, coarse_dd.ptr))
         check(handle.ctx, lib.mfmgb_hierarchy_finalize(handle.ctx, self.ptr))
         self.n = self.operators[0].size if isinstance(self.operators[0], MatrixFreeLaplaceDevice) \
             else self.operators[0].m()
@@ -513,7 +548,7 @@ class Hierarchy:
 
     @staticmethod
     def from_partition(handle: CudaHandle, part, params=None, omega: float = 1.0,
-                       matrix_free: bool = False) -> "Hierarchy":
+                       matrix_free: bool = False, coarse_dd: "bool | str" = "auto") -> "Hierarchy":
         """Row-partitioned two-level hierarchy of one rank (hostsetup.partition.LocalPart); the context must have
         an initialised communicator (CudaHandle.init_comm*).  matrix_free: level 0 is the matrix-free slab operator
         (part.mf, hostsetup.slab) instead of the assembled rows; R, P and A_c stay assembled."""
@@ -527,8 +562,25 @@ class Hierarchy:
         res = [SparseMatrixDevice.from_host(handle, part.R)]
         pro = [SparseMatrixDevice.from_host(handle, part.P)]
         plan = HaloPlan(handle, part)
+        # coarsest level: the domain-decomposed direct solve when the coarse operator is block tridiagonal in the
+        # ranks (z-slab partitions are) -- per-GPU work independent of the number of ranks; else the dense inverse,
+        # replicated or split by rows.  Every rank takes the same decision (it only depends on replicated data).
+        dd = None
+        if coarse_dd and part.world > 1 and os.environ.get("MFMGB_COARSE_DD", "1") != "0":
+            from .hostsetup import coarse_dd_plan
+
+            ddp = coarse_dd_plan(part.Ac, part.coarse_offsets, part.rank)
+            if ddp is not None:
+                if not np.all(np.isin(part.P.col, ddp["valid_cols"])):
+                    raise MfmgError(_lib.ERR_INVALID, "from_partition: prolongation rows read coarse entries outside "
+                                                      "this rank's rows and the separators")
+                dd = CoarseDD(handle, ddp)
+            elif coarse_dd is True:
+                raise MfmgError(_lib.ERR_INVALID, "from_partition: the coarse operator is not block tridiagonal in the "
+                                                  "ranks' row blocks; the domain-decomposed coarse solve cannot be used")
         return Hierarchy(handle, ops, res, params, omega, prolongators=pro, halo=plan,
-                         boundary=(part.boundary_lo, part.boundary_hi), coarse_offsets=part.coarse_offsets)
+                         boundary=(part.boundary_lo, part.boundary_hi), coarse_offsets=part.coarse_offsets,
+                         coarse_dd=dd)
 
     def build_vector(self) -> DeviceVector:
         """A level-0 vector with room for the ghost tail (Level::build_vector, level.hpp:63-70)."""

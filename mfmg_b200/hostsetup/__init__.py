@@ -6,5 +6,5 @@ from .amge import block_agglomerates, build_restrictor, galerkin, transpose  # n
 from .problems import (HostCSR, LaplaceProblem, assemble, boundary_mask,  # noqa: F401
                        coefficient_table, material_value, num_threads, reference_matrices,
                        set_num_threads)
-from .partition import LocalPart, make_parts, partition_two_level, slab_row_ranges  # noqa: F401,E402
+from .partition import LocalPart, coarse_dd_plan, make_parts, partition_two_level, slab_row_ranges  # noqa: F401,E402
 from .slab import build_slab_part  # noqa: F401,E402

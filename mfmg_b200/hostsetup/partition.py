@@ -157,3 +157,62 @@ def make_parts(problem, R: HostCSR, Ac: HostCSR, block, n_eigenvectors: int, wor
     ghost_lists = [p.ghost_global for p in parts]
     wanted = range(world) if ranks is None else ranks
     return [finalize_plan(parts[r], ghost_lists, row_off) for r in wanted], row_off, coarse_off
+
+
+def coarse_dd_plan(Ac: HostCSR, coarse_offsets, rank: int):
+    """Index sets and blocks of the domain-decomposed coarse solve (csrc/coarse_dd.cu) for `rank`, or None when the
+    coarse operator is not block tridiagonal in the ranks' row blocks (then the dense inverse is used).
+
+    Separator of rank r < N-1: its coarse rows from the first one coupled to rank r+1 to the end of its block (for
+    slab partitions: the last agglomerate layer).  The decision only uses the replicated A_c and the offsets, so every
+    rank reaches the same one without communication."""
+    import scipy.sparse as sp
+
+    co = np.asarray(coarse_offsets, dtype=np.int64)
+    world = len(co) - 1
+    if world < 2:
+        return None
+    A = Ac.to_scipy().tocsr()
+    n_c = A.shape[0]
+    row_of = np.repeat(np.arange(n_c), np.diff(A.indptr))
+    sep_begin = co[1:].copy()                      # S_r = [sep_begin[r], co[r+1]); empty on the last rank
+    for r in range(world - 1):
+        mask = (row_of >= co[r]) & (row_of < co[r + 1]) & (A.indices >= co[r + 1])
+        if mask.any():
+            sep_begin[r] = row_of[mask].min()
+        if (A.indices[(row_of >= co[r]) & (row_of < co[r + 1])] >= (co[r + 2] if r + 2 <= world else n_c)).any():
+            return None                             # couples beyond the next rank
+    s_off = np.concatenate([[0], np.cumsum(co[1:] - sep_begin)]).astype(np.int64)   # S numbering offsets per rank
+    n_S = int(s_off[-1])
+    if n_S == 0:
+        return None
+    sep_index = np.concatenate([np.arange(sep_begin[r], co[r + 1]) for r in range(world)]).astype(np.int32)
+    is_sep = np.zeros(n_c, dtype=bool)
+    is_sep[sep_index] = True
+    # every interior may only couple to itself and to the separators right below / above it
+    for r in range(world):
+        lo, hi = co[r], sep_begin[r]
+        if hi <= lo:
+            continue
+        cols = A.indices[A.indptr[lo]:A.indptr[hi]]
+        inside = (cols >= lo) & (cols < hi)
+        below = (cols >= (sep_begin[r - 1] if r > 0 else lo)) & (cols < lo) if r > 0 else np.zeros_like(inside)
+        above = (cols >= hi) & (cols < co[r + 1])
+        if not np.all(inside | below | above):
+            return None
+    lo, hi = int(co[rank]), int(sep_begin[rank])
+    adj_begin = int(s_off[rank - 1]) if rank > 0 else 0
+    adj_end = int(s_off[rank + 1])
+    adj_cols = sep_index[adj_begin:adj_end].astype(np.int64)
+    I = np.arange(lo, hi)
+    blocks = {
+        "A_II": HostCSR.from_scipy(A[lo:hi][:, lo:hi]),
+        "A_IS": HostCSR.from_scipy(A[lo:hi][:, adj_cols] if len(adj_cols) else sp.csr_matrix((hi - lo, 0))),
+        "A_SI": HostCSR.from_scipy(A[adj_cols][:, lo:hi] if len(adj_cols) else sp.csr_matrix((0, hi - lo))),
+        "A_SS": HostCSR.from_scipy(A[sep_index.astype(np.int64)][:, sep_index.astype(np.int64)]),
+    }
+    for m in blocks.values():
+        m.to_scipy().sort_indices()
+    return {"n_c": n_c, "own_begin": lo, "n_I": len(I), "n_S": n_S, "adj_begin": adj_begin,
+            "own_sep_begin": int(s_off[rank]), "own_sep_n": int(s_off[rank + 1] - s_off[rank]),
+            "sep_index": sep_index, "valid_cols": np.concatenate([np.arange(lo, co[rank + 1]), sep_index]), **blocks}

@@ -29,12 +29,16 @@ def main():
     cases = [(3, 1, 16, 2, 2, "constant", 1), (3, 1, 24, 4, 1, "discontinuous", 2), (3, 2, 8, 2, 2, "linear", 1),
              (2, 1, 64, 2, 2, "constant", 1)]
     # second pass: force the row-split (multi-GPU) dense coarse solve, which is normally used from n_c = 8192 on
-    cases = [c + (False,) for c in cases] + [c + (True,) for c in cases[:2]]
-    for dim, degree, cells, block, ne, mat, nu, split_dense in cases:
-        os.environ["MFMGB_DENSE_SPLIT_MIN"] = "1" if split_dense else "8192"
+    # coarse-solver variants: "dd" = domain-decomposed direct solve (the default for slab partitions), "split" = dense
+    # inverse split by rows over the ranks, "replicated" = dense inverse on every rank
+    cases = [c + ("dd",) for c in cases] + [c + ("split",) for c in cases[:2]] + [cases[0] + ("replicated",)]
+    for dim, degree, cells, block, ne, mat, nu, coarse in cases:
+        os.environ["MFMGB_DENSE_SPLIT_MIN"] = "1" if coarse == "split" else "8192"
+        os.environ["MFMGB_COARSE_DD"] = "1" if coarse == "dd" else "0"
         P, R, Ac = two_level_problem(dim, degree, cells, block, ne, mat)
         (part,), row_off, coarse_off = hs.make_parts(P, R, Ac, (block,) * dim, ne, world, ranks=[rank])
         H = d.Hierarchy.from_partition(handle, part, {"is preconditioner": True, "smoother": {"n_smoothing_steps": nu}})
+        assert (H.coarse_dd is not None) == (coarse == "dd"), (rank, coarse)
         Ho = oracle_hierarchy(P, R, Ac, nu, True)
         rng = np.random.default_rng(5)
         b_h = rng.standard_normal(P.n)
@@ -85,7 +89,7 @@ def main():
         err = np.linalg.norm(x.to_host()[:part.n_owned] - x_o[sl]) / max(np.linalg.norm(x_o[sl]), 1e-300)
         assert err < 1e-8 or np.linalg.norm(x_o[sl]) < 1e-6, (rank, "pcg x", err)
         if rank == 0:
-            print(f"case {dim}D Q{degree} {cells}^{dim} {mat} split_dense={split_dense}: vcycle OK, PCG {it.value} its (oracle {it_ref})", flush=True)
+            print(f"case {dim}D Q{degree} {cells}^{dim} {mat} coarse={coarse}: vcycle OK, PCG {it.value} its (oracle {it_ref})", flush=True)
     # matrix-free level 0 on z-slabs (cfg4): slab-local setup with real gathers, assembled R / P / A_c
     cells, h, block = (12, 10, 8 * world), (0.05, 0.04, 0.03), (4, 5, 4)
 
@@ -94,6 +98,7 @@ def main():
         dist.all_gather_object(out, obj)
         return out
 
+    os.environ["MFMGB_COARSE_DD"] = "1"
     for mat in ("discontinuous", "linear"):
         part = hs.build_slab_part(1, cells, h, mat, block, 1, world, rank, gather)
         assert part.mf is not None

@@ -182,3 +182,49 @@ def test_matrix_free_slab_data(world, cells, block, mat):
         assert np.max(np.abs(got - y_ref[part.row_begin:part.row_end])) <= 1e-12 * np.abs(y_ref).max()
         dl = Ml.diag()[own0 * plane:own1 * plane]
         assert np.max(np.abs(dl - Mo.diag()[part.row_begin:part.row_end])) <= 1e-12 * np.abs(Mo.diag()).max()
+
+
+@pytest.mark.parametrize("world,cells,block,ne", [(2, (4, 4, 8), (2, 2, 2), 1), (3, (6, 4, 18), (2, 2, 3), 2), (4, (4, 4, 8), (2, 2, 2), 1)])
+def test_coarse_dd_plan_block_elimination(world, cells, block, ne):
+    """hostsetup.coarse_dd_plan: the interior / separator blocks it hands to csrc/coarse_dd.cu reproduce A_c^-1 b by
+    block elimination (numpy restatement of the device algorithm), and the prolongation rows of every rank only read
+    coarse entries the solver leaves valid there."""
+    from helpers import slab_parts
+    from mfmg_b200 import hostsetup as hs
+
+    h = (0.1, 0.1, 0.1)
+    parts = slab_parts(world, cells, h, block, ne, 1, "linear")
+    Ac = parts[0].Ac.to_scipy().toarray()
+    n_c = Ac.shape[0]
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal(n_c)
+    x_ref = np.linalg.solve(Ac, b)
+    plans = [hs.coarse_dd_plan(p.Ac, p.coarse_offsets, p.rank) for p in parts]
+    assert all(pl is not None for pl in plans)
+    n_S, sep = plans[0]["n_S"], plans[0]["sep_index"]
+    S = plans[0]["A_SS"].to_scipy().toarray().copy()
+    E, Minv = [], []
+    for pl in plans:
+        AII, AIS, ASI = (pl[k].to_scipy().toarray() for k in ("A_II", "A_IS", "A_SI"))
+        Mi = np.linalg.inv(AII) if AII.shape[0] else AII
+        a0, na = pl["adj_begin"], AIS.shape[1]
+        S[a0:a0 + na, a0:a0 + na] -= ASI @ (Mi @ AIS)
+        E.append(Mi @ AIS)
+        Minv.append(Mi)
+    t, ys = np.zeros(n_S), []
+    for pl, Mi in zip(plans, Minv):
+        y = Mi @ b[pl["own_begin"]:pl["own_begin"] + pl["n_I"]]
+        ys.append(y)
+        a0, na = pl["adj_begin"], pl["A_IS"].n_cols
+        t[a0:a0 + na] -= pl["A_SI"].to_scipy() @ y
+        o0, on = pl["own_sep_begin"], pl["own_sep_n"]
+        t[o0:o0 + on] += b[sep[o0:o0 + on]]
+    xs = np.linalg.solve(S, t)
+    x = np.zeros(n_c)
+    x[sep] = xs
+    for pl, y, Er in zip(plans, ys, E):
+        a0, na = pl["adj_begin"], pl["A_IS"].n_cols
+        x[pl["own_begin"]:pl["own_begin"] + pl["n_I"]] = y - Er @ xs[a0:a0 + na]
+    assert np.linalg.norm(x - x_ref) <= 1e-12 * np.linalg.norm(x_ref)
+    for p, pl in zip(parts, plans):
+        assert np.all(np.isin(p.P.col, pl["valid_cols"]))
