@@ -93,7 +93,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
         _nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
         "-ccbin", _host_cxx(), "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",
         "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-I", nccl_inc,
-        "--expt-relaxed-constexpr",
+        "--expt-relaxed-constexpr", "--threads", "0",
     ]
     if verbose:
         cmd += ["-Xptxas", "-v"]

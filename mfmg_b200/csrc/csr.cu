@@ -95,6 +95,50 @@ __global__ void __launch_bounds__(kBlock)
     epilogue<EPI>(e, g, row, s);
 }
 
+// one CTA per row: rows of thousands of entries (restrictors of large agglomerates: 17^3 = 4913, 21^3 = 9261) in
+// matrices with too few rows to fill the GPU with one warp per row.  4 gathers in flight per thread, fixed block tree.
+template <int EPI, typename OffT>
+__global__ void __launch_bounds__(kBlock, 4)
+    csr_rowblock_kernel(int64_t row_begin, int64_t n_rows, const OffT *__restrict__ rowptr, const int *__restrict__ col,
+                        const double *__restrict__ val, const double *__restrict__ x, EpiArgs e)
+{
+  __shared__ double sm[kBlock / 32];
+  const int64_t row = row_begin + blockIdx.x;
+  if (row >= n_rows)
+    return;
+  EpiRegs g;
+  if (threadIdx.x == 0)
+    g = epilogue_load<EPI>(e, row);
+  const OffT k1 = rowptr[row + 1];
+  OffT k = rowptr[row] + threadIdx.x;
+  double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
+  for (; k + 3 * kBlock < k1; k += 4 * kBlock)
+  {
+    const int c0 = col[k], c1 = col[k + kBlock], c2 = col[k + 2 * kBlock], c3 = col[k + 3 * kBlock];
+    const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+    s0 = fma(val[k], x0, s0);
+    s1 = fma(val[k + kBlock], x1, s1);
+    s2 = fma(val[k + 2 * kBlock], x2, s2);
+    s3 = fma(val[k + 3 * kBlock], x3, s3);
+  }
+  for (; k < k1; k += kBlock)
+    s0 = fma(val[k], __ldg(x + col[k]), s0);
+  const double s = block_sum<kBlock>((s0 + s1) + (s2 + s3), sm);
+  if (threadIdx.x == 0)
+    epilogue<EPI>(e, g, row, s);
+}
+
+template <int EPI, typename OffT>
+int launch_rowblock(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArgs &e, int64_t r0, int64_t r1)
+{
+  if (r1 <= r0)
+    return MFMGB_OK;
+  csr_rowblock_kernel<EPI, OffT><<<(unsigned)(r1 - r0), kBlock, 0, ctx->stream>>>(r0, r1, (const OffT *)A->rowptr, A->col,
+                                                                                 A->val, x, e);
+  MFMGB_LAUNCHED(ctx);
+  return MFMGB_OK;
+}
+
 template <int LPR, int EPI, typename OffT>
 int launch_vec(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArgs &e, int64_t r0, int64_t r1)
 {
@@ -123,6 +167,8 @@ int dispatch_lanes(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const Ep
     return launch_vec<8, EPI, OffT>(ctx, A, x, e, r0, r1);
   case 16:
     return launch_vec<16, EPI, OffT>(ctx, A, x, e, r0, r1);
+  case 256:
+    return launch_rowblock<EPI, OffT>(ctx, A, x, e, r0, r1);
   default:
     return launch_vec<32, EPI, OffT>(ctx, A, x, e, r0, r1);
   }
@@ -153,6 +199,9 @@ int choose_lanes(int64_t n_rows, int64_t nnz)
   // Measured on B200 (profiles/r01_lanes_sweep.md): about 6-7 entries per lane is the sweet spot
   // (27-nnz rows: 4 lanes reach 88 % of the copy bandwidth, 8 lanes 65 %, 32 lanes 28 %).
   const double mean = (double)nnz / (double)n_rows;
+  // thousands of entries per row and too few rows for one warp each to fill 148 SMs: one CTA per row
+  if (mean >= 2048. && n_rows < 16384)
+    return 256;
   int lanes = 1;
   while (lanes < 32 && lanes * 2 * 6 <= mean)
     lanes *= 2;
@@ -389,8 +438,10 @@ extern "C"
 
   MFMGB_API int mfmgb_csr_set_lanes_per_row(mfmgb_csr *A, int lanes)
   {
-    if (!A || !(lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32))
-      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_csr_set_lanes_per_row: lanes must be 0,1,2,4,8,16,32");
+    if (!A || !(lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32 ||
+                lanes == 256))
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_csr_set_lanes_per_row: lanes must be 0,1,2,4,8,16,32 or 256 "
+                                                "(one CTA per row)");
     A->lanes_override = lanes;
     A->lanes = lanes ? lanes : choose_lanes(A->n_rows, A->nnz);
     csr_plan_tile(A);

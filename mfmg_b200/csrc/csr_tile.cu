@@ -367,7 +367,7 @@ int tile_cap_slot(int lanes)
 void csr_plan_tile(mfmgb_csr *A)
 {
   A->tile_ok = false;
-  if (!A->padded || A->n_rows == 0 || A->nnz == 0)
+  if (!A->padded || A->n_rows == 0 || A->nnz == 0 || A->lanes > 32)
     return;
   const int rpt = kConsumerWarps * 32 / A->lanes;
   const int64_t cap = A->tile_cap[tile_cap_slot(A->lanes)];

@@ -94,7 +94,17 @@ int level_apply_A(mfmgb_ctx *ctx, const mfmgb_level &l, double *x, Epi epi, cons
     return csr_apply(ctx, l.A, x, epi, e);
   // row-partitioned level: the halo exchange of x runs on the communication stream while the interior rows
   // are computed; the rows that reference ghost columns follow once the ghosts have landed
+  // (MFMGB_HALO_OVERLAP=0: exchange first, then one launch over all rows -- measurement aid)
+  static const bool overlap = [] {
+    const char *v = getenv("MFMGB_HALO_OVERLAP");
+    return !(v && v[0] == '0');
+  }();
   MFMGB_CHECK(halo_start(ctx, l.halo, x));
+  if (!overlap)
+  {
+    MFMGB_CHECK(halo_wait(ctx));
+    return csr_apply(ctx, l.A, x, epi, e);
+  }
   MFMGB_CHECK(csr_apply(ctx, l.A, x, epi, e, l.blo, l.bhi));
   MFMGB_CHECK(halo_wait(ctx));
   if (l.blo > 0)

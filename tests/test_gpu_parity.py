@@ -167,7 +167,7 @@ def test_kernels_vs_oracle(handle, dim, degree, cells, block, ne, mat):
     x, b = d.DeviceVector.from_host(handle, x_h), d.DeviceVector.from_host(handle, b_h)
     y = d.DeviceVector(handle, n)
     lib, ctx = handle.lib, handle.ctx
-    for lanes in (0, 1, 2, 4, 8, 32):
+    for lanes in (0, 1, 2, 4, 8, 32, 256):
         Ad.set_lanes_per_row(lanes)
         Ad.vmult(y, x)
         assert rel_err(y.to_host(), oracle.spmv(n, *A, x_h)) < TOL_OP
