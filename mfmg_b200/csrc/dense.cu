@@ -477,7 +477,7 @@ int launch_gemv(mfmgb_ctx *ctx, const mfmgb_dense *D, const double *b, double *o
 {
   if (n_out <= 0)
     return MFMGB_OK;
-  if (D->n >= 2048)
+  if (D->n >= 1024)
     gemv_kernel<256><<<(unsigned)n_out, 256, 0, ctx->stream>>>(D->n, D->inv, D->lda, b, out, row0, n_out);
   else
     gemv_kernel<32><<<(unsigned)ceil_div(n_out, 8), 256, 0, ctx->stream>>>(D->n, D->inv, D->lda, b, out, row0, n_out);
