@@ -220,6 +220,9 @@ extern "C"
    * [boundary_lo, boundary_hi) reference owned columns only and overlap the exchange */
   MFMGB_API int mfmgb_hierarchy_set_halo(mfmgb_hierarchy *H, int level, const mfmgb_halo *halo, int64_t boundary_lo,
                                          int64_t boundary_hi);
+  /* rows [0, first_boundary_row) of the level's restrictor reference owned fine columns only: they are computed while
+   * the residual's halo is exchanged (after mfmgb_hierarchy_set_restrictor; default 0 = no overlap) */
+  MFMGB_API int mfmgb_hierarchy_set_restrict_split(mfmgb_hierarchy *H, int level, int64_t first_boundary_row);
   /* offsets (nranks + 1) of the rank-owned rows of the replicated coarsest level */
   MFMGB_API int mfmgb_hierarchy_set_coarse_offsets(mfmgb_hierarchy *H, const int64_t *offsets, int nranks);
   /* Domain-decomposed form of the dense coarse solve for a row-partitioned hierarchy whose coarse operator is block

@@ -240,6 +240,20 @@ int csr_apply(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, cons
   return dispatch_epi<int32_t>(ctx, A, x, epi, args, row_begin, row_end);
 }
 
+int csr_apply2(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args, int64_t r0, int64_t r1,
+               int64_t q0, int64_t q1)
+{
+  if (r0 < 0 || r1 > A->n_rows || q0 < 0 || q1 > A->n_rows || (r1 > r0 && q1 > q0 && q0 < r1))
+    return fail(ctx, MFMGB_ERR_INVALID, "csr_apply2: row ranges out of bounds or overlapping");
+  if (csr_uses_tile_kernel(A))
+    return csr_apply_tile(ctx, A, x, epi, args, r0, r1, q0, q1);
+  if (r1 > r0)
+    MFMGB_CHECK(csr_apply(ctx, A, x, epi, args, r0, r1));
+  if (q1 > q0)
+    MFMGB_CHECK(csr_apply(ctx, A, x, epi, args, q0, q1));
+  return MFMGB_OK;
+}
+
 namespace
 {
 int finish_upload(mfmgb_ctx *ctx, mfmgb_csr *A)

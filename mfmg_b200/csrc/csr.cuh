@@ -46,7 +46,10 @@ int csr_apply(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, cons
 int choose_lanes(int64_t n_rows, int64_t nnz);
 // tile-streamed variant (csr_tile.cu): same contract as csr_apply; requires A->tile_ok
 int csr_apply_tile(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args, int64_t row_begin,
-                   int64_t row_end);
+                   int64_t row_end, int64_t row_begin2 = 0, int64_t row_end2 = 0);
+// two disjoint row ranges (the boundary blocks of a partitioned level): one launch with the tile kernel
+int csr_apply2(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args, int64_t r0, int64_t r1,
+               int64_t q0, int64_t q1);
 int csr_measure_tiles(mfmgb_ctx *ctx, mfmgb_csr *A); // fills tile_cap (setup time, synchronises)
 void csr_plan_tile(mfmgb_csr *A);                    // sets tile_ok / tile_stages / tile_ctas for the current lanes
 int tile_cap_slot(int lanes);

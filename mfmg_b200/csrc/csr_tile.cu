@@ -79,6 +79,9 @@ struct TileArgs
   int64_t n_rows;             // rows of the matrix
   int64_t row_begin, row_end; // rows this launch computes
   int64_t tile_begin, n_tiles;
+  // optional second row range [row_begin2, row_end2) in the same launch (the two boundary blocks of a partitioned
+  // level): tile slots [n_tiles1, n_tiles) map to tiles tile_begin2 + (slot - n_tiles1)
+  int64_t row_begin2, row_end2, tile_begin2, n_tiles1;
   const OffT *rowptr;
   const int *col;
   const double *val;
@@ -116,10 +119,11 @@ __global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArg
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
+  // this CTA's contiguous run of tile slots; slot -> tile (two row ranges may share one launch)
   const int64_t tpc = (a.n_tiles + gridDim.x - 1) / gridDim.x;
-  const int64_t t_begin = a.tile_begin + (int64_t)blockIdx.x * tpc;
-  const int64_t t_last = a.tile_begin + a.n_tiles;
-  const int64_t t_end = t_begin + tpc < t_last ? t_begin + tpc : t_last;
+  const int64_t t_begin = (int64_t)blockIdx.x * tpc;
+  const int64_t t_end = t_begin + tpc < a.n_tiles ? t_begin + tpc : a.n_tiles;
+  auto tile_of = [&](int64_t slot) { return slot < a.n_tiles1 ? a.tile_begin + slot : a.tile_begin2 + (slot - a.n_tiles1); };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == kConsumerWarps)
@@ -129,12 +133,15 @@ __global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArg
       return;
     const uint64_t policy = policy_evict_first();
     auto row_off = [&](int64_t r) { return a.rowptr[r < a.n_rows ? r : a.n_rows]; };
-    OffT k_lo = row_off(t_begin * RPT), k_hi = row_off((t_begin + 1) * RPT);
+    OffT k_lo = row_off(tile_of(t_begin) * RPT), k_hi = row_off((tile_of(t_begin) + 1) * RPT);
     int s = 0;
     uint32_t ph = 0;
-    for (int64_t t = t_begin; t < t_end; ++t)
+    for (int64_t i = t_begin; i < t_end; ++i)
     {
-      const OffT k_next = t + 1 < t_end ? row_off((t + 2) * RPT) : k_hi; // requested one tile ahead of its use
+      const int64_t t = tile_of(i);
+      // offsets of the next tile, requested one tile ahead of their use
+      const int64_t tn = i + 1 < t_end ? tile_of(i + 1) : t;
+      const OffT n_lo = row_off(tn * RPT), n_hi = row_off((tn + 1) * RPT);
       mbar_wait(empty + s, ph ^ 1u);
       const OffT a0 = k_lo & ~(OffT)3, a1 = (k_hi + 3) & ~(OffT)3;
       const uint32_t span = (uint32_t)(a1 - a0);
@@ -146,8 +153,8 @@ __global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArg
         bulk_g2s(st, a.val + a0, span * 8u, full + s, policy);
         bulk_g2s(st + (size_t)a.cap * 8, a.col + a0, span * 4u, full + s, policy);
       }
-      k_lo = k_hi;
-      k_hi = k_next;
+      k_lo = n_lo;
+      k_hi = n_hi;
       if (++s == S)
       {
         s = 0;
@@ -162,10 +169,11 @@ __global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArg
   const int sub = lane % LPR;
   int s = 0;
   uint32_t ph = 0;
-  for (int64_t t = t_begin; t < t_end; ++t)
+  for (int64_t i = t_begin; i < t_end; ++i)
   {
+    const int64_t t = tile_of(i);
     const int64_t row = t * RPT + lr;
-    const bool active = row >= a.row_begin && row < a.row_end;
+    const bool active = i < a.n_tiles1 ? (row >= a.row_begin && row < a.row_end) : (row >= a.row_begin2 && row < a.row_end2);
     const bool writer = active && sub == 0;
     // epilogue operands are requested before the wait so that their latency overlaps it
     double eb = 0., ed = 0., ex = 0.;
@@ -261,9 +269,16 @@ int env_int(const char *name, int dflt)
 }
 
 template <int LPR, int EPI, typename OffT>
-int launch_tile(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArgs &e, int64_t r0, int64_t r1)
+int launch_tile(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArgs &e, int64_t r0, int64_t r1,
+                int64_t q0, int64_t q1)
 {
   constexpr int RPT = kConsumerWarps * 32 / LPR;
+  if (r1 <= r0) // (an empty first range: the second one takes its place)
+  {
+    r0 = q0;
+    r1 = q1;
+    q0 = q1 = 0;
+  }
   if (r1 <= r0)
     return MFMGB_OK;
   TileArgs<OffT> a;
@@ -271,7 +286,11 @@ int launch_tile(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiAr
   a.row_begin = r0;
   a.row_end = r1;
   a.tile_begin = r0 / RPT;
-  a.n_tiles = ceil_div(r1, RPT) - a.tile_begin;
+  a.n_tiles1 = ceil_div(r1, RPT) - a.tile_begin;
+  a.row_begin2 = q0;
+  a.row_end2 = q1;
+  a.tile_begin2 = q1 > q0 ? q0 / RPT : 0;
+  a.n_tiles = a.n_tiles1 + (q1 > q0 ? ceil_div(q1, RPT) - a.tile_begin2 : 0);
   a.rowptr = (const OffT *)A->rowptr;
   a.col = A->col;
   a.val = A->val;
@@ -305,38 +324,40 @@ int launch_tile(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiAr
 }
 
 template <int EPI, typename OffT>
-int dispatch_lanes(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArgs &e, int64_t r0, int64_t r1)
+int dispatch_lanes(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArgs &e, int64_t r0, int64_t r1,
+                   int64_t q0, int64_t q1)
 {
   switch (A->lanes)
   {
   case 1:
-    return launch_tile<1, EPI, OffT>(ctx, A, x, e, r0, r1);
+    return launch_tile<1, EPI, OffT>(ctx, A, x, e, r0, r1, q0, q1);
   case 2:
-    return launch_tile<2, EPI, OffT>(ctx, A, x, e, r0, r1);
+    return launch_tile<2, EPI, OffT>(ctx, A, x, e, r0, r1, q0, q1);
   case 4:
-    return launch_tile<4, EPI, OffT>(ctx, A, x, e, r0, r1);
+    return launch_tile<4, EPI, OffT>(ctx, A, x, e, r0, r1, q0, q1);
   case 8:
-    return launch_tile<8, EPI, OffT>(ctx, A, x, e, r0, r1);
+    return launch_tile<8, EPI, OffT>(ctx, A, x, e, r0, r1, q0, q1);
   case 16:
-    return launch_tile<16, EPI, OffT>(ctx, A, x, e, r0, r1);
+    return launch_tile<16, EPI, OffT>(ctx, A, x, e, r0, r1, q0, q1);
   default:
-    return launch_tile<32, EPI, OffT>(ctx, A, x, e, r0, r1);
+    return launch_tile<32, EPI, OffT>(ctx, A, x, e, r0, r1, q0, q1);
   }
 }
 
 template <typename OffT>
-int dispatch_epi(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &e, int64_t r0, int64_t r1)
+int dispatch_epi(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &e, int64_t r0, int64_t r1,
+                 int64_t q0, int64_t q1)
 {
   switch (epi)
   {
   case Epi::Spmv:
-    return dispatch_lanes<(int)Epi::Spmv, OffT>(ctx, A, x, e, r0, r1);
+    return dispatch_lanes<(int)Epi::Spmv, OffT>(ctx, A, x, e, r0, r1, q0, q1);
   case Epi::Resid:
-    return dispatch_lanes<(int)Epi::Resid, OffT>(ctx, A, x, e, r0, r1);
+    return dispatch_lanes<(int)Epi::Resid, OffT>(ctx, A, x, e, r0, r1, q0, q1);
   case Epi::Jacobi:
-    return dispatch_lanes<(int)Epi::Jacobi, OffT>(ctx, A, x, e, r0, r1);
+    return dispatch_lanes<(int)Epi::Jacobi, OffT>(ctx, A, x, e, r0, r1, q0, q1);
   default:
-    return dispatch_lanes<(int)Epi::Sub, OffT>(ctx, A, x, e, r0, r1);
+    return dispatch_lanes<(int)Epi::Sub, OffT>(ctx, A, x, e, r0, r1, q0, q1);
   }
 }
 
@@ -424,10 +445,10 @@ int csr_measure_tiles(mfmgb_ctx *ctx, mfmgb_csr *A)
 }
 
 int csr_apply_tile(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args, int64_t row_begin,
-                   int64_t row_end)
+                   int64_t row_end, int64_t row_begin2, int64_t row_end2)
 {
   if (A->off64)
-    return dispatch_epi<int64_t>(ctx, A, x, epi, args, row_begin, row_end);
-  return dispatch_epi<int32_t>(ctx, A, x, epi, args, row_begin, row_end);
+    return dispatch_epi<int64_t>(ctx, A, x, epi, args, row_begin, row_end, row_begin2, row_end2);
+  return dispatch_epi<int32_t>(ctx, A, x, epi, args, row_begin, row_end, row_begin2, row_end2);
 }
 } // namespace mfmgb

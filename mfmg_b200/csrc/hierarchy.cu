@@ -35,6 +35,7 @@ struct mfmgb_level
   // row-partitioned (multi-GPU) level: ghost entries live in the tail [n, n + n_ghost) of every gathered vector
   const mfmgb_halo *halo = nullptr;
   int64_t blo = 0, bhi = 0; // rows [0, blo) and [bhi, n) reference ghost columns, [blo, bhi) is the interior
+  int64_t r_split = 0;      // (as coarse side) rows [0, r_split) of R reference owned fine columns only
 };
 
 struct mfmgb_hierarchy
@@ -107,11 +108,7 @@ int level_apply_A(mfmgb_ctx *ctx, const mfmgb_level &l, double *x, Epi epi, cons
   }
   MFMGB_CHECK(csr_apply(ctx, l.A, x, epi, e, l.blo, l.bhi));
   MFMGB_CHECK(halo_wait(ctx));
-  if (l.blo > 0)
-    MFMGB_CHECK(csr_apply(ctx, l.A, x, epi, e, 0, l.blo));
-  if (l.bhi < l.n)
-    MFMGB_CHECK(csr_apply(ctx, l.A, x, epi, e, l.bhi, l.n));
-  return MFMGB_OK;
+  return csr_apply2(ctx, l.A, x, epi, e, 0, l.blo, l.bhi, l.n); // both boundary blocks in one launch
 }
 
 #define STAGE_MARK(k)                                                                              \
@@ -169,11 +166,15 @@ int apply_level(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, 
   {
     // R's columns include the ghost plane of the residual; owned coarse rows go to this rank's slice of b_c,
     // then every rank gathers the whole (small) coarse right-hand side: the dense solve is replicated
+    // the rows of the agglomerates that do not touch the ghost plane overlap the exchange of the residual's halo
     MFMGB_CHECK(halo_start(ctx, fine.halo, fine.res));
-    MFMGB_CHECK(halo_wait(ctx));
     mfmgb_comm *c = ctx_comm(ctx);
     e.y = coarse.bc + H->coarse_offsets[c->rank];
-    MFMGB_CHECK(csr_apply(ctx, coarse.R, fine.res, Epi::Spmv, e));
+    if (coarse.r_split > 0)
+      MFMGB_CHECK(csr_apply(ctx, coarse.R, fine.res, Epi::Spmv, e, 0, coarse.r_split));
+    MFMGB_CHECK(halo_wait(ctx));
+    if (coarse.r_split < coarse.R->n_rows)
+      MFMGB_CHECK(csr_apply(ctx, coarse.R, fine.res, Epi::Spmv, e, coarse.r_split, coarse.R->n_rows));
     if (!H->dd) // (the domain-decomposed coarse solve reads only this rank's slice)
       MFMGB_CHECK(allgather_slices(ctx, coarse.bc, H->coarse_offsets));
   }
@@ -379,6 +380,15 @@ extern "C"
     l.blo = boundary_lo;
     l.bhi = boundary_hi;
     H->distributed = true;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_hierarchy_set_restrict_split(mfmgb_hierarchy *H, int level, int64_t first_boundary_row)
+  {
+    if (!H || level < 1 || level >= H->n_levels || H->finalized || !H->lev[level].R || first_boundary_row < 0 ||
+        first_boundary_row > H->lev[level].R->n_rows)
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_restrict_split: bad arguments");
+    H->lev[level].r_split = first_boundary_row;
     return MFMGB_OK;
   }
 

@@ -495,7 +495,7 @@ class Hierarchy:
 
     def __init__(self, handle: CudaHandle, operators, restrictors, params=None, omega: float = 1.0,
                  prolongators=None, halo: "HaloPlan | None" = None, boundary=(0, 0), coarse_offsets=None,
-                 coarse_dd: "CoarseDD | None" = None):
+                 coarse_dd: "CoarseDD | None" = None, restrict_split: int = 0):
         self.handle = handle
         self.halo = halo
         self.coarse_dd = coarse_dd
@@ -529,6 +529,8 @@ class Hierarchy:
         for li, r in enumerate(self.restrictors):
             pr = self.prolongators[li]
             check(handle.ctx, lib.mfmgb_hierarchy_set_restrictor(self.ptr, li + 1, r.ptr, pr.ptr if pr else None))
+        if restrict_split:
+            check(handle.ctx, lib.mfmgb_hierarchy_set_restrict_split(self.ptr, 1, int(restrict_split)))
         if halo is not None:
             check(handle.ctx, lib.mfmgb_hierarchy_set_halo(self.ptr, 0, halo.ptr, int(boundary[0]), int(boundary[1])))
         if coarse_dd is not None:
@@ -578,9 +580,13 @@ class Hierarchy:
             elif coarse_dd is True:
                 raise MfmgError(_lib.ERR_INVALID, "from_partition: the coarse operator is not block tridiagonal in the "
                                                   "ranks' row blocks; the domain-decomposed coarse solve cannot be used")
+        # (mfmgb_hierarchy_set_restrict_split could overlap the rows of R that only read owned entries with the
+        # exchange of the residual's halo; measured slower on 2 GPUs -- 0.047 vs 0.033 ms for the stage -- so it is
+        # left off: restrict_split=0)
+        r_split = 0
         return Hierarchy(handle, ops, res, params, omega, prolongators=pro, halo=plan,
                          boundary=(part.boundary_lo, part.boundary_hi), coarse_offsets=part.coarse_offsets,
-                         coarse_dd=dd)
+                         coarse_dd=dd, restrict_split=r_split)
 
     def build_vector(self) -> DeviceVector:
         """A level-0 vector with room for the ghost tail (Level::build_vector, level.hpp:63-70)."""

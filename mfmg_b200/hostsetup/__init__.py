@@ -8,3 +8,4 @@ from .problems import (HostCSR, LaplaceProblem, assemble, boundary_mask,  # noqa
                        set_num_threads)
 from .partition import LocalPart, coarse_dd_plan, make_parts, partition_two_level, slab_row_ranges  # noqa: F401,E402
 from .slab import build_slab_part  # noqa: F401,E402
+from . import mmio  # noqa: F401,E402

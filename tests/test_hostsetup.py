@@ -84,3 +84,23 @@ def test_chunked_galerkin_is_bitwise_the_plain_product():
     a = hs.galerkin(P.A, R)
     b = hs.galerkin(P.A, R, max_chunk_nnz=20000)
     assert np.array_equal(a.rowptr, b.rowptr) and np.array_equal(a.col, b.col) and np.array_equal(a.val, b.val)
+
+
+def test_matrix_market_round_trip(tmp_path):
+    """hostsetup.mmio writes / reads the two Matrix-Market forms mfmg produces through EpetraExt
+    (source/dealii/dealii_utils.cc:63-91): bit-exact round trip, and scipy reads the same files."""
+    import scipy.io
+
+    P = hs.LaplaceProblem.create(2, 1, 6, "linear")
+    R = hs.build_restrictor(P, (2, 2), 2)
+    for name, M in (("A", P.A), ("R", R)):
+        path = str(tmp_path / f"{name}.mtx")
+        hs.mmio.write_matrix(path, M, comment="mfmg_b200 test")
+        back = hs.mmio.read_matrix(path)
+        assert (back.n_rows, back.n_cols, back.nnz) == (M.n_rows, M.n_cols, M.nnz)
+        assert np.array_equal(back.rowptr, M.rowptr) and np.array_equal(back.col, M.col)
+        assert np.array_equal(back.val, M.val)          # %22.16e round-trips doubles exactly
+        assert abs(scipy.io.mmread(path).tocsr() - M.to_scipy()).max() == 0.0
+    v = np.random.default_rng(0).standard_normal(17)
+    hs.mmio.write_vector(str(tmp_path / "v.mtx"), v)
+    assert np.array_equal(hs.mmio.read_vector(str(tmp_path / "v.mtx")), v)
