@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(TX *TY, MINB) mf_q1_kernel(const Q1Params p, c
   const bool ok1 = has1 && li1 >= 0 && li1 < p.nx && lj1 >= 0 && lj1 < p.ny;
   const int64_t xy0 = ok0 ? lj0 * p.nx + li0 : 0, xy1 = ok1 ? lj1 * p.nx + li1 : 0;
   uint8_t fl0[NPL], fl1[NPL];
+  const double *xp0 = x + xy0, *xp1 = x + xy1;
+  const uint8_t *fp0 = p.constr + xy0, *fp1 = p.constr + xy1;
 #pragma unroll
   for (int s = 0; s < NPL; ++s)
   {
@@ -262,13 +264,21 @@ __global__ void __launch_bounds__(TX *TY, MINB) mf_q1_kernel(const Q1Params p, c
     const bool pl_ok = s < n_planes && g >= 0 && g < p.nz;
     const int64_t base = pl_ok ? plane_offset(p, g) : 0;
     if (s < n_planes)
+      cp_async_f64(xr + s * XS + tid, xp0 + base, pl_ok && ok0);
+    fl0[s] = pl_ok && ok0 ? fp0[base] : (uint8_t)1;
+  }
+  if (has1) // the XS - NT = 41 extra elements of a plane: only the first two warps take this branch
+  {
+#pragma unroll
+    for (int s = 0; s < NPL; ++s)
     {
-      cp_async_f64(xr + s * XS + tid, x + base + xy0, pl_ok && ok0);
-      if (has1)
-        cp_async_f64(xr + s * XS + r1, x + base + xy1, pl_ok && ok1);
+      const int64_t g = L0 + s;
+      const bool pl_ok = s < n_planes && g >= 0 && g < p.nz;
+      const int64_t base = pl_ok ? plane_offset(p, g) : 0;
+      if (s < n_planes)
+        cp_async_f64(xr + s * XS + r1, xp1 + base, pl_ok && ok1);
+      fl1[s] = pl_ok && ok1 ? fp1[base] : (uint8_t)1;
     }
-    fl0[s] = pl_ok && ok0 ? p.constr[base + xy0] : (uint8_t)1;
-    fl1[s] = pl_ok && ok1 ? p.constr[base + xy1] : (uint8_t)1;
   }
   if (!PERQ)
   {
@@ -284,11 +294,14 @@ __global__ void __launch_bounds__(TX *TY, MINB) mf_q1_kernel(const Q1Params p, c
 #pragma unroll
   for (int s = 0; s < NPL; ++s)
     if (s < n_planes)
-    {
       fs[s * XS + tid] = fl0[s];
-      if (has1)
+  if (has1)
+  {
+#pragma unroll
+    for (int s = 0; s < NPL; ++s)
+      if (s < n_planes)
         fs[s * XS + r1] = fl1[s];
-    }
+  }
   auto load_coef_q = [&](int64_t L, double *c) {
     const bool ok = cell_xy && L >= 0 && L < p.cz;
     const int64_t cell = ok ? gi + p.cx * (gj + p.cy * L) : 0;
@@ -304,13 +317,15 @@ __global__ void __launch_bounds__(TX *TY, MINB) mf_q1_kernel(const Q1Params p, c
   // fixes the elements it copied itself, which are visible to it after its own wait.
 #pragma unroll
   for (int s = 0; s < NPL; ++s)
-    if (s < n_planes)
-    {
-      if (fl0[s])
-        xr[s * XS + tid] = 0.;
-      if (has1 && fl1[s])
+    if (s < n_planes && fl0[s])
+      xr[s * XS + tid] = 0.;
+  if (has1)
+  {
+#pragma unroll
+    for (int s = 0; s < NPL; ++s)
+      if (s < n_planes && fl1[s])
         xr[s * XS + r1] = 0.;
-    }
+  }
   __syncthreads();
 
   auto get4 = [&](int s, double *v) { // u values (constrained -> 0) of this thread's cell corners on brick plane s
