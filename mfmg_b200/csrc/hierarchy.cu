@@ -84,10 +84,18 @@ int level_apply_A(mfmgb_ctx *ctx, const mfmgb_level &l, double *x, Epi epi, cons
 {
   if (l.M)
   {
-    if (l.halo) // (the z-sweep kernel needs its ghost planes up front: exchange, then apply)
+    if (l.halo)
     {
+      // the middle z chunks read owned planes only: they run while the ghost planes are exchanged
+      const int nc = mf_num_chunks(l.M);
       MFMGB_CHECK(halo_start(ctx, l.halo, x));
+      if (nc >= 3)
+        MFMGB_CHECK(mf_apply_chunks(ctx, l.M, x, epi, e, 1, nc - 1));
       MFMGB_CHECK(halo_wait(ctx));
+      if (nc < 3)
+        return mf_apply(ctx, l.M, x, epi, e);
+      MFMGB_CHECK(mf_apply_chunks(ctx, l.M, x, epi, e, 0, 1));
+      return mf_apply_chunks(ctx, l.M, x, epi, e, nc - 1, nc);
     }
     return mf_apply(ctx, l.M, x, epi, e);
   }

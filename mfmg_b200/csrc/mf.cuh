@@ -18,6 +18,8 @@ struct mfmgb_mf
   double *coef_cell = nullptr;    // device [n_cells]
   double Kref[64] = {0};          // sum_q G[q][a][b]: reference cell matrix with the Jacobian folded in
   bool force_generic = false;     // tests: run the generic colour-phase kernel instead
+  int q1_tz = 6;                  // owned node planes per CTA of mf_q1_kernel
+  uint8_t *brick_flags = nullptr; // device, one byte per CTA brick: does it contain a constrained node?
   // slab layout of the row-partitioned hierarchy: vectors are [owned planes | ghost planes below | ghost planes
   // above]; owned node planes are [own0, own1) of the local box (single GPU: all of them)
   int64_t own0 = 0, own1 = 0;
@@ -29,4 +31,8 @@ namespace mfmgb
 {
 // y = epilogue(A_mf x), same epilogues as the CSR kernels
 int mf_apply(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, Epi epi, const EpiArgs &args);
+// z chunks [zc0, zc1) of a 3D Q1 slab operator; chunk 0 is the only one that reads the ghost plane below, the last one
+// the only one that reads the ghost plane above
+int mf_apply_chunks(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, Epi epi, const EpiArgs &args, int zc0, int zc1);
+int mf_num_chunks(const mfmgb_mf *M);
 } // namespace mfmgb

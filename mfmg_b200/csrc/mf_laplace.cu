@@ -512,7 +512,7 @@ namespace mfmgb
 int mf_apply(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, Epi epi, const EpiArgs &args)
 {
   if (M->dim == 3 && M->degree == 1 && !M->force_generic)
-    return mf_q1_apply(ctx, M, x, epi, args); // node-owner z-sweep (mf_q1.cuh)
+    return mf_q1_apply(ctx, M, x, epi, args, -1, -1); // node-owner z-sweep (mf_q1.cuh)
   if (M->own0 != 0 || M->own1 != M->nodes[M->dim - 1])
     return fail(ctx, MFMGB_ERR_NOT_IMPLEMENTED, "mf_apply: slab layouts are implemented for 3D Q1 only");
   if (M->dim == 3 && M->degree == 1)
@@ -524,6 +524,17 @@ int mf_apply(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, Epi epi, const 
   if (M->dim == 2 && M->degree == 2)
     return dispatch_mf_epi<2, 2, 32, 8>(ctx, M, x, epi, args);
   return fail(ctx, MFMGB_ERR_NOT_IMPLEMENTED, "mf_apply: dim %d degree %d not implemented", M->dim, M->degree);
+}
+// partitioned level: middle z chunks first (they read owned planes only), the two end chunks after the halo has landed
+int mf_apply_chunks(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, Epi epi, const EpiArgs &args, int zc0, int zc1)
+{
+  if (!(M->dim == 3 && M->degree == 1 && !M->force_generic))
+    return fail(ctx, MFMGB_ERR_NOT_IMPLEMENTED, "mf_apply_chunks: 3D Q1 only");
+  return mf_q1_apply(ctx, M, x, epi, args, zc0, zc1);
+}
+int mf_num_chunks(const mfmgb_mf *M)
+{
+  return M->dim == 3 && M->degree == 1 && !M->force_generic ? mf_q1_num_chunks(M) : 1;
 }
 } // namespace mfmgb
 
@@ -669,6 +680,8 @@ extern "C"
           }
           M->Kref[a * 8 + b] = s;
         }
+      if (!M->force_generic)
+        MFMGB_CHECK(mf_q1_prepare(ctx, M));
     }
     *out = M;
     return MFMGB_OK;
@@ -682,6 +695,7 @@ extern "C"
     MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(M->coef);
     cudaFree(M->coef_cell);
+    cudaFree(M->brick_flags);
     cudaFree(M->constr);
     delete M;
     return MFMGB_OK;

@@ -31,7 +31,9 @@ struct Q1Params
   int64_t n_cells;
   const double *coef; // per-cell mode: [n_cells]; per-q mode: [8][n_cells]
   const uint8_t *constr; // vector layout
+  const uint8_t *brick_flags; // [grid.z][grid.y][grid.x]: 1 = the CTA's brick contains a constrained node (or NULL)
   int tz;                // owned node planes per CTA
+  int zc_begin;          // first z chunk of this launch (blockIdx.z + zc_begin = chunk index)
   double K[64];          // reference cell matrix (per-cell mode), row-major [a][b], Jacobian folded in
   double kx, ky, kz;     // per-q mode: (prod_{e != d} h_e) / h_d
   double ax, ay, az;     // per-cell mode: k_d / 36 (unscaled 1D mass / stiffness matrices)
@@ -234,7 +236,8 @@ __global__ void __launch_bounds__(TX *TY, MINB) mf_q1_kernel(const Q1Params p, c
   const bool cell_xy = gi >= 0 && gi < p.cx && gj >= 0 && gj < p.cy;
   const bool owner = tx >= 1 && ty >= 1 && node_ok;
   const int64_t node_xy = gj * p.nx + gi;
-  const int64_t P0 = p.own0 + (int64_t)blockIdx.z * tz;
+  const int64_t chunk = (int64_t)blockIdx.z + p.zc_begin;
+  const int64_t P0 = p.own0 + chunk * tz;
   const int64_t P1 = P0 + tz < p.own1 ? P0 + tz : p.own1;
   const int64_t L0 = P0 - 1; // first cell layer: contributes only the carry of plane P0
   const int sx = ty * (TX + 1) + tx;
@@ -254,6 +257,9 @@ __global__ void __launch_bounds__(TX *TY, MINB) mf_q1_kernel(const Q1Params p, c
   const bool ok0 = li0 >= 0 && li0 < p.nx && lj0 >= 0 && lj0 < p.ny;
   const bool ok1 = has1 && li1 >= 0 && li1 < p.nx && lj1 >= 0 && lj1 < p.ny;
   const int64_t xy0 = ok0 ? lj0 * p.nx + li0 : 0, xy1 = ok1 ? lj1 * p.nx + li1 : 0;
+  // most bricks contain no constrained node at all (Dirichlet nodes sit on the boundary): they skip every flag access
+  const bool any_c =
+      p.brick_flags == nullptr || p.brick_flags[((size_t)chunk * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] != 0;
   uint8_t fl0[NPL], fl1[NPL];
   const double *xp0 = x + xy0, *xp1 = x + xy1;
   const uint8_t *fp0 = p.constr + xy0, *fp1 = p.constr + xy1;
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(TX *TY, MINB) mf_q1_kernel(const Q1Params p, c
     const int64_t base = pl_ok ? plane_offset(p, g) : 0;
     if (s < n_planes)
       cp_async_f64(xr + s * XS + tid, xp0 + base, pl_ok && ok0);
-    fl0[s] = pl_ok && ok0 ? fp0[base] : (uint8_t)1;
+    fl0[s] = any_c ? (pl_ok && ok0 ? fp0[base] : (uint8_t)1) : (uint8_t)0;
   }
   if (has1) // the XS - NT = 41 extra elements of a plane: only the first two warps take this branch
   {
@@ -277,7 +283,7 @@ __global__ void __launch_bounds__(TX *TY, MINB) mf_q1_kernel(const Q1Params p, c
       const int64_t base = pl_ok ? plane_offset(p, g) : 0;
       if (s < n_planes)
         cp_async_f64(xr + s * XS + r1, xp1 + base, pl_ok && ok1);
-      fl1[s] = pl_ok && ok1 ? fp1[base] : (uint8_t)1;
+      fl1[s] = any_c ? (pl_ok && ok1 ? fp1[base] : (uint8_t)1) : (uint8_t)0;
     }
   }
   if (!PERQ)
@@ -291,16 +297,19 @@ __global__ void __launch_bounds__(TX *TY, MINB) mf_q1_kernel(const Q1Params p, c
       cp_async_f64(cs + l * NT + tid, p.coef + (ok ? cell_xy_off + cell_pl * L : 0), ok);
     }
   }
-#pragma unroll
-  for (int s = 0; s < NPL; ++s)
-    if (s < n_planes)
-      fs[s * XS + tid] = fl0[s];
-  if (has1)
+  if (any_c)
   {
 #pragma unroll
     for (int s = 0; s < NPL; ++s)
       if (s < n_planes)
-        fs[s * XS + r1] = fl1[s];
+        fs[s * XS + tid] = fl0[s];
+    if (has1)
+    {
+#pragma unroll
+      for (int s = 0; s < NPL; ++s)
+        if (s < n_planes)
+          fs[s * XS + r1] = fl1[s];
+    }
   }
   auto load_coef_q = [&](int64_t L, double *c) {
     const bool ok = cell_xy && L >= 0 && L < p.cz;
@@ -315,11 +324,14 @@ __global__ void __launch_bounds__(TX *TY, MINB) mf_q1_kernel(const Q1Params p, c
   asm volatile("cp.async.wait_all;" ::: "memory");
   // constrained entries read as 0 (the raw value is only needed by the identity row: re-read there).  Each thread
   // fixes the elements it copied itself, which are visible to it after its own wait.
+  if (any_c)
+  {
 #pragma unroll
-  for (int s = 0; s < NPL; ++s)
-    if (s < n_planes && fl0[s])
-      xr[s * XS + tid] = 0.;
-  if (has1)
+    for (int s = 0; s < NPL; ++s)
+      if (s < n_planes && fl0[s])
+        xr[s * XS + tid] = 0.;
+  }
+  if (any_c && has1)
   {
 #pragma unroll
     for (int s = 0; s < NPL; ++s)
@@ -395,7 +407,7 @@ __global__ void __launch_bounds__(TX *TY, MINB) mf_q1_kernel(const Q1Params p, c
       carry = up;
       if (emit)
       {
-        const bool constrained = fs[l * XS + sx] != 0;
+        const bool constrained = any_c && fs[l * XS + sx] != 0;
         const double xraw = constrained ? x[row] : xr[l * XS + sx];
         const double s = constrained ? xraw : total;
         if (EPI == (int)Epi::Spmv)
@@ -419,6 +431,28 @@ __global__ void __launch_bounds__(TX *TY, MINB) mf_q1_kernel(const Q1Params p, c
         coef[q] = coef_next[q];
     }
   }
+}
+
+// one CTA per brick of the apply grid: does it contain a constrained node?  (setup, once)
+template <int TY>
+__global__ void __launch_bounds__(256) mf_q1_brick_flags_kernel(const Q1Params p, int tz, uint8_t *__restrict__ out)
+{
+  const int64_t gi0 = (int64_t)blockIdx.x * (TX - 1) - 1, gj0 = (int64_t)blockIdx.y * (TY - 1) - 1;
+  const int64_t P0 = p.own0 + (int64_t)blockIdx.z * tz;
+  const int64_t P1 = P0 + tz < p.own1 ? P0 + tz : p.own1;
+  const int n_planes = (int)(P1 - (P0 - 1)) + 1;
+  constexpr int XS = (TX + 1) * (TY + 1);
+  int any = 0;
+  for (int i = threadIdx.x; i < n_planes * XS; i += 256)
+  {
+    const int s = i / XS, r = i % XS;
+    const int64_t g = P0 - 1 + s, li = gi0 + r % (TX + 1), lj = gj0 + r / (TX + 1);
+    if (g >= 0 && g < p.nz && li >= 0 && li < p.nx && lj >= 0 && lj < p.ny)
+      any |= p.constr[plane_offset(p, g) + lj * p.nx + li] != 0;
+  }
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0)
+    out[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = any ? 1 : 0;
 }
 
 // diagonal of the operator on the owned nodes (constrained entries := 1), thread per node
@@ -472,7 +506,9 @@ Q1Params make_q1_params(const mfmgb_mf *M)
   p.n_cells = M->n_cells;
   p.coef = M->q1_cell_constant ? M->coef_cell : M->coef;
   p.constr = M->constr;
-  p.tz = 32;
+  p.brick_flags = M->brick_flags;
+  p.tz = M->q1_tz;
+  p.zc_begin = 0;
   for (int i = 0; i < 64; ++i)
     p.K[i] = M->Kref[i];
   const double *h = M->h;
@@ -486,7 +522,7 @@ Q1Params make_q1_params(const mfmgb_mf *M)
 }
 
 template <int TY, int TZ, int EPI, bool PERQ, int MINB>
-int launch_q1_cfg(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, const EpiArgs &e)
+int launch_q1_cfg(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, const EpiArgs &e, int zc0, int zc1)
 {
   Q1Params p = make_q1_params(M);
   p.tz = TZ;
@@ -498,40 +534,45 @@ int launch_q1_cfg(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, const EpiA
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     configured = true;
   }
-  dim3 grid((unsigned)ceil_div(p.nx, TX - 1), (unsigned)ceil_div(p.ny, TY - 1),
-            (unsigned)ceil_div(p.own1 - p.own0, (int64_t)TZ));
+  const int n_chunks = (int)ceil_div(p.own1 - p.own0, (int64_t)TZ);
+  if (zc0 < 0) // all chunks
+  {
+    zc0 = 0;
+    zc1 = n_chunks;
+  }
+  zc1 = zc1 < n_chunks ? zc1 : n_chunks;
+  if (zc1 <= zc0)
+    return MFMGB_OK;
+  p.zc_begin = zc0;
+  dim3 grid((unsigned)ceil_div(p.nx, TX - 1), (unsigned)ceil_div(p.ny, TY - 1), (unsigned)(zc1 - zc0));
   mf_q1_kernel<TY, TZ, EPI, PERQ, MINB><<<grid, TX * TY, smem, ctx->stream>>>(p, x, e);
   MFMGB_LAUNCHED(ctx);
   return MFMGB_OK;
 }
 
 template <int TY, int EPI, bool PERQ>
-int launch_q1(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, const EpiArgs &e)
+int launch_q1(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, const EpiArgs &e, int zc0, int zc1)
 {
-  // owned planes per CTA / CTAs per SM: (6, 3) keeps three 68 KB bricks resident at 80 registers, (12, 2) halves the
-  // halo redundancy at 128 registers; MFMGB_MF_TZ=6|12 picks (tuning aid)
-  static const int env_tz = [] {
-    const char *v = getenv("MFMGB_MF_TZ");
-    return v && *v ? atoi(v) : 0;
-  }();
+  // owned planes per CTA / CTAs per SM, fixed at creation (mf_q1_prepare): per-q 8 / 2; per-cell 6 / 3 (three 68 KB
+  // bricks resident at 80 registers) or 12 / 2 (MFMGB_MF_TZ=12: half the halo redundancy at 128 registers)
   if (PERQ)
-    return launch_q1_cfg<TY, 8, EPI, PERQ, 2>(ctx, M, x, e);
-  if (env_tz == 6)
-    return launch_q1_cfg<TY, 6, EPI, PERQ, 3>(ctx, M, x, e);
-  return launch_q1_cfg<TY, 12, EPI, PERQ, 2>(ctx, M, x, e);
+    return launch_q1_cfg<TY, 8, EPI, PERQ, 2>(ctx, M, x, e, zc0, zc1);
+  if (M->q1_tz == 12)
+    return launch_q1_cfg<TY, 12, EPI, PERQ, 2>(ctx, M, x, e, zc0, zc1);
+  return launch_q1_cfg<TY, 6, EPI, PERQ, 3>(ctx, M, x, e, zc0, zc1);
 }
 
 template <int TY, bool PERQ>
-int dispatch_q1(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, Epi epi, const EpiArgs &e)
+int dispatch_q1(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, Epi epi, const EpiArgs &e, int zc0, int zc1)
 {
   switch (epi)
   {
   case Epi::Spmv:
-    return launch_q1<TY, (int)Epi::Spmv, PERQ>(ctx, M, x, e);
+    return launch_q1<TY, (int)Epi::Spmv, PERQ>(ctx, M, x, e, zc0, zc1);
   case Epi::Resid:
-    return launch_q1<TY, (int)Epi::Resid, PERQ>(ctx, M, x, e);
+    return launch_q1<TY, (int)Epi::Resid, PERQ>(ctx, M, x, e, zc0, zc1);
   case Epi::Jacobi:
-    return launch_q1<TY, (int)Epi::Jacobi, PERQ>(ctx, M, x, e);
+    return launch_q1<TY, (int)Epi::Jacobi, PERQ>(ctx, M, x, e, zc0, zc1);
   default:
     return fail(ctx, MFMGB_ERR_INVALID, "mf_apply: unsupported epilogue");
   }
@@ -540,11 +581,34 @@ int dispatch_q1(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, Epi epi, con
 
 namespace mfmgb
 {
-int mf_q1_apply(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, Epi epi, const EpiArgs &args)
+// z chunks [zc0, zc1) of the owned planes (zc0 < 0: all).  Only the first chunk reads the ghost plane below and only
+// the last one the ghost plane above, so a partitioned level runs the middle chunks while the halo is exchanged.
+int mf_q1_apply(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, Epi epi, const EpiArgs &args, int zc0, int zc1)
 {
   if (M->q1_cell_constant)
-    return dispatch_q1<8, false>(ctx, M, x, epi, args);
-  return dispatch_q1<8, true>(ctx, M, x, epi, args);
+    return dispatch_q1<8, false>(ctx, M, x, epi, args, zc0, zc1);
+  return dispatch_q1<8, true>(ctx, M, x, epi, args, zc0, zc1);
+}
+
+int mf_q1_num_chunks(const mfmgb_mf *M) { return (int)ceil_div(M->own1 - M->own0, (int64_t)M->q1_tz); }
+
+// fixes the brick height and marks the bricks that contain constrained nodes (called once by the create functions)
+int mf_q1_prepare(mfmgb_ctx *ctx, mfmgb_mf *M)
+{
+  const char *v = getenv("MFMGB_MF_TZ");
+  const int env_tz = v && *v ? atoi(v) : 0;
+  M->q1_tz = M->q1_cell_constant ? (env_tz == 12 ? 12 : 6) : 8;
+  M->brick_flags = nullptr;
+  Q1Params p = make_q1_params(M);
+  dim3 grid((unsigned)ceil_div(p.nx, TX - 1), (unsigned)ceil_div(p.ny, 8 - 1),
+            (unsigned)ceil_div(p.own1 - p.own0, (int64_t)M->q1_tz));
+  uint8_t *flags = nullptr;
+  MFMGB_CUDA(ctx, cudaMalloc(&flags, (size_t)grid.x * grid.y * grid.z));
+  mf_q1_brick_flags_kernel<8><<<grid, 256, 0, ctx->stream>>>(p, M->q1_tz, flags);
+  MFMGB_LAUNCHED(ctx);
+  MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  M->brick_flags = flags;
+  return MFMGB_OK;
 }
 
 int mf_q1_diagonal(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *gdiag_dev, double *diag_dev)
