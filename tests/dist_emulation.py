@@ -44,8 +44,37 @@ def gather_coarse(part, bc_full):
         bc_full[co[r]:co[r + 1]] = outs[r].numpy()
 
 
-def dist_vcycle_cpu(part, lu, piv, b_loc, nu=1):
-    """Preconditioner-mode V(nu,nu) on this rank's rows; returns x_loc (owned entries)."""
+def coarse_dd_solve_cpu(plan, bc_full):
+    """csrc/coarse_dd.cu restated with numpy + gloo: bc_full is valid on this rank's coarse rows only; the result is
+    valid on this rank's rows and on all separator rows (everything else is NaN to catch illegal reads)."""
+    AII, AIS, ASI = (plan[k].to_scipy().toarray() for k in ("A_II", "A_IS", "A_SI"))
+    n_I, n_S, sep = plan["n_I"], plan["n_S"], plan["sep_index"]
+    a0, na = plan["adj_begin"], AIS.shape[1]
+    Mi = np.linalg.inv(AII) if n_I else AII
+    E = Mi @ AIS
+    # setup: Schur complement summed over the ranks
+    S = plan["A_SS"].to_scipy().toarray() if dist.get_rank() == 0 else np.zeros((n_S, n_S))
+    S[a0:a0 + na, a0:a0 + na] -= ASI @ E
+    St = torch.from_numpy(S)
+    dist.all_reduce(St)
+    # apply
+    y = Mi @ bc_full[plan["own_begin"]:plan["own_begin"] + n_I]
+    t = np.zeros(n_S)
+    t[a0:a0 + na] -= ASI @ y
+    o0, on = plan["own_sep_begin"], plan["own_sep_n"]
+    t[o0:o0 + on] += bc_full[sep[o0:o0 + on]]
+    tt = torch.from_numpy(t)
+    dist.all_reduce(tt)                      # the only communication of the solve
+    xs = np.linalg.solve(St.numpy(), tt.numpy())
+    x = np.full(plan["n_c"], np.nan)
+    x[sep] = xs
+    x[plan["own_begin"]:plan["own_begin"] + n_I] = y - E @ xs[a0:a0 + na]
+    return x
+
+
+def dist_vcycle_cpu(part, lu, piv, b_loc, nu=1, dd_plan=None):
+    """Preconditioner-mode V(nu,nu) on this rank's rows; returns x_loc (owned entries).  dd_plan: use the
+    domain-decomposed coarse solve (no gather of the coarse right-hand side or solution) instead of the dense LU."""
     n, ng = part.n_owned, part.n_ghost
     A, R, P = part.A, part.R, part.P
     dinv = oracle.inv_diag(n, A.rowptr, A.col, A.val)
@@ -61,8 +90,13 @@ def dist_vcycle_cpu(part, lu, piv, b_loc, nu=1):
     co = part.coarse_offsets
     bc = np.zeros(part.Ac.n_rows)
     bc[co[part.rank]:co[part.rank + 1]] = oracle.spmv(R.n_rows, R.rowptr, R.col, R.val, res)
-    gather_coarse(part, bc)
-    xc = oracle.lu_solve(lu, piv, bc)
+    if dd_plan is not None:
+        xc = coarse_dd_solve_cpu(dd_plan, bc)
+        assert not np.any(np.isnan(xc[np.unique(P.col)])), "P reads coarse entries the DD solve does not provide"
+        xc = np.nan_to_num(xc)
+    else:
+        gather_coarse(part, bc)
+        xc = oracle.lu_solve(lu, piv, bc)
     x[:n] = x[:n] - oracle.spmv(n, P.rowptr, P.col, P.val, xc)
     for s in range(nu):
         halo_exchange(part, x)

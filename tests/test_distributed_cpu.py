@@ -44,6 +44,11 @@ def _worker(rank, world, port, case, out_q):
         x_loc = dist_vcycle_cpu(part, lu, piv, b[part.row_begin:part.row_end])
         x_ref = oracle_hierarchy(P, R, Ac, 1, True).vmult(b)[part.row_begin:part.row_end]
         err = np.linalg.norm(x_loc - x_ref) / np.linalg.norm(x_ref)
+        # the same cycle with the domain-decomposed coarse solve (one all-reduce, nothing gathered)
+        plan = hs.coarse_dd_plan(part.Ac, part.coarse_offsets, rank)
+        if plan is not None:
+            x_dd = dist_vcycle_cpu(part, lu, piv, b[part.row_begin:part.row_end], dd_plan=plan)
+            err = max(err, np.linalg.norm(x_dd - x_ref) / np.linalg.norm(x_ref))
         out_q.put((rank, float(err), part.n_owned, part.n_ghost, part.boundary_lo, part.boundary_hi))
     finally:
         dist.destroy_process_group()
