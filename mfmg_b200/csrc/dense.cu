@@ -1,4 +1,4 @@
-// dense.cu -- coarsest-level dense FP64 direct solver: factor ONCE, two triangular applies per solve.
+// dense.cu -- coarsest-level dense FP64 direct solver: factor and invert ONCE, one GEMV per solve.
 //
 // Replaces mfmg::CudaSolver "lu_dense" (source/cuda/cuda_solver.cu:496-515 -> lu_factorization,
 // source/cuda/dealii_operator_device_helpers.cu:169-228), which runs csr2dense + getrf + getrs and

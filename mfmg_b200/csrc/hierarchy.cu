@@ -490,8 +490,8 @@ extern "C"
         if (H->dd)
           continue;
         MFMGB_CHECK(mfmgb_dense_factor(ctx, l.A, &l.D));
-        // partitioned hierarchy: from n_c = 8192 on, splitting the two triangular GEMVs by rows across the ranks
-        // (2 small all-gathers) beats every rank streaming the whole factor (MFMGB_DENSE_SPLIT_MIN overrides)
+        // partitioned hierarchy without the domain-decomposed solve: from n_c = 8192 on, splitting the GEMV by rows
+        // across the ranks (one all-gather) beats every rank streaming the whole inverse (MFMGB_DENSE_SPLIT_MIN overrides)
         if (H->distributed)
         {
           int64_t split_min = 8192;
