@@ -223,6 +223,12 @@ extern "C"
   /* rows [0, first_boundary_row) of the level's restrictor reference owned fine columns only: they are computed while
    * the residual's halo is exchanged (after mfmgb_hierarchy_set_restrictor; default 0 = no overlap) */
   MFMGB_API int mfmgb_hierarchy_set_restrict_split(mfmgb_hierarchy *H, int level, int64_t first_boundary_row);
+  /* Halo-free restriction for hierarchies that use mfmgb_coarse_dd (call after set_restrictor / set_coarse_dd, on EVERY
+   * rank): the level's R must hold no ghost columns; R_below (NULL on rank 0) = the restrictor rows of the lower
+   * neighbour's separator restricted to this rank's fine entries.  Its product with the residual joins the all-reduce of
+   * the coarse solve, so the residual's halo is not exchanged.  R_below is borrowed. */
+  MFMGB_API int mfmgb_hierarchy_set_restrict_no_halo(mfmgb_ctx *ctx, mfmgb_hierarchy *H, int level,
+                                                     const mfmgb_csr *R_below);
   /* offsets (nranks + 1) of the rank-owned rows of the replicated coarsest level */
   MFMGB_API int mfmgb_hierarchy_set_coarse_offsets(mfmgb_hierarchy *H, const int64_t *offsets, int nranks);
   /* Domain-decomposed form of the dense coarse solve for a row-partitioned hierarchy whose coarse operator is block

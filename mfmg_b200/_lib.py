@@ -124,6 +124,7 @@ SIGNATURES = {
     "mfmgb_coarse_dd_solve": (_int, [_vp, _vp, _vp, _vp]),
     "mfmgb_hierarchy_set_coarse_dd": (_int, [_vp, _vp]),
     "mfmgb_hierarchy_set_restrict_split": (_int, [_vp, _int, _i64]),
+    "mfmgb_hierarchy_set_restrict_no_halo": (_int, [_vp, _vp, _int, _vp]),
 }
 
 _LIB = None

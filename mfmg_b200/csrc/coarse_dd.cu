@@ -43,10 +43,12 @@ struct mfmgb_coarse_dd
 namespace
 {
 // t[k] = (k adjacent ? -g[k - adj_begin] : 0) + (k in own separator ? b_c[sep_index[k]] : 0)
+//        + (k in the separator below ? g_below[k - adj_begin] : 0)   [this rank's share of R r on those rows]
 __global__ void __launch_bounds__(256) dd_rhs_kernel(int64_t n_S, int64_t adj_begin, int64_t n_adj, int64_t own_begin,
                                                      int64_t own_n, const double *__restrict__ g,
                                                      const int32_t *__restrict__ sep_index,
-                                                     const double *__restrict__ b_c, double *__restrict__ t)
+                                                     const double *__restrict__ b_c, const double *__restrict__ g_below,
+                                                     int64_t n_below, double *__restrict__ t)
 {
   const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (k >= n_S)
@@ -56,6 +58,8 @@ __global__ void __launch_bounds__(256) dd_rhs_kernel(int64_t n_S, int64_t adj_be
     v = -g[k - adj_begin];
   if (k >= own_begin && k < own_begin + own_n)
     v += b_c[sep_index[k]];
+  if (g_below && k >= adj_begin && k < adj_begin + n_below)
+    v += g_below[k - adj_begin];
   t[k] = v;
 }
 
@@ -106,7 +110,10 @@ __global__ void __launch_bounds__(256) dd_sub_block_kernel(int64_t n_adj, const 
 
 namespace mfmgb
 {
-int coarse_dd_solve_async(mfmgb_ctx *ctx, const mfmgb_coarse_dd *d, const double *b_c, double *x_c)
+int64_t coarse_dd_n_sep_below(const mfmgb_coarse_dd *d) { return d->n_adj - d->own_sep_n; }
+
+int coarse_dd_solve_async(mfmgb_ctx *ctx, const mfmgb_coarse_dd *d, const double *b_c, double *x_c,
+                          const double *g_below)
 {
   mfmgb_comm *c = ctx_comm(ctx);
   cudaStream_t st = ctx->stream;
@@ -124,7 +131,7 @@ int coarse_dd_solve_async(mfmgb_ctx *ctx, const mfmgb_coarse_dd *d, const double
     }
     dd_rhs_kernel<<<(unsigned)ceil_div(d->n_S, 256), 256, 0, st>>>(d->n_S, d->adj_begin, d->n_I > 0 ? d->n_adj : 0,
                                                                    d->own_sep_begin, d->own_sep_n, d->g, d->sep_index,
-                                                                   b_c, d->t);
+                                                                   b_c, g_below, d->n_adj - d->own_sep_n, d->t);
     MFMGB_LAUNCHED(ctx);
     MFMGB_NCCL(ctx, ncclAllReduce(d->t, d->t, (size_t)d->n_S, ncclDouble, ncclSum, c->nccl, st));
     // x_S = Schur^-1 t (replicated)
@@ -250,6 +257,6 @@ extern "C"
   MFMGB_API int mfmgb_coarse_dd_solve(mfmgb_ctx *ctx, const mfmgb_coarse_dd *d, const double *b_c, double *x_c)
   {
     MFMGB_REQUIRE(ctx, ctx && d && b_c && x_c && b_c != x_c, "mfmgb_coarse_dd_solve: bad arguments");
-    return coarse_dd_solve_async(ctx, d, b_c, x_c);
+    return coarse_dd_solve_async(ctx, d, b_c, x_c, nullptr);
   }
 }

@@ -27,7 +27,11 @@ int dense_solve_async(mfmgb_ctx *ctx, const mfmgb_dense *D, const double *b, dou
 int dense_enable_distributed(mfmgb_ctx *ctx, mfmgb_dense *D);
 // domain-decomposed coarse solve of a row-partitioned hierarchy (coarse_dd.cu): on return x_c is valid on this
 // rank's coarse rows and on all separator rows
-int coarse_dd_solve_async(mfmgb_ctx *ctx, const mfmgb_coarse_dd *d, const double *b_c, double *x_c);
+// g_below (may be NULL): this rank's share of the restricted residual on the separator rows of the rank below
+// (coarse_dd_n_sep_below values), added to the all-reduced separator right-hand side
+int coarse_dd_solve_async(mfmgb_ctx *ctx, const mfmgb_coarse_dd *d, const double *b_c, double *x_c,
+                          const double *g_below = nullptr);
+int64_t coarse_dd_n_sep_below(const mfmgb_coarse_dd *d);
 // building blocks shared with the domain-decomposed coarse solver (coarse_dd.cu)
 int csr_to_dense_device(mfmgb_ctx *ctx, const mfmgb_csr *A, int64_t lda, double **out); // n_rows x lda, zero padded
 int dense_factor_device(mfmgb_ctx *ctx, double *lu, int64_t n, mfmgb_dense **out);     // takes ownership of lu

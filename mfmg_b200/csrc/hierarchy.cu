@@ -36,6 +36,11 @@ struct mfmgb_level
   const mfmgb_halo *halo = nullptr;
   int64_t blo = 0, bhi = 0; // rows [0, blo) and [bhi, n) reference ghost columns, [blo, bhi) is the interior
   int64_t r_split = 0;      // (as coarse side) rows [0, r_split) of R reference owned fine columns only
+  // halo-free restriction (with the domain-decomposed coarse solve): R holds no ghost columns; R_below = the rows of
+  // the lower neighbour's separator restricted to this rank's entries (NULL on rank 0), gb = R_below r
+  bool restrict_no_halo = false;
+  const mfmgb_csr *R_below = nullptr;
+  double *gb = nullptr;
 };
 
 struct mfmgb_hierarchy
@@ -132,7 +137,8 @@ int apply_level(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, 
   const int64_t n = fine.n;
   const bool x_is_zero = li > 0 || H->is_preconditioner; // hierarchy.hpp:253-259
   if (li == H->n_levels - 1) // hierarchy.hpp:261-268 (the solve overwrites x)
-    return H->dd ? coarse_dd_solve_async(ctx, H->dd, b, x) : dense_solve_async(ctx, fine.D, b, x);
+    return H->dd ? coarse_dd_solve_async(ctx, H->dd, b, x, fine.restrict_no_halo ? fine.gb : nullptr)
+                 : dense_solve_async(ctx, fine.D, b, x);
 
   mfmgb_level &coarse = H->lev[li + 1];
   const int nu = H->nu;
@@ -170,11 +176,24 @@ int apply_level(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, 
   STAGE_MARK(2);
   // b_c = R res, hierarchy.hpp:289-290
   e = EpiArgs();
-  if (fine.halo)
+  if (fine.halo && coarse.restrict_no_halo)
   {
-    // R's columns include the ghost plane of the residual; owned coarse rows go to this rank's slice of b_c,
-    // then every rank gathers the whole (small) coarse right-hand side: the dense solve is replicated
-    // the rows of the agglomerates that do not touch the ghost plane overlap the exchange of the residual's halo
+    // no exchange at all: the ghost-plane entries of R were dropped at setup; the neighbour above computes them
+    // (its R_below) and they are summed by the all-reduce of the domain-decomposed coarse solve
+    mfmgb_comm *c = ctx_comm(ctx);
+    e.y = coarse.bc + H->coarse_offsets[c->rank];
+    MFMGB_CHECK(csr_apply(ctx, coarse.R, fine.res, Epi::Spmv, e));
+    if (coarse.R_below)
+    {
+      e.y = coarse.gb;
+      MFMGB_CHECK(csr_apply(ctx, coarse.R_below, fine.res, Epi::Spmv, e));
+    }
+  }
+  else if (fine.halo)
+  {
+    // R's columns include the ghost plane of the residual: exchange it (rows [0, r_split) of R that only read owned
+    // entries may overlap the exchange); owned coarse rows go to this rank's slice of b_c, then -- for the dense
+    // coarse solve -- every rank gathers the whole (small) coarse right-hand side
     MFMGB_CHECK(halo_start(ctx, fine.halo, fine.res));
     mfmgb_comm *c = ctx_comm(ctx);
     e.y = coarse.bc + H->coarse_offsets[c->rank];
@@ -400,6 +419,23 @@ extern "C"
     return MFMGB_OK;
   }
 
+  MFMGB_API int mfmgb_hierarchy_set_restrict_no_halo(mfmgb_ctx *ctx, mfmgb_hierarchy *H, int level,
+                                                     const mfmgb_csr *R_below)
+  {
+    MFMGB_REQUIRE(ctx, ctx && H && level >= 1 && level < H->n_levels && !H->finalized && H->lev[level].R && H->dd,
+                  "mfmgb_hierarchy_set_restrict_no_halo: needs a restrictor and the domain-decomposed coarse solve");
+    mfmgb_level &l = H->lev[level];
+    const int64_t n_below = coarse_dd_n_sep_below(H->dd);
+    if (R_below ? (R_below->n_rows != n_below || R_below->n_cols != l.R->n_cols) : n_below != 0)
+      return fail(ctx, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_restrict_no_halo: R_below must be %lld x %lld",
+                  (long long)n_below, (long long)l.R->n_cols);
+    l.restrict_no_halo = true;
+    l.R_below = R_below;
+    if (R_below)
+      MFMGB_CHECK(mfmgb_vec_alloc(ctx, n_below, &l.gb));
+    return MFMGB_OK;
+  }
+
   MFMGB_API int mfmgb_hierarchy_set_coarse_offsets(mfmgb_hierarchy *H, const int64_t *offsets, int nranks)
   {
     if (!H || !offsets || nranks < 1 || H->finalized)
@@ -555,6 +591,7 @@ extern "C"
       cudaFree(l.xtmp);
       cudaFree(l.bc);
       cudaFree(l.xc);
+      cudaFree(l.gb);
     }
     cudaFree(H->b_dev);
     cudaFree(H->x_dev);

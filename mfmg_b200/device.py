@@ -495,8 +495,10 @@ class Hierarchy:
 
     def __init__(self, handle: CudaHandle, operators, restrictors, params=None, omega: float = 1.0,
                  prolongators=None, halo: "HaloPlan | None" = None, boundary=(0, 0), coarse_offsets=None,
-                 coarse_dd: "CoarseDD | None" = None, restrict_split: int = 0):
+                 coarse_dd: "CoarseDD | None" = None, restrict_split: int = 0, restrict_no_halo: bool = False,
+                 restrict_below: "SparseMatrixDevice | None" = None):
         self.handle = handle
+        self.restrict_below = restrict_below
         self.halo = halo
         self.coarse_dd = coarse_dd
         lib = handle.lib
@@ -535,6 +537,9 @@ class Hierarchy:
             check(handle.ctx, lib.mfmgb_hierarchy_set_halo(self.ptr, 0, halo.ptr, int(boundary[0]), int(boundary[1])))
         if coarse_dd is not None:
             check(handle.ctx, lib.mfmgb_hierarchy_set_coarse_dd(self.ptr, coarse_dd.ptr))
+        if restrict_no_halo:
+            check(handle.ctx, lib.mfmgb_hierarchy_set_restrict_no_halo(
+                handle.ctx, self.ptr, 1, restrict_below.ptr if restrict_below is not None else None))
         check(handle.ctx, lib.mfmgb_hierarchy_finalize(handle.ctx, self.ptr))
         self.n = self.operators[0].size if isinstance(self.operators[0], MatrixFreeLaplaceDevice) \
             else self.operators[0].m()
@@ -561,7 +566,6 @@ class Hierarchy:
         else:
             fine = SparseMatrixDevice.from_host(handle, part.A)
         ops = [fine, SparseMatrixDevice.from_host(handle, part.Ac)]
-        res = [SparseMatrixDevice.from_host(handle, part.R)]
         pro = [SparseMatrixDevice.from_host(handle, part.P)]
         plan = HaloPlan(handle, part)
         # coarsest level: the domain-decomposed direct solve when the coarse operator is block tridiagonal in the
@@ -580,13 +584,32 @@ class Hierarchy:
             elif coarse_dd is True:
                 raise MfmgError(_lib.ERR_INVALID, "from_partition: the coarse operator is not block tridiagonal in the "
                                                   "ranks' row blocks; the domain-decomposed coarse solve cannot be used")
+        # With the domain-decomposed coarse solve the residual's halo is not exchanged at all: the entries of R on the
+        # ghost plane are dropped and the neighbour above supplies them through its R_below rows, which join the
+        # solver's all-reduce (MFMGB_RESTRICT_NO_HALO=0 keeps the exchange).
+        R_host, r_below, no_halo = part.R, None, False
+        if dd is not None and os.environ.get("MFMGB_RESTRICT_NO_HALO", "1") != "0" and \
+                (part.rank == 0 or part.R_below is not None):
+            from .hostsetup.partition import rows_restricted
+
+            no_halo = True
+            R_host = rows_restricted(part.R, 0, part.R.n_rows, 0, part.n_owned, part.R.n_cols)
+            if part.rank > 0:
+                f0, nb = ddp["sep_below_first_row"], ddp["n_sep_below"]
+                Rb = part.R_below
+                if int(Rb.rowptr[f0]) != 0 or Rb.n_rows - f0 != nb:
+                    raise MfmgError(_lib.ERR_INVALID, "from_partition: this rank's entries reach restrictor rows of the "
+                                                      "lower neighbour outside its separator")
+                r_below = SparseMatrixDevice.from_host(
+                    handle, rows_restricted(Rb, f0, Rb.n_rows, 0, part.n_owned, part.R.n_cols))
+        res = [SparseMatrixDevice.from_host(handle, R_host)]
         # (mfmgb_hierarchy_set_restrict_split could overlap the rows of R that only read owned entries with the
         # exchange of the residual's halo; measured slower on 2 GPUs -- 0.047 vs 0.033 ms for the stage -- so it is
         # left off: restrict_split=0)
         r_split = 0
         return Hierarchy(handle, ops, res, params, omega, prolongators=pro, halo=plan,
                          boundary=(part.boundary_lo, part.boundary_hi), coarse_offsets=part.coarse_offsets,
-                         coarse_dd=dd, restrict_split=r_split)
+                         coarse_dd=dd, restrict_split=r_split, restrict_no_halo=no_halo, restrict_below=r_below)
 
     def build_vector(self) -> DeviceVector:
         """A level-0 vector with room for the ghost tail (Level::build_vector, level.hpp:63-70)."""

@@ -39,6 +39,10 @@ class LocalPart:
     # touch ghosts are a prefix and a suffix of the owned range:
     boundary_lo: int = 0     # rows [0, boundary_lo) reference ghosts below
     boundary_hi: int = 0     # rows [boundary_hi, n_owned) reference ghosts above
+    # rows of R of the rank BELOW restricted to this rank's owned fine entries (local columns, one row per coarse row
+    # of that rank): what this rank contributes to the restriction onto the neighbour's top agglomerate layer.  With
+    # it the residual's halo need not be exchanged (device.Hierarchy.from_partition, coarse_dd).
+    R_below: HostCSR = None
 
 
 def slab_row_ranges(nodes, degree: int, cells_z: int, block_z: int, world: int):
@@ -72,6 +76,21 @@ def _localise(M: HostCSR, rows: slice, row_begin: int, row_end: int, ghost_globa
     loc[~owned] = (row_end - row_begin) + gpos
     return HostCSR(rows.stop - rows.start, (row_end - row_begin) + len(ghost_global),
                    np.ascontiguousarray(rp - k0), loc.astype(np.int32), np.ascontiguousarray(M.val[k0:k1]))
+
+
+def rows_restricted(M: HostCSR, r0: int, r1: int, lo: int, hi: int, n_cols: int, pad_rows_before: int = 0,
+                    n_rows: int | None = None) -> HostCSR:
+    """Rows [r0, r1) of M keeping the entries with lo <= col < hi (renumbered col - lo), as a matrix with `n_cols`
+    columns and `n_rows` rows of which the first `pad_rows_before` are empty."""
+    k0, k1 = int(M.rowptr[r0]), int(M.rowptr[r1])
+    col = M.col[k0:k1].astype(np.int64)
+    keep = (col >= lo) & (col < hi)
+    row_of = np.repeat(np.arange(r1 - r0), np.diff(M.rowptr[r0:r1 + 1]))
+    n_rows = (r1 - r0) + pad_rows_before if n_rows is None else n_rows
+    counts = np.bincount(row_of[keep] + pad_rows_before, minlength=n_rows)
+    rowptr = np.zeros(n_rows + 1, dtype=np.int64)
+    np.cumsum(counts, out=rowptr[1:])
+    return HostCSR(n_rows, n_cols, rowptr, (col[keep] - lo).astype(np.int32), np.ascontiguousarray(M.val[k0:k1][keep]))
 
 
 def partition_two_level(A: HostCSR, R: HostCSR, Ac: HostCSR, row_offsets, coarse_offsets, rank: int) -> LocalPart:
@@ -109,6 +128,8 @@ def partition_two_level(A: HostCSR, R: HostCSR, Ac: HostCSR, row_offsets, coarse
     hi_rows = idx[idx >= n_owned // 2]
     part.boundary_lo = int(lo_rows.max() + 1) if len(lo_rows) else 0
     part.boundary_hi = int(hi_rows.min()) if len(hi_rows) else n_owned
+    if rank > 0:
+        part.R_below = rows_restricted(R, int(coarse_offsets[rank - 1]), cb, rb, re_, n_owned + len(ghost_global))
     return part
 
 
@@ -214,5 +235,7 @@ def coarse_dd_plan(Ac: HostCSR, coarse_offsets, rank: int):
     for m in blocks.values():
         m.to_scipy().sort_indices()
     return {"n_c": n_c, "own_begin": lo, "n_I": len(I), "n_S": n_S, "adj_begin": adj_begin,
+            "n_sep_below": int(s_off[rank] - s_off[rank - 1]) if rank > 0 else 0,
+            "sep_below_first_row": int(sep_begin[rank - 1] - co[rank - 1]) if rank > 0 else 0,
             "own_sep_begin": int(s_off[rank]), "own_sep_n": int(s_off[rank + 1] - s_off[rank]),
             "sep_index": sep_index, "valid_cols": np.concatenate([np.arange(lo, co[rank + 1]), sep_index]), **blocks}

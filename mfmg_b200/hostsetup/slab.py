@@ -22,7 +22,7 @@ from __future__ import annotations
 
 import numpy as np
 from .amge import build_restrictor, galerkin_rows
-from .partition import LocalPart, finalize_plan, slab_row_ranges
+from .partition import LocalPart, finalize_plan, rows_restricted, slab_row_ranges
 from .problems import HostCSR, LaplaceProblem
 
 
@@ -141,6 +141,11 @@ def build_slab_part(degree: int, cells, h, material: str, block, n_eigenvectors:
     # extras for the driver
     part.constrained = ext.constrained[rb - off:re_ - off]
     part.n_global = n_global
+    if rank > 0:
+        # rows of the rank below present in the sub-box (its top agglomerate layer) restricted to the owned nodes
+        c_prev = int(coarse_off[rank - 1])
+        part.R_below = rows_restricted(R_ext, 0, cb - coff, lo, hi, n_owned + len(ghost_global),
+                                       pad_rows_before=coff - c_prev, n_rows=cb - c_prev)
     part.mf = _matrix_free_slab(ext, p, cells, h, e0, cz0, cz1, rank, world, plane, ghost_global, rb, re_)
     return part
 

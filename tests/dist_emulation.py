@@ -44,7 +44,7 @@ def gather_coarse(part, bc_full):
         bc_full[co[r]:co[r + 1]] = outs[r].numpy()
 
 
-def coarse_dd_solve_cpu(plan, bc_full):
+def coarse_dd_solve_cpu(plan, bc_full, g_below=None):
     """csrc/coarse_dd.cu restated with numpy + gloo: bc_full is valid on this rank's coarse rows only; the result is
     valid on this rank's rows and on all separator rows (everything else is NaN to catch illegal reads)."""
     AII, AIS, ASI = (plan[k].to_scipy().toarray() for k in ("A_II", "A_IS", "A_SI"))
@@ -63,6 +63,8 @@ def coarse_dd_solve_cpu(plan, bc_full):
     t[a0:a0 + na] -= ASI @ y
     o0, on = plan["own_sep_begin"], plan["own_sep_n"]
     t[o0:o0 + on] += bc_full[sep[o0:o0 + on]]
+    if g_below is not None and len(g_below):   # this rank's share of the restriction onto the separator below
+        t[a0:a0 + len(g_below)] += g_below
     tt = torch.from_numpy(t)
     dist.all_reduce(tt)                      # the only communication of the solve
     xs = np.linalg.solve(St.numpy(), tt.numpy())
@@ -86,15 +88,27 @@ def dist_vcycle_cpu(part, lu, piv, b_loc, nu=1, dd_plan=None):
     res = np.zeros(n + ng)
     halo_exchange(part, x)
     res[:n] = oracle.spmv(n, A.rowptr, A.col, A.val, x) - b_loc
-    halo_exchange(part, res)
     co = part.coarse_offsets
     bc = np.zeros(part.Ac.n_rows)
-    bc[co[part.rank]:co[part.rank + 1]] = oracle.spmv(R.n_rows, R.rowptr, R.col, R.val, res)
     if dd_plan is not None:
-        xc = coarse_dd_solve_cpu(dd_plan, bc)
+        # no exchange of the residual's halo: the entries of R on the ghost plane are dropped here and come in
+        # through the neighbour's R_below share, summed by the all-reduce of the separator right-hand sides
+        res[n:] = np.nan
+        Rs = R.to_scipy().tocsc()[:, :n].tocsr()
+        bc[co[part.rank]:co[part.rank + 1]] = Rs @ res[:n]
+        g_below = None
+        if part.rank > 0:
+            f0 = dd_plan["sep_below_first_row"]
+            Rb = part.R_below.to_scipy()
+            assert Rb[:f0].nnz == 0
+            g_below = Rb[f0:, :n] @ res[:n]
+            assert len(g_below) == dd_plan["n_sep_below"]
+        xc = coarse_dd_solve_cpu(dd_plan, bc, g_below)
         assert not np.any(np.isnan(xc[np.unique(P.col)])), "P reads coarse entries the DD solve does not provide"
         xc = np.nan_to_num(xc)
     else:
+        halo_exchange(part, res)
+        bc[co[part.rank]:co[part.rank + 1]] = oracle.spmv(R.n_rows, R.rowptr, R.col, R.val, res)
         gather_coarse(part, bc)
         xc = oracle.lu_solve(lu, piv, bc)
     x[:n] = x[:n] - oracle.spmv(n, P.rowptr, P.col, P.val, xc)

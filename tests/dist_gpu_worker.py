@@ -31,14 +31,18 @@ def main():
     # second pass: force the row-split (multi-GPU) dense coarse solve, which is normally used from n_c = 8192 on
     # coarse-solver variants: "dd" = domain-decomposed direct solve (the default for slab partitions), "split" = dense
     # inverse split by rows over the ranks, "replicated" = dense inverse on every rank
-    cases = [c + ("dd",) for c in cases] + [c + ("split",) for c in cases[:2]] + [cases[0] + ("replicated",)]
+    # "dd_halo": the same with the residual's halo still exchanged (by default it is not: the neighbour's share of the
+    # restriction joins the coarse solver's all-reduce)
+    cases = [c + ("dd",) for c in cases] + [c + ("split",) for c in cases[:2]] + [cases[0] + ("replicated",)] + \
+        [cases[1] + ("dd_halo",)]
     for dim, degree, cells, block, ne, mat, nu, coarse in cases:
         os.environ["MFMGB_DENSE_SPLIT_MIN"] = "1" if coarse == "split" else "8192"
-        os.environ["MFMGB_COARSE_DD"] = "1" if coarse == "dd" else "0"
+        os.environ["MFMGB_COARSE_DD"] = "1" if coarse.startswith("dd") else "0"
+        os.environ["MFMGB_RESTRICT_NO_HALO"] = "0" if coarse == "dd_halo" else "1"
         P, R, Ac = two_level_problem(dim, degree, cells, block, ne, mat)
         (part,), row_off, coarse_off = hs.make_parts(P, R, Ac, (block,) * dim, ne, world, ranks=[rank])
         H = d.Hierarchy.from_partition(handle, part, {"is preconditioner": True, "smoother": {"n_smoothing_steps": nu}})
-        assert (H.coarse_dd is not None) == (coarse == "dd"), (rank, coarse)
+        assert (H.coarse_dd is not None) == coarse.startswith("dd"), (rank, coarse)
         Ho = oracle_hierarchy(P, R, Ac, nu, True)
         rng = np.random.default_rng(5)
         b_h = rng.standard_normal(P.n)
@@ -99,6 +103,7 @@ def main():
         return out
 
     os.environ["MFMGB_COARSE_DD"] = "1"
+    os.environ["MFMGB_RESTRICT_NO_HALO"] = "1"
     for mat in ("discontinuous", "linear"):
         part = hs.build_slab_part(1, cells, h, mat, block, 1, world, rank, gather)
         assert part.mf is not None
