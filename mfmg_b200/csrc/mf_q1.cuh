@@ -3,20 +3,26 @@
 // Same operator as mf_laplace.cu (tests/laplace_matrix_free.hpp:121-156 inside deal.II's MatrixFree vmult semantics:
 // constrained entries read as 0, constrained rows act as identity), restructured so that a layer of cells costs ONE
 // block barrier and no shared-memory read-modify-write:
-//   * thread (tx, ty) of a 32 x TY tile owns the node column (X0-1+tx, Y0-1+ty) and the cell whose low corner is that
-//     node; the CTA sweeps upwards in z.  Per cell layer L the thread
-//       - holds the 4+4 nodal values of its cell in registers (the lower plane is last layer's upper plane),
-//       - evaluates the cell operator,
-//       - publishes its 8 local results to shared memory,                      __syncthreads()
-//       - as NODE owner adds the 4 lower-plane results of the 4 cells around it to the carry of the previous layer
-//         (that is plane L, finished: fused epilogue, one coalesced store) and keeps the 4 upper-plane results as the
-//         new carry.  Fixed order => bit-reproducible, no atomics, no colouring.
-//   * x planes go through a double-buffered shared tile (33 x (TY+1), the +1 column/row is the high-side halo);
-//     the global loads of plane L+3 (own node, coefficient of layer L+1) are issued a full layer ahead.
+//   * thread (tx, ty) of a 32 x 8 tile owns the node column (X0-1+tx, Y0-1+ty) and the cell whose low corner is that
+//     node; a CTA owns TZ node planes of its tile and sweeps upwards through the TZ+1 cell layers that touch them.
+//   * ONE load phase per CTA: the brick (x of the TZ+2 planes incl. the high-side halo column / row, the per-cell
+//     coefficients of the TZ+1 layers) goes global -> shared with 8-byte cp.async, every request in flight at once;
+//     constraint flags are batched through registers, constrained entries are zeroed in place.  Bricks without any
+//     constrained node (brick_flags, computed once at creation) skip every flag access.
+//   * per cell layer L the thread reads the 4 upper nodal values of its cell (the lower 4 are last layer's upper ones),
+//     evaluates the cell operator, publishes its 8 local results to shared memory,            __syncthreads()
+//     and as NODE owner adds the 4 lower-plane results of the 4 cells around it to the carry of the previous layer --
+//     that is plane L, finished: fused epilogue (operands requested before the cell work), one coalesced store -- and
+//     keeps the 4 upper-plane results as the new carry.  Fixed order => bit-reproducible, no atomics, no colouring.
 //   * coefficient modes: per-cell constant (detected at creation: the (cell, q) table has equal entries per cell,
-//     e.g. every piecewise-constant material) -> out = c K_ref u with the 8x8 reference matrix in the constant bank
-//     (64 FMA per cell, 8 B per cell); general per-quadrature-point table -> sum factorisation (mf_laplace.cu's).
-//   * vectors may be the [owned | ghost-below | ghost-above] slab layout of the row-partitioned hierarchy.
+//     e.g. every cell-wise constant material) -> c (ax D(x)M(x)M + ay M(x)D(x)M + az M(x)M(x)D) u in 71 FP64
+//     operations with literal constants; general per-quadrature-point table -> sum factorisation in ~160 (the
+//     derivative in direction d does not depend on q_d, so only partial sums of the table enter).
+//   * vectors may be the [owned | ghost-below | ghost-above] slab layout of the row-partitioned hierarchy; z chunks can
+//     be launched separately (only the first / last chunk read a ghost plane), so the middle ones overlap the exchange.
+// History of what did NOT work is in profiles/r01_summary.md section 5 (register pipeline: one exposed DRAM round trip
+// per layer; load->store loops: not unrolled by the compiler; reference matrix in the parameter bank: R2UR + IMAD.MOV
+// per DFMA).
 // Algorithmic bytes per apply: 16 n + 8 n_cells (+ 56 n_cells in the per-q mode) + n (flags).
 // (included by mf_laplace.cu after cell_apply<DIM, P>: one translation unit, shared constant tables)
 
