@@ -128,6 +128,35 @@ def local_eigenvectors(problem: LaplaceProblem, coef_loc: np.ndarray, constr_loc
     return vecs, diag_agg
 
 
+def restriction_from_local(eigenvectors, diag_elements, dof_indices_maps, n_local_eigenvectors, global_diag,
+                           n_cols: int) -> HostCSR:
+    """AMGe::compute_restriction_sparse_matrix with its own argument list
+    (include/mfmg/common/amge.templates.hpp:271-324): row `pos` (agglomerate-major, eigenvector-minor) gets
+    `diag_elements[i][j] / global_diag[g] * eigenvectors[pos][j]` ADDED at column g = dof_indices_maps[i][j].
+    Columns come out ascending; repeated columns within a row are summed (Trilinos `add` + `compress(add)`)."""
+    import scipy.sparse as sp
+
+    rows, cols, vals = [], [], []
+    pos = 0
+    for i, n_eig in enumerate(n_local_eigenvectors):
+        g = np.asarray(dof_indices_maps[i], dtype=np.int64)
+        w = np.asarray(diag_elements[i], dtype=np.float64) / np.asarray(global_diag, dtype=np.float64)[g]
+        for _ in range(int(n_eig)):
+            v = np.asarray(eigenvectors[pos], dtype=np.float64)
+            if len(v) != len(g):
+                raise ValueError(f"dof_indices_maps[{i}] has the wrong size: {len(g)} instead of {len(v)}")
+            rows.append(np.full(len(g), pos, dtype=np.int64))
+            cols.append(g)
+            vals.append(w * v)
+            pos += 1
+    if pos == 0:
+        return HostCSR(0, n_cols, np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int32), np.zeros(0))
+    m = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(pos, n_cols)).tocsr()
+    m.sum_duplicates()
+    m.sort_indices()
+    return HostCSR.from_scipy(m)
+
+
 def build_restrictor(problem: LaplaceProblem, block, n_eigenvectors: int,
                      eigensolver: str = "free") -> HostCSR:
     """The restriction matrix R (n_c x n) of AMGe::setup_restrictor for block agglomerates."""

@@ -217,3 +217,47 @@ def test_vcycle_is_spd_preconditioner_and_reduces_error():
     Mu, Mv = H.vmult(u), H.vmult(v)
     assert abs(v @ Mu - u @ Mv) < 1e-10 * abs(v @ Mu)  # symmetric (nu pre == nu post, Jacobi)
     assert u @ Mu > 0
+
+
+def test_restriction_matrix_kat():
+    """tests/test_restriction_matrix.cc:62-165 restated: 5 x 5 nodes (hyper_cube refined twice, Q1), one "agglomerate"
+    per node with 3 distinct random DoFs drawn from libstdc++'s default engine through uniform_int_distribution(0, 24)
+    (rejection of repeats, exactly like the reference loop), eigenvector entries 75 + 3 i + j, weights 1 / multiplicity,
+    identity system matrix.  The reference asserts R(row, dof) == diag_elements * eigenvectors at 1e-14; the weights of
+    every column must also sum to one (partition of unity), which is what makes R^T reproduce constants."""
+    from mfmg_b200 import hostsetup as hs
+
+    n, size = 25, 3
+    stream = iter(oracle.std_uniform_int(4000, 0, n - 1, seed=1))
+    maps = []
+    for _ in range(n):
+        seen = []
+        while len(seen) < size:
+            d = int(next(stream))
+            if d not in seen:
+                seen.append(d)
+        maps.append(seen)
+    eig = [[n * size + i * size + j for j in range(size)] for i in range(n)]
+    count = np.zeros(n)
+    for row in maps:
+        for d in row:
+            count[d] += 1.0
+    diag = [[1.0 / count[d] for d in row] for row in maps]
+    R = hs.restriction_from_local(eig, diag, maps, [1] * n, np.ones(n), n)
+    dense = R.to_scipy().toarray()
+    for i in range(n):
+        for j in range(size):
+            assert abs(dense[i, maps[i][j]] - diag[i][j] * eig[i][j]) <= 1e-14 * abs(dense[i, maps[i][j]])
+    assert R.nnz == n * size
+    # the weights alone (eigenvector entries := 1) sum to one in every column that is hit
+    W = hs.restriction_from_local([[1.0] * size] * n, diag, maps, [1] * n, np.ones(n), n).to_scipy().toarray()
+    hit = count > 0
+    assert np.allclose(W.sum(axis=0)[hit], 1.0, atol=1e-15)
+    # build_restrictor's rows obey the same formula (cross-check on a real agglomerate)
+    P = hs.LaplaceProblem.create(2, 1, 4, "linear")
+    Rb = hs.build_restrictor(P, (2, 2), 1).to_scipy().toarray()
+    g = np.flatnonzero(Rb[0])
+    vecs, diag_agg = hs.amge.local_eigenvectors(P, P.coef[[0, 1, 4, 5]], P.constrained[[0, 1, 2, 5, 6, 7, 10, 11, 12]],
+                                                (2, 2), 1)
+    ref = hs.restriction_from_local([vecs[0]], [diag_agg], [[0, 1, 2, 5, 6, 7, 10, 11, 12]], [1], P.diag, P.n)
+    assert np.allclose(ref.to_scipy().toarray()[0], Rb[0], rtol=1e-13, atol=1e-15) and len(g) > 0
