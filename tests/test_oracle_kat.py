@@ -261,3 +261,30 @@ def test_restriction_matrix_kat():
                                                 (2, 2), 1)
     ref = hs.restriction_from_local([vecs[0]], [diag_agg], [[0, 1, 2, 5, 6, 7, 10, 11, 12]], [1], P.diag, P.n)
     assert np.allclose(ref.to_scipy().toarray()[0], Rb[0], rtol=1e-13, atol=1e-15) and len(g) > 0
+
+
+def test_two_grid_gold_rate_is_renumbering_invariant():
+    """tests/test_hierarchy_device.cu:365-371 lists the SAME gold for the "None" and "Reverse Cuthill_McKee" DoF
+    orderings: the two-grid method does not depend on the numbering.  Restated with a random symmetric permutation of
+    the fine DoFs (A -> P A P^T, R -> R P^T, x0 drawn in the NEW order like the reference draws it in its order)."""
+    import scipy.sparse as sp
+
+    from mfmg_b200 import hostsetup as hs
+
+    P, R, Ac = two_level_problem(3, 1, 4, 2, 2, "constant", "device_lapack")
+    rng = np.random.default_rng(7)
+    perm = rng.permutation(P.n)                      # new index i holds old DoF perm[i]
+    Pm = sp.csr_matrix((np.ones(P.n), (np.arange(P.n), perm)), shape=(P.n, P.n))
+    A2 = hs.HostCSR.from_scipy((Pm @ P.A.to_scipy() @ Pm.T).tocsr())
+    R2 = hs.HostCSR.from_scipy((R.to_scipy() @ Pm.T).tocsr())
+    Ac2 = hs.galerkin(A2, R2)
+    H = oracle.Hierarchy([(P.n, A2.rowptr, A2.col, A2.val), (Ac2.n_rows, Ac2.rowptr, Ac2.col, Ac2.val)],
+                         [(R2.n_rows, R2.n_cols, R2.rowptr, R2.col, R2.val)], 1, False)
+    x = oracle.std_uniform01(P.n)
+    b = np.zeros(P.n)
+    res = []
+    for _ in range(20):
+        x = H.vmult(b, x)
+        res.append(np.linalg.norm(oracle.spmv(P.n, A2.rowptr, A2.col, A2.val, x)))
+    gold = float(golden()["gold_rate_device_cube"])
+    assert abs(res[-1] / res[-2] - gold) / gold < 1e-8
