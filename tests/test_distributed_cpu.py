@@ -233,3 +233,39 @@ def test_coarse_dd_plan_block_elimination(world, cells, block, ne):
     assert np.linalg.norm(x - x_ref) <= 1e-12 * np.linalg.norm(x_ref)
     for p, pl in zip(parts, plans):
         assert np.all(np.isin(p.P.col, pl["valid_cols"]))
+
+
+def test_coarse_dd_plan_rejects_operators_that_are_not_block_tridiagonal():
+    """The plan is only offered when interiors of different ranks are decoupled once the separators are removed;
+    otherwise from_partition falls back to the dense inverse.  All ranks must reach the same decision."""
+    import scipy.sparse as sp
+
+    from mfmg_b200 import hostsetup as hs
+
+    n, world = 40, 4
+    co = np.array([0, 10, 20, 30, 40])
+    tri = sp.diags([np.ones(n - 1), 4 * np.ones(n), np.ones(n - 1)], [-1, 0, 1]).tocsr()
+    ok = [hs.coarse_dd_plan(hs.HostCSR.from_scipy(tri), co, r) for r in range(world)]
+    assert all(p is not None for p in ok)
+    assert [p["n_S"] for p in ok] == [3] * world and ok[0]["n_sep_below"] == 0 and ok[2]["n_sep_below"] == 1
+    far = tri.tolil()
+    far[2, 35] = far[35, 2] = 0.5                     # rank 0 coupled to rank 3: not block tridiagonal
+    bad = [hs.coarse_dd_plan(hs.HostCSR.from_scipy(far.tocsr()), co, r) for r in range(world)]
+    assert all(p is None for p in bad)
+    assert hs.coarse_dd_plan(hs.HostCSR.from_scipy(tri), np.array([0, n]), 0) is None   # one rank: nothing to do
+
+
+def test_rows_restricted():
+    from mfmg_b200 import hostsetup as hs
+    from mfmg_b200.hostsetup.partition import rows_restricted
+
+    rng = np.random.default_rng(0)
+    import scipy.sparse as sp
+
+    M = sp.random(12, 30, density=0.3, random_state=1, format="csr")
+    M.sort_indices()
+    H = hs.HostCSR.from_scipy(M)
+    sub = rows_restricted(H, 3, 9, 10, 22, 40, pad_rows_before=2, n_rows=10)
+    ref = np.zeros((10, 40))
+    ref[2:8, :12] = M.toarray()[3:9, 10:22]
+    assert (sub.n_rows, sub.n_cols) == (10, 40) and np.array_equal(sub.to_scipy().toarray(), ref)
