@@ -316,3 +316,30 @@ class LaplaceProblem:
         if self.coef.shape[1] == nq:
             return self.coef
         return np.ascontiguousarray(np.repeat(self.coef, nq, axis=1))
+
+
+def csr_from_dealii_sparse_matrix(rowstart, colnums, values, n_cols: int) -> HostCSR:
+    """Upload layout from deal.II's `SparseMatrix` storage, the host half of `convert_matrix`
+    (source/cuda/utils.cu:39-89).  deal.II keeps the rows of a SQUARE matrix with the diagonal entry FIRST and the
+    other columns ascending; the reference moves the diagonal to its sorted position (:64-81) so that the device sees
+    a regular CSR with ascending columns.  Rectangular matrices are already ascending and pass through."""
+    rowstart = np.asarray(rowstart, dtype=np.int64)
+    col = np.array(colnums, dtype=np.int32)
+    val = np.array(values, dtype=np.float64)
+    n_rows = len(rowstart) - 1
+    if n_rows == n_cols:
+        for row in range(n_rows):
+            k0, k1 = int(rowstart[row]), int(rowstart[row + 1])
+            if k1 - k0 < 2:
+                continue
+            if col[k0] != row:
+                raise ValueError(f"row {row}: deal.II stores the diagonal first, found column {col[k0]}")
+            d_val = val[k0]
+            pos = 1
+            while pos < k1 - k0 and col[k0 + pos] < row:       # utils.cu:71-76
+                col[k0 + pos - 1] = col[k0 + pos]
+                val[k0 + pos - 1] = val[k0 + pos]
+                pos += 1
+            col[k0 + pos - 1] = row
+            val[k0 + pos - 1] = d_val
+    return HostCSR(n_rows, n_cols, rowstart.copy(), col, val)

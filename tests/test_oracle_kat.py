@@ -288,3 +288,33 @@ def test_two_grid_gold_rate_is_renumbering_invariant():
         res.append(np.linalg.norm(oracle.spmv(P.n, A2.rowptr, A2.col, A2.val, x)))
     gold = float(golden()["gold_rate_device_cube"])
     assert abs(res[-1] / res[-2] - gold) / gold < 1e-8
+
+
+def test_convert_matrix_layout_kat():
+    """tests/test_utils_device.cu:58-106 (dealii_sparse_matrix_square) and :108-150 (rectangle) restated for the host
+    half of convert_matrix: row i of the 30 x 30 matrix has the columns drawn by std::default_random_engine(i) through
+    uniform_int_distribution(0, 29) (5 draws) plus the diagonal, values i + j, stored deal.II-style (diagonal first);
+    after the conversion every row is ascending and val == matrix(i, col)."""
+    from mfmg_b200 import hostsetup as hs
+
+    size = 30
+    rowstart, colnums, values = [0], [], []
+    for i in range(size):
+        idx = sorted(set(int(c) for c in oracle.std_uniform_int(5, 0, size - 1, seed=i)) | {i})
+        stored = [i] + [c for c in idx if c != i]          # deal.II: diagonal first, the rest ascending
+        colnums += stored
+        values += [float(i + c) for c in stored]
+        rowstart.append(len(colnums))
+    A = hs.csr_from_dealii_sparse_matrix(rowstart, colnums, values, size)
+    for i in range(size):
+        c = A.col[A.rowptr[i]:A.rowptr[i + 1]]
+        assert np.all(np.diff(c) > 0) and i in c
+        assert np.array_equal(A.val[A.rowptr[i]:A.rowptr[i + 1]], (i + c).astype(float))
+    # rectangle: 30 x 39, columns i .. i+9, values i + j: passes through unchanged
+    rs = np.arange(0, 301, 10)
+    cols = np.concatenate([np.arange(i, i + 10) for i in range(30)])
+    vals = np.concatenate([np.arange(i, i + 10) for i in range(30)]).astype(float)   # value (i, i+j) = i + j
+    B = hs.csr_from_dealii_sparse_matrix(rs, cols, vals, 39)
+    assert np.array_equal(B.col, cols) and np.array_equal(B.val, vals)
+    with pytest.raises(ValueError):
+        hs.csr_from_dealii_sparse_matrix([0, 2, 3], [1, 0, 1], [1.0, 2.0, 3.0], 2)   # row 0 does not start with its diagonal
