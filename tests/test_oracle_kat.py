@@ -318,3 +318,47 @@ def test_convert_matrix_layout_kat():
     assert np.array_equal(B.col, cols) and np.array_equal(B.val, vals)
     with pytest.raises(ValueError):
         hs.csr_from_dealii_sparse_matrix([0, 2, 3], [1, 0, 1], [1.0, 2.0, 3.0], 2)   # row 0 does not start with its diagonal
+
+
+@pytest.mark.parametrize("dim,cells", [(2, 4), (3, 3)])
+def test_matrix_free_laplace_exact_for_quadratic(dim, cells):
+    """tests/test_laplace_matrix_free.cc:97-135 (laplace_2d / laplace_3d, FE_Q(2), material 1): the exact solution
+    u = prod_d (x_d - 1) x_d lies in the Q2 space, so the matrix-free operator applied to its nodal values equals the
+    load vector of f = -Lap u on the unconstrained DoFs (the reference solves and asserts a zero error at 1e-14)."""
+    from mfmg_b200 import hostsetup as hs
+
+    P = hs.LaplaceProblem.create(dim, 2, cells, "constant", assemble_matrix=False)
+    M = oracle.MatrixFreeLaplace(dim, 2, P.cells, P.h, P.coef_per_q(), P.constrained)
+    N = P.nodes[0]
+    xs = np.arange(N) / (N - 1)
+    grids = np.meshgrid(*([xs] * dim), indexing="ij")          # grids[d][i_{dim-1}, ..., i_0]: index order z, y, x
+    coords = grids[::-1]                                       # coords[0] = x (fastest index last)
+    u = np.ones_like(coords[0])
+    for d in range(dim):
+        u = u * (coords[d] - 1.0) * coords[d]
+    u = u.reshape(-1)
+    qp, qw = hs.problems.gauss_unit(3)
+    S, _ = hs.problems.lagrange_1d(2, qp)
+    h = P.h[0]
+    b = np.zeros(P.n)
+    import itertools
+
+    for cell in itertools.product(range(cells), repeat=dim):           # cell = (c_{dim-1}, ..., c_0)
+        for q in itertools.product(range(3), repeat=dim):
+            x = [(cell[dim - 1 - d] + qp[q[dim - 1 - d]]) * h for d in range(dim)]
+            f = 0.0
+            for d in range(dim):
+                t = 1.0
+                for i in range(dim):
+                    if i != d:
+                        t *= (x[i] - 1.0) * x[i]
+                f -= 2.0 * t
+            w = np.prod([qw[qi] for qi in q]) * h ** dim
+            for a in itertools.product(range(3), repeat=dim):
+                g = 0
+                for k in range(dim):                                   # k = 0 is the slowest index
+                    g = g * N + (cell[k] * 2 + a[k])
+                b[g] += f * np.prod([S[q[k], a[k]] for k in range(dim)]) * w
+    free = P.constrained == 0
+    r = M.apply(u) - b
+    assert np.max(np.abs(r[free])) < 1e-14 * max(1.0, np.max(np.abs(b)))
