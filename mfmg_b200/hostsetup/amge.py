@@ -100,32 +100,48 @@ def local_eigenvectors(problem: LaplaceProblem, coef_loc: np.ndarray, constr_loc
             raise RuntimeError("lapack branch: only %d eigenvalues in (-0.5, 100]" % len(keep))
         vecs[:] = v[:, keep[:n_eigenvectors]].T
         return vecs, diag_agg
-    free = np.flatnonzero(constr_loc == 0)
-    if len(free) == 0:
-        return vecs, diag_agg
-    Kff = K[free][:, free]
+    w, v = lowest_eigenpairs(K, constr_loc, n_eigenvectors, shift=float(np.mean(diag_agg)), dense_limit=dense_limit)
+    vecs[:v.shape[0]] = v
+    return vecs, diag_agg
+
+
+def lowest_eigenpairs(K, constrained, n_eigenvectors: int, shift: float = 0.0, dense_limit: int = 1500):
+    """The n algebraically smallest eigenpairs of the local matrix K restricted to its unconstrained DoFs, the
+    post-processed form AMGe_host::compute_local_eigenvectors returns (include/mfmg/dealii/amge_host.templates.hpp:
+    378-394,446-475): eigenvalues ascending, eigenvectors of unit 2-norm with zeros at the constrained DoFs.
+    Returns (eigenvalues[k], eigenvectors[k, n_loc]) with k = min(n_eigenvectors, number of free DoFs).
+    Small blocks: dense symmetric solve; large ones: shift-invert Lanczos around 0 after adding `shift` to the
+    diagonal (the reference shifts by mean(diag), :384-388; the eigenvalues returned are un-shifted)."""
+    import scipy.sparse as sp
+
+    K = sp.csr_matrix(K)
+    constrained = np.asarray(constrained)
+    nloc = K.shape[0]
+    free = np.flatnonzero(constrained == 0)
     ne = min(n_eigenvectors, len(free))
+    vecs = np.zeros((ne, nloc))
+    if ne == 0:
+        return np.zeros(0), vecs
+    Kff = K[free][:, free]
     if len(free) <= dense_limit:
         w, v = np.linalg.eigh(Kff.toarray())
-        v = v[:, :ne]
+        w, v = w[:ne], v[:, :ne]
     else:
-        import scipy.sparse as sp
         import scipy.sparse.linalg as spla
 
-        shift = float(np.mean(diag_agg))  # amge_host.templates.hpp:384-388
         Ks = (Kff + shift * sp.identity(len(free))).tocsc()
         rng = np.random.default_rng(0)
         w, v = spla.eigsh(Ks, k=ne, sigma=0.0, which="LM", v0=rng.standard_normal(len(free)),
                           tol=1e-13)
         order = np.argsort(w)
-        v = v[:, order]
+        w, v = w[order] - shift, v[:, order]
     # deterministic sign: make the entry of largest magnitude positive
     for k in range(ne):
         j = np.argmax(np.abs(v[:, k]))
         if v[j, k] < 0:
             v[:, k] = -v[:, k]
         vecs[k, free] = v[:, k] / np.linalg.norm(v[:, k])
-    return vecs, diag_agg
+    return w, vecs
 
 
 def restriction_from_local(eigenvectors, diag_elements, dof_indices_maps, n_local_eigenvectors, global_diag,

@@ -104,3 +104,28 @@ def test_matrix_market_round_trip(tmp_path):
     v = np.random.default_rng(0).standard_normal(17)
     hs.mmio.write_vector(str(tmp_path / "v.mtx"), v)
     assert np.array_equal(hs.mmio.read_vector(str(tmp_path / "v.mtx")), v)
+
+
+@pytest.mark.parametrize("dense_limit", [1500, 10])
+def test_local_eigenvectors_diagonal_kats(dense_limit):
+    """tests/test_eigenvectors.cc:74-127 (diagonal) and :178-232 (diagonal_constraint) for the eigensolve core of the
+    host setup: local matrix diag(1, 2, ..., 81) on the 9 x 9 Q1 nodes (hyper_cube refined 3 times); 5 lowest pairs =
+    (i + 1, e_i); with DoF 0 constrained = (i + 2, e_{i+1}); eigenvector entries compared in absolute value, 1e-12.
+    Both the dense branch and the shift-invert Lanczos branch (dense_limit = 10)."""
+    import scipy.sparse as sp
+
+    n, ne = 81, 5
+    K = sp.diags(np.arange(1, n + 1, dtype=float)).tocsr()
+    w, v = hs.lowest_eigenpairs(K, np.zeros(n, dtype=np.uint8), ne, shift=float(np.mean(K.diagonal())),
+                                dense_limit=dense_limit)
+    assert np.allclose(w, np.arange(1, ne + 1), rtol=0, atol=1e-10)
+    ref = np.zeros((ne, n))
+    ref[np.arange(ne), np.arange(ne)] = 1.0
+    assert np.max(np.abs(np.abs(v) - ref)) < 1e-10
+    c = np.zeros(n, dtype=np.uint8)
+    c[0] = 1
+    w, v = hs.lowest_eigenpairs(K, c, ne, shift=float(np.mean(K.diagonal())), dense_limit=dense_limit)
+    assert np.allclose(w, np.arange(2, ne + 2), rtol=0, atol=1e-10)
+    ref = np.zeros((ne, n))
+    ref[np.arange(ne), np.arange(1, ne + 1)] = 1.0
+    assert np.max(np.abs(np.abs(v) - ref)) < 1e-10
