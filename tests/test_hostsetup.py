@@ -129,3 +129,35 @@ def test_local_eigenvectors_diagonal_kats(dense_limit):
     ref = np.zeros((ne, n))
     ref[np.arange(ne), np.arange(1, ne + 1)] = 1.0
     assert np.max(np.abs(np.abs(v) - ref)) < 1e-10
+
+
+def test_block_agglomerates_match_reference_partition():
+    """tests/test_agglomerate.cc:69-117 (simple_agglomerate_2d, one rank): 8 x 8 cells (hyper_cube refined 3 times),
+    block partitioner nx = 2, ny = 3.  The reference lists the agglomerate id of every cell in deal.II's traversal
+    order (Morton / z-order), ids numbered by first visit.  hostsetup.block_agglomerates numbers its blocks
+    lexicographically (a permutation); the PARTITION -- which cells share an agglomerate, including
+    the 3 + 3 + 2 split of the 8 cell rows -- must be the reference's."""
+    ref = [1, 1, 1, 1, 2, 2, 2, 2, 1, 1, 3, 3, 2, 2, 4, 4, 5, 5, 5, 5, 6, 6, 6, 6, 5, 5, 7, 7, 6, 6, 8, 8,
+           3, 3, 3, 3, 4, 4, 4, 4, 9, 9, 9, 9, 10, 10, 10, 10, 7, 7, 7, 7, 8, 8, 8, 8, 11, 11, 11, 11, 12, 12, 12, 12]
+    aggs = hs.block_agglomerates(2, (8, 8), (2, 3))
+    assert len(aggs) == 12
+    owner = {}
+    for ia, ((ox, oy), (sx, sy)) in enumerate(aggs):
+        for y in range(oy, oy + sy):
+            for x in range(ox, ox + sx):
+                owner[(x, y)] = ia
+
+    def morton(k):   # deal.II child order on a refined hyper_cube: bit pairs (y, x) from the coarsest level down
+        x = y = 0
+        for level in range(3):
+            d = (k >> (2 * (2 - level))) & 3
+            x = 2 * x + (d & 1)
+            y = 2 * y + (d >> 1)
+        return x, y
+
+    first_visit, got = {}, []
+    for k in range(64):
+        a = owner[morton(k)]
+        first_visit.setdefault(a, len(first_visit) + 1)
+        got.append(first_visit[a])
+    assert got == ref
