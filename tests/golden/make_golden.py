@@ -43,5 +43,23 @@ out["gold_rate_device_cube"] = np.array(0.14933479171507894)
 # tests/test_smoother_device.cu:36-114: tridiag(-1,4,-1), b = 1, x0 = 0 -> x = 0.25
 out["smoother_expected"] = np.full(30, 0.25)
 
+# tests/test_agglomerate.cc:120-286 (simple_agglomerate_3d, one rank): agglomerate id of every cell of the 8 x 8 x 8
+# mesh in deal.II's traversal order for the block partitioner nx = 2, ny = 3, nz = 4.  512 integers: transcribed from
+# the reference test file when it is available (this container), kept from the previous fixture otherwise.
+ref_test = "/root/reference/tests/test_agglomerate.cc"
+old = os.path.join(ROOT, "tests", "golden", "kat.npz")
+if os.path.exists(ref_test):
+    import re
+
+    text = open(ref_test).read()
+    body = text[text.index("simple_agglomerate_3d"):]
+    block = body[body.index("ref_agglomerates = {"):]
+    block = block[:block.index("};")]
+    ids = [int(t) for t in re.findall(r"\d+", block)]
+    assert len(ids) == 512, len(ids)
+    out["agglomerates_3d_ids"] = np.array(ids, dtype=np.int32)
+elif os.path.exists(old) and "agglomerates_3d_ids" in np.load(old).files:
+    out["agglomerates_3d_ids"] = np.load(old)["agglomerates_3d_ids"]
+
 np.savez(os.path.join(ROOT, "tests", "golden", "kat.npz"), **out)
 print("wrote tests/golden/kat.npz:", {k: v.shape for k, v in out.items()})

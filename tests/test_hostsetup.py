@@ -161,3 +161,32 @@ def test_block_agglomerates_match_reference_partition():
         first_visit.setdefault(a, len(first_visit) + 1)
         got.append(first_visit[a])
     assert got == ref
+
+
+def test_block_agglomerates_3d_match_reference_partition():
+    """tests/test_agglomerate.cc:120-286 (simple_agglomerate_3d, one rank): 8^3 cells, blocks 2 x 3 x 4; the reference's
+    512 per-cell ids (tests/golden/kat.npz, transcribed by tests/golden/make_golden.py) in z-order, first-visit ids."""
+    from helpers import golden
+
+    ref = golden()["agglomerates_3d_ids"].tolist()
+    aggs = hs.block_agglomerates(3, (8, 8, 8), (2, 3, 4))
+    owner = {}
+    for ia, ((ox, oy, oz), (sx, sy, sz)) in enumerate(aggs):
+        for z in range(oz, oz + sz):
+            for y in range(oy, oy + sy):
+                for x in range(ox, ox + sx):
+                    owner[(x, y, z)] = ia
+
+    def morton(k):
+        x = y = z = 0
+        for level in range(3):
+            d = (k >> (3 * (2 - level))) & 7
+            x, y, z = 2 * x + (d & 1), 2 * y + ((d >> 1) & 1), 2 * z + (d >> 2)
+        return x, y, z
+
+    first_visit, got = {}, []
+    for k in range(512):
+        a = owner[morton(k)]
+        first_visit.setdefault(a, len(first_visit) + 1)
+        got.append(first_visit[a])
+    assert got == ref
