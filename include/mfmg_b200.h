@@ -59,6 +59,15 @@ extern "C"
   MFMGB_API int64_t mfmgb_ctx_launch_count(mfmgb_ctx *ctx);
   MFMGB_API const char *mfmgb_version(void);
 
+  /* ---- raw device memory: replaces cuda_malloc / cuda_free / cuda_mem_copy_to_dev / cuda_mem_copy_to_host
+   *      (include/mfmg/cuda/utils.cuh:66-99), the helpers the reference's callers use to fill the arrays they hand to
+   *      SparseMatrixDevice's take-ownership constructor.  Plain cudaMalloc memory: mfmgb_csr_adopt_device accepts it.
+   *      ctx may be NULL here (the reference's helpers take no handle). ---- */
+  MFMGB_API int mfmgb_dev_malloc(mfmgb_ctx *ctx, int64_t bytes, void **out);
+  MFMGB_API int mfmgb_dev_free(mfmgb_ctx *ctx, void *ptr);
+  MFMGB_API int mfmgb_dev_upload(mfmgb_ctx *ctx, void *dst_dev, const void *src_host, int64_t bytes);
+  MFMGB_API int mfmgb_dev_download(mfmgb_ctx *ctx, const void *src_dev, void *dst_host, int64_t bytes);
+
   /* ---- device vectors: replaces cuda_malloc/cuda_free/cuda_mem_copy_to_{dev,host} (include/mfmg/cuda/utils.cuh:66-99)
    *      and the deal.II CUDA-vector ops used on the path (hierarchy.hpp:258,286,302; cuda_smoother.cu:50-59) ---- */
   MFMGB_API int mfmgb_vec_alloc(mfmgb_ctx *ctx, int64_t n, double **out);
@@ -190,7 +199,9 @@ extern "C"
 
   /* Preconditioned CG with deal.II's SolverCG recurrence; A = level-0 operator of H.  Device vectors.
    * Stops when |A x - b|_2 <= tol (absolute) or after max_it iterations.  res_hist_host (may be NULL)
-   * receives max_it + 1 residual norms.  H == NULL: unpreconditioned CG on A. */
+   * receives max_it + 1 residual norms.  H == NULL: unpreconditioned CG on A.
+   * Row-partitioned hierarchy: b and x hold mfmgb_hierarchy_vector_size(H, 0) entries -- the owned rows followed by
+   * the ghost tail the halo exchange writes (mfmgb_pcg_host sizes its staging vectors that way itself). */
   MFMGB_API int mfmgb_pcg(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const mfmgb_csr *A, const double *b, double *x, double tol,
                           int max_it, int *iterations, double *res_hist_host);
   MFMGB_API int mfmgb_pcg_host(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const mfmgb_csr *A, const double *b_host,

@@ -60,6 +60,32 @@ inline void check_status(mfmgb_ctx *ctx, int rc)
   throw std::runtime_error(msg);
 }
 
+// include/mfmg/cuda/utils.cuh:66-99 -- the raw device-memory helpers callers use to fill the arrays they hand to
+// SparseMatrixDevice's take-ownership constructor (same names and argument order; no CUDA headers needed here)
+template <typename T>
+inline void cuda_malloc(T *&pointer, unsigned int n_elements)
+{
+  void *p = nullptr;
+  check_status(nullptr, mfmgb_dev_malloc(nullptr, (int64_t)(sizeof(T) * (std::size_t)n_elements), &p));
+  pointer = static_cast<T *>(p);
+}
+template <typename T>
+inline void cuda_free(T *&pointer)
+{
+  check_status(nullptr, mfmgb_dev_free(nullptr, pointer));
+  pointer = nullptr;
+}
+template <typename T>
+inline void cuda_mem_copy_to_dev(std::vector<T> const &vector_host, T *pointer_dev)
+{
+  check_status(nullptr, mfmgb_dev_upload(nullptr, pointer_dev, vector_host.data(), (int64_t)(sizeof(T) * vector_host.size())));
+}
+template <typename T>
+inline void cuda_mem_copy_to_host(T const *pointer_dev, std::vector<T> &vector_host)
+{
+  check_status(nullptr, mfmgb_dev_download(nullptr, pointer_dev, vector_host.data(), (int64_t)(sizeof(T) * vector_host.size())));
+}
+
 enum class OperatorMode
 {
   NO_TRANS,

@@ -49,6 +49,10 @@ SIGNATURES = {
     "mfmgb_last_error": (ctypes.c_char_p, [_vp]),
     "mfmgb_ctx_launch_count": (_i64, [_vp]),
     "mfmgb_version": (ctypes.c_char_p, []),
+    "mfmgb_dev_malloc": (_int, [_vp, _i64, _pp]),
+    "mfmgb_dev_free": (_int, [_vp, _vp]),
+    "mfmgb_dev_upload": (_int, [_vp, _vp, _vp, _i64]),
+    "mfmgb_dev_download": (_int, [_vp, _vp, _vp, _i64]),
     "mfmgb_vec_alloc": (_int, [_vp, _i64, _pp]),
     "mfmgb_vec_free": (_int, [_vp, _vp]),
     "mfmgb_vec_upload": (_int, [_vp, _vp, _vp, _i64]),

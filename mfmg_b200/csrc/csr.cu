@@ -235,6 +235,12 @@ int csr_apply(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, cons
     return fail(ctx, MFMGB_ERR_INVALID, "csr_apply: row range out of bounds");
   if (csr_uses_tile_kernel(A))
     return csr_apply_tile(ctx, A, x, epi, args, row_begin, row_end);
+  return csr_apply_vec(ctx, A, x, epi, args, row_begin, row_end);
+}
+
+int csr_apply_vec(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args, int64_t row_begin,
+                  int64_t row_end)
+{
   if (A->off64)
     return dispatch_epi<int64_t>(ctx, A, x, epi, args, row_begin, row_end);
   return dispatch_epi<int32_t>(ctx, A, x, epi, args, row_begin, row_end);
@@ -350,7 +356,7 @@ extern "C"
     A->rowptr = rowptr_dev;
     A->off64 = false;
     A->owns = true;
-    A->padded = false; // the caller's allocations have no slack: served by the direct-load kernel
+    A->padded = false; // the caller's allocations have no slack: the tile kernel serves all but the last tile(s)
     MFMGB_CHECK(finish_upload(ctx, A));
     *out = A;
     return MFMGB_OK;

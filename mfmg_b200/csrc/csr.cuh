@@ -15,7 +15,12 @@ struct mfmgb_csr
   int device = 0;
   // tile-streamed kernel (csr_tile.cu)
   bool padded = false;        // arrays carry slack for 16-byte-granular bulk copies (uploads do; adopted arrays do not)
+  bool aligned16 = true;      // all three arrays start on 16-byte boundaries (bulk copies need it)
   int64_t tile_cap[6] = {0, 0, 0, 0, 0, 0}; // widest aligned nnz span of a tile, per lanes = 1, 2, 4, 8, 16, 32
+  // rows [0, tile_rows[slot]) are served by the tile kernel: all rows when the arrays carry slack; for adopted arrays
+  // the tiles whose 16-byte-granular copies would leave the allocations (the last one or two) go to the direct-load
+  // kernel, which sums in the same order (bit-identical)
+  int64_t tile_rows[6] = {0, 0, 0, 0, 0, 0};
   bool tile_ok = false;       // the tile kernel can serve this matrix with the current lanes
   int tile_stages = 0, tile_ctas = 0;
   int kernel_override = -1;   // -1 = automatic, 0 = vector-CSR (csr.cu), 1 = tile-streamed (csr_tile.cu)
@@ -43,6 +48,9 @@ struct EpiArgs
 // one launch: y = epilogue(A x) on rows [row_begin, row_end) (row_end < 0: all rows)
 int csr_apply(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args,
               int64_t row_begin = 0, int64_t row_end = -1);
+// the direct-load (vector-CSR) kernels, whatever csr_uses_tile_kernel says
+int csr_apply_vec(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args, int64_t row_begin,
+                  int64_t row_end);
 int choose_lanes(int64_t n_rows, int64_t nnz);
 // tile-streamed variant (csr_tile.cu): same contract as csr_apply; requires A->tile_ok
 int csr_apply_tile(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args, int64_t row_begin,

@@ -16,6 +16,7 @@
 // Summation order depends only on (LPR, row length): deterministic, and graph replay == eager launch.
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 
 #include "csr.cuh"
 
@@ -300,20 +301,33 @@ int launch_tile(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiAr
   const size_t smem = (size_t)a.stages * tile_stage_bytes<LPR, OffT>(a.cap) + (size_t)a.stages * 16;
   // per instantiation: opt in to large dynamic shared memory once, and ask how many CTAs are really co-resident
   // (registers can allow fewer than the planned number; the grid must not spill into a second wave)
-  static bool attr_set = false;
-  static size_t occ_smem = 0;
-  static int occ_ctas = 0;
-  if (!attr_set)
+  // (cached per device: the attribute is a per-device property, and one process may hold contexts on several devices)
+  constexpr int kMaxDevices = 64;
+  struct PerDevice
   {
-    MFMGB_CUDA(ctx, cudaFuncSetAttribute(csr_tile_kernel<LPR, EPI, OffT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(227 * 1024)));
-    attr_set = true;
-  }
-  if (occ_smem != smem)
+    bool attr_set = false;
+    size_t occ_smem = 0;
+    int occ_ctas = 0;
+  };
+  static PerDevice cache[kMaxDevices];
+  static std::mutex cache_mutex;
+  int occ_ctas = 0;
   {
-    MFMGB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ctas, csr_tile_kernel<LPR, EPI, OffT>,
-                                                                  kTileThreads, smem));
-    occ_smem = smem;
+    std::lock_guard<std::mutex> lock(cache_mutex);
+    PerDevice &pd = cache[ctx->device % kMaxDevices];
+    if (!pd.attr_set)
+    {
+      MFMGB_CUDA(ctx, cudaFuncSetAttribute(csr_tile_kernel<LPR, EPI, OffT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(227 * 1024)));
+      pd.attr_set = true;
+    }
+    if (pd.occ_smem != smem)
+    {
+      MFMGB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pd.occ_ctas, csr_tile_kernel<LPR, EPI, OffT>,
+                                                                    kTileThreads, smem));
+      pd.occ_smem = smem;
+    }
+    occ_ctas = pd.occ_ctas;
   }
   if (occ_ctas < 1)
     return fail(ctx, MFMGB_ERR_CUDA, "csr_tile_kernel: %zu bytes of shared memory do not fit an SM", smem);
@@ -388,7 +402,9 @@ int tile_cap_slot(int lanes)
 void csr_plan_tile(mfmgb_csr *A)
 {
   A->tile_ok = false;
-  if (!A->padded || A->n_rows == 0 || A->nnz == 0 || A->lanes > 32)
+  if (!A->aligned16 || A->n_rows == 0 || A->nnz == 0 || A->lanes > 32)
+    return;
+  if (A->tile_rows[tile_cap_slot(A->lanes)] <= 0)
     return;
   const int rpt = kConsumerWarps * 32 / A->lanes;
   const int64_t cap = A->tile_cap[tile_cap_slot(A->lanes)];
@@ -418,8 +434,10 @@ void csr_plan_tile(mfmgb_csr *A)
 int csr_measure_tiles(mfmgb_ctx *ctx, mfmgb_csr *A)
 {
   for (int s = 0; s < 6; ++s)
-    A->tile_cap[s] = 0;
-  if (!A->padded || A->n_rows == 0)
+    A->tile_cap[s] = A->tile_rows[s] = 0;
+  A->aligned16 = ((reinterpret_cast<uintptr_t>(A->val) | reinterpret_cast<uintptr_t>(A->col) |
+                   reinterpret_cast<uintptr_t>(A->rowptr)) & 15) == 0;
+  if (!A->aligned16 || A->n_rows == 0)
     return MFMGB_OK;
   unsigned long long *dmax = nullptr;
   MFMGB_CUDA(ctx, cudaMalloc(&dmax, sizeof(unsigned long long) * 6));
@@ -440,13 +458,57 @@ int csr_measure_tiles(mfmgb_ctx *ctx, mfmgb_csr *A)
   MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   cudaFree(dmax);
   for (int s = 0; s < 6; ++s)
+  {
     A->tile_cap[s] = (int64_t)hmax[s];
+    A->tile_rows[s] = A->n_rows;
+  }
+  if (A->padded)
+    return MFMGB_OK;
+  // Arrays without slack (the reference's take-ownership constructor): a tile is servable when its staged row
+  // offsets [t rpt, t rpt + rpt + 4) lie inside rowptr[0 .. n_rows] and its rounded-up val/col span ends inside nnz.
+  for (int s = 0; s < 6; ++s)
+  {
+    const int rpt = kConsumerWarps * 32 / (1 << s);
+    int64_t t = (A->n_rows + 1 - (rpt + 4)) / rpt + 1; // tiles [0, t) keep their row offsets in bounds
+    if (A->n_rows + 1 < rpt + 4)
+      t = 0;
+    while (t > 0)
+    {
+      int64_t end = 0;
+      if (A->off64)
+        MFMGB_CUDA(ctx, cudaMemcpy(&end, (const int64_t *)A->rowptr + t * rpt, sizeof(int64_t), cudaMemcpyDeviceToHost));
+      else
+      {
+        int32_t e32 = 0;
+        MFMGB_CUDA(ctx, cudaMemcpy(&e32, (const int32_t *)A->rowptr + t * rpt, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        end = e32;
+      }
+      if (((end + 3) & ~(int64_t)3) <= A->nnz)
+        break;
+      --t;
+    }
+    A->tile_rows[s] = t * rpt;
+  }
   return MFMGB_OK;
 }
 
 int csr_apply_tile(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args, int64_t row_begin,
                    int64_t row_end, int64_t row_begin2, int64_t row_end2)
 {
+  // adopted arrays: rows past the last servable tile go to the direct-load kernel (same summation order)
+  const int64_t lim = A->tile_rows[tile_cap_slot(A->lanes)];
+  if (row_end > lim || row_end2 > lim)
+  {
+    const int64_t b1 = std::max(row_begin, lim), b2 = std::max(row_begin2, lim);
+    if (row_end > b1)
+      MFMGB_CHECK(csr_apply_vec(ctx, A, x, epi, args, b1, row_end));
+    if (row_end2 > b2)
+      MFMGB_CHECK(csr_apply_vec(ctx, A, x, epi, args, b2, row_end2));
+    row_end = std::min(row_end, lim);
+    row_end2 = std::min(row_end2, lim);
+    if (row_end <= row_begin && row_end2 <= row_begin2)
+      return MFMGB_OK;
+  }
   if (A->off64)
     return dispatch_epi<int64_t>(ctx, A, x, epi, args, row_begin, row_end, row_begin2, row_end2);
   return dispatch_epi<int32_t>(ctx, A, x, epi, args, row_begin, row_end, row_begin2, row_end2);

@@ -1,4 +1,6 @@
 // ctx.cu -- context lifetime and the BLAS-1 vector operations on the path.
+#include <algorithm>
+
 #include "common.cuh"
 #include "vecops.cuh"
 
@@ -62,6 +64,7 @@ extern "C"
     if (!ctx)
       return MFMGB_OK;
     cudaSetDevice(ctx->device);
+    mfmgb_comm_finalize(ctx); // drops the communicator registered for this context, if any (no stale registry entry)
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->red_partials);
     cudaFree(ctx->red_result);
@@ -84,6 +87,52 @@ extern "C"
   MFMGB_API void *mfmgb_ctx_stream(mfmgb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
   MFMGB_API int64_t mfmgb_ctx_launch_count(mfmgb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+  // ctx may be NULL in the four mfmgb_dev_* calls (the reference's cuda_malloc & co. take no handle): errors then go to
+  // the calling thread's message, copies and frees synchronise the whole device instead of the context's stream.
+  MFMGB_API int mfmgb_dev_malloc(mfmgb_ctx *ctx, int64_t bytes, void **out)
+  {
+    MFMGB_REQUIRE(ctx, out && bytes >= 0, "mfmgb_dev_malloc: bad arguments");
+    *out = nullptr;
+    MFMGB_CUDA(ctx, cudaMalloc(out, (size_t)std::max<int64_t>(bytes, 1)));
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_dev_free(mfmgb_ctx *ctx, void *ptr)
+  {
+    if (ptr)
+    {
+      MFMGB_CUDA(ctx, ctx ? cudaStreamSynchronize(ctx->stream) : cudaDeviceSynchronize());
+      MFMGB_CUDA(ctx, cudaFree(ptr));
+    }
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_dev_upload(mfmgb_ctx *ctx, void *dst_dev, const void *src_host, int64_t bytes)
+  {
+    MFMGB_REQUIRE(ctx, bytes >= 0 && (bytes == 0 || (dst_dev && src_host)), "mfmgb_dev_upload: bad arguments");
+    if (!ctx)
+    {
+      MFMGB_CUDA(ctx, cudaMemcpy(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice));
+      return MFMGB_OK;
+    }
+    MFMGB_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_dev_download(mfmgb_ctx *ctx, const void *src_dev, void *dst_host, int64_t bytes)
+  {
+    MFMGB_REQUIRE(ctx, bytes >= 0 && (bytes == 0 || (dst_host && src_dev)), "mfmgb_dev_download: bad arguments");
+    if (!ctx)
+    {
+      MFMGB_CUDA(ctx, cudaMemcpy(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost));
+      return MFMGB_OK;
+    }
+    MFMGB_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MFMGB_OK;
+  }
 
   MFMGB_API int mfmgb_vec_alloc(mfmgb_ctx *ctx, int64_t n, double **out)
   {

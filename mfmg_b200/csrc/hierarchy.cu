@@ -8,6 +8,7 @@
 //   * optional CUDA-graph replay of the whole cycle (launch-latency bound on small levels).
 // PCG: the recurrence of dealii::SolverCG (tests/hierarchy_driver.cc:200-213), scalars kept on
 // the device, one host read-back per iteration for the reference's stopping test.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <vector>
@@ -800,9 +801,16 @@ extern "C"
   {
     MFMGB_REQUIRE(ctx, ctx && (H || A) && b_host && x_host, "mfmgb_pcg_host: bad arguments");
     const int64_t n = A ? A->n_rows : H->lev[0].n;
+    // a row-partitioned level gathers from [owned | ghost]: the device vectors carry the ghost tail (mfmgb_pcg
+    // receives the neighbours' entries there); only the n owned entries travel to and from the host
+    int64_t n_vec = n;
+    if (H && !H->lev.empty() && H->lev[0].halo)
+      n_vec = std::max(n_vec, mfmgb_hierarchy_vector_size(H, 0));
+    if (A)
+      n_vec = std::max(n_vec, A->n_cols);
     double *b = nullptr, *x = nullptr;
-    MFMGB_CHECK(mfmgb_vec_alloc(ctx, n, &b));
-    MFMGB_CHECK(mfmgb_vec_alloc(ctx, n, &x));
+    MFMGB_CHECK(mfmgb_vec_alloc(ctx, n_vec, &b));
+    MFMGB_CHECK(mfmgb_vec_alloc(ctx, n_vec, &x));
     MFMGB_CHECK(mfmgb_vec_upload(ctx, b, b_host, n));
     MFMGB_CHECK(mfmgb_vec_upload(ctx, x, x_host, n));
     const int rc = mfmgb_pcg(ctx, H, A, b, x, tol, max_it, iterations, res_hist_host);

@@ -89,9 +89,10 @@ extern "C"
     *out = nullptr;
     mfmgb_jacobi *J = new mfmgb_jacobi();
     J->n = A->n_rows;
+    J->n_vec = A->n_cols; // a row-partitioned operator gathers from [owned | ghost]: the copy keeps the ghost tail
     J->omega = omega;
     MFMGB_CUDA(ctx, cudaMalloc(&J->dinv, sizeof(double) * (size_t)(J->n + 2)));
-    MFMGB_CUDA(ctx, cudaMalloc(&J->tmp, sizeof(double) * (size_t)(J->n + 2)));
+    MFMGB_CUDA(ctx, cudaMalloc(&J->tmp, sizeof(double) * (size_t)(J->n_vec + 2)));
     int *missing_dev = nullptr;
     MFMGB_CUDA(ctx, cudaMalloc(&missing_dev, sizeof(int)));
     MFMGB_CUDA(ctx, cudaMemsetAsync(missing_dev, 0, sizeof(int), ctx->stream));
@@ -127,6 +128,7 @@ extern "C"
     MFMGB_REQUIRE(ctx, ctx && out && n >= 0 && (n == 0 || diag_dev), "mfmgb_jacobi_setup_diag: bad arguments");
     mfmgb_jacobi *J = new mfmgb_jacobi();
     J->n = n;
+    J->n_vec = n;
     J->omega = omega;
     MFMGB_CUDA(ctx, cudaMalloc(&J->dinv, sizeof(double) * (size_t)(n + 2)));
     MFMGB_CUDA(ctx, cudaMalloc(&J->tmp, sizeof(double) * (size_t)(n + 2)));
@@ -171,8 +173,11 @@ extern "C"
   MFMGB_API int mfmgb_jacobi_apply(mfmgb_ctx *ctx, const mfmgb_jacobi *J, const mfmgb_csr *A, const double *b, double *x)
   {
     MFMGB_REQUIRE(ctx, ctx && J && A && b && x, "mfmgb_jacobi_apply: bad arguments");
-    // Jacobi reads neighbouring x entries while others are written: keep the old iterate.
-    MFMGB_CUDA(ctx, cudaMemcpyAsync(J->tmp, x, sizeof(double) * (size_t)J->n, cudaMemcpyDeviceToDevice, ctx->stream));
+    // Jacobi reads neighbouring x entries while others are written: keep the old iterate (with its ghost tail when
+    // the operator is a row-partitioned block, n_cols > n_rows).
+    MFMGB_REQUIRE(ctx, A->n_cols <= J->n_vec, "mfmgb_jacobi_apply: the operator gathers from more columns than the "
+                                              "smoother was set up for; use mfmgb_jacobi_apply_oop");
+    MFMGB_CUDA(ctx, cudaMemcpyAsync(J->tmp, x, sizeof(double) * (size_t)A->n_cols, cudaMemcpyDeviceToDevice, ctx->stream));
     return mfmgb_jacobi_apply_oop(ctx, J, A, b, J->tmp, x);
   }
 

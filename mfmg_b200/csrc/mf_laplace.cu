@@ -474,11 +474,11 @@ int launch_mf(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, const EpiArgs 
   constexpr int PLANE = (TXC * P + 1) * (TYC * P + 1);
   const size_t smem = (size_t)SLOTS * PLANE * (2 * sizeof(double) + 1) + 16;
   auto kern = mf_apply_kernel<DIM, P, TXC, TYC, EPI>;
-  static bool configured = false;
-  if (!configured)
+  static unsigned long long configured = 0; // one bit per device: the attribute is a per-device property
+  if (!((configured >> (ctx->device & 63)) & 1ull))
   {
     MFMGB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configured |= 1ull << (ctx->device & 63);
   }
   MfParams prm = make_params(M);
   dim3 grid((unsigned)ceil_div(M->cells[0], TXC - 1), (unsigned)ceil_div(M->cells[1], TYC - 1),

@@ -533,12 +533,12 @@ int launch_q1_cfg(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, const EpiA
   Q1Params p = make_q1_params(M);
   p.tz = TZ;
   const size_t smem = q1_smem_bytes<TY, PERQ>(TZ);
-  static bool configured = false;
-  if (!configured)
+  static unsigned long long configured = 0; // one bit per device: the attribute is a per-device property
+  if (!((configured >> (ctx->device & 63)) & 1ull))
   {
     MFMGB_CUDA(ctx, cudaFuncSetAttribute(mf_q1_kernel<TY, TZ, EPI, PERQ, MINB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-    configured = true;
+    configured |= 1ull << (ctx->device & 63);
   }
   const int n_chunks = (int)ceil_div(p.own1 - p.own0, (int64_t)TZ);
   if (zc0 < 0) // all chunks

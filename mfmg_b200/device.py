@@ -101,6 +101,29 @@ class CudaHandle:
             pass
 
 
+def cuda_malloc(handle: "CudaHandle", nbytes: int) -> int:
+    """cuda_malloc (include/mfmg/cuda/utils.cuh:66-73): a plain cudaMalloc'ed block, returned as an address."""
+    p = ctypes.c_void_p()
+    check(handle.ctx, handle.lib.mfmgb_dev_malloc(handle.ctx, int(nbytes), ctypes.byref(p)))
+    return int(p.value or 0)
+
+
+def cuda_free(handle: "CudaHandle", ptr: int) -> None:
+    check(handle.ctx, handle.lib.mfmgb_dev_free(handle.ctx, ctypes.c_void_p(ptr)))
+
+
+def cuda_mem_copy_to_dev(handle: "CudaHandle", host: np.ndarray, ptr: int) -> None:
+    """cuda_mem_copy_to_dev (include/mfmg/cuda/utils.cuh:83-90)"""
+    host = np.ascontiguousarray(host)
+    check(handle.ctx, handle.lib.mfmgb_dev_upload(handle.ctx, ctypes.c_void_p(ptr), host.ctypes.data, host.nbytes))
+
+
+def cuda_mem_copy_to_host(handle: "CudaHandle", ptr: int, host: np.ndarray) -> None:
+    """cuda_mem_copy_to_host (include/mfmg/cuda/utils.cuh:92-99)"""
+    assert host.flags["C_CONTIGUOUS"]
+    check(handle.ctx, handle.lib.mfmgb_dev_download(handle.ctx, ctypes.c_void_p(ptr), host.ctypes.data, host.nbytes))
+
+
 class DeviceVector:
     """A device-resident FP64 vector (raw cudaMalloc storage, like Vector<double, CUDA>::get_values())."""
 
@@ -193,6 +216,17 @@ class SparseMatrixDevice:
             A = A.tocsr()
             return SparseMatrixDevice(handle, A.shape[0], A.shape[1], A.indptr.astype(np.int64), A.indices, A.data)
         return SparseMatrixDevice(handle, A.n_rows, A.n_cols, A.rowptr, A.col, A.val)
+
+    @staticmethod
+    def from_device_arrays(handle: CudaHandle, val_dev: int, column_index_dev: int, row_ptr_dev: int, local_nnz: int,
+                           n_rows: int, n_cols: int) -> "SparseMatrixDevice":
+        """The reference's own constructor (sparse_matrix_device.templates.cuh:244-272): TAKES OWNERSHIP of three
+        cudaMalloc'ed device arrays (double values, int columns, int row offsets) and frees them on destruction."""
+        p = ctypes.c_void_p()
+        check(handle.ctx, handle.lib.mfmgb_csr_adopt_device(handle.ctx, n_rows, n_cols, local_nnz,
+                                                            ctypes.c_void_p(val_dev), ctypes.c_void_p(column_index_dev),
+                                                            ctypes.c_void_p(row_ptr_dev), ctypes.byref(p)))
+        return SparseMatrixDevice(handle, 0, 0, None, None, None, _adopt=p)
 
     # sparse_matrix_device.cuh:61-71
     def m(self) -> int:

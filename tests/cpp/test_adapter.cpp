@@ -87,6 +87,47 @@ int main()
     CHECK(threw);
   }
 
+  // ---- the reference's own constructor: cuda_malloc'ed arrays WITHOUT slack, ownership taken
+  //      (tests/test_sparse_matrix_device.cu:59-75, sparse_matrix_device.templates.cuh:244-272) ----
+  for (unsigned size : {30u, 5000u, 70000u})
+  {
+    auto a = tridiag(size);
+    std::vector<int> rp32(a.rp.begin(), a.rp.end());
+    double *val_dev = nullptr;
+    int *col_dev = nullptr, *rp_dev = nullptr;
+    mfmg::cuda_malloc(val_dev, (unsigned)a.val.size());
+    mfmg::cuda_malloc(col_dev, (unsigned)a.col.size());
+    mfmg::cuda_malloc(rp_dev, (unsigned)rp32.size());
+    mfmg::cuda_mem_copy_to_dev(a.val, val_dev);
+    mfmg::cuda_mem_copy_to_dev(a.col, col_dev);
+    mfmg::cuda_mem_copy_to_dev(rp32, rp_dev);
+    auto m = std::make_shared<mfmg::SparseMatrixDevice<double>>(handle, val_dev, col_dev, rp_dev,
+                                                                (unsigned)a.val.size(), size, size);
+    CHECK(m->m() == size && m->n() == size && m->local_nnz() == a.val.size());
+    CHECK(m->val_dev == val_dev && m->column_index_dev == col_dev && m->row_ptr_dev == rp_dev);
+    std::vector<double> xh(size);
+    std::default_random_engine gen(3);
+    std::uniform_real_distribution<double> dist(-1., 1.);
+    for (auto &v : xh)
+      v = dist(gen);
+    V x(handle, size), y(handle, size);
+    x.import_from_host(xh);
+    m->vmult(y, x);
+    auto ref = host_spmv(a, xh);
+    auto got = y.export_to_host();
+    for (unsigned i = 0; i < size; ++i)
+      CHECK(std::abs(got[i] - ref[i]) <= 1e-14 * (std::abs(ref[i]) + 1.));
+    // smoother on the adopted matrix: one sweep from x = 0 with b = 1 gives D^-1 b = 0.25
+    std::shared_ptr<mfmg::Operator<V>> op = std::make_shared<mfmg::CudaMatrixOperator<V>>(m);
+    mfmg::CudaSmoother<V> smoother(op, params);
+    V b(handle, size);
+    b = 1.;
+    y = 0.;
+    smoother.apply(b, y);
+    for (double v : y.export_to_host())
+      CHECK(v == 0.25);
+  } // (the destructor frees the three adopted arrays)
+
   // ---- direct solver ----
   {
     auto a = tridiag(30);

@@ -453,3 +453,100 @@ def test_int64_row_offsets_path(handle, monkeypatch):
     Ho = oracle_hierarchy(P, R, Ac, 1, True)
     H.vmult(y, b)
     assert rel_err(y.to_host(), Ho.vmult(b_h)) < TOL_OP
+
+
+def _adopted(d, handle, n_rows, n_cols, rowptr, col, val):
+    """Build a SparseMatrixDevice the way the reference's callers do (tests/test_sparse_matrix_device.cu:59-75):
+    cuda_malloc three arrays WITHOUT slack, copy the CSR in, hand them to the take-ownership constructor."""
+    rp32 = np.ascontiguousarray(rowptr, dtype=np.int32)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    pv, pc, pr = d.cuda_malloc(handle, val.nbytes), d.cuda_malloc(handle, col.nbytes), d.cuda_malloc(handle, rp32.nbytes)
+    d.cuda_mem_copy_to_dev(handle, val, pv)
+    d.cuda_mem_copy_to_dev(handle, col, pc)
+    d.cuda_mem_copy_to_dev(handle, rp32, pr)
+    return d.SparseMatrixDevice.from_device_arrays(handle, pv, pc, pr, len(val), n_rows, n_cols)
+
+
+def test_adopted_device_arrays_serial_mv_kat(handle):
+    # the reference's own constructor on the reference's own KAT (tests/test_sparse_matrix_device.cu:59-107)
+    d = _dev()
+    g = golden()
+    n, m, rp, col, val = csr_arrays(serial_mv_matrix())
+    Ad = _adopted(d, handle, n, m, rp, col, val)
+    assert (Ad.m(), Ad.n(), Ad.local_nnz()) == (n, m, len(val))
+    x = d.DeviceVector.from_host(handle, g["serial_mv_x"])
+    y = d.DeviceVector(handle, n)
+    Ad.vmult(y, x)
+    assert np.array_equal(y.to_host(), g["serial_mv_y"])
+    rp2, col2, val2 = Ad.to_host()
+    assert np.array_equal(rp2, rp) and np.array_equal(col2, col) and np.array_equal(val2, val)
+
+
+@pytest.mark.parametrize("n_rows,n_cols,max_len", [(1000, 1000, 40), (4099, 4099, 9), (70000, 70000, 30), (300, 300, 5)])
+def test_adopted_arrays_tile_kernel_bitwise(handle, n_rows, n_cols, max_len):
+    """Arrays without slack run on the TMA tile kernel too (all tiles whose 16-byte-granular copies stay inside the
+    allocations; the last rows on the direct-load kernel): identical bits to the uploaded matrix on both kernel
+    families, for every lanes value and fused epilogue."""
+    d = _dev()
+    rng = np.random.default_rng(7 * n_rows + max_len)
+    rowptr, col, val = _ragged_matrix(rng, n_rows, n_cols, max_len)
+    A_up = d.SparseMatrixDevice(handle, n_rows, n_cols, rowptr, col, val)
+    A_ad = _adopted(d, handle, n_rows, n_cols, rowptr, col, val)
+    lib, ctx = handle.lib, handle.ctx
+    x_h, b_h, dinv_h = rng.standard_normal(n_cols), rng.standard_normal(n_rows), rng.standard_normal(n_rows)
+    x, b = d.DeviceVector.from_host(handle, x_h), d.DeviceVector.from_host(handle, b_h)
+    ref = oracle.spmv(n_rows, rowptr, col, val, x_h)
+    scale = np.abs(oracle.spmv(n_rows, rowptr, col, np.abs(val), np.abs(x_h))).max() + 1.0
+    J = ctypes_jacobi(d, handle, dinv_h)
+    n_tile = 0
+    for lanes in (1, 2, 4, 8, 16, 32):
+        outs = []
+        for A, kern in ((A_up, 0), (A_ad, 0), (A_ad, 1)):
+            A.set_lanes_per_row(lanes)
+            try:
+                A.set_kernel(kern)
+            except d.MfmgError:
+                assert kern == 1
+                continue
+            n_tile += kern
+            y, r, w = (d.DeviceVector(handle, n_rows) for _ in range(3))
+            A.vmult(y, x)
+            d.check(ctx, lib.mfmgb_residual_neg(ctx, A.ptr, x.ptr, b.ptr, r.ptr))
+            d.check(ctx, lib.mfmgb_jacobi_apply_oop(ctx, J, A.ptr, b.ptr, x.ptr, w.ptr))
+            outs.append((y.to_host(), r.to_host(), w.to_host()))
+        assert np.max(np.abs(outs[0][0] - ref)) <= TOL_OP * scale
+        for o in outs[1:]:
+            for a_, b_ in zip(outs[0], o):
+                assert np.array_equal(a_, b_), f"lanes={lanes}"
+    assert n_tile >= 2 or n_rows < 600
+    d.check(ctx, lib.mfmgb_jacobi_destroy(ctx, J))
+
+
+def test_adopted_arrays_hierarchy_vs_oracle(handle):
+    """A two-level hierarchy whose operators all come from the reference's take-ownership constructor: Jacobi setup,
+    transpose, dense factorisation, V-cycle (eager and graph) and PCG against the oracle."""
+    d = _dev()
+    P, R, Ac = two_level_problem(3, 1, 40, 4, 1, "constant")
+    ops = [_adopted(d, handle, M.n_rows, M.n_cols, M.rowptr, M.col, M.val) for M in (P.A, Ac)]
+    res = [_adopted(d, handle, R.n_rows, R.n_cols, R.rowptr, R.col, R.val)]
+    assert ops[0].kernel == "tile"   # 68 921 rows x 27: automatic choice, adopted arrays included
+    H = d.Hierarchy(handle, ops, res, {"is preconditioner": True})
+    Ho = oracle_hierarchy(P, R, Ac, 1, True)
+    rng = np.random.default_rng(2)
+    b_h = rng.standard_normal(P.n)
+    b, x = d.DeviceVector.from_host(handle, b_h), d.DeviceVector(handle, P.n)
+    H.vmult(x, b)
+    ref = Ho.vmult(b_h)
+    assert rel_err(x.to_host(), ref) < TOL_OP
+    eager = x.to_host().copy()
+    H.use_graph(True)
+    for _ in range(2):
+        H.vmult(x, b)
+    assert np.array_equal(x.to_host(), eager)
+    x0 = oracle.std_uniform01(P.n, skip=P.constrained)
+    _, it_ref, hist_ref = Ho.pcg(np.zeros(P.n), x0, 1e-8, 200)
+    xd = d.DeviceVector.from_host(handle, x0)
+    it, hist = d.solver_cg(handle, ops[0], xd, d.DeviceVector.from_host(handle, np.zeros(P.n)), H, 1e-8, 200)
+    assert it == it_ref
+    assert np.max(np.abs(hist - hist_ref) / hist_ref) < TOL_PCG
