@@ -1,14 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- V-cycle-apply throughput on B200 (BASELINE.json metric: V-cycles/s and SpMV HBM GB/s).
 
-  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA path through the C ABI)
-  python bench.py --impl reference --steps K --warmup W    # the reference arm: CPU oracle port, all host cores
+  python bench.py --gpus N --steps K --warmup W                    # our arm (CUDA path through the C ABI)
+  python bench.py --impl reference --gpus N --steps K --warmup W   # the reference arm: CPU oracle port, all host cores
 
-A "step" is one multigrid V-cycle apply (mfmg::Hierarchy::vmult, preconditioner mode, V(1,1) Jacobi,
-dense coarse solve) on the synthetic cfg1 workload: 3D Q1 Laplace on 128^3 cells (2 146 689 DoFs,
-57 066 625 nnz), spectral-AMGe two-level hierarchy with 8^3-cell agglomerates x 1 eigenvector
-(n_c = 4096).  Operators are generated by the host setup path and uploaded once; the timed region
-contains only V-cycles.  Prints ONE JSON line.
+A "step" is one multigrid V-cycle apply (mfmg::Hierarchy::vmult, preconditioner mode, V(1,1) Jacobi, direct coarse
+solve).  Default workload = BASELINE configs[1]: 3D Q1 Laplace on 128^3 cells (2 146 689 DoFs, 57 066 625 nnz),
+spectral-AMGe two-level hierarchy with 8^3-cell agglomerates x 1 eigenvector (n_c = 4096); with --gpus N it is weak
+scaled: N such cubes stacked along z, one z-slab per GPU.  Operators come from the host setup path and are uploaded
+once; the timed region contains only V-cycles.  Prints ONE JSON line, which also carries
+
+  parity      the timed hierarchy's V-cycle and PCG against the SERIAL CPU oracle on the same global problem (every N);
+              the process exits non-zero when a north-star tolerance is exceeded
+  north_star  BASELINE configs[3] (3D Q1, 512^3 cells, 135 M DoFs): one GPU at N = 1, row-partitioned strong scaling
+              at N > 1 (skipped with a reason when host memory or time do not allow it)
 """
 from __future__ import annotations
 
@@ -28,9 +33,10 @@ sys.path.insert(0, ROOT)
 _emit = print
 METRIC = "vcycle_apply_throughput"
 UNIT = "V-cycles/s"
+TOL_VCYCLE, TOL_HIST, TOL_PCG = 1e-12, 1e-10, 1e-8     # north star: per-application 1e-12, histories 1e-10
 
 
-def parse_args():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -44,43 +50,78 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--lanes", type=int, default=0, help="override lanes per row of A (0 = automatic)")
-    ap.add_argument("--pcg", action="store_true",
-                    help="N=1: also solve A x = 0 from the driver's random initial guess (tests/hierarchy_driver.cc:153-164) "
-                         "with the V-cycle as preconditioner, on the GPU and with the CPU oracle: iteration counts, "
-                         "residual histories, times")
+    ap.add_argument("--repeats", type=int, default=10, help="extra K-step regions timed for min / median / spread")
+    ap.add_argument("--parity", default="oracle", choices=["oracle", "props", "none"],
+                    help="oracle: V-cycle + PCG against the serial CPU oracle on the same global problem; props: "
+                         "size-independent properties only (configurations the oracle cannot finish in the budget)")
+    ap.add_argument("--pcg", action="store_true", help="(kept for compatibility: PCG is part of --parity oracle)")
     ap.add_argument("--matrix-free", action="store_true",
                     help="level 0 is the matrix-free operator (BASELINE configs[4]); R, P and A_c stay assembled")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = N cubes of --cells^3 stacked along z (the default the driver runs); "
                          "strong = one --cells^3 cube row-partitioned over the N GPUs (BASELINE configs[3])")
-    return ap.parse_args()
+    ap.add_argument("--north-star", default="auto", choices=["auto", "on", "off"],
+                    help="also measure BASELINE configs[3] (512^3 cells): auto = only for the default workload")
+    ap.add_argument("--north-star-cells", type=int, default=512)
+    ap.add_argument("--north-star-timeout", type=float, default=480.0)
+    return ap.parse_args(argv)
 
 
-def build_workload(args):
+# ---------------------------------------------------------------------------------------------------------------
+# the workload, described identically by both arms
+# ---------------------------------------------------------------------------------------------------------------
+def global_cells(args, world):
+    c = args.cells
+    return (c, c, c * world if args.scaling == "weak" else c)
+
+
+def canonical_config(args, world, n, nnz, n_c):
+    """`config` of the JSON line: a function of the command line and the problem sizes only, so that the reference arm
+    and ours print the same dict for the same problem."""
+    cx, cy, cz = global_cells(args, world)
+    units = world if args.scaling == "weak" else 1
+    return {
+        "workload": (f"3D Q{args.degree} {args.material} Laplace, {cx}x{cy}x{cz} cells (h=1/{args.cells}), n={n}, "
+                     f"nnz={nnz}; two-level spectral AMGe, {args.block}^3-cell agglomerates x {args.neig} eigvec "
+                     f"(n_c={n_c}); V(1,1) Jacobi omega=1, direct LU coarse solve, preconditioner mode; level 0 "
+                     + ("matrix-free (laplace_matrix_free)" if args.matrix_free else "assembled CSR")),
+        "scaling": args.scaling,
+        "units_per_step": units,
+        "value_definition": ("single-GPU-sized V-cycle units per second = units_per_step x (V-cycles of the global "
+                             "problem per second); the global problem is units_per_step cubes stacked along z"
+                             if args.scaling == "weak" else "V-cycles per second of the one global problem"),
+        "l2_policy": ("inputs larger than L2, no flush: one cycle streams the level-0 operator twice, "
+                      "%.2f GB per GPU-sized unit vs 126 MB L2" % (12.0 * nnz / max(world, 1) / 1e9)
+                      if not args.matrix_free else
+                      "inputs larger than L2, no flush: vectors of %.2f GB per GPU-sized unit vs 126 MB L2"
+                      % (8.0 * n / max(world, 1) / 1e9)),
+    }
+
+
+def build_global(args, world):
+    """Global operators on this host process (N = 1 workload, the reference arm and the parity oracle at every N)."""
     from mfmg_b200 import hostsetup as hs
 
-    # refuse to start a host setup that cannot fit (large configs: cfg3 needs ~3x the 45 GB CSR of A on the host)
-    nodes = args.cells * args.degree + 1
-    est = 3.0 * 12.0 * (2 * args.degree + 1) ** 3 * nodes ** 3
+    cells = global_cells(args, world)
+    nodes = [c * args.degree + 1 for c in cells]
+    est = 3.0 * 12.0 * (2 * args.degree + 1) ** 3 * float(np.prod(nodes))
     try:
         import psutil
 
         avail = psutil.virtual_memory().available
         if est > 0.9 * avail:
-            raise MemoryError(f"host setup of {nodes}^3 DoFs needs ~{est / 1e9:.0f} GB, {avail / 1e9:.0f} GB available")
+            raise MemoryError(f"host setup of {np.prod(nodes)} DoFs needs ~{est / 1e9:.0f} GB, {avail / 1e9:.0f} GB available")
     except ImportError:
         pass
     t0 = time.time()
-    P = hs.LaplaceProblem.create(3, args.degree, args.cells, args.material)
+    h = (1.0 / args.cells,) * 3
+    if world == 1 or args.scaling == "strong":
+        P = hs.LaplaceProblem.create(3, args.degree, args.cells, args.material)
+    else:
+        P = hs.LaplaceProblem.create_box(3, args.degree, cells, h, args.material)
     R = hs.build_restrictor(P, (args.block,) * 3, args.neig)
     Ac = hs.galerkin(P.A, R)
     return P, R, Ac, time.time() - t0
-
-
-def workload_name(args, P, R, Ac):
-    return (f"3D Q{args.degree} {args.material} Laplace, {args.cells}^3 cells, n={P.n}, nnz={P.A.nnz}; two-level "
-            f"spectral AMGe, {args.block}^3-cell agglomerates x {args.neig} eigvec (n_c={Ac.n_rows}, nnz_R={R.nnz}); "
-            f"V(1,1) Jacobi omega=1, dense LU coarse, preconditioner mode")
 
 
 def algorithmic_bytes(P, R, Ac, mf_cells=None, mf_nq=8):
@@ -161,30 +202,32 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+NCU_TILE_CSV = ("profiles/r02_ncu_full_csr_tile_raw.csv", "profiles/r01_ncu_full_csr_tile_raw.csv")
+
+
 def ncu_traffic_of_dominant_kernel(args, world):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the fused Jacobi sweep from the committed `ncu --set full` capture
-    (profiles/r01_ncu_full_csr_tile_raw.csv, taken with this very command line).  Only valid for the default single-GPU
-    cfg1 workload; None otherwise."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fused Jacobi sweep from the committed `ncu --set full`
+    capture of this very command line.  Only valid for the default single-GPU cfg1 workload; None otherwise."""
     if world != 1 or args.matrix_free or (args.cells, args.block, args.neig, args.degree, args.material) != \
             (128, 8, 1, 1, "constant"):
-        return None
-    path = os.path.join(ROOT, "profiles", "r01_ncu_full_csr_tile_raw.csv")
-    try:
-        import csv
+        return None, None
+    import csv
 
-        rows = list(csv.reader(open(path)))
-        hdr, units = rows[0], rows[1]
-        for r in rows[2:]:
-            if "csr_tile_kernel<4, 2," in r[hdr.index("Kernel Name")]:
-                total = 0.0
-                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                    i = hdr.index(key)
-                    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
-                    total += float(r[i]) * scale
-                return total
-    except (OSError, ValueError, KeyError, IndexError):
-        pass
-    return None
+    for rel in NCU_TILE_CSV:
+        try:
+            rows = list(csv.reader(open(os.path.join(ROOT, rel))))
+            hdr, units = rows[0], rows[1]
+            for r in rows[2:]:
+                if "csr_tile_kernel<4, 2," in r[hdr.index("Kernel Name")]:
+                    total = 0.0
+                    for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                        i = hdr.index(key)
+                        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+                        total += float(r[i]) * scale
+                    return total, rel + " (ncu --set full, same command line)"
+        except (OSError, ValueError, KeyError, IndexError):
+            continue
+    return None, None
 
 
 def measured_peak():
@@ -195,177 +238,249 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_vcycle_rate(P, R, Ac, budget_s=12.0, max_cycles=40, threads=None):
+def host_threads() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def oracle_hierarchy(P, R, Ac, matrix_free=False):
+    import oracle
+
+    fine = (P.n, P.A.rowptr, P.A.col, P.A.val)
+    if matrix_free:
+        fine = oracle.MatrixFreeLaplace(3, P.degree, P.cells, P.h, P.coef_per_q(), P.constrained)
+    return oracle.Hierarchy([fine, (Ac.n_rows, Ac.rowptr, Ac.col, Ac.val)],
+                            [(R.n_rows, R.n_cols, R.rowptr, R.col, R.val)], 1, True)
+
+
+def cpu_vcycle_rate(Ho, n, budget_s=12.0, max_cycles=40):
     """The oracle (CPU port of the reference host path) on a bounded sample of the same workload."""
     import oracle
 
-    if not threads:   # all the host threads this process may use
-        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    oracle.set_num_threads(threads)
     cores = oracle.num_threads()
-    H = oracle.Hierarchy([(P.n, P.A.rowptr, P.A.col, P.A.val), (Ac.n_rows, Ac.rowptr, Ac.col, Ac.val)],
-                         [(R.n_rows, R.n_cols, R.rowptr, R.col, R.val)], 1, True)
     rng = np.random.default_rng(0)
-    b = rng.standard_normal(P.n)
-    H.vmult(b)  # warm-up
+    b = rng.standard_normal(n)
+    Ho.vmult(b)  # warm-up
     t0 = time.perf_counter()
     k = 0
     while k < max_cycles and (time.perf_counter() - t0 < budget_s or k < 2):
-        H.vmult(b)
+        Ho.vmult(b)
         k += 1
     dt = time.perf_counter() - t0
-    return k / dt, cores, k, H
+    return k / dt, cores, k
 
 
 def run_reference(args):
+    """The reference arm: the CPU restatement of the reference host path (oracle/, OpenMP over all host threads) on
+    the SAME global problem as our arm at --gpus N / --scaling (rank 0 alone works)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
 
-    # all the host threads this process may use (launchers like torchrun export OMP_NUM_THREADS=1)
-    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    world = max(1, args.gpus)
+    avail = host_threads()   # launchers like torchrun export OMP_NUM_THREADS=1
     oracle.set_num_threads(avail)
     from mfmg_b200 import hostsetup as hs
 
     hs.set_num_threads(avail)
-    P, R, Ac, setup_s = build_workload(args)
-    H = oracle.Hierarchy([(P.n, P.A.rowptr, P.A.col, P.A.val), (Ac.n_rows, Ac.rowptr, Ac.col, Ac.val)],
-                         [(R.n_rows, R.n_cols, R.rowptr, R.col, R.val)], 1, True)
+    P, R, Ac, setup_s = build_global(args, world)
+    t0 = time.time()
+    Ho = oracle_hierarchy(P, R, Ac, args.matrix_free)
+    factor_s = time.time() - t0
     cores = oracle.num_threads()
     rng = np.random.default_rng(0)
     b = rng.standard_normal(P.n)
     for _ in range(max(args.warmup, 1)):
-        H.vmult(b)
+        Ho.vmult(b)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        H.vmult(b)
+        Ho.vmult(b)
     dt = time.perf_counter() - t0
-    value = args.steps / dt
+    cfg = canonical_config(args, world, P.n, P.A.nnz, Ac.n_rows)
+    value = cfg["units_per_step"] * args.steps / dt
     out = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args, P, R, Ac)},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} full V-cycles of the same workload; CPU restatement of the reference "
-                                   f"host path (oracle/mfmg_oracle.c, OpenMP row-parallel), not the reference binary "
-                                   f"(deal.II/Trilinos/MPI unavailable)"},
+                         "sample": f"{args.steps} full V-cycles of the same global problem; CPU restatement of the "
+                                   f"reference host path (oracle/mfmg_oracle.c, OpenMP row-parallel, coarse LU on band "
+                                   f"storage), not the reference binary (deal.II/Trilinos/MPI unavailable)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "setup_s": {"host_setup": setup_s, "oracle_finalize": factor_s},
     }
     _emit(json.dumps(out))
 
 
-def run_ours(args):
+# ---------------------------------------------------------------------------------------------------------------
+# parity of the timed hierarchy against the serial oracle
+# ---------------------------------------------------------------------------------------------------------------
+def parity_oracle(args, d, handle, H, dist, rank, world, n_local, row_begin, global_ops, n_global):
+    """V-cycle output and PCG (iteration count, residual history) of the hierarchy that was just timed against the
+    serial CPU oracle on the same global problem.  global_ops = (P, R, Ac) on rank 0 (None elsewhere).
+    Every rank calls this; rank 0 returns the dict."""
+    import ctypes
+
+    import oracle
+
+    t_start = time.time()
+    rng = np.random.default_rng(20261018)
+    b_glob = rng.standard_normal(n_global)          # the same stream on every rank
+    sl = slice(row_begin, row_begin + n_local)
+    bl = np.zeros(H.vector_size)
+    bl[:n_local] = b_glob[sl]
+    b = d.DeviceVector.from_host(handle, bl)
+    x = d.DeviceVector(handle, H.vector_size)
+    H.vmult(x, b)
+    handle.synchronize()
+    x_loc = x.to_host()[:n_local].copy()
+    Ho = x0_glob = None
+    if rank == 0:
+        P, R, Ac = global_ops
+        Ho = oracle_hierarchy(P, R, Ac, args.matrix_free)
+        x0_glob = oracle.std_uniform01(P.n, skip=P.constrained)   # tests/hierarchy_driver.cc:153-164
+    if dist is not None:
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object((row_begin, x_loc), parts, dst=0)
+        x0_list = [None]
+        sizes = [None] * world
+        dist.all_gather_object(sizes, (row_begin, n_local))
+        scatter = [x0_glob[rb:rb + nl] for rb, nl in sizes] if rank == 0 else None
+        dist.scatter_object_list(x0_list, scatter, src=0)
+        x0_loc = x0_list[0]
+    else:
+        parts = [(row_begin, x_loc)]
+        x0_loc = x0_glob
+    # PCG on the GPU(s): b = 0, x0 = the driver's random guess, absolute tolerance 1e-8
+    max_it = 200
+    xl = np.zeros(H.vector_size)
+    xl[:n_local] = x0_loc
+    x.upload(xl)
+    b.fill(0.0)
+    hist = np.zeros(max_it + 1)
+    it = ctypes.c_int(0)
+    A0 = H.operators[0]
+    a_ptr = A0.ptr if isinstance(A0, d.SparseMatrixDevice) else None
+    H.use_graph(not args.no_graph)
+    t0 = time.perf_counter()
+    rc = handle.lib.mfmgb_pcg(handle.ctx, H.ptr, a_ptr, b.ptr, x.ptr, TOL_PCG, max_it, ctypes.byref(it),
+                              hist.ctypes.data)
+    handle.synchronize()
+    gpu_s = time.perf_counter() - t0
+    d.check(handle.ctx, rc)
+    if rank != 0:
+        return None, None
+    x_gpu = np.empty(n_global)
+    for rb, xs in parts:
+        x_gpu[rb:rb + len(xs)] = xs
+    x_ref = Ho.vmult(b_glob)
+    v_err = float(np.linalg.norm(x_gpu - x_ref) / np.linalg.norm(x_ref))
+    t0 = time.perf_counter()
+    _, it_ref, hist_ref = Ho.pcg(np.zeros(n_global), x0_glob, TOL_PCG, max_it)
+    cpu_s = time.perf_counter() - t0
+    hist = hist[:it.value + 1]
+    m = min(len(hist), len(hist_ref))
+    h_err = float(np.max(np.abs(hist[:m] - hist_ref[:m]) / hist_ref[:m]))
+    ok = v_err <= TOL_VCYCLE and it.value == it_ref and h_err <= TOL_HIST
+    return Ho, {"against": "serial CPU oracle (oracle/mfmg_oracle.c) on the same global problem, n=%d" % n_global,
+            "vcycle_rel_err": v_err, "vcycle_tol": TOL_VCYCLE,
+            "pcg_tol_abs": TOL_PCG, "pcg_iters_gpu": int(it.value), "pcg_iters_oracle": int(it_ref),
+            "hist_max_rel": h_err, "hist_tol": TOL_HIST, "residual_0": float(hist[0]), "residual_last": float(hist[-1]),
+            "gpu_solve_s": gpu_s, "oracle_solve_s": cpu_s, "oracle_threads": oracle.num_threads(), "ok": bool(ok),
+            "wall_s": time.time() - t_start}
+
+
+def parity_props(args, d, handle, H, dist, rank, world, n_local):
+    """Size-independent properties for configurations whose oracle does not finish in the bench budget: the V-cycle is
+    linear and symmetric (it is a CG preconditioner), CUDA-graph replay equals eager launches bit for bit, and PCG
+    reaches the tolerance with a true residual below it."""
+    import ctypes
+
     import torch
 
-    from mfmg_b200 import device as d
+    def dot(u, v):
+        s = float(np.dot(u, v))
+        if dist is not None:
+            t = torch.tensor([s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t)
+            s = float(t[0])
+        return s
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
+    rng = np.random.default_rng(77 + rank)
+    u_h, v_h = rng.standard_normal(n_local), rng.standard_normal(n_local)
 
-        dist = dist_mod
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    def apply(w_h, graph):
+        H.use_graph(graph)
+        wl = np.zeros(H.vector_size)
+        wl[:n_local] = w_h
+        b = d.DeviceVector.from_host(handle, wl)
+        x = d.DeviceVector(handle, H.vector_size)
+        H.vmult(x, b)
+        if graph:
+            H.vmult(x, b)
+        handle.synchronize()
+        return x.to_host()[:n_local].copy()
+
+    Mu, Mv = apply(u_h, False), apply(v_h, False)
+    Muv = apply(2.0 * u_h - 3.0 * v_h, False)
+    lin = np.sqrt(dot(Muv - (2.0 * Mu - 3.0 * Mv), Muv - (2.0 * Mu - 3.0 * Mv)) / dot(Muv, Muv))
+    sym = abs(dot(u_h, Mv) - dot(Mu, v_h)) / np.sqrt(dot(u_h, u_h) * dot(Mv, Mv))
+    replay_equal = bool(np.array_equal(apply(u_h, True), Mu))
+    if dist is not None:
+        t = torch.tensor([1.0 if replay_equal else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        replay_equal = bool(t[0] > 0.5)
+    # PCG from a random guess with b = 0
+    max_it = 200
+    xl = np.zeros(H.vector_size)
+    xl[:n_local] = rng.random(n_local)
+    x = d.DeviceVector.from_host(handle, xl)
+    b = d.DeviceVector(handle, H.vector_size)
+    b.fill(0.0)
+    hist = np.zeros(max_it + 1)
+    it = ctypes.c_int(0)
+    A0 = H.operators[0]
+    H.use_graph(not args.no_graph)
+    rc = handle.lib.mfmgb_pcg(handle.ctx, H.ptr, A0.ptr if isinstance(A0, d.SparseMatrixDevice) else None, b.ptr,
+                              x.ptr, TOL_PCG, max_it, ctypes.byref(it), hist.ctypes.data)
+    handle.synchronize()
+    d.check(handle.ctx, rc)
+    ok = lin < 1e-12 and sym < 1e-12 and replay_equal and hist[it.value] <= TOL_PCG
+    return {"against": "size-independent properties (the oracle does not finish in the bench budget at this size)",
+            "linearity_rel": float(lin), "symmetry_rel": float(sym), "graph_replay_bitwise": replay_equal,
+            "pcg_iters_gpu": int(it.value), "residual_0": float(hist[0]), "residual_last": float(hist[it.value]),
+            "ok": bool(ok)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------
+def measure(args, d, handle, stream, H, dist, rank, world, local_rank, n_local, nbytes, units):
+    """Timed region + repeats + stage times + SpMV + e2e for one finalized hierarchy; returns a dict of raw numbers."""
+    import torch
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    stream = torch.cuda.Stream()
-    handle = d.CudaHandle(local_rank, stream=stream.cuda_stream)
-    if world == 1:
-        P, R, Ac, setup_s = build_workload(args)
-        t0 = time.time()
-        if args.matrix_free:
-            M = d.MatrixFreeLaplaceDevice(handle, 3, args.degree, P.cells, P.h, P.coef_per_q(), P.constrained)
-            H = d.Hierarchy(handle, [M, d.SparseMatrixDevice.from_host(handle, Ac)],
-                            [d.SparseMatrixDevice.from_host(handle, R)], {"is preconditioner": True})
-            mf_nq = 1 if "per-cell" in M.kernel else (args.degree + 1) ** 3
-            nbytes = algorithmic_bytes(P, R, Ac, int(np.prod(P.cells)), mf_nq)
-        else:
-            H = d.Hierarchy.from_host(handle, P.A, R, Ac, {"is preconditioner": True})
-            nbytes = algorithmic_bytes(P, R, Ac)
-        handle.synchronize()
-        upload_s = time.time() - t0
-        n_local = P.n
-        wl = workload_name(args, P, R, Ac)
-        if args.matrix_free:
-            wl = wl.replace("; two-level", f"; level 0 MATRIX-FREE ({M.kernel}), assembled R / A_c; two-level")
-        parallelism = "1 GPU"
-    else:
-        # weak scaling: `world` cfg1 cubes stacked along z, one z-slab per GPU; every rank builds only its slab
-        from mfmg_b200 import hostsetup as hs
+    def max_over_ranks(values):
+        if dist is None:
+            return [float(v) for v in values]
+        t = torch.tensor(values, device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
 
-        handle.init_comm_from_torch()
-        hs.set_num_threads(max(1, (os.cpu_count() or 1) // world))  # torchrun exports OMP_NUM_THREADS=1
-
-        def gather(obj):
-            out = [None] * world
-            dist.all_gather_object(out, obj)
-            return out
-
-        t0 = time.time()
-        c = args.cells
-        cz = c * world if args.scaling == "weak" else c
-        part = hs.build_slab_part(args.degree, (c, c, cz), (1.0 / c,) * 3, args.material, (args.block,) * 3,
-                                  args.neig, world, rank, gather)
-        setup_s = time.time() - t0
-        t0 = time.time()
-        H = d.Hierarchy.from_partition(handle, part, {"is preconditioner": True}, matrix_free=args.matrix_free)
-        handle.synchronize()
-        if H.coarse_dd is not None:
-            coarse_desc = (f"domain-decomposed direct coarse solve (interior {H.coarse_dd.n_interior} rows per rank, "
-                           f"{H.coarse_dd.n_separator} separator rows, one all-reduce)")
-        else:
-            coarse_desc = ("dense coarse solve " + ("split by rows over the ranks (one all-gather)"
-                                                    if part.Ac.n_rows >= 8192 else "replicated"))
-        upload_s = time.time() - t0
-        n_local = part.n_owned
-
-        class _Shape:  # sizes of this rank's share for the byte counts
-            pass
-
-        Pl, Rl, Acl = _Shape(), _Shape(), _Shape()
-        Pl.n, Pl.A = part.n_owned, part.A
-        Rl.nnz = part.R.nnz
-        Acl.n_rows = part.Ac.n_rows
-        if args.matrix_free:
-            M = H.operators[0]
-            nbytes = algorithmic_bytes(Pl, Rl, Acl, int(np.prod(part.mf["cells"])), 1 if "per-cell" in M.kernel else 8)
-        else:
-            nbytes = algorithmic_bytes(Pl, Rl, Acl)
-        if H.coarse_dd is not None:   # per-GPU bytes of the domain-decomposed coarse solve instead of 8 n_c^2
-            nbytes["vcycle"] += H.coarse_dd.bytes_per_solve - nbytes["dense"]
-            nbytes["dense"] = H.coarse_dd.bytes_per_solve
-        wl = (f"3D Q{args.degree} {args.material} Laplace, {c}x{c}x{cz} cells (h=1/{c}), n={part.n_global} "
-              f"row-partitioned in {world} z-slabs ({part.n_owned} rows, {part.A.nnz} nnz, {part.n_ghost} ghosts on "
-              f"rank 0); two-level spectral AMGe, {args.block}^3-cell agglomerates x {args.neig} eigvec "
-              f"(n_c={part.Ac.n_rows}, {coarse_desc}); V(1,1) Jacobi, preconditioner mode")
-        if args.matrix_free:
-            wl = wl.replace("; two-level", f"; level 0 MATRIX-FREE ({M.kernel}), assembled R / A_c; two-level")
-        parallelism = (f"{world} GPUs, rows partitioned in z-slabs, NCCL halo exchange (1 node plane each way) overlapped "
-                       f"with interior rows, {coarse_desc}")
-    if args.lanes and not args.matrix_free:
-        H.operators[0].set_lanes_per_row(args.lanes)
     H.use_graph(not args.no_graph)
     rng = np.random.default_rng(rank)
     b_h = np.zeros(H.vector_size)
     b_h[:n_local] = rng.standard_normal(n_local)
     b = d.DeviceVector.from_host(handle, b_h)
     x = d.DeviceVector(handle, H.vector_size)
-    peak, peak_src = measured_peak()
-
     K, W = args.steps, max(args.warmup, 3)
     sampler = ClockSampler(local_rank)
+    res = {}
     with torch.cuda.stream(stream):
         for _ in range(W):
             H.vmult(x, b)
@@ -381,16 +496,32 @@ def run_ours(args):
             H.vmult(x, b)
         ev1.record(stream)
         barrier()
-        t_end = time.time()
         launches = handle.launch_count - launches0
         ms_total = ev0.elapsed_time(ev1)
+        # the same K-step region repeated: min / median / max of the per-step time (max over ranks each)
+        reps = []
+        for _ in range(max(0, args.repeats)):
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(stream)
+            for _ in range(K):
+                H.vmult(x, b)
+            r1.record(stream)
+            barrier()
+            reps.append(r0.elapsed_time(r1) / K)
+        t_end = time.time()
         clocks = sampler.stop(t_begin, t_end)
 
-        # per-stage durations of the same cycle (CUDA events between the level-0 stages, un-captured launches)
+        # per-stage durations of the same cycle (CUDA events between the level-0 stages, un-captured launches); the
+        # ranks are aligned by a barrier before every profiled cycle, so a stage holds its own wait for the
+        # neighbours, not the skew accumulated over earlier cycles
+        n_prof = min(K, 20)
         stages = {k: 0.0 for k in d.Hierarchy.STAGES}
-        for _ in range(K):
+        H.profile(x, b)
+        for _ in range(n_prof):
+            barrier()
             for k, v in H.profile(x, b).items():
-                stages[k] += v / K
+                stages[k] += v / n_prof
 
         # plain SpMV y = A x (the BASELINE's "SpMV HBM GB/s")
         Ad = H.operators[0]
@@ -426,100 +557,308 @@ def run_ours(args):
         e2e_ms = max(g0.elapsed_time(g1), 1e3 * (tw1 - tw0)) / K
         checksum = float(x_pin.double().abs().sum())
 
-    # max over ranks
-    if dist is not None:
-        t = torch.tensor([ms_total, e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_ms = float(t[0]), float(t[1])
-    ms_per_step = ms_total / K
-    units = world if args.scaling == "weak" else 1   # weak: one partitioned cycle = `world` single-GPU-sized units
-    value = units * 1e3 / ms_per_step
-    e2e_value = units * 1e3 / e2e_ms
+    vals = max_over_ranks([ms_total, e2e_ms] + reps + [stages[k] for k in d.Hierarchy.STAGES])
+    ms_total, e2e_ms = vals[0], vals[1]
+    reps = vals[2:2 + len(reps)]
+    stages = dict(zip(d.Hierarchy.STAGES, vals[2 + len(reps):]))
+    res.update(ms_per_step=ms_total / K, e2e_ms=e2e_ms, reps=reps, stages=stages, spmv_ms=spmv_ms, clocks=clocks,
+               launches=int(launches), checksum=checksum, K=K, W=W)
+    return res
 
+
+def build_ours(args, d, handle, dist, rank, world):
+    """Host setup + upload of this rank's share.  Returns (H, info)."""
+    from mfmg_b200 import hostsetup as hs
+
+    info = {}
+    if world == 1:
+        P, R, Ac, setup_s = build_global(args, 1)
+        t0 = time.time()
+        if args.matrix_free:
+            M = d.MatrixFreeLaplaceDevice(handle, 3, args.degree, P.cells, P.h, P.coef_per_q(), P.constrained)
+            H = d.Hierarchy(handle, [M, d.SparseMatrixDevice.from_host(handle, Ac)],
+                            [d.SparseMatrixDevice.from_host(handle, R)], {"is preconditioner": True})
+            mf_nq = 1 if "per-cell" in M.kernel else (args.degree + 1) ** 3
+            nbytes = algorithmic_bytes(P, R, Ac, int(np.prod(P.cells)), mf_nq)
+        else:
+            H = d.Hierarchy.from_host(handle, P.A, R, Ac, {"is preconditioner": True})
+            nbytes = algorithmic_bytes(P, R, Ac)
+        handle.synchronize()
+        info.update(setup_s=setup_s, upload_s=time.time() - t0, n_local=P.n, row_begin=0, n_global=P.n,
+                    nnz_global=P.A.nnz, n_c=Ac.n_rows, global_ops=(P, R, Ac), nbytes=nbytes,
+                    parallelism="1 GPU", coarse="dense LU (explicit inverse, one GEMV per apply)")
+        return H, info
+
+    handle.init_comm_from_torch()
+    hs.set_num_threads(max(1, host_threads() // world))  # torchrun exports OMP_NUM_THREADS=1
+
+    def gather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    t0 = time.time()
+    c = args.cells
+    cells = global_cells(args, world)
+    part = hs.build_slab_part(args.degree, cells, (1.0 / c,) * 3, args.material, (args.block,) * 3, args.neig, world,
+                              rank, gather)
+    setup_s = time.time() - t0
+    t0 = time.time()
+    H = d.Hierarchy.from_partition(handle, part, {"is preconditioner": True}, matrix_free=args.matrix_free)
+    handle.synchronize()
+    if H.coarse_dd is not None:
+        coarse_desc = (f"domain-decomposed direct coarse solve (interior {H.coarse_dd.n_interior} rows per rank, "
+                       f"{H.coarse_dd.n_separator} separator rows, one all-reduce)")
+    else:
+        coarse_desc = ("dense coarse solve " + ("split by rows over the ranks (one all-gather)"
+                                                if part.Ac.n_rows >= 8192 else "replicated"))
+    upload_s = time.time() - t0
+
+    class _Shape:  # sizes of this rank's share for the byte counts
+        pass
+
+    Pl, Rl, Acl = _Shape(), _Shape(), _Shape()
+    Pl.n, Pl.A = part.n_owned, part.A
+    Rl.nnz = part.R.nnz
+    Acl.n_rows = part.Ac.n_rows
+    if args.matrix_free:
+        M = H.operators[0]
+        nbytes = algorithmic_bytes(Pl, Rl, Acl, int(np.prod(part.mf["cells"])), 1 if "per-cell" in M.kernel else 8)
+    else:
+        nbytes = algorithmic_bytes(Pl, Rl, Acl)
+    if H.coarse_dd is not None:   # per-GPU bytes of the domain-decomposed coarse solve instead of 8 n_c^2
+        nbytes["vcycle"] += H.coarse_dd.bytes_per_solve - nbytes["dense"]
+        nbytes["dense"] = H.coarse_dd.bytes_per_solve
+    import torch
+
+    t = torch.tensor([part.A.nnz], dtype=torch.int64, device="cuda")
+    dist.all_reduce(t)
+    info.update(setup_s=setup_s, upload_s=upload_s, n_local=part.n_owned, row_begin=part.row_begin,
+                n_global=part.n_global, nnz_global=int(t[0]), n_c=part.Ac.n_rows, global_ops=None, nbytes=nbytes,
+                coarse=coarse_desc,
+                parallelism=(f"{world} GPUs, rows partitioned in z-slabs ({part.n_owned} rows, {part.A.nnz} nnz, "
+                             f"{part.n_ghost} ghosts on rank 0), halo exchange of 1 node plane each way overlapped with "
+                             f"interior rows ({H.transport}), {coarse_desc}"))
+    return H, info
+
+
+def north_star_subprocess(args):
+    """N = 1: BASELINE configs[3] on one GPU in a child process (its own host setup of 135 M DoFs), bounded in time."""
+    try:
+        import psutil
+
+        avail = psutil.virtual_memory().available
+    except ImportError:
+        avail = 0
+    nodes = args.north_star_cells + 1
+    need = 3.0 * 12.0 * 27.0 * nodes ** 3 * 1.15
+    if avail and need > avail:
+        return {"skipped": f"host setup of {nodes}^3 DoFs needs ~{need / 1e9:.0f} GB, {avail / 1e9:.0f} GB available"}
+    cmd = [sys.executable, os.path.abspath(__file__), "--cells", str(args.north_star_cells), "--block", "16",
+           "--steps", str(max(3, min(args.steps, 10))), "--warmup", "3", "--repeats", "3", "--no-cpu-baseline",
+           "--parity", "props", "--north-star", "off"]
+    t0 = time.time()
+    try:
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                             timeout=args.north_star_timeout)
+    except subprocess.TimeoutExpired:
+        return {"skipped": f"did not finish within {args.north_star_timeout:.0f} s"}
+    if res.returncode != 0:
+        return {"skipped": f"child exited {res.returncode}: {res.stderr[-300:]}"}
+    try:
+        line = json.loads(res.stdout.strip().splitlines()[-1])
+    except (ValueError, IndexError):
+        return {"skipped": "child printed no JSON line"}
+    return summarise_north_star(line, time.time() - t0)
+
+
+def summarise_north_star(line, wall_s):
+    return {"config": "BASELINE configs[3]: " + line["config"]["workload"], "n_gpus": line["n_gpus"],
+            "scaling": "strong", "vcycles_per_s": line["value"], "ms_per_step": line["ms_per_step"],
+            "steps": line["steps"], "timing": line.get("timing"),
+            "vcycle_roofline": line["vcycle_roofline"], "roofline": line["roofline"], "spmv": line["spmv"],
+            "e2e": line["e2e"], "clocks": line["clocks"], "parity": line.get("parity"),
+            "setup_s": line["details"]["setup_s"], "wall_s": wall_s,
+            "target": ">= 70 % of HBM roofline per GPU at 1 GPU; >= 80 % parallel efficiency at 8 GPUs = "
+                      "vcycles_per_s(8) / (8 x vcycles_per_s(1))"}
+
+
+def assemble_line(args, d, H, info, m, world, units):
+    """The JSON line of one measured hierarchy."""
+    peak, peak_src = measured_peak()
+    nbytes = info["nbytes"]
+    ms_per_step = m["ms_per_step"]
+    value = units * 1e3 / ms_per_step
+    e2e_value = units * 1e3 / m["e2e_ms"]
+    stages = m["stages"]
     dom_ms = stages["post_smooth"]
     achieved = nbytes["jacobi"] / (dom_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic_of_dominant_kernel(args, world)
+    reps = sorted(m["reps"])
+    timing = None
+    if reps:
+        med = float(np.median(reps))
+        timing = {"repeats": len(reps), "steps_per_repeat": m["K"], "ms_per_step_min": reps[0],
+                  "ms_per_step_median": med, "ms_per_step_max": reps[-1],
+                  "spread_pct": 100.0 * (reps[-1] - reps[0]) / med,
+                  "value_from_median": units * 1e3 / med}
+    n_local = info["n_local"]
+    kern0 = H.operators[0].kernel
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": m["K"], "warmup": m["W"],
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl,
-                   "l2_policy": "inputs larger than L2: one cycle streams %.2f GB per GPU (A alone %.2f GB) vs 126 MB L2"
-                                % (nbytes["vcycle"] / 1e9, nbytes["spmv"] / 1e9),
-                   "parallelism": parallelism,
-                   "value_definition": ("single-GPU-sized V-cycle units per second = n_gpus x (partitioned V-cycles per "
-                                        "second); one partitioned cycle over n_gpus x the per-GPU DoFs counts n_gpus "
-                                        "units (weak scaling)") if args.scaling == "weak" else
-                                       "V-cycles per second of the one global problem (strong scaling)",
-                   "cuda_graph": not args.no_graph, "lanes_per_row_A": None if args.matrix_free else H.operators[0].lanes_per_row,
-                   "kernel_A": H.operators[0].kernel,
-                   "lanes_per_row_R": H.restrictors[0].lanes_per_row},
-        "clocks": clocks,
+        "config": canonical_config(args, world, info["n_global"], info["nnz_global"], info["n_c"]),
+        "clocks": m["clocks"],
+        "timing": timing,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n_local * world,
-                "d2h_bytes_per_step": 8 * n_local * world,
-                "ms_per_step": e2e_ms, "checksum_abs_x": checksum},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": (f"mf_q1_kernel<Jacobi epilogue> ({H.operators[0].kernel})" if args.matrix_free else
-                                f"csr_{H.operators[0].kernel}_kernel<Jacobi epilogue>") + " (post-smoothing sweep on A)",
+                "d2h_bytes_per_step": 8 * n_local * world, "ms_per_step": m["e2e_ms"], "checksum_abs_x": m["checksum"]},
+        "gpu_launches": m["launches"],
+        "roofline": {"bound": "hbm",
+                     "kernel": (f"mf_q1_kernel<Jacobi epilogue> ({kern0})" if args.matrix_free else
+                                f"csr_{kern0}_kernel<Jacobi epilogue>") + " (post-smoothing sweep on A)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "traffic": ncu_traffic_of_dominant_kernel(args, world),
-                     "traffic_source": "profiles/r01_ncu_full_csr_tile_raw.csv (ncu --set full, same command line)",
-                     "algorithmic_bytes_per_launch": nbytes["jacobi"],
-                     "launch_ms": dom_ms},
+                     "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_launch": nbytes["jacobi"], "launch_ms": dom_ms},
         "vcycle_roofline": {"algorithmic_bytes_per_cycle": nbytes["vcycle"],
                             "achieved_gbs": nbytes["vcycle"] / (ms_per_step * 1e-3) / 1e9,
                             "frac_of_measured_peak": nbytes["vcycle"] / (ms_per_step * 1e-3) / 1e9 / peak,
                             "frac_of_nominal_8TBs": nbytes["vcycle"] / (ms_per_step * 1e-3) / 1e9 / 8000.0},
-        "spmv": {"gbs": nbytes["spmv"] / (spmv_ms * 1e-3) / 1e9, "ms": spmv_ms,
-                 "frac_of_measured_peak": nbytes["spmv"] / (spmv_ms * 1e-3) / 1e9 / peak,
-                 "frac_of_nominal_8TBs": nbytes["spmv"] / (spmv_ms * 1e-3) / 1e9 / 8000.0},
+        "spmv": {"gbs": nbytes["spmv"] / (m["spmv_ms"] * 1e-3) / 1e9, "ms": m["spmv_ms"],
+                 "frac_of_measured_peak": nbytes["spmv"] / (m["spmv_ms"] * 1e-3) / 1e9 / peak,
+                 "frac_of_nominal_8TBs": nbytes["spmv"] / (m["spmv_ms"] * 1e-3) / 1e9 / 8000.0},
         "stage_ms": stages,
         "stage_gbs": {"residual": nbytes["resid"] / (stages["residual"] * 1e-3) / 1e9,
                       "restrict": nbytes["restrict"] / (stages["restrict"] * 1e-3) / 1e9,
                       "coarse": nbytes["dense"] / (stages["coarse"] * 1e-3) / 1e9,
                       "prolong_correct": nbytes["prolong"] / (stages["prolong_correct"] * 1e-3) / 1e9,
                       "post_smooth": achieved},
-        "setup_s": {"host_setup": setup_s, "upload_and_factor": upload_s},
-        "partitioned_vcycles_per_s": 1e3 / ms_per_step,
+        "details": {"parallelism": info["parallelism"], "coarse_solver": info["coarse"], "cuda_graph": not args.no_graph,
+                    "lanes_per_row_A": None if args.matrix_free else H.operators[0].lanes_per_row, "kernel_A": kern0,
+                    "lanes_per_row_R": H.restrictors[0].lanes_per_row,
+                    "launches_per_cycle": m["launches"] // max(m["K"], 1),
+                    "setup_s": {"host_setup": info["setup_s"], "upload_and_factor": info["upload_s"]},
+                    "global_vcycles_per_s": 1e3 / ms_per_step},
     }
-    if rank == 0 and world == 1 and args.pcg and not args.matrix_free:
+    return out
+
+
+def run_ours(args):
+    import torch
+
+    from mfmg_b200 import device as d
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    stream = torch.cuda.Stream()
+    handle = d.CudaHandle(local_rank, stream=stream.cuda_stream)
+    units = world if args.scaling == "weak" else 1
+    H, info = build_ours(args, d, handle, dist, rank, world)
+    if args.lanes and not args.matrix_free:
+        H.operators[0].set_lanes_per_row(args.lanes)
+    m = measure(args, d, handle, stream, H, dist, rank, world, local_rank, info["n_local"], info["nbytes"], units)
+    out = assemble_line(args, d, H, info, m, world, units) if rank == 0 else None
+
+    # ---- parity of the hierarchy that was just timed ----
+    parity = None
+    Ho = gops = None
+    if args.parity == "oracle":
         import oracle
 
-        tol, max_it = 1e-8, 200
-        x0 = oracle.std_uniform01(P.n, skip=P.constrained)
-        xd = d.DeviceVector.from_host(handle, x0)
-        bd = d.DeviceVector.from_host(handle, np.zeros(P.n))
-        H.use_graph(True)
-        d.solver_cg(handle, H.operators[0], xd, bd, H, tol, max_it)      # warm-up (graph capture)
-        xd.upload(x0)
-        handle.synchronize()
-        t0 = time.perf_counter()
-        it, hist = d.solver_cg(handle, H.operators[0], xd, bd, H, tol, max_it)
-        handle.synchronize()
-        gpu_s = time.perf_counter() - t0
-        Ho = oracle.Hierarchy([(P.n, P.A.rowptr, P.A.col, P.A.val), (Ac.n_rows, Ac.rowptr, Ac.col, Ac.val)],
-                              [(R.n_rows, R.n_cols, R.rowptr, R.col, R.val)], 1, True)
-        t0 = time.perf_counter()
-        _, it_ref, hist_ref = Ho.pcg(np.zeros(P.n), x0, tol, max_it)
-        cpu_s = time.perf_counter() - t0
-        m = min(len(hist), len(hist_ref))
-        out["pcg"] = {"tol_abs": tol, "iterations_gpu": int(it), "iterations_oracle": int(it_ref),
-                      "max_rel_diff_residual_history": float(np.max(np.abs(hist[:m] - hist_ref[:m]) / hist_ref[:m])),
-                      "residual_0": float(hist[0]), "residual_last": float(hist[-1]),
-                      "gpu_solve_s": gpu_s, "oracle_solve_s": cpu_s, "oracle_threads": oracle.num_threads()}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and Ac.n_rows > 8192:
-        out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
-                               "sample": "skipped: the oracle's unblocked dense LU of the coarse operator does not "
-                                         "finish in the bench budget at this n_c"}
-    elif rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, cores, k, _ = cpu_vcycle_rate(P, R, Ac)
-        out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                               "sample": f"{k} full V-cycles of the same workload on the host cores (oracle port of the "
-                                         f"reference host path; the reference binary cannot be built here)"}
+        oracle.set_num_threads(host_threads())
+        gops = info["global_ops"]
+        if world > 1 and rank == 0:
+            from mfmg_b200 import hostsetup as hs
+
+            hs.set_num_threads(host_threads())
+            P, R, Ac, _ = build_global(args, world)
+            gops = (P, R, Ac)
+        Ho, parity = parity_oracle(args, d, handle, H, dist, rank, world, info["n_local"], info["row_begin"], gops,
+                                   info["n_global"])
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            rate, cores, k = cpu_vcycle_rate(Ho, info["n_global"])
+            out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"{k} full V-cycles of the same workload on the host cores (oracle port "
+                                             f"of the reference host path; the reference binary cannot be built here)"}
+    elif args.parity == "props":
+        parity = parity_props(args, d, handle, H, dist, rank, world, info["n_local"])
+    if rank == 0:
+        out["parity"] = parity
+        if "cpu_baseline" not in out and world == 1:
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                   "sample": "skipped (--no-cpu-baseline or --parity != oracle)"}
+
+    # ---- BASELINE configs[3], driver-visible ----
+    default_workload = (args.cells, args.block, args.neig, args.degree, args.material, args.scaling) == \
+        (128, 8, 1, 1, "constant", "weak") and not args.matrix_free
+    want_ns = args.north_star == "on" or (args.north_star == "auto" and default_workload)
+    if want_ns:
+        del H   # the cfg1 operators leave the device and the host before the 135 M-DoF leg
+        Ho = None
+        info["global_ops"] = gops = None
+        import gc
+
+        gc.collect()
+        if world == 1:
+            ns = north_star_subprocess(args)
+        else:
+            ns = north_star_in_process(args, d, handle, stream, dist, rank, world, local_rank)
+        if rank == 0:
+            out["north_star"] = ns
     if rank == 0:
         _emit(json.dumps(out))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity["ok"]:
+        sys.stderr.write("bench.py: PARITY FAILED: %s\n" % json.dumps(parity))
+        sys.exit(3)
+
+
+def north_star_in_process(args, d, handle, stream, dist, rank, world, local_rank):
+    """N > 1: BASELINE configs[3] row-partitioned over the N GPUs (strong scaling), same processes."""
+    import copy
+
+    import torch
+
+    a = copy.copy(args)
+    a.cells, a.block, a.neig, a.degree, a.material = args.north_star_cells, 16, 1, 1, "constant"
+    a.scaling, a.matrix_free, a.lanes = "strong", False, 0
+    a.steps, a.warmup, a.repeats = max(3, min(args.steps, 10)), 3, 3
+    try:
+        import psutil
+
+        avail = psutil.virtual_memory().available
+    except ImportError:
+        avail = 0
+    nodes = a.cells + 1
+    need = 3.0 * 12.0 * 27.0 * nodes ** 3 * (1.0 + 2.0 * 16 * world / a.cells) * 1.15   # slabs + their overlap layers
+    flag = torch.tensor([1 if (not avail or need <= avail) else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag[0]) == 0:
+        return {"skipped": f"host setup of {nodes}^3 DoFs over {world} ranks needs ~{need / 1e9:.0f} GB, "
+                           f"{avail / 1e9:.0f} GB available"}
+    t0 = time.time()
+    H, info = build_ours(a, d, handle, dist, rank, world)
+    m = measure(a, d, handle, stream, H, dist, rank, world, local_rank, info["n_local"], info["nbytes"], 1)
+    par = parity_props(a, d, handle, H, dist, rank, world, info["n_local"])
+    if rank != 0:
+        return None
+    line = assemble_line(a, d, H, info, m, world, 1)
+    line["parity"] = par
+    return summarise_north_star(line, time.time() - t0)
 
 
 def main():

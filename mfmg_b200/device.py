@@ -645,6 +645,14 @@ class Hierarchy:
                          boundary=(part.boundary_lo, part.boundary_hi), coarse_offsets=part.coarse_offsets,
                          coarse_dd=dd, restrict_split=r_split, restrict_no_halo=no_halo, restrict_below=r_below)
 
+    @property
+    def transport(self) -> str:
+        """How the ghost entries and the coarse reduction travel between the GPUs of this hierarchy."""
+        fn = getattr(self.handle.lib, "mfmgb_comm_transport", None)
+        if self.halo is None:
+            return "none (single GPU)"
+        return fn(self.handle.ctx).decode() if fn else "NCCL send/recv + all-reduce"
+
     def build_vector(self) -> DeviceVector:
         """A level-0 vector with room for the ghost tail (Level::build_vector, level.hpp:63-70)."""
         return DeviceVector(self.handle, self.vector_size)

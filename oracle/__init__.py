@@ -47,6 +47,7 @@ def lib():
         L.orc_hierarchy_new.restype = _vp
         L.orc_hierarchy_new.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double]
         L.orc_hierarchy_set_explicit_transpose.argtypes = [_vp, ctypes.c_int]
+        L.orc_hierarchy_set_coarse_storage.argtypes = [_vp, ctypes.c_int]
         L.orc_hierarchy_set_operator.argtypes = [_vp, ctypes.c_int, ctypes.c_int64, _vp, _vp, _vp]
         L.orc_hierarchy_set_mf_operator.argtypes = [_vp, _vp]
         L.orc_hierarchy_set_restrictor.argtypes = [_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, _vp, _vp, _vp]
@@ -251,12 +252,15 @@ class Hierarchy:
     maps level i to level i+1."""
 
     def __init__(self, operators, restrictors, n_smoothing_steps=1, is_preconditioner=True, omega=1.0,
-                 explicit_transpose=True):
+                 explicit_transpose=True, coarse_storage="auto"):
+        """coarse_storage: "dense" = the dense getrf/getrs restatement, "band" = the same factorisation on band
+        storage (bit-identical results, orc_band_lu_factor), "auto" = band when the bandwidth is below n / 4."""
         L = lib()
         self._keep = []
         self.n_levels = len(operators)
         self.ptr = L.orc_hierarchy_new(self.n_levels, n_smoothing_steps, int(is_preconditioner), omega)
         L.orc_hierarchy_set_explicit_transpose(self.ptr, int(explicit_transpose))
+        L.orc_hierarchy_set_coarse_storage(self.ptr, {"auto": 0, "dense": 1, "band": 2}[coarse_storage])
         self.A0 = None
         for li, op in enumerate(operators):
             if isinstance(op, MatrixFreeLaplace):

@@ -244,6 +244,121 @@ void orc_lu_solve(i64 n, const double *lu, const i32 *piv, const double *b, doub
   }
 }
 
+/* ---- the same LU with partial pivoting on BAND storage -------------------------------------------------
+ * The coarse operators of structured agglomerate grids are banded (lexicographic agglomerates: bandwidth
+ * ~ agglomerates per plane), and at n_c = 32 768 (BASELINE configs[3]) the dense array above would be 8.6 GB and its
+ * factorisation 2.3e13 flops.  This is the SAME algorithm -- getrf's pivot rule (first entry of maximal magnitude in
+ * the column), the same multipliers, the same update order -- restricted to the entries that can be non-zero:
+ * with lower / upper bandwidths kl / ku, step k only touches rows (k, k + kl] and columns (k, k + ku + kl].
+ * Every skipped operation of the dense routine is x - l * 0 (exact), so the factors and the solutions are
+ * bit-identical to orc_lu_factor / orc_lu_solve (checked in tests/test_oracle_kat.py).  As in LAPACK's band
+ * routines the multipliers are not interchanged; the solve applies interchange k right before eliminating with
+ * column k, which performs the same subtractions in the same order as permuting first.
+ * Storage: row i holds columns [i - kl, i + ku + kl] in ab[i * w + (j - i + kl)], w = 2 kl + ku + 1. */
+#define BAND(i, j) ab[(size_t)(i) * (size_t)w + (size_t)((j) - (i) + kl)]
+
+void orc_csr_bandwidths(i64 n, const i64 *rowptr, const i32 *col, i64 *kl_out, i64 *ku_out)
+{
+  i64 kl = 0, ku = 0;
+  for (i64 i = 0; i < n; ++i)
+    for (i64 k = rowptr[i]; k < rowptr[i + 1]; ++k)
+    {
+      const i64 d = (i64)col[k] - i;
+      if (-d > kl)
+        kl = -d;
+      if (d > ku)
+        ku = d;
+    }
+  *kl_out = kl;
+  *ku_out = ku;
+}
+
+void orc_csr_to_band(i64 n, const i64 *rowptr, const i32 *col, const double *val, i64 kl, i64 ku, double *ab)
+{
+  const i64 w = 2 * kl + ku + 1;
+  memset(ab, 0, sizeof(double) * (size_t)n * (size_t)w);
+  for (i64 i = 0; i < n; ++i)
+    for (i64 k = rowptr[i]; k < rowptr[i + 1]; ++k)
+      BAND(i, (i64)col[k]) += val[k];
+}
+
+int orc_band_lu_factor(i64 n, i64 kl, i64 ku, double *ab, i32 *piv)
+{
+  const i64 w = 2 * kl + ku + 1;
+  int info = 0;
+  for (i64 k = 0; k < n; ++k)
+  {
+    const i64 i_end = k + kl < n - 1 ? k + kl : n - 1;      /* last row with an entry in column k */
+    const i64 j_end = k + ku + kl < n - 1 ? k + ku + kl : n - 1; /* last column of row k after fill-in */
+    i64 p = k;
+    double amax = fabs(BAND(k, k));
+    for (i64 i = k + 1; i <= i_end; ++i)
+    {
+      double v = fabs(BAND(i, k));
+      if (v > amax)
+      {
+        amax = v;
+        p = i;
+      }
+    }
+    piv[k] = (i32)p;
+    if (amax == 0.)
+    {
+      if (!info)
+        info = (int)(k + 1);
+      continue;
+    }
+    if (p != k)
+      for (i64 j = k; j <= j_end; ++j)
+      {
+        double t = BAND(k, j);
+        BAND(k, j) = BAND(p, j);
+        BAND(p, j) = t;
+      }
+    const double inv = 1. / BAND(k, k);
+#pragma omp parallel for schedule(static) if ((i_end - k) * (j_end - k) > 200000)
+    for (i64 i = k + 1; i <= i_end; ++i)
+    {
+      double l = BAND(i, k) * inv;
+      BAND(i, k) = l;
+      if (l != 0.)
+        for (i64 j = k + 1; j <= j_end; ++j)
+          BAND(i, j) -= l * BAND(k, j);
+    }
+  }
+  return info;
+}
+
+void orc_band_lu_solve(i64 n, i64 kl, i64 ku, const double *ab, const i32 *piv, const double *b, double *x)
+{
+  const i64 w = 2 * kl + ku + 1;
+  if (x != b)
+    memcpy(x, b, sizeof(double) * (size_t)n);
+  for (i64 k = 0; k < n; ++k)
+  {
+    const i64 p = piv[k];
+    if (p != k)
+    {
+      double t = x[k];
+      x[k] = x[p];
+      x[p] = t;
+    }
+    const i64 i_end = k + kl < n - 1 ? k + kl : n - 1;
+    const double xk = x[k];
+    for (i64 i = k + 1; i <= i_end; ++i)
+      x[i] -= BAND(i, k) * xk;
+  }
+  for (i64 i = n - 1; i >= 0; --i)
+  {
+    const i64 j_end = i + ku + kl < n - 1 ? i + ku + kl : n - 1;
+    double s = x[i];
+    for (i64 j = i + 1; j <= j_end; ++j)
+      s -= BAND(i, j) * x[j];
+    x[i] = s / BAND(i, i);
+  }
+}
+#undef BAND
+
 /* ------------------------------------------------------------------------------------------
  * Hierarchy: levels[0] finest ... levels[L-1] coarsest.  Mirrors mfmg::Hierarchy / Level
  * (include/mfmg/common/hierarchy.hpp:159-309, level.hpp:22-76).  Operators are given, not
@@ -268,9 +383,10 @@ typedef struct
   i32 *p_col;
   double *p_val;
   double *dinv;
-  /* coarsest level */
+  /* coarsest level: dense LU, or the same factorisation on band storage (band_kl >= 0) */
   double *lu;
   i32 *piv;
+  i64 band_kl, band_ku;
   /* work vectors */
   double *res, *work, *bc, *xc;
 } orc_level;
@@ -282,6 +398,7 @@ typedef struct
   int is_preconditioner; /* "is preconditioner", hierarchy.hpp:168 */
   double omega;
   int explicit_transpose; /* 1: prolong with stored R^T; 0: implicit Tvmult */
+  int coarse_storage;     /* 0: automatic, 1: dense array, 2: band storage (same arithmetic, see orc_band_lu_factor) */
   orc_level *lev;
 } orc_hierarchy;
 
@@ -303,6 +420,7 @@ orc_hierarchy *orc_hierarchy_new(int n_levels, int n_smoothing_steps, int is_pre
 }
 
 void orc_hierarchy_set_explicit_transpose(orc_hierarchy *h, int flag) { h->explicit_transpose = flag; }
+void orc_hierarchy_set_coarse_storage(orc_hierarchy *h, int mode) { h->coarse_storage = mode; }
 
 /* The arrays are borrowed: the caller keeps them alive for the life of the hierarchy. */
 void orc_hierarchy_set_operator(orc_hierarchy *h, int level, i64 n, const i64 *rowptr,
@@ -368,10 +486,25 @@ int orc_hierarchy_finalize(orc_hierarchy *h)
     }
     else
     {
-      l->lu = (double *)malloc(sizeof(double) * (size_t)n * (size_t)n);
+      i64 kl = 0, ku = 0;
+      orc_csr_bandwidths(n, l->a_rowptr, l->a_col, &kl, &ku);
+      const int band = h->coarse_storage == 2 || (h->coarse_storage == 0 && n >= 1024 && 4 * (2 * kl + ku + 1) <= n);
       l->piv = (i32 *)malloc(sizeof(i32) * (size_t)(n > 0 ? n : 1));
-      orc_csr_to_dense(n, l->a_rowptr, l->a_col, l->a_val, l->lu);
-      info = orc_lu_factor(n, l->lu, l->piv);
+      l->band_kl = -1;
+      if (band)
+      {
+        l->band_kl = kl;
+        l->band_ku = ku;
+        l->lu = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1) * (size_t)(2 * kl + ku + 1));
+        orc_csr_to_band(n, l->a_rowptr, l->a_col, l->a_val, kl, ku, l->lu);
+        info = orc_band_lu_factor(n, kl, ku, l->lu, l->piv);
+      }
+      else
+      {
+        l->lu = (double *)malloc(sizeof(double) * (size_t)n * (size_t)n);
+        orc_csr_to_dense(n, l->a_rowptr, l->a_col, l->a_val, l->lu);
+        info = orc_lu_factor(n, l->lu, l->piv);
+      }
     }
   }
   return info;
@@ -433,7 +566,10 @@ void orc_hierarchy_apply(orc_hierarchy *h, const double *b, double *x, int level
 
   if (level_index == h->n_levels - 1)
   {
-    orc_lu_solve(n, fine->lu, fine->piv, b, x); /* :261-268 -> cuda_solver.cu:496-515 */
+    if (fine->band_kl >= 0)
+      orc_band_lu_solve(n, fine->band_kl, fine->band_ku, fine->lu, fine->piv, b, x);
+    else
+      orc_lu_solve(n, fine->lu, fine->piv, b, x); /* :261-268 -> cuda_solver.cu:496-515 */
     return;
   }
   orc_level *coarse = &h->lev[level_index + 1];

@@ -25,6 +25,10 @@ def test_partitioned_hierarchy_on_gpus(world, kernel):
            os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
     env = dict(os.environ, MFMGB_CSR_KERNEL=kernel)  # "tile": interior/boundary row ranges through csr_tile.cu
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, env=env)
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):   # keep the worker's log as evidence (copied to profiles/ by the builder)
+        with open(os.path.join(out_dir, f"multi_gpu_parity_w{world}_{kernel}.log"), "w") as f:
+            f.write(res.stdout)
     assert res.returncode == 0, res.stdout[-4000:]
     for r in range(world):
         assert f"RANK {r} OK" in res.stdout, res.stdout[-4000:]

@@ -362,3 +362,41 @@ def test_matrix_free_laplace_exact_for_quadratic(dim, cells):
     free = P.constrained == 0
     r = M.apply(u) - b
     assert np.max(np.abs(r[free])) < 1e-14 * max(1.0, np.max(np.abs(b)))
+
+
+def test_band_lu_is_bit_identical_to_dense_lu():
+    """The oracle's coarse solve on band storage (used from n_c = 1024 on, so that BASELINE configs[3]'s n_c = 32 768
+    has a CPU comparator) performs the dense getrf/getrs arithmetic restricted to the band: identical bits."""
+    from helpers import oracle_hierarchy, two_level_problem
+    import oracle
+
+    for dim, cells, block, ne, mat in [(3, 12, 3, 2, "linear"), (2, 32, 4, 2, "discontinuous"), (3, 16, 2, 1, "constant")]:
+        P, R, Ac = two_level_problem(dim, 1, cells, block, ne, mat)
+        ops = [(P.n, P.A.rowptr, P.A.col, P.A.val), (Ac.n_rows, Ac.rowptr, Ac.col, Ac.val)]
+        res = [(R.n_rows, R.n_cols, R.rowptr, R.col, R.val)]
+        Hd = oracle.Hierarchy(ops, res, 1, True, coarse_storage="dense")
+        Hb = oracle.Hierarchy(ops, res, 1, True, coarse_storage="band")
+        rng = np.random.default_rng(dim + cells)
+        for _ in range(3):
+            b = rng.standard_normal(P.n)
+            assert np.array_equal(Hd.vmult(b), Hb.vmult(b))
+    # a matrix that really pivots: random band, small diagonal
+    import scipy.sparse as sp
+
+    n, kl, ku = 300, 7, 4
+    rng = np.random.default_rng(0)
+    diags = [rng.standard_normal(n - abs(k)) * (0.05 if k == 0 else 1.0) for k in range(-kl, ku + 1)]
+    A = sp.diags(diags, list(range(-kl, ku + 1)), format="csr")
+    A.sort_indices()
+    rp, col, val = A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data.copy()
+    ident = sp.identity(n, format="csr")
+    eye = (n, ident.indptr.astype(np.int64), ident.indices.astype(np.int32), ident.data.copy())
+    ops = [eye, (n, rp, col, val)]
+    res = [(n, n, eye[1], eye[2], eye[3])]
+    Hd = oracle.Hierarchy(ops, res, 0, True, coarse_storage="dense")
+    Hb = oracle.Hierarchy(ops, res, 0, True, coarse_storage="band")
+    b = rng.standard_normal(n)
+    xd, xb = Hd.vmult(b), Hb.vmult(b)
+    assert np.array_equal(xd, xb)
+    # nu = 0, R = I: the cycle returns x = -(-A^-1 ... ) i.e. the coarse solve of the residual -b: x = A^-1 b
+    assert np.linalg.norm(A @ xd - b) < 1e-9 * np.linalg.norm(b)
