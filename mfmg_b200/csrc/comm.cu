@@ -1,10 +1,22 @@
-// comm.cu -- multi-GPU plumbing: one process per GPU, NCCL over NVLink/NVSwitch.
+// comm.cu -- multi-GPU plumbing: one process per GPU; ghost entries and small reductions travel over NVLink / NVSwitch
+// PEER MEMORY written by our own kernels, NCCL is the bootstrap (and the fallback when CUDA IPC is unavailable).
 //
 // Replaces the reference's per-SpMV host MPI_Allgatherv of the WHOLE source vector
-// (include/mfmg/cuda/sparse_matrix_device.templates.cuh:104-138, source/cuda/utils.cu:305-482) by a halo
-// exchange of the boundary entries only: grouped ncclSend/ncclRecv on a communication stream that overlaps the
-// interior rows of the SpMV; CG dot products use ncclAllReduce; the coarse right-hand side is all-gathered
-// (the dense coarse solve is replicated).
+// (include/mfmg/cuda/sparse_matrix_device.templates.cuh:104-138, source/cuda/utils.cu:305-482) by a halo exchange of
+// the boundary entries only, overlapped with the interior rows of the SpMV:
+//   * peer path (default): every rank exports one window of device memory with CUDA IPC; the push kernel gathers the
+//     boundary entries of v and STORES them into the neighbour's mailbox through the mapped pointer, fences, and raises
+//     a sequence flag there (st.release.sys); the neighbour's wait kernel spins on its own flag (ld.acquire.sys), then
+//     copies the mailbox into the ghost tail.  Mailboxes are double-buffered by the parity of the exchange count:
+//     a sender can only be one exchange ahead of its neighbour (its next-but-one push needs the neighbour's next
+//     push, which the neighbour issues after it has emptied the mailbox), so no acknowledgement travels back.
+//     Sequence numbers live in device memory and are advanced by the kernels: CUDA-graph replay == eager launches.
+//   * small reductions (CG dots, the separator right-hand side of the coarse solve): ONE kernel -- store the local
+//     values into every rank's slot, flag, wait for all flags, sum the slots in rank order (identical bits on all ranks).
+//   * NCCL path (MFMGB_PEER=0, or IPC mapping failed on some rank): grouped ncclSend/ncclRecv and ncclAllReduce.
+// No kernel of a rank ever waits for something a LATER kernel of the same rank produces, and pushes never wait:
+// every wait is satisfied by work the peer issues unconditionally (no deadlock across GPUs).
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -26,6 +38,289 @@ __global__ void __launch_bounds__(256)
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i < n)
     buf[i] = v[idx[i]];
+}
+
+// ---- peer-memory primitives ------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until *flag >= want; gives up after timeout_ns and reports through *err (the host checks it at sync points)
+__device__ __forceinline__ void wait_flag(const unsigned long long *flag, unsigned long long want,
+                                          unsigned long long timeout_ns, int *err)
+{
+  if (ld_acquire_sys(flag) >= want)
+    return;
+  const unsigned long long t0 = global_timer_ns();
+  while (ld_acquire_sys(flag) < want)
+  {
+    __nanosleep(40);
+    if (global_timer_ns() - t0 > timeout_ns)
+    {
+      *err = 1;
+      __threadfence_system();
+      return;
+    }
+  }
+}
+
+struct PushArgs
+{
+  const mfmgb_halo::Link *links;
+  int n_links, nranks, rank;
+  const int32_t *send_idx; // concatenated local indices (NULL: contiguous ranges starting at send_first)
+  const double *v;
+  unsigned char *const *base; // mapped windows of all ranks
+  size_t box_off, flag_off;
+  long long box_cap;
+  unsigned long long *seq; // [0] pushes so far
+  unsigned int *done;      // [0] CTA completion counter
+};
+
+// boundary entries of v -> the neighbours' mailboxes (remote stores over NVLink), then one flag per neighbour
+__global__ void __launch_bounds__(256) halo_push_kernel(const PushArgs a)
+{
+  const unsigned long long s = a.seq[0] + 1; // (stable: only the last CTA to finish advances it)
+  const size_t slot = ((size_t)(s & 1ull) * (size_t)a.nranks + (size_t)a.rank) * (size_t)a.box_cap;
+  for (int k = 0; k < a.n_links; ++k)
+  {
+    const mfmgb_halo::Link l = a.links[k];
+    double *dst = reinterpret_cast<double *>(a.base[l.rank] + a.box_off) + slot;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < l.send_cnt; i += (long long)gridDim.x * 256)
+      dst[i] = a.send_idx ? a.v[a.send_idx[l.send_off + i]] : a.v[l.send_first + i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    const unsigned int prev = atomicAdd(&a.done[0], 1u);
+    if (prev == gridDim.x - 1)
+    {
+      a.done[0] = 0;
+      __threadfence_system();
+      for (int k = 0; k < a.n_links; ++k)
+      {
+        unsigned long long *flag = reinterpret_cast<unsigned long long *>(a.base[a.links[k].rank] + a.flag_off) +
+                                   ((s & 1ull) * (unsigned long long)a.nranks + (unsigned long long)a.rank);
+        st_release_sys(flag, s);
+      }
+      a.seq[0] = s;
+    }
+  }
+}
+
+struct WaitArgs
+{
+  const mfmgb_halo::Link *links;
+  int n_links, nranks;
+  double *v;
+  long long n_owned;
+  unsigned char *local; // this rank's window
+  size_t box_off, flag_off;
+  long long box_cap;
+  unsigned long long *seq; // [1] waits so far
+  unsigned int *done;      // [1]
+  unsigned long long timeout_ns;
+  int *err;
+};
+
+// wait for every neighbour's flag of this exchange, then mailbox -> ghost tail of v
+__global__ void __launch_bounds__(256) halo_wait_kernel(const WaitArgs a)
+{
+  const unsigned long long s = a.seq[1] + 1;
+  const size_t par = (size_t)(s & 1ull);
+  if ((int)threadIdx.x < a.n_links)
+  {
+    const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(a.local + a.flag_off) +
+                                     (par * (size_t)a.nranks + (size_t)a.links[threadIdx.x].rank);
+    wait_flag(flag, s, a.timeout_ns, a.err);
+  }
+  __syncthreads();
+  for (int k = 0; k < a.n_links; ++k)
+  {
+    const mfmgb_halo::Link l = a.links[k];
+    const double *src = reinterpret_cast<const double *>(a.local + a.box_off) +
+                        (par * (size_t)a.nranks + (size_t)l.rank) * (size_t)a.box_cap;
+    double *dst = a.v + a.n_owned + l.recv_off;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < l.recv_cnt; i += (long long)gridDim.x * 256)
+      dst[i] = __ldcg(src + i);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    __threadfence();
+    const unsigned int prev = atomicAdd(&a.done[1], 1u);
+    if (prev == gridDim.x - 1)
+    {
+      a.done[1] = 0;
+      a.seq[1] = s;
+    }
+  }
+}
+
+// one-kernel all-reduce (sum) of n <= cap doubles over all ranks through peer memory; one CTA
+__global__ void __launch_bounds__(1024)
+    peer_allreduce_kernel(double *__restrict__ buf, int n, int nranks, int rank, unsigned char *const *base,
+                          unsigned char *local, size_t ar_off, size_t flag_off, int cap, unsigned long long *seq,
+                          unsigned long long timeout_ns, int *err)
+{
+  const unsigned long long s = seq[0] + 1;
+  const size_t par = (size_t)(s & 1ull);
+  const size_t my_slot = (par * (size_t)nranks + (size_t)rank) * (size_t)cap;
+  for (int r = 0; r < nranks; ++r)
+  {
+    double *dst = reinterpret_cast<double *>(base[r] + ar_off) + my_slot;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      dst[i] = buf[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < nranks)
+    st_release_sys(reinterpret_cast<unsigned long long *>(base[threadIdx.x] + flag_off) + (par * (size_t)nranks + (size_t)rank), s);
+  if ((int)threadIdx.x < nranks)
+    wait_flag(reinterpret_cast<const unsigned long long *>(local + flag_off) + (par * (size_t)nranks + threadIdx.x), s,
+              timeout_ns, err);
+  __syncthreads();
+  const double *slots = reinterpret_cast<const double *>(local + ar_off) + par * (size_t)nranks * (size_t)cap;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+  {
+    double acc = 0.;
+    for (int r = 0; r < nranks; ++r) // fixed rank order: the same bits on every rank
+      acc += __ldcg(slots + (size_t)r * (size_t)cap + i);
+    buf[i] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    seq[0] = s;
+}
+
+int env_int(const char *name, int dflt)
+{
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+// collective max over the ranks of one 64-bit value (setup time; synchronises)
+int agree_max(mfmgb_ctx *ctx, mfmgb_comm *c, long long *value)
+{
+  long long *dev = nullptr;
+  MFMGB_CUDA(ctx, cudaMalloc(&dev, sizeof(long long)));
+  MFMGB_CUDA(ctx, cudaMemcpy(dev, value, sizeof(long long), cudaMemcpyHostToDevice));
+  MFMGB_NCCL(ctx, ncclAllReduce(dev, dev, 1, ncclInt64, ncclMax, c->nccl, c->stream));
+  MFMGB_CUDA(ctx, cudaStreamSynchronize(c->stream));
+  MFMGB_CUDA(ctx, cudaMemcpy(value, dev, sizeof(long long), cudaMemcpyDeviceToHost));
+  cudaFree(dev);
+  return MFMGB_OK;
+}
+
+// Export this rank's window, map everybody else's.  Any failure on any rank switches the whole communicator to NCCL.
+int peer_setup(mfmgb_ctx *ctx, mfmgb_comm *c)
+{
+  mfmgb_peer &p = c->peer;
+  p.enabled = false;
+  if (c->nranks < 2 || env_int("MFMGB_PEER", 1) == 0)
+    return MFMGB_OK;
+  p.bytes = (size_t)std::max(8, env_int("MFMGB_PEER_WINDOW_MB", 96)) << 20;
+  p.timeout_ns = (unsigned long long)std::max(1, env_int("MFMGB_PEER_TIMEOUT_MS", 20000)) * 1000000ull;
+  long long ok = 1;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (cudaMalloc(&p.local, p.bytes) != cudaSuccess || cudaMemset(p.local, 0, p.bytes) != cudaSuccess ||
+      cudaIpcGetMemHandle(&mine, p.local) != cudaSuccess)
+    ok = 0;
+  cudaGetLastError();
+  cudaDeviceSynchronize();
+  // all-gather the 64-byte handles with NCCL (device staging)
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+  std::vector<cudaIpcMemHandle_t> all((size_t)c->nranks);
+  char *dsend = nullptr, *dall = nullptr;
+  MFMGB_CUDA(ctx, cudaMalloc(&dsend, 64));
+  MFMGB_CUDA(ctx, cudaMalloc(&dall, 64 * (size_t)c->nranks));
+  MFMGB_CUDA(ctx, cudaMemcpy(dsend, &mine, 64, cudaMemcpyHostToDevice));
+  MFMGB_NCCL(ctx, ncclAllGather(dsend, dall, 64, ncclChar, c->nccl, c->stream));
+  MFMGB_CUDA(ctx, cudaStreamSynchronize(c->stream));
+  MFMGB_CUDA(ctx, cudaMemcpy(all.data(), dall, 64 * (size_t)c->nranks, cudaMemcpyDeviceToHost));
+  cudaFree(dsend);
+  cudaFree(dall);
+  long long all_ok = -ok; // max of -ok == -(min of ok)
+  MFMGB_CHECK(agree_max(ctx, c, &all_ok));
+  p.base.assign((size_t)c->nranks, nullptr);
+  if (all_ok == -1)
+  {
+    for (int r = 0; r < c->nranks && ok; ++r)
+    {
+      if (r == c->rank)
+      {
+        p.base[(size_t)r] = p.local;
+        continue;
+      }
+      void *mapped = nullptr;
+      if (cudaIpcOpenMemHandle(&mapped, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+      {
+        cudaGetLastError();
+        ok = 0;
+      }
+      p.base[(size_t)r] = static_cast<unsigned char *>(mapped);
+    }
+    all_ok = -ok;
+    MFMGB_CHECK(agree_max(ctx, c, &all_ok));
+  }
+  if (all_ok != -1)
+  {
+    for (int r = 0; r < c->nranks; ++r)
+      if (r != c->rank && p.base[(size_t)r])
+        cudaIpcCloseMemHandle(p.base[(size_t)r]);
+    cudaFree(p.local);
+    p.local = nullptr;
+    p.base.clear();
+    return MFMGB_OK; // NCCL transport
+  }
+  MFMGB_CUDA(ctx, cudaMalloc(&p.base_dev, sizeof(unsigned char *) * (size_t)c->nranks));
+  MFMGB_CUDA(ctx, cudaMemcpy(p.base_dev, p.base.data(), sizeof(unsigned char *) * (size_t)c->nranks,
+                             cudaMemcpyHostToDevice));
+  MFMGB_CUDA(ctx, cudaHostAlloc(&p.err_host, sizeof(int), cudaHostAllocMapped));
+  *p.err_host = 0;
+  MFMGB_CUDA(ctx, cudaHostGetDevicePointer(&p.err_dev, p.err_host, 0));
+  MFMGB_CUDA(ctx, cudaMalloc(&p.ar_seq, sizeof(unsigned long long)));
+  MFMGB_CUDA(ctx, cudaMemset(p.ar_seq, 0, sizeof(unsigned long long)));
+  p.enabled = true;
+  // the small all-reduce channel
+  p.ar_cap = std::max(64, env_int("MFMGB_PEER_ALLREDUCE_CAP", 8192));
+  size_t off = 0;
+  MFMGB_CHECK(peer_alloc(ctx, (size_t)2 * (size_t)c->nranks * (size_t)p.ar_cap * sizeof(double), &off));
+  p.ar_off = off;
+  MFMGB_CHECK(peer_alloc(ctx, (size_t)2 * (size_t)c->nranks * sizeof(unsigned long long), &off));
+  p.ar_flag_off = off;
+  MFMGB_CUDA(ctx, cudaDeviceSynchronize());
+  return MFMGB_OK;
+}
+
+void peer_teardown(mfmgb_comm *c)
+{
+  mfmgb_peer &p = c->peer;
+  if (!p.local)
+    return;
+  for (int r = 0; r < c->nranks; ++r)
+    if (r != c->rank && r < (int)p.base.size() && p.base[(size_t)r])
+      cudaIpcCloseMemHandle(p.base[(size_t)r]);
+  cudaFree(p.local);
+  cudaFree(p.base_dev);
+  cudaFree(p.ar_seq);
+  if (p.err_host)
+    cudaFreeHost(p.err_host);
+  p = mfmgb_peer();
 }
 } // namespace
 
