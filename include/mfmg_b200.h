@@ -215,11 +215,19 @@ extern "C"
   MFMGB_API int mfmgb_comm_unique_id(char *out128);
   MFMGB_API int mfmgb_comm_init(mfmgb_ctx *ctx, const char *id128, int nranks, int rank);
   MFMGB_API int mfmgb_comm_finalize(mfmgb_ctx *ctx);
+  /* how ghost entries and small reductions travel: NVLink peer-memory stores by the library's own kernels (CUDA IPC
+   * window mapped at mfmgb_comm_init; MFMGB_PEER=0 switches it off) or NCCL */
+  MFMGB_API const char *mfmgb_comm_transport(mfmgb_ctx *ctx);
+  /* MFMGB_ERR_NCCL when a kernel of this context gave up waiting for a peer GPU (MFMGB_PEER_TIMEOUT_MS, default 20 s);
+   * call after mfmgb_ctx_synchronize */
+  MFMGB_API int mfmgb_comm_check(mfmgb_ctx *ctx);
   MFMGB_API int mfmgb_comm_rank(mfmgb_ctx *ctx);
   MFMGB_API int mfmgb_comm_size(mfmgb_ctx *ctx);
   /* Halo plan of a row-partitioned level.  Vectors that are gathered from have n_owned + n_ghost entries; the ghost
    * tail is ordered by neighbour (neighbor_ranks order, recv_counts entries each).  send_indices: concatenated LOCAL
-   * owned indices sent to each neighbour (send_counts each), in the order the receiver stores them. */
+   * owned indices sent to each neighbour (send_counts each), in the order the receiver stores them.
+   * COLLECTIVE when the context has an initialised communicator (the peer-memory mailboxes are allocated symmetrically:
+   * every rank creates its plans in the same order). */
   MFMGB_API int mfmgb_halo_create(mfmgb_ctx *ctx, int64_t n_owned, int64_t n_ghost, int n_neighbors,
                                   const int *neighbor_ranks, const int64_t *send_counts, const int32_t *send_indices,
                                   const int64_t *recv_counts, mfmgb_halo **out);

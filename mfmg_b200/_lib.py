@@ -114,6 +114,8 @@ SIGNATURES = {
     "mfmgb_comm_unique_id": (_int, [ctypes.c_char_p]),
     "mfmgb_comm_init": (_int, [_vp, ctypes.c_char_p, _int, _int]),
     "mfmgb_comm_finalize": (_int, [_vp]),
+    "mfmgb_comm_transport": (ctypes.c_char_p, [_vp]),
+    "mfmgb_comm_check": (_int, [_vp]),
     "mfmgb_comm_rank": (_int, [_vp]),
     "mfmgb_comm_size": (_int, [_vp]),
     "mfmgb_halo_create": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _pp]),

@@ -133,7 +133,7 @@ int coarse_dd_solve_async(mfmgb_ctx *ctx, const mfmgb_coarse_dd *d, const double
                                                                    d->own_sep_begin, d->own_sep_n, d->g, d->sep_index,
                                                                    b_c, g_below, d->n_adj - d->own_sep_n, d->t);
     MFMGB_LAUNCHED(ctx);
-    MFMGB_NCCL(ctx, ncclAllReduce(d->t, d->t, (size_t)d->n_S, ncclDouble, ncclSum, c->nccl, st));
+    MFMGB_CHECK(allreduce_sum(ctx, d->t, (int)d->n_S)); // one kernel over peer memory (NCCL when the window is off)
     // x_S = Schur^-1 t (replicated)
     MFMGB_CHECK(dense_solve_async(ctx, d->D_S, d->t, d->xs));
     dd_scatter_kernel<<<(unsigned)ceil_div(d->n_S, 256), 256, 0, st>>>(d->n_S, d->sep_index, d->xs, x_c);

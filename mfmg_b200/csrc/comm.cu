@@ -16,6 +16,7 @@
 //   * NCCL path (MFMGB_PEER=0, or IPC mapping failed on some rank): grouped ncclSend/ncclRecv and ncclAllReduce.
 // No kernel of a rank ever waits for something a LATER kernel of the same rank produces, and pushes never wait:
 // every wait is satisfied by work the peer issues unconditionally (no deadlock across GPUs).
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -332,6 +333,27 @@ mfmgb_comm *ctx_comm(mfmgb_ctx *ctx)
   return it == registry().end() ? nullptr : it->second;
 }
 
+int peer_alloc(mfmgb_ctx *ctx, size_t bytes, size_t *offset)
+{
+  *offset = (size_t)-1;
+  mfmgb_comm *c = ctx_comm(ctx);
+  if (!c || !c->peer.local)
+    return MFMGB_OK;
+  long long agreed = (long long)((bytes + 255) & ~(size_t)255);
+  MFMGB_CHECK(agree_max(ctx, c, &agreed));
+  if (c->peer.used + (size_t)agreed > c->peer.bytes)
+    return MFMGB_OK; // full: the caller falls back to NCCL (every rank takes the same decision)
+  *offset = c->peer.used;
+  c->peer.used += (size_t)agreed;
+  return MFMGB_OK;
+}
+
+int peer_error(mfmgb_ctx *ctx)
+{
+  mfmgb_comm *c = ctx_comm(ctx);
+  return c && c->peer.err_host ? *c->peer.err_host : 0;
+}
+
 int halo_start(mfmgb_ctx *ctx, const mfmgb_halo *h, double *v)
 {
   mfmgb_comm *c = ctx_comm(ctx);
@@ -339,6 +361,32 @@ int halo_start(mfmgb_ctx *ctx, const mfmgb_halo *h, double *v)
     return fail(ctx, MFMGB_ERR_INVALID, "halo exchange requested but mfmgb_comm_init was not called");
   MFMGB_CUDA(ctx, cudaEventRecord(c->ev_ready, ctx->stream));
   MFMGB_CUDA(ctx, cudaStreamWaitEvent(c->stream, c->ev_ready, 0));
+  if (h->peer)
+  {
+    // our own kernel stores the boundary entries into the neighbours' mailboxes over NVLink and raises their flags
+    PushArgs a;
+    a.links = h->links;
+    a.n_links = h->n_neighbors;
+    a.nranks = c->nranks;
+    a.rank = c->rank;
+    a.send_idx = h->contiguous ? nullptr : h->send_idx;
+    a.v = v;
+    a.base = c->peer.base_dev;
+    a.box_off = h->box_off;
+    a.flag_off = h->flag_off;
+    a.box_cap = (long long)h->box_cap;
+    a.seq = h->seq;
+    a.done = h->done;
+    int64_t widest = 1;
+    for (int k = 0; k < h->n_neighbors; ++k)
+      widest = std::max(widest, h->send_cnt[k]);
+    const unsigned grid = (unsigned)std::min<int64_t>(32, ceil_div(widest, 256 * 4));
+    halo_push_kernel<<<grid, 256, 0, c->stream>>>(a);
+    ctx->launches++;
+    MFMGB_CUDA(ctx, cudaGetLastError());
+    MFMGB_CUDA(ctx, cudaEventRecord(c->ev_done, c->stream));
+    return MFMGB_OK;
+  }
   if (!h->contiguous && h->n_send > 0)
   {
     pack_kernel<<<(unsigned)ceil_div(h->n_send, 256), 256, 0, c->stream>>>(h->n_send, h->send_idx, v, h->sendbuf);
@@ -362,18 +410,52 @@ int halo_start(mfmgb_ctx *ctx, const mfmgb_halo *h, double *v)
   return MFMGB_OK;
 }
 
-int halo_wait(mfmgb_ctx *ctx)
+int halo_wait(mfmgb_ctx *ctx, const mfmgb_halo *h, double *v)
 {
   mfmgb_comm *c = ctx_comm(ctx);
+  // (peer path too: the push kernel reads v; later kernels of the compute stream may overwrite it)
   MFMGB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, c->ev_done, 0));
+  if (!h->peer)
+    return MFMGB_OK;
+  WaitArgs a;
+  a.links = h->links;
+  a.n_links = h->n_neighbors;
+  a.nranks = c->nranks;
+  a.v = v;
+  a.n_owned = (long long)h->n_owned;
+  a.local = c->peer.local;
+  a.box_off = h->box_off;
+  a.flag_off = h->flag_off;
+  a.box_cap = (long long)h->box_cap;
+  a.seq = h->seq;
+  a.done = h->done;
+  a.timeout_ns = c->peer.timeout_ns;
+  a.err = c->peer.err_dev;
+  int64_t widest = 1;
+  for (int k = 0; k < h->n_neighbors; ++k)
+    widest = std::max(widest, h->recv_cnt[k]);
+  const unsigned grid = (unsigned)std::min<int64_t>(32, ceil_div(widest, 256 * 4));
+  halo_wait_kernel<<<grid, 256, 0, ctx->stream>>>(a);
+  ctx->launches++;
+  MFMGB_CUDA(ctx, cudaGetLastError());
   return MFMGB_OK;
 }
 
 int allreduce_sum(mfmgb_ctx *ctx, double *dev, int n)
 {
   mfmgb_comm *c = ctx_comm(ctx);
-  if (!c || c->nranks == 1)
+  if (!c || c->nranks == 1 || n <= 0)
     return MFMGB_OK;
+  const mfmgb_peer &p = c->peer;
+  if (p.enabled && n <= p.ar_cap)
+  {
+    const int threads = n >= 1024 ? 1024 : std::max(32, ((std::max(n, c->nranks) + 31) / 32) * 32);
+    peer_allreduce_kernel<<<1, threads, 0, ctx->stream>>>(dev, n, c->nranks, c->rank, p.base_dev, p.local, p.ar_off,
+                                                         p.ar_flag_off, p.ar_cap, p.ar_seq, p.timeout_ns, p.err_dev);
+    ctx->launches++;
+    MFMGB_CUDA(ctx, cudaGetLastError());
+    return MFMGB_OK;
+  }
   MFMGB_NCCL(ctx, ncclAllReduce(dev, dev, (size_t)n, ncclDouble, ncclSum, c->nccl, ctx->stream));
   return MFMGB_OK;
 }
@@ -433,10 +515,16 @@ extern "C"
     ncclUniqueId id;
     memcpy(&id, id128, 128);
     MFMGB_NCCL(ctx, ncclCommInitRank(&c->nccl, nranks, id, rank));
-    MFMGB_CUDA(ctx, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // the communication stream has the highest priority: its few CTAs (push kernels) are scheduled ahead of the
+    // persistent CTAs of the interior-row kernel launched at the same time on the compute stream
+    int prio_least = 0, prio_greatest = 0;
+    MFMGB_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    MFMGB_CUDA(ctx, cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
     MFMGB_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
     MFMGB_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
     registry()[ctx] = c;
+    if (nranks > 1)
+      MFMGB_CHECK(peer_setup(ctx, c)); // collective; leaves c->peer.enabled == false when CUDA IPC is unavailable
     return MFMGB_OK;
   }
 
@@ -449,12 +537,31 @@ extern "C"
     cudaStreamSynchronize(c->stream);
     for (auto &o : ctx->graph_owners) // captured V-cycles reference the communicator
       o.second(o.first);
+    peer_teardown(c);
     ncclCommDestroy(c->nccl);
     cudaEventDestroy(c->ev_ready);
     cudaEventDestroy(c->ev_done);
     cudaStreamDestroy(c->stream);
     registry().erase(ctx);
     delete c;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API const char *mfmgb_comm_transport(mfmgb_ctx *ctx)
+  {
+    mfmgb_comm *c = ctx_comm(ctx);
+    if (!c || c->nranks < 2)
+      return "none (single GPU)";
+    return c->peer.enabled ? "NVLink peer-memory stores by our own kernels (CUDA IPC window, flag-synchronised)"
+                           : "NCCL send/recv + all-reduce";
+  }
+
+  MFMGB_API int mfmgb_comm_check(mfmgb_ctx *ctx)
+  {
+    MFMGB_REQUIRE(ctx, ctx, "ctx is NULL");
+    if (peer_error(ctx))
+      return fail(ctx, MFMGB_ERR_NCCL, "a kernel gave up waiting for a peer GPU (MFMGB_PEER_TIMEOUT_MS): the ranks do "
+                                       "not execute the same sequence of exchanges, or a peer died");
     return MFMGB_OK;
   }
 
@@ -517,6 +624,39 @@ extern "C"
       MFMGB_CUDA(ctx, cudaMemcpy(h->send_idx, send_indices, sizeof(int32_t) * (size_t)so, cudaMemcpyHostToDevice));
       MFMGB_CUDA(ctx, cudaMalloc(&h->sendbuf, sizeof(double) * (size_t)so));
     }
+    // peer-memory mailboxes (collective when the communicator has a mapped window: every rank creates its plans in
+    // the same order)
+    mfmgb_comm *c = ctx_comm(ctx);
+    if (c && c->peer.enabled)
+    {
+      int64_t cap = 1;
+      for (int k = 0; k < n_neighbors; ++k)
+        cap = std::max(cap, std::max(send_counts[k], recv_counts[k]));
+      long long agreed_cap = (long long)((cap + 31) & ~(int64_t)31);
+      MFMGB_CHECK(agree_max(ctx, c, &agreed_cap));
+      size_t box = 0, flag = 0;
+      MFMGB_CHECK(peer_alloc(ctx, (size_t)2 * (size_t)c->nranks * (size_t)agreed_cap * sizeof(double), &box));
+      if (box != (size_t)-1)
+        MFMGB_CHECK(peer_alloc(ctx, (size_t)2 * (size_t)c->nranks * sizeof(unsigned long long), &flag));
+      if (box != (size_t)-1 && flag != (size_t)-1)
+      {
+        h->peer = true;
+        h->box_off = box;
+        h->flag_off = flag;
+        h->box_cap = agreed_cap;
+        std::vector<mfmgb_halo::Link> links((size_t)std::max(n_neighbors, 1));
+        for (int k = 0; k < n_neighbors; ++k)
+          links[(size_t)k] = {h->ranks[(size_t)k], (long long)h->send_off[(size_t)k], (long long)h->send_cnt[(size_t)k],
+                              (long long)h->send_first[(size_t)k], (long long)h->recv_off[(size_t)k],
+                              (long long)h->recv_cnt[(size_t)k]};
+        MFMGB_CUDA(ctx, cudaMalloc(&h->links, sizeof(mfmgb_halo::Link) * links.size()));
+        MFMGB_CUDA(ctx, cudaMemcpy(h->links, links.data(), sizeof(mfmgb_halo::Link) * links.size(), cudaMemcpyHostToDevice));
+        MFMGB_CUDA(ctx, cudaMalloc(&h->seq, sizeof(unsigned long long) * 2));
+        MFMGB_CUDA(ctx, cudaMemset(h->seq, 0, sizeof(unsigned long long) * 2));
+        MFMGB_CUDA(ctx, cudaMalloc(&h->done, sizeof(unsigned int) * 2));
+        MFMGB_CUDA(ctx, cudaMemset(h->done, 0, sizeof(unsigned int) * 2));
+      }
+    }
     *out = h;
     return MFMGB_OK;
   }
@@ -529,6 +669,9 @@ extern "C"
     MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(h->send_idx);
     cudaFree(h->sendbuf);
+    cudaFree(h->links);
+    cudaFree(h->seq);
+    cudaFree(h->done);
     delete h;
     return MFMGB_OK;
   }
@@ -537,7 +680,7 @@ extern "C"
   {
     MFMGB_REQUIRE(ctx, ctx && h && v, "mfmgb_halo_exchange: bad arguments");
     MFMGB_CHECK(halo_start(ctx, h, v));
-    return halo_wait(ctx);
+    return halo_wait(ctx, h, v);
   }
 
   MFMGB_API int mfmgb_allreduce_sum(mfmgb_ctx *ctx, double *dev, int n)

@@ -81,7 +81,7 @@ extern "C"
   {
     MFMGB_REQUIRE(ctx, ctx, "ctx is NULL");
     MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return MFMGB_OK;
+    return mfmgb_comm_check(ctx); // a kernel that gave up waiting for a peer GPU is reported here
   }
 
   MFMGB_API void *mfmgb_ctx_stream(mfmgb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }

@@ -97,7 +97,7 @@ int level_apply_A(mfmgb_ctx *ctx, const mfmgb_level &l, double *x, Epi epi, cons
       MFMGB_CHECK(halo_start(ctx, l.halo, x));
       if (nc >= 3)
         MFMGB_CHECK(mf_apply_chunks(ctx, l.M, x, epi, e, 1, nc - 1));
-      MFMGB_CHECK(halo_wait(ctx));
+      MFMGB_CHECK(halo_wait(ctx, l.halo, x));
       if (nc < 3)
         return mf_apply(ctx, l.M, x, epi, e);
       MFMGB_CHECK(mf_apply_chunks(ctx, l.M, x, epi, e, 0, 1));
@@ -117,11 +117,11 @@ int level_apply_A(mfmgb_ctx *ctx, const mfmgb_level &l, double *x, Epi epi, cons
   MFMGB_CHECK(halo_start(ctx, l.halo, x));
   if (!overlap)
   {
-    MFMGB_CHECK(halo_wait(ctx));
+    MFMGB_CHECK(halo_wait(ctx, l.halo, x));
     return csr_apply(ctx, l.A, x, epi, e);
   }
   MFMGB_CHECK(csr_apply(ctx, l.A, x, epi, e, l.blo, l.bhi));
-  MFMGB_CHECK(halo_wait(ctx));
+  MFMGB_CHECK(halo_wait(ctx, l.halo, x));
   return csr_apply2(ctx, l.A, x, epi, e, 0, l.blo, l.bhi, l.n); // both boundary blocks in one launch
 }
 
@@ -200,7 +200,7 @@ int apply_level(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, 
     e.y = coarse.bc + H->coarse_offsets[c->rank];
     if (coarse.r_split > 0)
       MFMGB_CHECK(csr_apply(ctx, coarse.R, fine.res, Epi::Spmv, e, 0, coarse.r_split));
-    MFMGB_CHECK(halo_wait(ctx));
+    MFMGB_CHECK(halo_wait(ctx, fine.halo, fine.res));
     if (coarse.r_split < coarse.R->n_rows)
       MFMGB_CHECK(csr_apply(ctx, coarse.R, fine.res, Epi::Spmv, e, coarse.r_split, coarse.R->n_rows));
     if (!H->dd) // (the domain-decomposed coarse solve reads only this rank's slice)
@@ -664,7 +664,7 @@ extern "C"
     MFMGB_CHECK(run_vcycle(ctx, H, H->b_dev, H->x_dev));
     MFMGB_CUDA(ctx, cudaMemcpyAsync(x_host, H->x_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return MFMGB_OK;
+    return mfmgb_comm_check(ctx);
   }
 
   MFMGB_API int mfmgb_pcg(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const mfmgb_csr *A, const double *b, double *x, double tol,
@@ -764,6 +764,7 @@ extern "C"
         PCG_TRY(allreduce_sum(ctx, scal + 3, 1));
         PCG_CUDA(cudaMemcpyAsync(sh, scal + 3, sizeof(double), cudaMemcpyDeviceToHost, st));
         PCG_CUDA(cudaStreamSynchronize(st));
+        PCG_TRY(mfmgb_comm_check(ctx));
         res = std::sqrt(sh[0]);
         if (res_hist_host)
           res_hist_host[it] = res;

@@ -26,6 +26,21 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     handle = d.CudaHandle(local)
     handle.init_comm_from_torch()
+    transport = handle.lib.mfmgb_comm_transport(handle.ctx).decode()
+    if rank == 0:
+        print(f"transport: {transport}", flush=True)
+    want_peer = os.environ.get("MFMGB_PEER", "1") != "0"
+    assert ("peer-memory" in transport) == want_peer, transport
+    # small all-reduce through peer memory (or NCCL): exact integer sums, back to back without synchronisation
+    tri = world * (world + 1) // 2
+    for n in (1, 3, 100, 5000, 9000):      # 9000 > the peer slot capacity: NCCL serves it
+        pattern = (np.arange(n) % 13).astype(np.float64)
+        vecs = [d.DeviceVector.from_host(handle, (rank + 1) * pattern * (k + 1)) for k in range(12)]
+        for v in vecs:
+            d.check(handle.ctx, handle.lib.mfmgb_allreduce_sum(handle.ctx, v.ptr, n))
+        handle.synchronize()
+        for k, v in enumerate(vecs):
+            assert np.array_equal(v.to_host(), tri * pattern * (k + 1)), (rank, "allreduce", n, k)
     cases = [(3, 1, 16, 2, 2, "constant", 1), (3, 1, 24, 4, 1, "discontinuous", 2), (3, 2, 8, 2, 2, "linear", 1),
              (2, 1, 64, 2, 2, "constant", 1)]
     # second pass: force the row-split (multi-GPU) dense coarse solve, which is normally used from n_c = 8192 on
@@ -60,7 +75,7 @@ def main():
         if os.environ.get("MFMGB_DIST_GRAPH", "1") != "0":
             x_eager = x.to_host()[:part.n_owned].copy()
             H.use_graph(True)
-            for _ in range(3):
+            for _ in range(40):     # back to back, no host synchronisation: ranks may run ahead of each other
                 H.vmult(x, b)
             assert np.array_equal(x.to_host()[:part.n_owned], x_eager), (rank, "graph replay")
             H.use_graph(False)
@@ -72,6 +87,19 @@ def main():
         H.halo.exchange(v)
         handle.synchronize()
         assert np.array_equal(v.to_host()[part.n_owned:], b_h[part.ghost_global]), (rank, "halo")
+        # many exchanges of different vectors in flight (mailbox parity / sequence flags), checked afterwards
+        vs = []
+        for k in range(9):
+            w = H.build_vector()
+            wl = np.zeros(H.vector_size)
+            wl[:part.n_owned] = b_h[sl] * (k + 2)
+            w.upload(wl)
+            vs.append(w)
+        for w in vs:
+            H.halo.exchange(w)
+        handle.synchronize()
+        for k, w in enumerate(vs):
+            assert np.array_equal(w.to_host()[part.n_owned:], b_h[part.ghost_global] * (k + 2)), (rank, "halo burst", k)
         # PCG: equal iteration counts, residual history within 1e-10 (north star)
         x0 = oracle.std_uniform01(P.n, skip=P.constrained)
         x_o, it_ref, hist_ref = Ho.pcg(np.zeros(P.n), x0, 1e-8, 500)

@@ -15,19 +15,21 @@ def _n_gpus():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kernel", ["auto", "tile"])
+@pytest.mark.parametrize("kernel,transport", [("auto", "peer"), ("tile", "peer"), ("auto", "nccl")])
 @pytest.mark.parametrize("world", [2, 4])
-def test_partitioned_hierarchy_on_gpus(world, kernel):
+def test_partitioned_hierarchy_on_gpus(world, kernel, transport):
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world),
            os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
-    env = dict(os.environ, MFMGB_CSR_KERNEL=kernel)  # "tile": interior/boundary row ranges through csr_tile.cu
+    # "tile": interior/boundary row ranges through csr_tile.cu; "peer": ghost entries and small reductions stored
+    # into peer memory over NVLink by our own kernels, "nccl": the NCCL send/recv + all-reduce path
+    env = dict(os.environ, MFMGB_CSR_KERNEL=kernel, MFMGB_PEER="1" if transport == "peer" else "0")
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, env=env)
     out_dir = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(out_dir):   # keep the worker's log as evidence (copied to profiles/ by the builder)
-        with open(os.path.join(out_dir, f"multi_gpu_parity_w{world}_{kernel}.log"), "w") as f:
+        with open(os.path.join(out_dir, f"multi_gpu_parity_w{world}_{kernel}_{transport}.log"), "w") as f:
             f.write(res.stdout)
     assert res.returncode == 0, res.stdout[-4000:]
     for r in range(world):
