@@ -523,6 +523,17 @@ def measure(args, d, handle, stream, H, dist, rank, world, local_rank, n_local, 
             for k, v in H.profile(x, b).items():
                 stages[k] += v / n_prof
 
+        # the same cycle resolved per kernel group, timed INSIDE a CUDA-graph replay (event-record nodes); rank 0's view
+        n_tl = 5
+        timeline = None
+        for _ in range(n_tl):
+            barrier()
+            tl = H.timeline(x, b, graph=not args.no_graph)
+            if timeline is None:
+                timeline = [[name, 0.0] for name, _ in tl]
+            for k, (_, v) in enumerate(tl):
+                timeline[k][1] += v / n_tl
+
         # plain SpMV y = A x (the BASELINE's "SpMV HBM GB/s")
         Ad = H.operators[0]
         y = d.DeviceVector(handle, n_local)
@@ -562,6 +573,7 @@ def measure(args, d, handle, stream, H, dist, rank, world, local_rank, n_local, 
     reps = vals[2:2 + len(reps)]
     stages = dict(zip(d.Hierarchy.STAGES, vals[2 + len(reps):]))
     res.update(ms_per_step=ms_total / K, e2e_ms=e2e_ms, reps=reps, stages=stages, spmv_ms=spmv_ms, clocks=clocks,
+               timeline=timeline,
                launches=int(launches), checksum=checksum, K=K, W=W)
     return res
 
@@ -578,7 +590,7 @@ def build_ours(args, d, handle, dist, rank, world):
             M = d.MatrixFreeLaplaceDevice(handle, 3, args.degree, P.cells, P.h, P.coef_per_q(), P.constrained)
             H = d.Hierarchy(handle, [M, d.SparseMatrixDevice.from_host(handle, Ac)],
                             [d.SparseMatrixDevice.from_host(handle, R)], {"is preconditioner": True})
-            mf_nq = 1 if "per-cell" in M.kernel else (args.degree + 1) ** 3
+            mf_nq = 0 if "stencil" in M.kernel else (1 if "per-cell" in M.kernel else (args.degree + 1) ** 3)
             nbytes = algorithmic_bytes(P, R, Ac, int(np.prod(P.cells)), mf_nq)
         else:
             H = d.Hierarchy.from_host(handle, P.A, R, Ac, {"is preconditioner": True})
@@ -623,7 +635,8 @@ def build_ours(args, d, handle, dist, rank, world):
     Acl.n_rows = part.Ac.n_rows
     if args.matrix_free:
         M = H.operators[0]
-        nbytes = algorithmic_bytes(Pl, Rl, Acl, int(np.prod(part.mf["cells"])), 1 if "per-cell" in M.kernel else 8)
+        nbytes = algorithmic_bytes(Pl, Rl, Acl, int(np.prod(part.mf["cells"])),
+                                   0 if "stencil" in M.kernel else (1 if "per-cell" in M.kernel else 8))
     else:
         nbytes = algorithmic_bytes(Pl, Rl, Acl)
     if H.coarse_dd is not None:   # per-GPU bytes of the domain-decomposed coarse solve instead of 8 n_c^2
@@ -728,6 +741,7 @@ def assemble_line(args, d, H, info, m, world, units):
                  "frac_of_measured_peak": nbytes["spmv"] / (m["spmv_ms"] * 1e-3) / 1e9 / peak,
                  "frac_of_nominal_8TBs": nbytes["spmv"] / (m["spmv_ms"] * 1e-3) / 1e9 / 8000.0},
         "stage_ms": stages,
+        "timeline_in_graph_ms": [[name, round(v, 5)] for name, v in (m.get("timeline") or [])],
         "stage_gbs": {"residual": nbytes["resid"] / (stages["residual"] * 1e-3) / 1e9,
                       "restrict": nbytes["restrict"] / (stages["restrict"] * 1e-3) / 1e9,
                       "coarse": nbytes["dense"] / (stages["coarse"] * 1e-3) / 1e9,

@@ -161,7 +161,8 @@ extern "C"
   MFMGB_API int64_t mfmgb_mf_size(const mfmgb_mf *M);        /* rows = owned nodes */
   MFMGB_API int64_t mfmgb_mf_vector_size(const mfmgb_mf *M); /* owned + ghost nodes */
   /* which kernel serves the operator: 0 = generic colour-phase cell kernel (2D, Q2), 1 = 3D Q1 node-owner z-sweep with a
-   * per-cell coefficient, 2 = the same with the per-quadrature-point table */
+   * per-cell coefficient, 2 = the same with the per-quadrature-point table, 3 = 3D Q1 with ONE coefficient for the whole
+   * grid: factorised 27-point stencil, persistent z-sweep (csrc/mf_q1_sweep.cuh) */
   MFMGB_API int mfmgb_mf_kernel(const mfmgb_mf *M);
   MFMGB_API int mfmgb_mf_apply(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, double *y);
   /* diagonal with constrained entries set to 1 (compute_diagonal) into a device vector */
@@ -192,6 +193,12 @@ extern "C"
    * stage_ms[6] = pre-smoothing, residual, restriction, coarse levels (recursion), prolongation+correction,
    * post-smoothing -- the "Apply: fine levels" / "Apply: coarsest level" timer sections of hierarchy.hpp:263,271. */
   MFMGB_API int mfmgb_vcycle_profile(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, double *stage_ms);
+  /* finer timeline of one V-cycle: CUDA events between the pieces of the cycle (stages, interior / boundary rows of a
+   * partitioned level, the steps of the coarse solve).  use_graph = 1: the events are captured as event-record nodes and
+   * the times are those of a CUDA-graph REPLAY (what mfmgb_vcycle runs).  names: ';'-separated piece names, ms[k] =
+   * duration of piece k.  (The "Apply: ..." timer sections of hierarchy.hpp:263,271, resolved per kernel.) */
+  MFMGB_API int mfmgb_vcycle_timeline(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, int use_graph,
+                                      char *names, int names_len, double *ms, int max_marks, int *n_marks);
   /* capture the V-cycle into a CUDA graph and replay it on later mfmgb_vcycle calls (1 = on) */
   MFMGB_API int mfmgb_hierarchy_use_graph(mfmgb_hierarchy *H, int on);
   /* kernels launched by one V-cycle of this hierarchy */

@@ -22,6 +22,7 @@
 
 #include "comm.cuh"
 #include "dense.cuh"
+#include "peer.cuh"
 
 using namespace mfmgb;
 
@@ -42,32 +43,83 @@ struct mfmgb_coarse_dd
 
 namespace
 {
-// t[k] = (k adjacent ? -g[k - adj_begin] : 0) + (k in own separator ? b_c[sep_index[k]] : 0)
-//        + (k in the separator below ? g_below[k - adj_begin] : 0)   [this rank's share of R r on those rows]
-__global__ void __launch_bounds__(256) dd_rhs_kernel(int64_t n_S, int64_t adj_begin, int64_t n_adj, int64_t own_begin,
-                                                     int64_t own_n, const double *__restrict__ g,
-                                                     const int32_t *__restrict__ sep_index,
-                                                     const double *__restrict__ b_c, const double *__restrict__ g_below,
-                                                     int64_t n_below, double *__restrict__ t)
+struct DdRhsArgs
 {
-  const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (k >= n_S)
-    return;
+  int64_t n_S, adj_begin, n_adj, own_begin, own_n, n_below;
+  const void *si_rowptr; // A_SI (n_adj x n_I), CSR
+  const int *si_col;
+  const double *si_val;
+  const double *y;       // A_II^-1 b_I
+  const int32_t *sep_index;
+  const double *b_c, *g_below;
+  double *t;
+};
+
+// this rank's contribution to the separator right-hand side:
+// t[k] = (k adjacent ? -(A_SI y)[k - adj_begin] : 0) + (k in own separator ? b_c[sep_index[k]] : 0)
+//        + (k in the separator below ? g_below[k - adj_begin] : 0)   [this rank's share of R r on those rows]
+template <typename OffT>
+__device__ __forceinline__ double dd_rhs_value(const DdRhsArgs &a, int64_t k)
+{
   double v = 0.;
-  if (k >= adj_begin && k < adj_begin + n_adj)
-    v = -g[k - adj_begin];
-  if (k >= own_begin && k < own_begin + own_n)
-    v += b_c[sep_index[k]];
-  if (g_below && k >= adj_begin && k < adj_begin + n_below)
-    v += g_below[k - adj_begin];
-  t[k] = v;
+  if (k >= a.adj_begin && k < a.adj_begin + a.n_adj)
+  {
+    const OffT *rp = static_cast<const OffT *>(a.si_rowptr);
+    const int64_t r = k - a.adj_begin;
+    double s0 = 0., s1 = 0.;
+    OffT j = rp[r];
+    const OffT je = rp[r + 1];
+    for (; j + 1 < je; j += 2)
+    {
+      s0 = fma(a.si_val[j], a.y[a.si_col[j]], s0);
+      s1 = fma(a.si_val[j + 1], a.y[a.si_col[j + 1]], s1);
+    }
+    if (j < je)
+      s0 = fma(a.si_val[j], a.y[a.si_col[j]], s0);
+    v = -(s0 + s1);
+  }
+  if (k >= a.own_begin && k < a.own_begin + a.own_n)
+    v += a.b_c[a.sep_index[k]];
+  if (a.g_below && k >= a.adj_begin && k < a.adj_begin + a.n_below)
+    v += a.g_below[k - a.adj_begin];
+  return v;
 }
 
-// x_I[i] = y[i] - sum_j E[i][j] xs[j]   (one warp per row, fixed shuffle tree)
-__global__ void __launch_bounds__(256) dd_interior_kernel(int64_t n_I, int64_t n_adj, const double *__restrict__ E,
-                                                          int64_t ldE, const double *__restrict__ xs,
-                                                          const double *__restrict__ y, double *__restrict__ x_I)
+// ONE CTA: the local contributions, then the sum over the ranks through NVLink peer memory (peer.cuh) -- the SpMV with
+// A_SI, the right-hand-side assembly and the all-reduce of the reference solve's Schur step in a single launch
+template <typename OffT>
+__global__ void __launch_bounds__(1024) dd_rhs_allreduce_kernel(const DdRhsArgs a, const PeerAllreduceArgs pa)
 {
+  for (int64_t k = threadIdx.x; k < a.n_S; k += blockDim.x)
+    a.t[k] = dd_rhs_value<OffT>(a, k);
+  __syncthreads();
+  peer_allreduce_cta(a.t, (int)a.n_S, pa);
+}
+
+// the same without the reduction (NCCL transport: ncclAllReduce follows)
+template <typename OffT>
+__global__ void __launch_bounds__(256) dd_rhs_kernel(const DdRhsArgs a)
+{
+  const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (k < a.n_S)
+    a.t[k] = dd_rhs_value<OffT>(a, k);
+}
+
+// blocks [0, interior_blocks): x_I[i] = y[i] - sum_j E[i][j] xs[j]   (one warp per row, fixed shuffle tree)
+// the remaining blocks:        x_c[sep_index[k]] = xs_all[k]         (the separator solution, replicated)
+__global__ void __launch_bounds__(256)
+    dd_interior_scatter_kernel(int64_t n_I, int64_t n_adj, const double *__restrict__ E, int64_t ldE,
+                               const double *__restrict__ xs, const double *__restrict__ y, double *__restrict__ x_I,
+                               int interior_blocks, int64_t n_S, const int32_t *__restrict__ sep_index,
+                               const double *__restrict__ xs_all, double *__restrict__ x_c)
+{
+  if ((int)blockIdx.x >= interior_blocks)
+  {
+    const int64_t k = (int64_t)(blockIdx.x - interior_blocks) * 256 + threadIdx.x;
+    if (k < n_S)
+      x_c[sep_index[k]] = xs_all[k];
+    return;
+  }
   const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   double s0 = 0., s1 = 0.;
@@ -86,15 +138,6 @@ __global__ void __launch_bounds__(256) dd_interior_kernel(int64_t n_I, int64_t n
   const double s = subwarp_sum<32>(s0 + s1);
   if (lane == 0 && i < n_I)
     x_I[i] = y[i] - s;
-}
-
-// x_c[sep_index[k]] = xs[k]
-__global__ void __launch_bounds__(256) dd_scatter_kernel(int64_t n_S, const int32_t *__restrict__ sep_index,
-                                                         const double *__restrict__ xs, double *__restrict__ x_c)
-{
-  const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (k < n_S)
-    x_c[sep_index[k]] = xs[k];
 }
 
 // S[(adj_begin + i) * ldS + adj_begin + j] -= C[i * ldC + j]
@@ -120,32 +163,59 @@ int coarse_dd_solve_async(mfmgb_ctx *ctx, const mfmgb_coarse_dd *d, const double
   // y = A_II^-1 b_I
   if (d->n_I > 0)
     MFMGB_CHECK(dense_solve_async(ctx, d->D_II, b_c + d->own_begin, d->y));
+  prof_mark(ctx, "coarse: y = A_II^-1 b_I (GEMV)");
   if (d->n_S > 0)
   {
-    // t = (own part of b_S) - A_SI y, summed over the ranks
-    if (d->n_adj > 0 && d->n_I > 0)
+    // t = (own part of b_S) - A_SI y [+ this rank's share of R r below], summed over the ranks
+    DdRhsArgs a;
+    a.n_S = d->n_S;
+    a.adj_begin = d->adj_begin;
+    a.n_adj = d->n_I > 0 ? d->n_adj : 0;
+    a.own_begin = d->own_sep_begin;
+    a.own_n = d->own_sep_n;
+    a.n_below = d->n_adj - d->own_sep_n;
+    a.si_rowptr = d->A_SI->rowptr;
+    a.si_col = d->A_SI->col;
+    a.si_val = d->A_SI->val;
+    a.y = d->y;
+    a.sep_index = d->sep_index;
+    a.b_c = b_c;
+    a.g_below = g_below;
+    a.t = d->t;
+    if (c->peer.enabled && d->n_S <= c->peer.ar_cap)
     {
-      EpiArgs e;
-      e.y = d->g;
-      MFMGB_CHECK(csr_apply(ctx, d->A_SI, d->y, Epi::Spmv, e));
+      // one launch: contributions + sum over the ranks through peer memory
+      if (d->A_SI->off64)
+        dd_rhs_allreduce_kernel<int64_t><<<1, 1024, 0, st>>>(a, peer_allreduce_args(c));
+      else
+        dd_rhs_allreduce_kernel<int32_t><<<1, 1024, 0, st>>>(a, peer_allreduce_args(c));
+      MFMGB_LAUNCHED(ctx);
     }
-    dd_rhs_kernel<<<(unsigned)ceil_div(d->n_S, 256), 256, 0, st>>>(d->n_S, d->adj_begin, d->n_I > 0 ? d->n_adj : 0,
-                                                                   d->own_sep_begin, d->own_sep_n, d->g, d->sep_index,
-                                                                   b_c, g_below, d->n_adj - d->own_sep_n, d->t);
-    MFMGB_LAUNCHED(ctx);
-    MFMGB_CHECK(allreduce_sum(ctx, d->t, (int)d->n_S)); // one kernel over peer memory (NCCL when the window is off)
+    else
+    {
+      if (d->A_SI->off64)
+        dd_rhs_kernel<int64_t><<<(unsigned)ceil_div(d->n_S, 256), 256, 0, st>>>(a);
+      else
+        dd_rhs_kernel<int32_t><<<(unsigned)ceil_div(d->n_S, 256), 256, 0, st>>>(a);
+      MFMGB_LAUNCHED(ctx);
+      MFMGB_CHECK(allreduce_sum(ctx, d->t, (int)d->n_S));
+    }
+    prof_mark(ctx, "coarse: separator rhs + all-reduce");
     // x_S = Schur^-1 t (replicated)
     MFMGB_CHECK(dense_solve_async(ctx, d->D_S, d->t, d->xs));
-    dd_scatter_kernel<<<(unsigned)ceil_div(d->n_S, 256), 256, 0, st>>>(d->n_S, d->sep_index, d->xs, x_c);
-    MFMGB_LAUNCHED(ctx);
+    prof_mark(ctx, "coarse: x_S = Schur^-1 t (GEMV)");
   }
-  // x_I = y - E x_S|adjacent
-  if (d->n_I > 0)
+  // x_I = y - E x_S|adjacent, and the separator solution into x_c: one launch
+  const int interior_blocks = (int)ceil_div(d->n_I, 8);
+  const int scatter_blocks = (int)ceil_div(d->n_S, 256);
+  if (interior_blocks + scatter_blocks > 0)
   {
-    dd_interior_kernel<<<(unsigned)ceil_div(d->n_I, 8), 256, 0, st>>>(d->n_I, d->n_adj, d->E, d->ldE,
-                                                                      d->xs + d->adj_begin, d->y, x_c + d->own_begin);
+    dd_interior_scatter_kernel<<<(unsigned)(interior_blocks + scatter_blocks), 256, 0, st>>>(
+        d->n_I, d->n_adj, d->E, d->ldE, d->xs + d->adj_begin, d->y, x_c + d->own_begin, interior_blocks, d->n_S,
+        d->sep_index, d->xs, x_c);
     MFMGB_LAUNCHED(ctx);
   }
+  prof_mark(ctx, "coarse: interior update + scatter");
   return MFMGB_OK;
 }
 } // namespace mfmgb

@@ -22,6 +22,7 @@
 #include <map>
 
 #include "comm.cuh"
+#include "peer.cuh"
 
 using namespace mfmgb;
 
@@ -39,42 +40,6 @@ __global__ void __launch_bounds__(256)
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i < n)
     buf[i] = v[idx[i]];
-}
-
-// ---- peer-memory primitives ------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_timer_ns()
-{
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-// spin until *flag >= want; gives up after timeout_ns and reports through *err (the host checks it at sync points)
-__device__ __forceinline__ void wait_flag(const unsigned long long *flag, unsigned long long want,
-                                          unsigned long long timeout_ns, int *err)
-{
-  if (ld_acquire_sys(flag) >= want)
-    return;
-  const unsigned long long t0 = global_timer_ns();
-  while (ld_acquire_sys(flag) < want)
-  {
-    __nanosleep(40);
-    if (global_timer_ns() - t0 > timeout_ns)
-    {
-      *err = 1;
-      __threadfence_system();
-      return;
-    }
-  }
 }
 
 struct PushArgs
@@ -172,39 +137,9 @@ __global__ void __launch_bounds__(256) halo_wait_kernel(const WaitArgs a)
 }
 
 // one-kernel all-reduce (sum) of n <= cap doubles over all ranks through peer memory; one CTA
-__global__ void __launch_bounds__(1024)
-    peer_allreduce_kernel(double *__restrict__ buf, int n, int nranks, int rank, unsigned char *const *base,
-                          unsigned char *local, size_t ar_off, size_t flag_off, int cap, unsigned long long *seq,
-                          unsigned long long timeout_ns, int *err)
+__global__ void __launch_bounds__(1024) peer_allreduce_kernel(double *__restrict__ buf, int n, const PeerAllreduceArgs a)
 {
-  const unsigned long long s = seq[0] + 1;
-  const size_t par = (size_t)(s & 1ull);
-  const size_t my_slot = (par * (size_t)nranks + (size_t)rank) * (size_t)cap;
-  for (int r = 0; r < nranks; ++r)
-  {
-    double *dst = reinterpret_cast<double *>(base[r] + ar_off) + my_slot;
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-      dst[i] = buf[i];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < nranks)
-    st_release_sys(reinterpret_cast<unsigned long long *>(base[threadIdx.x] + flag_off) + (par * (size_t)nranks + (size_t)rank), s);
-  if ((int)threadIdx.x < nranks)
-    wait_flag(reinterpret_cast<const unsigned long long *>(local + flag_off) + (par * (size_t)nranks + threadIdx.x), s,
-              timeout_ns, err);
-  __syncthreads();
-  const double *slots = reinterpret_cast<const double *>(local + ar_off) + par * (size_t)nranks * (size_t)cap;
-  for (int i = threadIdx.x; i < n; i += blockDim.x)
-  {
-    double acc = 0.;
-    for (int r = 0; r < nranks; ++r) // fixed rank order: the same bits on every rank
-      acc += __ldcg(slots + (size_t)r * (size_t)cap + i);
-    buf[i] = acc;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0)
-    seq[0] = s;
+  peer_allreduce_cta(buf, n, a);
 }
 
 int env_int(const char *name, int dflt)
@@ -450,8 +385,7 @@ int allreduce_sum(mfmgb_ctx *ctx, double *dev, int n)
   if (p.enabled && n <= p.ar_cap)
   {
     const int threads = n >= 1024 ? 1024 : std::max(32, ((std::max(n, c->nranks) + 31) / 32) * 32);
-    peer_allreduce_kernel<<<1, threads, 0, ctx->stream>>>(dev, n, c->nranks, c->rank, p.base_dev, p.local, p.ar_off,
-                                                         p.ar_flag_off, p.ar_cap, p.ar_seq, p.timeout_ns, p.err_dev);
+    peer_allreduce_kernel<<<1, threads, 0, ctx->stream>>>(dev, n, peer_allreduce_args(c));
     ctx->launches++;
     MFMGB_CUDA(ctx, cudaGetLastError());
     return MFMGB_OK;

@@ -42,6 +42,12 @@ struct mfmgb_ctx
   // objects holding instantiated CUDA graphs with NCCL nodes: they must be dropped before the communicator is
   // destroyed (ncclCommDestroy otherwise waits forever).  (owner, drop function)
   std::vector<std::pair<void *, void (*)(void *)>> graph_owners;
+  // timeline marks (mfmgb_vcycle_timeline): CUDA events recorded on the compute stream between the pieces of a cycle;
+  // inside a stream capture they become event-record nodes, so the times are those of the GRAPH replay
+  bool prof_on = false;
+  int prof_n = 0;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<std::string> prof_names;
 };
 
 namespace mfmgb
@@ -92,6 +98,25 @@ inline int fail(mfmgb_ctx *ctx, int code, const char *fmt, ...)
   } while (0)
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// marks the END of the piece called `name` on the compute stream (no-op unless a timeline is being taken)
+inline void prof_mark(mfmgb_ctx *ctx, const char *name)
+{
+  if (!ctx->prof_on)
+    return;
+  if (ctx->prof_n >= (int)ctx->prof_ev.size())
+  {
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreate(&ev) != cudaSuccess)
+      return;
+    ctx->prof_ev.push_back(ev);
+    ctx->prof_names.emplace_back();
+  }
+  if (cudaEventRecord(ctx->prof_ev[(size_t)ctx->prof_n], ctx->stream) != cudaSuccess)
+    return;
+  ctx->prof_names[(size_t)ctx->prof_n] = name;
+  ctx->prof_n++;
+}
 
 // ---- device helpers -------------------------------------------------------------------------
 __device__ __forceinline__ double ldg_f64(const double *p) { return __ldg(p); }

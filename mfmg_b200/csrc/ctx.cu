@@ -66,6 +66,8 @@ extern "C"
     cudaSetDevice(ctx->device);
     mfmgb_comm_finalize(ctx); // drops the communicator registered for this context, if any (no stale registry entry)
     cudaStreamSynchronize(ctx->stream);
+    for (cudaEvent_t ev : ctx->prof_ev)
+      cudaEventDestroy(ev);
     cudaFree(ctx->red_partials);
     cudaFree(ctx->red_result);
     cudaFreeHost(ctx->red_result_host);

@@ -10,7 +10,9 @@
 // the device, one host read-back per iteration for the reference's stopping test.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "comm.cuh"
@@ -121,15 +123,23 @@ int level_apply_A(mfmgb_ctx *ctx, const mfmgb_level &l, double *x, Epi epi, cons
     return csr_apply(ctx, l.A, x, epi, e);
   }
   MFMGB_CHECK(csr_apply(ctx, l.A, x, epi, e, l.blo, l.bhi));
+  prof_mark(ctx, "A interior rows");
   MFMGB_CHECK(halo_wait(ctx, l.halo, x));
-  return csr_apply2(ctx, l.A, x, epi, e, 0, l.blo, l.bhi, l.n); // both boundary blocks in one launch
+  prof_mark(ctx, "A halo wait");
+  MFMGB_CHECK(csr_apply2(ctx, l.A, x, epi, e, 0, l.blo, l.bhi, l.n)); // both boundary blocks in one launch
+  prof_mark(ctx, "A boundary rows");
+  return MFMGB_OK;
 }
 
+static const char *const kStageNames[7] = {"(start)", "pre-smooth", "residual", "restrict", "coarse solve",
+                                           "prolong+correct", "post-smooth"};
 #define STAGE_MARK(k)                                                                              \
   do                                                                                                \
   {                                                                                                 \
     if (H->profiling && li == 0)                                                                    \
       MFMGB_CUDA(ctx, cudaEventRecord(H->ev[k], ctx->stream));                                      \
+    if (li == 0)                                                                                    \
+      prof_mark(ctx, kStageNames[k]);                                                               \
   } while (0)
 
 int apply_level(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, int li)
@@ -650,6 +660,58 @@ extern "C"
       stage_ms[k] = (double)ms;
     }
     return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_vcycle_timeline(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, int use_graph,
+                                      char *names, int names_len, double *ms, int max_marks, int *n_marks)
+  {
+    MFMGB_REQUIRE(ctx, ctx && H && H->finalized && b && x && names && names_len > 0 && ms && n_marks,
+                  "mfmgb_vcycle_timeline: bad arguments");
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    ctx->prof_on = true;
+    ctx->prof_n = 0;
+    int rc = MFMGB_OK;
+    const int64_t launches_before = ctx->launches;
+    if (use_graph)
+    {
+      MFMGB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      rc = apply_level(ctx, H, b, x, 0);
+      cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+      ctx->prof_on = false;
+      if (rc == MFMGB_OK && ce == cudaSuccess)
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+      if (graph)
+        cudaGraphDestroy(graph);
+      MFMGB_CHECK(rc);
+      MFMGB_CUDA(ctx, ce);
+      ctx->launches = launches_before;
+      for (int rep = 0; rep < 3; ++rep) // the event nodes keep the timestamps of the last replay
+        MFMGB_CUDA(ctx, cudaGraphLaunch(exec, ctx->stream));
+    }
+    else
+    {
+      rc = apply_level(ctx, H, b, x, 0);
+      ctx->prof_on = false;
+      MFMGB_CHECK(rc);
+    }
+    MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (exec)
+      cudaGraphExecDestroy(exec);
+    std::string joined;
+    int n = 0;
+    for (int k = 1; k < ctx->prof_n && n < max_marks; ++k)
+    {
+      float t = 0.f;
+      MFMGB_CUDA(ctx, cudaEventElapsedTime(&t, ctx->prof_ev[(size_t)k - 1], ctx->prof_ev[(size_t)k]));
+      ms[n++] = (double)t;
+      if (!joined.empty())
+        joined += ";";
+      joined += ctx->prof_names[(size_t)k];
+    }
+    *n_marks = n;
+    snprintf(names, (size_t)names_len, "%s", joined.c_str());
+    return mfmgb_comm_check(ctx);
   }
 
   MFMGB_API int mfmgb_vcycle_host(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b_host, double *x_host)

@@ -17,6 +17,10 @@ struct mfmgb_mf
   bool q1_cell_constant = false;  // every cell's (cell, q) entries are equal: coef_cell + Kref are used
   double *coef_cell = nullptr;    // device [n_cells]
   double Kref[64] = {0};          // sum_q G[q][a][b]: reference cell matrix with the Jacobian folded in
+  // one coefficient for the whole grid and every owned unconstrained node interior to the local box: the factorised
+  // 27-point stencil z-sweep (mf_q1_sweep.cuh) serves the operator
+  bool q1_stencil = false;
+  double q1_const_coef = 0.;
   bool force_generic = false;     // tests: run the generic colour-phase kernel instead
   int q1_tz = 6;                  // owned node planes per CTA of mf_q1_kernel
   uint8_t *brick_flags = nullptr; // device, one byte per CTA brick: does it contain a constrained node?

@@ -599,6 +599,21 @@ extern "C"
     M->q1_cell_constant = cell_constant;
     if (cell_constant)
     {
+      // one coefficient for the whole grid, and all 8 cells exist around every owned unconstrained node (vector layout
+      // [owned planes | ghost planes]): the factorised-stencil z-sweep applies (MFMGB_MF_STENCIL=0 keeps the cell kernel)
+      const char *st = getenv("MFMGB_MF_STENCIL");
+      bool stencil = !(st && st[0] == '0') && M->nodes[0] >= 3 && M->nodes[1] >= 3;
+      for (int64_t c = 1; c < M->n_cells && stencil; ++c)
+        stencil = coef[(size_t)c * M->nq] == coef[0];
+      const int64_t nx = M->nodes[0], ny = M->nodes[1], pl = nx * ny;
+      for (int64_t r = 0; r < M->n && stencil; ++r)
+      {
+        const int64_t g = own_plane_begin + r / pl, j = (r % pl) / nx, i = r % nx;
+        if ((i == 0 || i == nx - 1 || j == 0 || j == ny - 1 || g == 0 || g == M->nodes[2] - 1) && !constrained[r])
+          stencil = false;
+      }
+      M->q1_stencil = stencil;
+      M->q1_const_coef = coef[0];
       std::vector<double> cc((size_t)M->n_cells);
       for (int64_t c = 0; c < M->n_cells; ++c)
         cc[(size_t)c] = coef[(size_t)c * M->nq];
@@ -705,7 +720,9 @@ extern "C"
   MFMGB_API int64_t mfmgb_mf_vector_size(const mfmgb_mf *M) { return M ? M->n_local : 0; }
   MFMGB_API int mfmgb_mf_kernel(const mfmgb_mf *M)
   {
-    return !M ? -1 : (M->dim == 3 && M->degree == 1 && !M->force_generic ? (M->q1_cell_constant ? 1 : 2) : 0);
+    return !M ? -1
+              : (M->dim == 3 && M->degree == 1 && !M->force_generic ? (M->q1_stencil ? 3 : (M->q1_cell_constant ? 1 : 2))
+                                                                    : 0);
   }
 
   MFMGB_API int mfmgb_mf_apply(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, double *y)

@@ -585,18 +585,39 @@ int dispatch_q1(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, Epi epi, con
 }
 } // namespace
 
+#include "mf_q1_sweep.cuh"
+
 namespace mfmgb
 {
+int mf_q1_num_chunks(const mfmgb_mf *M);
 // z chunks [zc0, zc1) of the owned planes (zc0 < 0: all).  Only the first chunk reads the ghost plane below and only
 // the last one the ghost plane above, so a partitioned level runs the middle chunks while the halo is exchanged.
 int mf_q1_apply(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, Epi epi, const EpiArgs &args, int zc0, int zc1)
 {
+  if (M->q1_stencil)
+  {
+    // plane ranges of the sweep kernel: chunk 0 = the first owned plane (the only one that reads the ghost plane
+    // below), chunk 2 = the last one (ghost plane above), chunk 1 = everything in between
+    const int nc = mf_q1_num_chunks(M);
+    if (zc0 < 0 || nc == 1)
+      return zc0 <= 0 ? dispatch_q1_stencil(ctx, M, x, epi, args, M->own0, M->own1) : MFMGB_OK;
+    const int64_t cut[4] = {M->own0, M->own0 + 1, M->own1 - 1, M->own1};
+    zc1 = zc1 < nc ? zc1 : nc;
+    if (zc1 <= zc0)
+      return MFMGB_OK;
+    return dispatch_q1_stencil(ctx, M, x, epi, args, cut[zc0], cut[zc1]);
+  }
   if (M->q1_cell_constant)
     return dispatch_q1<8, false>(ctx, M, x, epi, args, zc0, zc1);
   return dispatch_q1<8, true>(ctx, M, x, epi, args, zc0, zc1);
 }
 
-int mf_q1_num_chunks(const mfmgb_mf *M) { return (int)ceil_div(M->own1 - M->own0, (int64_t)M->q1_tz); }
+int mf_q1_num_chunks(const mfmgb_mf *M)
+{
+  if (M->q1_stencil)
+    return M->own1 - M->own0 >= 3 ? 3 : 1;
+  return (int)ceil_div(M->own1 - M->own0, (int64_t)M->q1_tz);
+}
 
 // fixes the brick height and marks the bricks that contain constrained nodes (called once by the create functions)
 int mf_q1_prepare(mfmgb_ctx *ctx, mfmgb_mf *M)

@@ -59,29 +59,17 @@ __global__ void __launch_bounds__(SW_TX *SW_TY, 2)
   unsigned fa, fb;
   load_node(P0 - 1, ua, fa);
   load_node(P0, ub, fb);
-  double ba = 0., bb = 0., da = 0., db = 0.; // epilogue operands of planes g - 1 (a) and g (b)
+  // epilogue operands: "b" slot = plane g of the current step, "a" slot = plane g - 1 (the one that is emitted).  The
+  // operands of plane P0 enter the pipeline as the "next" of step 0, like every later plane's do one step ahead.
+  double ba = 0., bb = 0., da = 0., db = 0.;
+  double pend_b = 0., pend_d = 0.;
   if (emit_xy && EPI != (int)Epi::Spmv)
   {
     const int64_t row = (P0 - p.own0) * pl + node_xy;
-    bb = e.b[row];
+    pend_b = e.b[row];
     if (EPI == (int)Epi::Jacobi)
-      db = e.dinv[row];
+      pend_d = e.dinv[row];
   }
-  // the step for plane g = P0 - 1 has "b" = P0 - 1 (never emitted): shift so that bb belongs to plane g at every step
-  {
-    const double tb = bb, td = db;
-    ba = 0., da = 0.;
-    bb = 0., db = 0.;
-    // operands of plane P0 are needed at the step that processes plane P0 + 1; they ride as "next" of the first step
-    // (see the rotation at the end of the loop body): keep them in bn0 / dn0
-    sm_m[0][0][0] = 0.; // (no-op write keeps the compiler from hoisting the loads below the first barrier)
-    ba = tb;
-    da = td;
-  }
-  // after the block above: ba / da hold the operands of plane P0; they are consumed at step t = 2.  To keep one
-  // rotation rule (a <- b <- next) they enter the pipeline as "next" of step 0.
-  double pend_b = ba, pend_d = da;
-  ba = bb = da = db = 0.;
   double u_prev = 0.;
   unsigned f_prev = 1u;
   double Pm = 0., Pc = 0., Qm = 0., Qc = 0.;

@@ -414,7 +414,8 @@ class MatrixFreeLaplaceDevice:
     """The matrix-free fine-level operator (CudaMatrixFreeOperator slot)."""
 
     KERNELS = {0: "generic colour-phase cell kernel", 1: "Q1 node-owner z-sweep, per-cell coefficient",
-               2: "Q1 node-owner z-sweep, per-quadrature-point coefficient"}
+               2: "Q1 node-owner z-sweep, per-quadrature-point coefficient",
+               3: "Q1 constant-coefficient factorised 27-point stencil, persistent z-sweep"}
 
     def __init__(self, handle: CudaHandle, dim, degree, cells, h, coef_per_q, constrained, own_planes=None):
         """own_planes = (begin, end): the z-slab form of a row-partitioned grid -- `cells` is the local box, node
@@ -690,6 +691,16 @@ class Hierarchy:
         check(self.handle.ctx, self.handle.lib.mfmgb_vcycle_profile(self.handle.ctx, self.ptr, b.ptr, x.ptr,
                                                                     ms.ctypes.data))
         return dict(zip(self.STAGES, ms.tolist()))
+
+    def timeline(self, x: DeviceVector, b: DeviceVector, graph: bool = True):
+        """[(piece, ms), ...] of one V-cycle, resolved per kernel group; graph=True: times of a CUDA-graph replay."""
+        names = ctypes.create_string_buffer(4096)
+        ms = np.zeros(128)
+        n = ctypes.c_int(0)
+        check(self.handle.ctx, self.handle.lib.mfmgb_vcycle_timeline(self.handle.ctx, self.ptr, b.ptr, x.ptr, int(graph),
+                                                                     names, 4096, ms.ctypes.data, 128, ctypes.byref(n)))
+        labels = names.value.decode().split(";") if n.value else []
+        return list(zip(labels, ms[:n.value].tolist()))
 
     def grid_complexity(self) -> float:
         sizes = [op.size if isinstance(op, MatrixFreeLaplaceDevice) else op.m() for op in self.operators]

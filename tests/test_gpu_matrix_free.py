@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 MF_CASES = [(2, 1, 40, "constant"), (2, 1, 33, "discontinuous"), (2, 2, 20, "linear"), (2, 2, 17, "discontinuous"),
             (3, 1, 40, "linear"), (3, 1, 12, "discontinuous"), (3, 1, 35, "constant"), (3, 2, 8, "linear_x"),
-            (3, 2, 18, "discontinuous")]
+            (3, 2, 18, "discontinuous"), (3, 1, 3, "constant"), (3, 1, 70, "constant")]
 
 
 def _mf(handle, P):
@@ -28,6 +28,8 @@ def test_mf_apply_and_diagonal_vs_oracle(handle, dim, degree, cells, mat):
     P = hs.LaplaceProblem.create(dim, degree, cells, mat)
     M = _mf(handle, P)
     assert M.size == P.n
+    if dim == 3 and degree == 1:   # one coefficient for the whole grid: the factorised-stencil z-sweep serves it
+        assert ("stencil" in M.kernel) == (mat == "constant"), M.kernel
     Mo = oracle.MatrixFreeLaplace(dim, degree, P.cells, P.h, P.coef_per_q(), P.constrained)
     rng = np.random.default_rng(3)
     x_h = rng.standard_normal(P.n)          # non-zero on constrained DoFs too: y_i = x_i there
@@ -103,7 +105,9 @@ def test_mf_unsupported_degree_raises(handle):
 
 
 @pytest.mark.parametrize("world,cells,block,mat", [(3, (33, 9, 12), (3, 3, 2), "linear"),
-                                                   (2, (40, 20, 16), (4, 4, 4), "discontinuous")])
+                                                   (2, (40, 20, 16), (4, 4, 4), "discontinuous"),
+                                                   (3, (33, 9, 12), (3, 3, 2), "constant"),
+                                                   (2, (70, 40, 16), (5, 4, 4), "constant")])
 def test_mf_slab_operator_on_one_gpu(handle, world, cells, block, mat):
     """The z-slab form of the 3D Q1 operator (row-partitioned hierarchy): every rank's slab operator, fed with its
     [owned | ghost] copy of a global vector, reproduces the owned rows of the global operator and of its diagonal."""
@@ -122,6 +126,7 @@ def test_mf_slab_operator_on_one_gpu(handle, world, cells, block, mat):
         M = d.MatrixFreeLaplaceDevice(handle, 3, 1, mf["cells"], mf["h"], mf["coef"], mf["constrained"],
                                       own_planes=mf["own_planes"])
         assert M.size == part.n_owned and M.vector_size == part.n_owned + part.n_ghost
+        assert ("stencil" in M.kernel) == (mat == "constant"), M.kernel
         x = d.DeviceVector.from_host(handle, slab_vector(part, x_h))
         y = d.DeviceVector(handle, part.n_owned)
         M.apply(x, y)
@@ -146,3 +151,38 @@ def test_generic_kernel_still_serves_3d_q1(handle, monkeypatch):
     fast.apply(x, y1)
     slow.apply(x, y2)
     assert rel_err(y1.to_host(), y2.to_host()) < 1e-13
+
+
+@pytest.mark.parametrize("mat", ["constant"])
+def test_stencil_sweep_equals_cell_kernel_and_fused_epilogues(handle, monkeypatch, mat):
+    """The constant-coefficient stencil z-sweep against the per-cell kernel of the same operator (MFMGB_MF_STENCIL=0),
+    and its fused residual / Jacobi epilogues against their unfused definitions."""
+    import ctypes
+
+    from mfmg_b200 import device as d
+    from mfmg_b200 import hostsetup as hs
+
+    P = hs.LaplaceProblem.create_box(3, 1, (45, 31, 23), (0.02, 0.03, 0.05), mat)
+    fast = _mf(handle, P)
+    monkeypatch.setenv("MFMGB_MF_STENCIL", "0")
+    cell = _mf(handle, P)
+    assert "stencil" in fast.kernel and "per-cell" in cell.kernel
+    rng = np.random.default_rng(4)
+    x_h, b_h = rng.standard_normal(P.n), rng.standard_normal(P.n)
+    x, b = d.DeviceVector.from_host(handle, x_h), d.DeviceVector.from_host(handle, b_h)
+    y1, y2 = d.DeviceVector(handle, P.n), d.DeviceVector(handle, P.n)
+    fast.apply(x, y1)
+    cell.apply(x, y2)
+    assert rel_err(y1.to_host(), y2.to_host()) < 1e-13
+    # fused epilogues through a hierarchy's smoother path: one V-cycle of each operator agrees to 1e-12
+    R = hs.build_restrictor(P, (5, 4, 4), 1)
+    Ac = hs.galerkin(P.A, R)
+    outs = []
+    for M in (fast, cell):
+        H = d.Hierarchy(handle, [M, d.SparseMatrixDevice.from_host(handle, Ac)],
+                        [d.SparseMatrixDevice.from_host(handle, R)], {"is preconditioner": False,
+                                                                      "smoother": {"n_smoothing_steps": 2}})
+        xx = d.DeviceVector.from_host(handle, x_h)
+        H.vmult(xx, b)
+        outs.append(xx.to_host())
+    assert rel_err(outs[0], outs[1]) < 1e-12
