@@ -179,6 +179,16 @@ extern "C"
   MFMGB_API int mfmgb_hierarchy_set_mf_operator(mfmgb_hierarchy *H, const mfmgb_mf *M); /* level 0 only */
   /* R maps level-1 -> level (n_level x n_{level-1}); P = R^T explicit (may be NULL: built internally) */
   MFMGB_API int mfmgb_hierarchy_set_restrictor(mfmgb_hierarchy *H, int level, const mfmgb_csr *R, const mfmgb_csr *P);
+  /* "smoother.type" Chebyshev instead of Jacobi: mfmg::DealIIMatrixFreeSmoother (source/dealii/dealii_matrix_free_smoother.cc:
+   * 34-79), i.e. dealii::PreconditionChebyshev with the inverse diagonal as inner preconditioner, applied as
+   * x -= p(D^-1 A) D^-1 (A x - b).  Arguments = the reference's "smoother.degree" / "smoother.smoothing_range" /
+   * "smoother.max_eigenvalue" and deal.II's eig_cg_n_iterations (reference defaults: 0, 0., 1., 8).  degree counts the
+   * operator applications AFTER the first damped-Jacobi step (deal.II @89057dff semantics: degree 0 == Jacobi with
+   * omega = 1 / theta, fused into the SpMV like the Jacobi smoother).  Before finalize; single-GPU hierarchies. */
+  MFMGB_API int mfmgb_hierarchy_set_smoother_chebyshev(mfmgb_hierarchy *H, int degree, double smoothing_range,
+                                                       double max_eigenvalue, int eig_cg_n_iterations);
+  /* out4 = lambda_min, lambda_max (incl. deal.II's safety factor 1.2), theta, delta of a level's smoother */
+  MFMGB_API int mfmgb_hierarchy_chebyshev_info(const mfmgb_hierarchy *H, int level, double *out4);
   /* builds smoothers, the coarse factorisation and all level workspaces (no allocation afterwards) */
   MFMGB_API int mfmgb_hierarchy_finalize(mfmgb_ctx *ctx, mfmgb_hierarchy *H);
   MFMGB_API int mfmgb_hierarchy_destroy(mfmgb_ctx *ctx, mfmgb_hierarchy *H);

@@ -101,6 +101,8 @@ SIGNATURES = {
     "mfmgb_hierarchy_set_operator": (_int, [_vp, _int, _vp]),
     "mfmgb_hierarchy_set_mf_operator": (_int, [_vp, _vp]),
     "mfmgb_hierarchy_set_restrictor": (_int, [_vp, _int, _vp, _vp]),
+    "mfmgb_hierarchy_set_smoother_chebyshev": (_int, [_vp, _int, _dbl, _dbl, _int]),
+    "mfmgb_hierarchy_chebyshev_info": (_int, [_vp, _int, _vp]),
     "mfmgb_hierarchy_finalize": (_int, [_vp, _vp]),
     "mfmgb_hierarchy_destroy": (_int, [_vp, _vp]),
     "mfmgb_vcycle": (_int, [_vp, _vp, _vp, _vp]),

@@ -45,6 +45,7 @@ struct mfmgb_ctx
   // timeline marks (mfmgb_vcycle_timeline): CUDA events recorded on the compute stream between the pieces of a cycle;
   // inside a stream capture they become event-record nodes, so the times are those of the GRAPH replay
   bool prof_on = false;
+  bool prof_capturing = false; // the marks are recorded inside a stream capture (event-record nodes)
   int prof_n = 0;
   std::vector<cudaEvent_t> prof_ev;
   std::vector<std::string> prof_names;
@@ -112,7 +113,10 @@ inline void prof_mark(mfmgb_ctx *ctx, const char *name)
     ctx->prof_ev.push_back(ev);
     ctx->prof_names.emplace_back();
   }
-  if (cudaEventRecord(ctx->prof_ev[(size_t)ctx->prof_n], ctx->stream) != cudaSuccess)
+  // inside a capture a plain cudaEventRecord only marks a dependency; the External flag makes it a real
+  // event-record node whose timestamp is taken at every replay (the flag is invalid outside a capture)
+  if (cudaEventRecordWithFlags(ctx->prof_ev[(size_t)ctx->prof_n], ctx->stream,
+                               ctx->prof_capturing ? cudaEventRecordExternal : cudaEventRecordDefault) != cudaSuccess)
     return;
   ctx->prof_names[(size_t)ctx->prof_n] = name;
   ctx->prof_n++;

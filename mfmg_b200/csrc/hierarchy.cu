@@ -44,6 +44,9 @@ struct mfmgb_level
   bool restrict_no_halo = false;
   const mfmgb_csr *R_below = nullptr;
   double *gb = nullptr;
+  // Chebyshev smoother (dealii::PreconditionChebyshev as DealIIMatrixFreeSmoother uses it): estimate and work vectors
+  double cheb_lmin = 1., cheb_lmax = 1., cheb_theta = 1., cheb_delta = 0.;
+  double *c_r = nullptr, *c_dst = nullptr, *c_u1 = nullptr, *c_u2 = nullptr;
 };
 
 struct mfmgb_hierarchy
@@ -53,6 +56,12 @@ struct mfmgb_hierarchy
   bool is_preconditioner = true;
   double omega = 1.;
   bool finalized = false;
+  // smoother.type: Jacobi (source/cuda/cuda_smoother.cu) or Chebyshev (source/dealii/dealii_matrix_free_smoother.cc:34-60)
+  bool chebyshev = false;
+  int cheb_degree = 0;          // smoother.degree: matrix-vector products after the first damped-Jacobi step
+  double cheb_range = 0.;       // smoother.smoothing_range
+  double cheb_max_ev = 1.;      // smoother.max_eigenvalue (used when cheb_cg_its == 0)
+  int cheb_cg_its = 8;          // eig_cg_n_iterations
   std::vector<mfmgb_level> lev;
   // graph replay
   bool use_graph = false;
@@ -142,6 +151,243 @@ static const char *const kStageNames[7] = {"(start)", "pre-smooth", "residual", 
       prof_mark(ctx, kStageNames[k]);                                                               \
   } while (0)
 
+// ---- Chebyshev smoother kernels (elementwise; the operator applications go through level_apply_A) ----------------
+__global__ void __launch_bounds__(kBlock) negate_into_kernel(int64_t n, const double *__restrict__ a, double *__restrict__ out)
+{
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+    out[i] = -a[i];
+}
+// vector_updates(start_zero): dst = D^-1 (f2 src), u1 = -dst
+__global__ void __launch_bounds__(kBlock)
+    cheb_start_kernel(int64_t n, double f2, const double *__restrict__ dinv, const double *__restrict__ src,
+                      double *__restrict__ dst, double *__restrict__ u1)
+{
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+  {
+    const double d = __dmul_rn(dinv[i], __dmul_rn(f2, src[i]));
+    dst[i] = d;
+    u1[i] = -d;
+  }
+}
+// vector_updates(!start_zero) with u2 = A dst - src already formed: u1 = f1 u1 + f2 D^-1 u2, dst -= u1
+__global__ void __launch_bounds__(kBlock)
+    cheb_step_kernel(int64_t n, double f1, double f2, const double *__restrict__ dinv, const double *__restrict__ u2,
+                     double *__restrict__ u1, double *__restrict__ dst)
+{
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+  {
+    const double t = __dmul_rn(dinv[i], u2[i]);
+    const double u = __dadd_rn(__dmul_rn(f1, u1[i]), __dmul_rn(f2, t));
+    u1[i] = u;
+    dst[i] = __dsub_rn(dst[i], u);
+  }
+}
+// x = (zero ? 0 : x) - dst      (DealIIMatrixFreeSmoother::apply: x.add(-1., tmp))
+__global__ void __launch_bounds__(kBlock)
+    cheb_finish_kernel(int64_t n, int zero, const double *__restrict__ dst, double *__restrict__ x)
+{
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+    x[i] = __dsub_rn(zero ? 0. : x[i], dst[i]);
+}
+__global__ void __launch_bounds__(kBlock)
+    scale_rows_kernel(int64_t n, const double *__restrict__ dinv, const double *__restrict__ g, double *__restrict__ h)
+{
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+    h[i] = dinv[i] * g[i];
+}
+__global__ void __launch_bounds__(kBlock)
+    cg_direction_host_beta_kernel(int64_t n, double beta, const double *__restrict__ h, double *__restrict__ d)
+{
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+    d[i] = fma(beta, d[i], -h[i]);
+}
+__global__ void __launch_bounds__(kBlock) mod11_guess_kernel(int64_t n, double mean, double *__restrict__ g)
+{
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+    g[i] = -((double)(i % 11) - mean); // g = A 0 - v
+}
+
+inline unsigned ew_grid(const mfmgb_ctx *ctx, int64_t n)
+{
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, kBlock), (int64_t)ctx->num_sms * 16));
+}
+
+// ascending eigenvalues of the symmetric tridiagonal matrix (d, e), k <= 64: cyclic Jacobi rotations (setup, host)
+void tridiag_eigenvalues(int k, const double *d, const double *e, double *w)
+{
+  std::vector<double> a((size_t)k * (size_t)k, 0.);
+  for (int i = 0; i < k; ++i)
+  {
+    a[(size_t)i * k + i] = d[i];
+    if (i + 1 < k)
+      a[(size_t)i * k + i + 1] = a[(size_t)(i + 1) * k + i] = e[i];
+  }
+  for (int sweep = 0; sweep < 100; ++sweep)
+  {
+    double off = 0.;
+    for (int i = 0; i < k; ++i)
+      for (int j = i + 1; j < k; ++j)
+        off += a[(size_t)i * k + j] * a[(size_t)i * k + j];
+    if (off < 1e-300)
+      break;
+    for (int p = 0; p < k; ++p)
+      for (int q = p + 1; q < k; ++q)
+      {
+        const double apq = a[(size_t)p * k + q];
+        if (apq == 0.)
+          continue;
+        const double tau = (a[(size_t)q * k + q] - a[(size_t)p * k + p]) / (2. * apq);
+        const double t = (tau >= 0. ? 1. : -1.) / (std::fabs(tau) + std::sqrt(1. + tau * tau));
+        const double c = 1. / std::sqrt(1. + t * t), sn = t * c;
+        for (int r = 0; r < k; ++r)
+        {
+          const double arp = a[(size_t)r * k + p], arq = a[(size_t)r * k + q];
+          a[(size_t)r * k + p] = c * arp - sn * arq;
+          a[(size_t)r * k + q] = sn * arp + c * arq;
+        }
+        for (int r = 0; r < k; ++r)
+        {
+          const double apr = a[(size_t)p * k + r], aqr = a[(size_t)q * k + r];
+          a[(size_t)p * k + r] = c * apr - sn * aqr;
+          a[(size_t)q * k + r] = sn * apr + c * aqr;
+        }
+      }
+  }
+  for (int i = 0; i < k; ++i)
+    w[i] = a[(size_t)i * k + i];
+  std::sort(w, w + k);
+}
+
+// dealii::PreconditionChebyshev::estimate_eigenvalues (deal.II @89057dff, pinned by mfmg's ci/Dockerfile; restated from
+// its published algorithm, see oracle/mfmg_oracle.c cheb_estimate): eig_cg_n_iterations steps of D^-1-preconditioned CG
+// on A x = v from x = 0 give the Lanczos tridiagonal matrix whose extreme eigenvalues estimate those of D^-1 A.
+// Setup-time: the operator applications and dots run on the device, the scalar recurrence on the host.
+int cheb_estimate(mfmgb_ctx *ctx, mfmgb_hierarchy *H, mfmgb_level &l)
+{
+  const int64_t n = l.n;
+  double lmin = 1., lmax = 1.;
+  if (H->cheb_cg_its > 0 && n > 0)
+  {
+    double *g = l.c_r, *hh = l.c_u1, *d = l.c_dst, *Ad = l.c_u2;
+    cudaStream_t st = ctx->stream;
+    const unsigned grid = ew_grid(ctx, n);
+    auto dot = [&](const double *a, const double *b, double *out) {
+      MFMGB_CHECK(mfmgb_vec_dot(ctx, a, b, n, out));
+      return (int)MFMGB_OK;
+    };
+    const double mean = [&] { // mean of (i mod 11), i < n
+      const int64_t full = n / 11, rem = n % 11;
+      return ((double)full * 55. + (double)(rem * (rem - 1) / 2)) / (double)n;
+    }();
+    mod11_guess_kernel<<<grid, kBlock, 0, st>>>(n, mean, g);
+    MFMGB_LAUNCHED(ctx);
+    double gg = 0.;
+    MFMGB_CHECK(dot(g, g, &gg));
+    double res = std::sqrt(gg);
+    const double res0 = res, tol = std::sqrt(2.220446049250313e-16), reduce = 1e-10;
+    double diag[64], offd[64];
+    int k = 0;
+    if (res > tol)
+    {
+      scale_rows_kernel<<<grid, kBlock, 0, st>>>(n, l.J->dinv, g, hh);
+      MFMGB_LAUNCHED(ctx);
+      negate_into_kernel<<<grid, kBlock, 0, st>>>(n, hh, d);
+      MFMGB_LAUNCHED(ctx);
+      double gh = 0., beta_alpha = 0.;
+      MFMGB_CHECK(dot(g, hh, &gh));
+      const int max_it = std::min(H->cheb_cg_its, 64);
+      for (int it = 1; it <= max_it; ++it)
+      {
+        EpiArgs e;
+        e.y = Ad;
+        MFMGB_CHECK(level_apply_A(ctx, l, d, Epi::Spmv, e));
+        double dAd = 0.;
+        MFMGB_CHECK(dot(d, Ad, &dAd));
+        const double alpha = gh / dAd;
+        MFMGB_CHECK(vec_axpy(ctx, g, alpha, Ad, n));
+        MFMGB_CHECK(dot(g, g, &gg));
+        res = std::sqrt(gg);
+        scale_rows_kernel<<<grid, kBlock, 0, st>>>(n, l.J->dinv, g, hh);
+        MFMGB_LAUNCHED(ctx);
+        double beta = gh;
+        MFMGB_CHECK(dot(g, hh, &gh));
+        beta = gh / beta;
+        diag[k] = 1. / alpha + beta_alpha;
+        beta_alpha = beta / alpha;
+        offd[k] = std::sqrt(beta) / alpha;
+        ++k;
+        if (res <= tol || res <= reduce * res0)
+          break;
+        cg_direction_host_beta_kernel<<<grid, kBlock, 0, st>>>(n, beta, hh, d);
+        MFMGB_LAUNCHED(ctx);
+      }
+    }
+    if (k > 0)
+    {
+      double w[64];
+      tridiag_eigenvalues(k, diag, offd, w);
+      lmin = w[0];
+      lmax = 1.2 * w[k - 1]; // safety factor: the CG is not converged in general
+    }
+  }
+  else
+  {
+    lmax = H->cheb_max_ev;
+    lmin = H->cheb_range != 0. ? H->cheb_max_ev / H->cheb_range : H->cheb_max_ev;
+  }
+  const double alpha = H->cheb_range > 1. ? lmax / H->cheb_range : std::min(0.9 * lmax, lmin);
+  l.cheb_lmin = lmin;
+  l.cheb_lmax = lmax;
+  l.cheb_delta = (lmax - alpha) * 0.5;
+  l.cheb_theta = (lmax + alpha) * 0.5;
+  return MFMGB_OK;
+}
+
+// One Chebyshev smoothing step in place (degree >= 1), DealIIMatrixFreeSmoother::apply
+// (source/dealii/dealii_matrix_free_smoother.cc:67-79): r = A x - b; tmp = p(D^-1 A) D^-1 r; x -= tmp.
+// zero: x == 0 on entry (r = -b without an operator application).
+int cheb_sweep(mfmgb_ctx *ctx, mfmgb_hierarchy *H, mfmgb_level &l, const double *b, double *x, bool zero)
+{
+  const int64_t n = l.n;
+  cudaStream_t st = ctx->stream;
+  const unsigned grid = ew_grid(ctx, n);
+  if (zero)
+  {
+    negate_into_kernel<<<grid, kBlock, 0, st>>>(n, b, l.c_r);
+    MFMGB_LAUNCHED(ctx);
+  }
+  else
+  {
+    EpiArgs e;
+    e.y = l.c_r;
+    e.b = b;
+    MFMGB_CHECK(level_apply_A(ctx, l, x, Epi::Resid, e));
+  }
+  const double theta = l.cheb_theta, delta = l.cheb_delta;
+  cheb_start_kernel<<<grid, kBlock, 0, st>>>(n, 1. / theta, l.J->dinv, l.c_r, l.c_dst, l.c_u1);
+  MFMGB_LAUNCHED(ctx);
+  if (std::fabs(delta) >= 1e-40)
+  {
+    double rhok = delta / theta;
+    const double sigma = theta / delta;
+    for (int k = 0; k < H->cheb_degree; ++k)
+    {
+      EpiArgs e;
+      e.y = l.c_u2;
+      e.b = l.c_r;
+      MFMGB_CHECK(level_apply_A(ctx, l, l.c_dst, Epi::Resid, e)); // u2 = A dst - src
+      const double rhokp = 1. / (2. * sigma - rhok);
+      const double f1 = rhokp * rhok, f2 = 2. * rhokp / delta;
+      rhok = rhokp;
+      cheb_step_kernel<<<grid, kBlock, 0, st>>>(n, f1, f2, l.J->dinv, l.c_u2, l.c_u1, l.c_dst);
+      MFMGB_LAUNCHED(ctx);
+    }
+  }
+  cheb_finish_kernel<<<grid, kBlock, 0, st>>>(n, zero ? 1 : 0, l.c_dst, x);
+  MFMGB_LAUNCHED(ctx);
+  return MFMGB_OK;
+}
+
 int apply_level(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, int li)
 {
   mfmgb_level &fine = H->lev[li];
@@ -153,11 +399,22 @@ int apply_level(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, 
 
   mfmgb_level &coarse = H->lev[li + 1];
   const int nu = H->nu;
+  // Chebyshev of degree >= 1: every sweep works in place on x (1 + degree operator applications, own work vectors).
+  // Degree 0 is damped Jacobi with omega = 1 / theta (set at finalize) and takes the fused path below.
+  const bool cheb_in_place = H->chebyshev && H->cheb_degree > 0;
   // sweeps that run as an out-of-place fused SpMV (each flips the buffer the iterate lives in)
-  const int n_oop = (x_is_zero && nu > 0 ? nu - 1 : nu) + nu;
+  const int n_oop = cheb_in_place ? 0 : (x_is_zero && nu > 0 ? nu - 1 : nu) + nu;
   double *cur = x, *other = fine.xtmp;
+  const double omega = fine.J->omega;
   STAGE_MARK(0);
-  if (x_is_zero)
+  if (cheb_in_place)
+  {
+    if (x_is_zero && nu == 0)
+      MFMGB_CHECK(vec_fill(ctx, cur, 0., n));
+    for (int s = 0; s < nu; ++s)
+      MFMGB_CHECK(cheb_sweep(ctx, H, fine, b, cur, x_is_zero && s == 0));
+  }
+  else if (x_is_zero)
   {
     if (n_oop & 1)
       std::swap(cur, other); // start in xtmp so the last sweep lands in x
@@ -167,14 +424,14 @@ int apply_level(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, 
       MFMGB_CHECK(vec_fill(ctx, cur, 0., n));
   }
   EpiArgs e;
-  for (int s = (x_is_zero && nu > 0 ? 1 : 0); s < nu; ++s) // pre-smoothing, hierarchy.hpp:277-279
+  for (int s = (x_is_zero && nu > 0 ? 1 : 0); s < nu && !cheb_in_place; ++s) // pre-smoothing, hierarchy.hpp:277-279
   {
     e = EpiArgs();
     e.y = other;
     e.b = b;
     e.dinv = fine.J->dinv;
     e.xin = cur;
-    e.omega = H->omega;
+    e.omega = omega;
     MFMGB_CHECK(level_apply_A(ctx, fine, cur, Epi::Jacobi, e));
     std::swap(cur, other);
   }
@@ -232,12 +489,17 @@ int apply_level(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, 
   STAGE_MARK(5);
   for (int s = 0; s < nu; ++s) // post-smoothing, hierarchy.hpp:305-306
   {
+    if (cheb_in_place)
+    {
+      MFMGB_CHECK(cheb_sweep(ctx, H, fine, b, cur, false));
+      continue;
+    }
     e = EpiArgs();
     e.y = other;
     e.b = b;
     e.dinv = fine.J->dinv;
     e.xin = cur;
-    e.omega = H->omega;
+    e.omega = omega;
     MFMGB_CHECK(level_apply_A(ctx, fine, cur, Epi::Jacobi, e));
     std::swap(cur, other);
   }
@@ -456,6 +718,33 @@ extern "C"
     return MFMGB_OK;
   }
 
+  MFMGB_API int mfmgb_hierarchy_set_smoother_chebyshev(mfmgb_hierarchy *H, int degree, double smoothing_range,
+                                                       double max_eigenvalue, int eig_cg_n_iterations)
+  {
+    if (!H || H->finalized || degree < 0 || eig_cg_n_iterations < 0 || eig_cg_n_iterations > 64 ||
+        (eig_cg_n_iterations > 0 && eig_cg_n_iterations <= 2))
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_set_smoother_chebyshev: bad arguments (degree >= 0; "
+                                                "eig_cg_n_iterations 0 or 3..64, as deal.II asserts)");
+    H->chebyshev = true;
+    H->cheb_degree = degree;
+    H->cheb_range = smoothing_range;
+    H->cheb_max_ev = max_eigenvalue;
+    H->cheb_cg_its = eig_cg_n_iterations;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API int mfmgb_hierarchy_chebyshev_info(const mfmgb_hierarchy *H, int level, double *out4)
+  {
+    if (!H || !out4 || level < 0 || level >= H->n_levels - 1 || !H->chebyshev || !H->finalized)
+      return fail(nullptr, MFMGB_ERR_INVALID, "mfmgb_hierarchy_chebyshev_info: bad arguments");
+    const mfmgb_level &l = H->lev[level];
+    out4[0] = l.cheb_lmin;
+    out4[1] = l.cheb_lmax;
+    out4[2] = l.cheb_theta;
+    out4[3] = l.cheb_delta;
+    return MFMGB_OK;
+  }
+
   MFMGB_API int mfmgb_hierarchy_set_coarse_dd(mfmgb_hierarchy *H, const mfmgb_coarse_dd *dd)
   {
     if (!H || !dd || H->finalized)
@@ -528,6 +817,19 @@ extern "C"
         const int64_t ng = l.halo ? l.halo->n_ghost : 0;
         MFMGB_CHECK(mfmgb_vec_alloc(ctx, l.n + ng, &l.res));
         MFMGB_CHECK(mfmgb_vec_alloc(ctx, l.n + ng, &l.xtmp));
+        if (H->chebyshev)
+        {
+          if (H->distributed)
+            return fail(ctx, MFMGB_ERR_NOT_IMPLEMENTED, "mfmgb_hierarchy_finalize: the Chebyshev smoother is implemented "
+                                                        "for single-GPU hierarchies (the reference pairs it with its "
+                                                        "host matrix-free path only)");
+          for (double **v : {&l.c_r, &l.c_dst, &l.c_u1, &l.c_u2})
+            MFMGB_CHECK(mfmgb_vec_alloc(ctx, l.n + ng, v));
+          MFMGB_CHECK(cheb_estimate(ctx, H, l));
+          // degree 0 == damped Jacobi with omega = 1 / theta: served by the fused Jacobi sweep
+          if (H->cheb_degree == 0)
+            l.J->omega = 1. / l.cheb_theta;
+        }
       }
       else
       {
@@ -603,6 +905,10 @@ extern "C"
       cudaFree(l.bc);
       cudaFree(l.xc);
       cudaFree(l.gb);
+      cudaFree(l.c_r);
+      cudaFree(l.c_dst);
+      cudaFree(l.c_u1);
+      cudaFree(l.c_u2);
     }
     cudaFree(H->b_dev);
     cudaFree(H->x_dev);
@@ -676,9 +982,10 @@ extern "C"
     if (use_graph)
     {
       MFMGB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      ctx->prof_capturing = true;
       rc = apply_level(ctx, H, b, x, 0);
       cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
-      ctx->prof_on = false;
+      ctx->prof_on = ctx->prof_capturing = false;
       if (rc == MFMGB_OK && ce == cudaSuccess)
         ce = cudaGraphInstantiate(&exec, graph, 0);
       if (graph)

@@ -538,8 +538,11 @@ class Hierarchy:
         self.coarse_dd = coarse_dd
         lib = handle.lib
         self.params = params or {}
-        if str(_get(params, "smoother.type", "Jacobi")).lower() != "jacobi":
-            raise MfmgError(_lib.ERR_INVALID, "Only Jacobi smoother is implemented.")
+        smoother = str(_get(params, "smoother.type", "Jacobi")).lower()
+        if smoother not in ("jacobi", "chebyshev"):
+            # CudaSmoother: "Only Jacobi smoother is implemented." (cuda_smoother.cu:110); Chebyshev is the smoother of
+            # the reference's matrix-free path (dealii_matrix_free_smoother.cc:34-60), available here on the device
+            raise MfmgError(_lib.ERR_INVALID, f'Unknown smoother name: "{smoother}"')
         solver = str(_get(params, "solver.type", "lu_dense"))
         if solver == "amgx":
             raise NotImplementedExc(_lib.ERR_NOT_IMPLEMENTED, "solver.type amgx is not available in mfmg_b200")
@@ -560,6 +563,10 @@ class Hierarchy:
                 check(handle.ctx, lib.mfmgb_hierarchy_set_mf_operator(self.ptr, op.ptr))
             else:
                 check(handle.ctx, lib.mfmgb_hierarchy_set_operator(self.ptr, li, op.ptr))
+        if smoother == "chebyshev":
+            check(handle.ctx, lib.mfmgb_hierarchy_set_smoother_chebyshev(
+                self.ptr, int(_get(params, "smoother.degree", 0)), float(_get(params, "smoother.smoothing_range", 0.0)),
+                float(_get(params, "smoother.max_eigenvalue", 1.0)), int(_get(params, "smoother.eig_cg_n_iterations", 8))))
         if coarse_offsets is not None:  # (marks the hierarchy as row-partitioned before R / P are checked)
             co = np.ascontiguousarray(coarse_offsets, dtype=np.int64)
             check(handle.ctx, lib.mfmgb_hierarchy_set_coarse_offsets(self.ptr, co.ctypes.data, len(co) - 1))
@@ -691,6 +698,12 @@ class Hierarchy:
         check(self.handle.ctx, self.handle.lib.mfmgb_vcycle_profile(self.handle.ctx, self.ptr, b.ptr, x.ptr,
                                                                     ms.ctypes.data))
         return dict(zip(self.STAGES, ms.tolist()))
+
+    def chebyshev_info(self, level: int = 0):
+        """(lambda_min, lambda_max incl. the safety factor 1.2, theta, delta) of a level's Chebyshev smoother."""
+        out = np.zeros(4)
+        check(self.handle.ctx, self.handle.lib.mfmgb_hierarchy_chebyshev_info(self.ptr, level, out.ctypes.data))
+        return tuple(out)
 
     def timeline(self, x: DeviceVector, b: DeviceVector, graph: bool = True):
         """[(piece, ms), ...] of one V-cycle, resolved per kernel group; graph=True: times of a CUDA-graph replay."""

@@ -48,6 +48,8 @@ def lib():
         L.orc_hierarchy_new.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double]
         L.orc_hierarchy_set_explicit_transpose.argtypes = [_vp, ctypes.c_int]
         L.orc_hierarchy_set_coarse_storage.argtypes = [_vp, ctypes.c_int]
+        L.orc_hierarchy_set_chebyshev.argtypes = [_vp, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int]
+        L.orc_hierarchy_chebyshev_info.argtypes = [_vp, ctypes.c_int, _vp]
         L.orc_hierarchy_set_operator.argtypes = [_vp, ctypes.c_int, ctypes.c_int64, _vp, _vp, _vp]
         L.orc_hierarchy_set_mf_operator.argtypes = [_vp, _vp]
         L.orc_hierarchy_set_restrictor.argtypes = [_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, _vp, _vp, _vp]
@@ -252,7 +254,7 @@ class Hierarchy:
     maps level i to level i+1."""
 
     def __init__(self, operators, restrictors, n_smoothing_steps=1, is_preconditioner=True, omega=1.0,
-                 explicit_transpose=True, coarse_storage="auto"):
+                 explicit_transpose=True, coarse_storage="auto", chebyshev=None):
         """coarse_storage: "dense" = the dense getrf/getrs restatement, "band" = the same factorisation on band
         storage (bit-identical results, orc_band_lu_factor), "auto" = band when the bandwidth is below n / 4."""
         L = lib()
@@ -261,6 +263,13 @@ class Hierarchy:
         self.ptr = L.orc_hierarchy_new(self.n_levels, n_smoothing_steps, int(is_preconditioner), omega)
         L.orc_hierarchy_set_explicit_transpose(self.ptr, int(explicit_transpose))
         L.orc_hierarchy_set_coarse_storage(self.ptr, {"auto": 0, "dense": 1, "band": 2}[coarse_storage])
+        if chebyshev is not None:
+            # smoother.type Chebyshev (source/dealii/dealii_matrix_free_smoother.cc:34-60); keys = the reference's
+            # parameter names, defaults = dealii::PreconditionChebyshev::AdditionalData at the pinned deal.II
+            c = dict(chebyshev)
+            L.orc_hierarchy_set_chebyshev(self.ptr, int(c.get("degree", 0)), float(c.get("smoothing_range", 0.0)),
+                                          float(c.get("max_eigenvalue", 1.0)), int(c.get("eig_cg_n_iterations", 8)),
+                                          {"mod11": 0, "constant": 1}[c.get("initial_guess", "mod11")])
         self.A0 = None
         for li, op in enumerate(operators):
             if isinstance(op, MatrixFreeLaplace):
@@ -283,6 +292,12 @@ class Hierarchy:
             L.orc_hierarchy_set_restrictor(self.ptr, li + 1, n_rows, n_cols, rowptr.ctypes.data,
                                            col.ctypes.data, val.ctypes.data)
         self.info = L.orc_hierarchy_finalize(self.ptr)
+
+    def chebyshev_info(self, level=0):
+        """(lambda_min, lambda_max incl. the 1.2 safety factor, theta, delta) of a level's Chebyshev smoother."""
+        out = np.zeros(4)
+        lib().orc_hierarchy_chebyshev_info(self.ptr, level, out.ctypes.data)
+        return tuple(out)
 
     def vmult(self, b, x0=None):
         """x = Hierarchy::vmult(x, b); x0 only matters when is_preconditioner is false."""

@@ -383,6 +383,10 @@ typedef struct
   i32 *p_col;
   double *p_val;
   double *dinv;
+  /* Chebyshev smoother (dealii::PreconditionChebyshev as used by DealIIMatrixFreeSmoother): theta, delta from the
+   * eigenvalue estimate; work vectors */
+  double cheb_theta, cheb_delta, cheb_lambda_min, cheb_lambda_max;
+  double *cw1, *cw2, *cw3, *cw4;
   /* coarsest level: dense LU, or the same factorisation on band storage (band_kl >= 0) */
   double *lu;
   i32 *piv;
@@ -399,6 +403,13 @@ typedef struct
   double omega;
   int explicit_transpose; /* 1: prolong with stored R^T; 0: implicit Tvmult */
   int coarse_storage;     /* 0: automatic, 1: dense array, 2: band storage (same arithmetic, see orc_band_lu_factor) */
+  /* smoother.type: 0 = Jacobi (source/cuda/cuda_smoother.cu), 1 = Chebyshev (source/dealii/dealii_matrix_free_smoother.cc) */
+  int smoother_type;
+  int cheb_degree;        /* smoother.degree            (PreconditionChebyshev::AdditionalData::degree, default 0)          */
+  double cheb_range;      /* smoother.smoothing_range   (default 0: alpha = min(0.9 lambda_max, lambda_min))                 */
+  double cheb_max_ev;     /* smoother.max_eigenvalue    (default 1; only used when cheb_cg_its == 0)                         */
+  int cheb_cg_its;        /* eig_cg_n_iterations        (default 8; the reference never changes it)                          */
+  int cheb_guess;         /* initial vector of the eigenvalue CG: 0 = (i mod 11) minus its mean, 1 = 1/sqrt(n) with v_0 = 0  */
   orc_level *lev;
 } orc_hierarchy;
 
@@ -421,6 +432,16 @@ orc_hierarchy *orc_hierarchy_new(int n_levels, int n_smoothing_steps, int is_pre
 
 void orc_hierarchy_set_explicit_transpose(orc_hierarchy *h, int flag) { h->explicit_transpose = flag; }
 void orc_hierarchy_set_coarse_storage(orc_hierarchy *h, int mode) { h->coarse_storage = mode; }
+void orc_hierarchy_set_chebyshev(orc_hierarchy *h, int degree, double smoothing_range, double max_eigenvalue,
+                                 int eig_cg_n_iterations, int initial_guess)
+{
+  h->smoother_type = 1;
+  h->cheb_degree = degree;
+  h->cheb_range = smoothing_range;
+  h->cheb_max_ev = max_eigenvalue;
+  h->cheb_cg_its = eig_cg_n_iterations;
+  h->cheb_guess = initial_guess;
+}
 
 /* The arrays are borrowed: the caller keeps them alive for the life of the hierarchy. */
 void orc_hierarchy_set_operator(orc_hierarchy *h, int level, i64 n, const i64 *rowptr,
@@ -448,6 +469,178 @@ void orc_hierarchy_set_restrictor(orc_hierarchy *h, int level, i64 n_rows, i64 n
   l->r_rowptr = rowptr;
   l->r_col = col;
   l->r_val = val;
+}
+
+static void level_apply_A(const orc_level *l, const double *x, double *y);
+double orc_dot(i64 n, const double *a, const double *b);
+
+/* eigenvalues of a symmetric tridiagonal matrix (diagonal d[0..k), off-diagonal e[0..k-1)) by cyclic Jacobi rotations
+ * on the dense k x k matrix (k <= 64); ascending on return in w */
+static void tridiag_eigenvalues(int k, const double *d, const double *e, double *w)
+{
+  double a[64 * 64];
+  memset(a, 0, sizeof(double) * (size_t)k * (size_t)k);
+  for (int i = 0; i < k; ++i)
+  {
+    a[i * k + i] = d[i];
+    if (i + 1 < k)
+      a[i * k + i + 1] = a[(i + 1) * k + i] = e[i];
+  }
+  for (int sweep = 0; sweep < 100; ++sweep)
+  {
+    double off = 0.;
+    for (int i = 0; i < k; ++i)
+      for (int j = i + 1; j < k; ++j)
+        off += a[i * k + j] * a[i * k + j];
+    if (off < 1e-300)
+      break;
+    for (int p = 0; p < k; ++p)
+      for (int q = p + 1; q < k; ++q)
+      {
+        const double apq = a[p * k + q];
+        if (apq == 0.)
+          continue;
+        const double tau = (a[q * k + q] - a[p * k + p]) / (2. * apq);
+        const double t = (tau >= 0. ? 1. : -1.) / (fabs(tau) + sqrt(1. + tau * tau));
+        const double c = 1. / sqrt(1. + t * t), sn = t * c;
+        for (int r = 0; r < k; ++r)
+        {
+          const double arp = a[r * k + p], arq = a[r * k + q];
+          a[r * k + p] = c * arp - sn * arq;
+          a[r * k + q] = sn * arp + c * arq;
+        }
+        for (int r = 0; r < k; ++r)
+        {
+          const double apr = a[p * k + r], aqr = a[q * k + r];
+          a[p * k + r] = c * apr - sn * aqr;
+          a[q * k + r] = sn * apr + c * aqr;
+        }
+      }
+  }
+  for (int i = 0; i < k; ++i)
+    w[i] = a[i * k + i];
+  for (int i = 1; i < k; ++i) /* insertion sort */
+  {
+    double v = w[i];
+    int j = i - 1;
+    for (; j >= 0 && w[j] > v; --j)
+      w[j + 1] = w[j];
+    w[j + 1] = v;
+  }
+}
+
+/* dealii::PreconditionChebyshev::estimate_eigenvalues (deal.II @89057dff, the version mfmg's ci/Dockerfile pins;
+ * third-party, restated from its published algorithm): eig_cg_n_iterations steps of CG preconditioned with D^-1 on
+ * A x = v from x = 0, v = the "high-frequency" start vector; the CG coefficients give the Lanczos tridiagonal matrix
+ *   T_jj = 1/alpha_j + beta_{j-1}/alpha_{j-1},  T_{j,j+1} = sqrt(beta_j)/alpha_j
+ * whose extreme eigenvalues estimate those of D^-1 A; lambda_max gets the safety factor 1.2.  Then
+ *   alpha = smoothing_range > 1 ? lambda_max / smoothing_range : min(0.9 lambda_max, lambda_min)
+ *   delta = (lambda_max - alpha) / 2,  theta = (lambda_max + alpha) / 2.
+ * CG recurrence and stopping rule as SolverCG with ReductionControl(n_its, sqrt(eps), 1e-10). */
+static void cheb_estimate(orc_hierarchy *h, orc_level *l)
+{
+  const i64 n = l->n;
+  l->cw1 = (double *)calloc((size_t)n, sizeof(double));
+  l->cw2 = (double *)calloc((size_t)n, sizeof(double));
+  l->cw3 = (double *)calloc((size_t)n, sizeof(double));
+  l->cw4 = (double *)calloc((size_t)n, sizeof(double));
+  double lmin = 1., lmax = 1.;
+  if (h->cheb_cg_its > 0 && n > 0)
+  {
+    double *x = l->cw1, *g = l->cw2, *hh = l->cw3, *d = l->cw4;
+    double *Ad = (double *)calloc((size_t)n, sizeof(double));
+    /* right-hand side = start vector (set_initial_guess) */
+    if (h->cheb_guess == 0)
+    {
+      double mean = 0.;
+      for (i64 i = 0; i < n; ++i)
+      {
+        g[i] = (double)(i % 11);
+        mean += g[i];
+      }
+      mean /= (double)n;
+      for (i64 i = 0; i < n; ++i)
+        g[i] -= mean;
+    }
+    else
+    {
+      for (i64 i = 0; i < n; ++i)
+        g[i] = 1. / sqrt((double)n);
+      g[0] = 0.;
+    }
+    /* x = 0: g = A x - b = -b */
+    for (i64 i = 0; i < n; ++i)
+    {
+      x[i] = 0.;
+      g[i] = -g[i];
+    }
+    double res = sqrt(orc_dot(n, g, g));
+    const double res0 = res, tol = sqrt(2.220446049250313e-16), reduce = 1e-10;
+    double diag[64], offd[64];
+    int k = 0;
+    if (res > tol)
+    {
+      for (i64 i = 0; i < n; ++i)
+      {
+        hh[i] = l->dinv[i] * g[i];
+        d[i] = -hh[i];
+      }
+      double gh = orc_dot(n, g, hh), beta_alpha = 0.;
+      const int max_it = h->cheb_cg_its < 64 ? h->cheb_cg_its : 64;
+      for (int it = 1; it <= max_it; ++it)
+      {
+        level_apply_A(l, d, Ad);
+        double alpha = orc_dot(n, d, Ad);
+        alpha = gh / alpha;
+        for (i64 i = 0; i < n; ++i)
+        {
+          g[i] += alpha * Ad[i];
+          x[i] += alpha * d[i];
+        }
+        res = sqrt(orc_dot(n, g, g));
+        for (i64 i = 0; i < n; ++i)
+          hh[i] = l->dinv[i] * g[i];
+        double beta = gh;
+        gh = orc_dot(n, g, hh);
+        beta = gh / beta;
+        diag[k] = 1. / alpha + beta_alpha;
+        beta_alpha = beta / alpha;
+        offd[k] = sqrt(beta) / alpha;
+        ++k;
+        if (res <= tol || res <= reduce * res0)
+          break;
+        for (i64 i = 0; i < n; ++i)
+          d[i] = beta * d[i] - hh[i];
+      }
+    }
+    free(Ad);
+    if (k > 0)
+    {
+      double w[64];
+      tridiag_eigenvalues(k, diag, offd, w);
+      lmin = w[0];
+      lmax = 1.2 * w[k - 1];
+    }
+  }
+  else
+  {
+    lmax = h->cheb_max_ev;
+    lmin = h->cheb_range != 0. ? h->cheb_max_ev / h->cheb_range : h->cheb_max_ev;
+  }
+  const double alpha = h->cheb_range > 1. ? lmax / h->cheb_range : (0.9 * lmax < lmin ? 0.9 * lmax : lmin);
+  l->cheb_lambda_min = lmin;
+  l->cheb_lambda_max = lmax;
+  l->cheb_delta = (lmax - alpha) * 0.5;
+  l->cheb_theta = (lmax + alpha) * 0.5;
+}
+
+void orc_hierarchy_chebyshev_info(const orc_hierarchy *h, int level, double *out4)
+{
+  const orc_level *l = &h->lev[level];
+  out4[0] = l->cheb_lambda_min;
+  out4[1] = l->cheb_lambda_max;
+  out4[2] = l->cheb_theta;
+  out4[3] = l->cheb_delta;
 }
 
 /* Build smoothers (all but last level) and the coarse dense LU (last level):
@@ -483,6 +676,8 @@ int orc_hierarchy_finalize(orc_hierarchy *h)
       }
       else
         orc_inv_diag(n, l->a_rowptr, l->a_col, l->a_val, l->dinv);
+      if (h->smoother_type == 1)
+        cheb_estimate(h, l);
     }
     else
     {
@@ -525,6 +720,10 @@ void orc_hierarchy_free(orc_hierarchy *h)
     free(l->p_col);
     free(l->p_val);
     free(l->dinv);
+    free(l->cw1);
+    free(l->cw2);
+    free(l->cw3);
+    free(l->cw4);
     free(l->lu);
     free(l->piv);
   }
@@ -540,10 +739,56 @@ static void level_apply_A(const orc_level *l, const double *x, double *y)
     orc_spmv(l->n, l->a_rowptr, l->a_col, l->a_val, x, y);
 }
 
+/* dealii::PreconditionChebyshev::vmult (deal.II @89057dff): dst = p_degree(D^-1 A) D^-1 src from a zero start;
+ * `degree` further matrix-vector products after the first damped-Jacobi step (degree 0 == Jacobi with omega = 1/theta) */
+static void cheb_vmult(const orc_hierarchy *h, orc_level *l, double *dst, const double *src)
+{
+  const i64 n = l->n;
+  double *u1 = l->cw1, *u2 = l->cw2;
+  const double theta = l->cheb_theta, delta = l->cheb_delta;
+  const double f2 = 1. / theta;
+  for (i64 i = 0; i < n; ++i) /* vector_updates(start_zero = true) */
+  {
+    u1[i] = f2 * src[i];
+    dst[i] = l->dinv[i] * u1[i];
+    u1[i] = -dst[i];
+  }
+  if (fabs(delta) < 1e-40)
+    return;
+  double rhok = delta / theta;
+  const double sigma = theta / delta;
+  for (int k = 0; k < h->cheb_degree; ++k)
+  {
+    level_apply_A(l, dst, u2);
+    const double rhokp = 1. / (2. * sigma - rhok);
+    const double factor1 = rhokp * rhok, factor2 = 2. * rhokp / delta;
+    rhok = rhokp;
+    for (i64 i = 0; i < n; ++i)
+    {
+      double t = u2[i] - src[i];
+      t = l->dinv[i] * t;
+      u1[i] = factor1 * u1[i] + factor2 * t;
+      dst[i] -= u1[i];
+    }
+  }
+}
+
 static void level_smooth(const orc_hierarchy *h, orc_level *l, const double *b, double *x)
 {
-  /* source/cuda/cuda_smoother.cu:49-59 */
   i64 n = l->n;
+  if (h->smoother_type == 1)
+  {
+    /* DealIIMatrixFreeSmoother::apply, source/dealii/dealii_matrix_free_smoother.cc:67-79:
+     * r = A x - b;  tmp = Chebyshev(r);  x -= tmp */
+    level_apply_A(l, x, l->cw3);
+    for (i64 i = 0; i < n; ++i)
+      l->cw3[i] -= b[i];
+    cheb_vmult(h, l, l->cw4, l->cw3);
+    for (i64 i = 0; i < n; ++i)
+      x[i] -= l->cw4[i];
+    return;
+  }
+  /* source/cuda/cuda_smoother.cu:49-59 */
   level_apply_A(l, x, l->work);
   const double om = h->omega;
 #pragma omp parallel for schedule(static)

@@ -550,3 +550,54 @@ def test_adopted_arrays_hierarchy_vs_oracle(handle):
     it, hist = d.solver_cg(handle, ops[0], xd, d.DeviceVector.from_host(handle, np.zeros(P.n)), H, 1e-8, 200)
     assert it == it_ref
     assert np.max(np.abs(hist - hist_ref) / hist_ref) < TOL_PCG
+
+
+@pytest.mark.parametrize("matrix_free", [True, False])
+@pytest.mark.parametrize("degree", [0, 1, 3])
+@pytest.mark.parametrize("nu,precond", [(1, True), (2, False)])
+def test_chebyshev_smoother_vs_oracle(handle, matrix_free, degree, nu, precond):
+    """smoother.type Chebyshev (mfmg::DealIIMatrixFreeSmoother, source/dealii/dealii_matrix_free_smoother.cc:34-79) on
+    the device: eigenvalue estimate and V-cycle against the oracle's restatement, which the reference's own gold rate
+    pins (tests/test_oracle_kat.py)."""
+    d = _dev()
+    P, R, Ac = two_level_problem(3, 1, 12, 3, 2, "discontinuous")
+    params = {"is preconditioner": precond, "smoother": {"type": "Chebyshev", "degree": degree, "n_smoothing_steps": nu}}
+    fine_o = (P.n, P.A.rowptr, P.A.col, P.A.val)
+    if matrix_free:
+        fine_d = d.MatrixFreeLaplaceDevice(handle, 3, 1, P.cells, P.h, P.coef_per_q(), P.constrained)
+        fine_o = oracle.MatrixFreeLaplace(3, 1, P.cells, P.h, P.coef_per_q(), P.constrained)
+    else:
+        fine_d = d.SparseMatrixDevice.from_host(handle, P.A)
+    H = d.Hierarchy(handle, [fine_d, d.SparseMatrixDevice.from_host(handle, Ac)],
+                    [d.SparseMatrixDevice.from_host(handle, R)], params)
+    Ho = oracle.Hierarchy([fine_o, (Ac.n_rows, Ac.rowptr, Ac.col, Ac.val)], [(R.n_rows, R.n_cols, R.rowptr, R.col, R.val)],
+                          nu, precond, chebyshev={"degree": degree})
+    assert np.allclose(H.chebyshev_info(0), Ho.chebyshev_info(0), rtol=1e-10, atol=0)
+    rng = np.random.default_rng(degree + nu)
+    b_h, x_h = rng.standard_normal(P.n), rng.standard_normal(P.n)
+    for graph in (False, True):
+        H.use_graph(graph)
+        b, x = d.DeviceVector.from_host(handle, b_h), d.DeviceVector.from_host(handle, x_h)
+        H.vmult(x, b)
+        assert rel_err(x.to_host(), Ho.vmult(b_h, x_h)) < TOL_OP
+
+
+def test_chebyshev_gold_rate_on_gpu(handle):
+    # tests/test_hierarchy.cc:353: matrix-free + Chebyshev two-grid rate 0.0880045475 (reference tolerance 1e-2)
+    d = _dev()
+    P, R, Ac = two_level_problem(3, 1, 4, 2, 2, "constant")
+    M = d.MatrixFreeLaplaceDevice(handle, 3, 1, P.cells, P.h, P.coef_per_q(), P.constrained)
+    H = d.Hierarchy(handle, [M, d.SparseMatrixDevice.from_host(handle, Ac)], [d.SparseMatrixDevice.from_host(handle, R)],
+                    {"is preconditioner": False, "smoother": {"type": "Chebyshev"}})
+    x = d.DeviceVector.from_host(handle, oracle.std_uniform01(P.n, skip=P.constrained))
+    b = d.DeviceVector.from_host(handle, np.zeros(P.n))
+    y = d.DeviceVector(handle, P.n)
+    res = []
+    for _ in range(20):
+        H.vmult(x, b)
+        M.apply(x, y)
+        res.append(y.l2_norm())
+    assert abs(res[-1] / res[-2] - 0.0880045475) / 0.0880045475 < 1e-2
+    with pytest.raises(d.MfmgError):
+        d.Hierarchy(handle, [M, d.SparseMatrixDevice.from_host(handle, Ac)],
+                    [d.SparseMatrixDevice.from_host(handle, R)], {"smoother": {"type": "Gauss-Seidel"}})

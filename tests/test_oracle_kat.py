@@ -400,3 +400,53 @@ def test_band_lu_is_bit_identical_to_dense_lu():
     assert np.array_equal(xd, xb)
     # nu = 0, R = I: the cycle returns x = -(-A^-1 ... ) i.e. the coarse solve of the residual -b: x = A^-1 b
     assert np.linalg.norm(A @ xd - b) < 1e-9 * np.linalg.norm(b)
+
+
+def test_chebyshev_two_grid_gold_rate_host_matrix_free():
+    """tests/test_hierarchy.cc:281-353,412: 3D hyper_cube refine 2, matrix-free operator, smoother.type Chebyshev with
+    deal.II's defaults (degree 0, eigenvalue estimate by 8 CG steps), 2x2x2 agglomerates x 2 eigenvectors, solver mode,
+    x0 ~ U(0,1) on unconstrained DoFs, 20 cycles: rate = res20 / res19.  Reference gold (lanczos eigensolver)
+    0.0880045475, asserted there to 1e-2 relative; the oracle's restatement of DealIIMatrixFreeSmoother +
+    dealii::PreconditionChebyshev reproduces it to ~1e-4, with either start vector of the eigenvalue CG."""
+    gold = 0.0880045475
+    P, R, Ac = two_level_problem(3, 1, 4, 2, 2, "constant")
+    Mo = oracle.MatrixFreeLaplace(3, 1, P.cells, P.h, P.coef_per_q(), P.constrained)
+    for guess in ("mod11", "constant"):
+        H = oracle.Hierarchy([Mo, (Ac.n_rows, Ac.rowptr, Ac.col, Ac.val)], [(R.n_rows, R.n_cols, R.rowptr, R.col, R.val)],
+                             1, False, chebyshev={"initial_guess": guess})
+        x = oracle.std_uniform01(P.n, skip=P.constrained)
+        b = np.zeros(P.n)
+        res = []
+        for _ in range(20):
+            x = H.vmult(b, x)
+            res.append(np.linalg.norm(Mo.apply(x)))
+        rate = res[-1] / res[-2]
+        assert abs(rate - gold) / gold < 1e-3, (guess, rate)
+        lmin, lmax, theta, delta = H.chebyshev_info(0)
+        assert 0 < lmin < lmax and abs(theta - 0.5 * (lmax + min(0.9 * lmax, lmin))) < 1e-14
+    # higher degrees smooth more: the rate drops monotonically
+    rates = []
+    for degree in (0, 1, 2):
+        H = oracle.Hierarchy([Mo, (Ac.n_rows, Ac.rowptr, Ac.col, Ac.val)], [(R.n_rows, R.n_cols, R.rowptr, R.col, R.val)],
+                             1, False, chebyshev={"degree": degree})
+        x = oracle.std_uniform01(P.n, skip=P.constrained)
+        res = []
+        for _ in range(12):
+            x = H.vmult(np.zeros(P.n), x)
+            res.append(np.linalg.norm(Mo.apply(x)))
+        rates.append(res[-1] / res[-2])
+    assert rates[0] > rates[1] > rates[2]
+
+
+def test_chebyshev_degree_zero_is_damped_jacobi():
+    """PreconditionChebyshev of degree 0 is Jacobi with omega = 1 / theta: the oracle's Chebyshev cycle equals its Jacobi
+    cycle with that damping to rounding."""
+    P, R, Ac = two_level_problem(3, 1, 8, 2, 2, "discontinuous")
+    ops = [(P.n, P.A.rowptr, P.A.col, P.A.val), (Ac.n_rows, Ac.rowptr, Ac.col, Ac.val)]
+    res = [(R.n_rows, R.n_cols, R.rowptr, R.col, R.val)]
+    Hc = oracle.Hierarchy(ops, res, 2, True, chebyshev={})
+    theta = Hc.chebyshev_info(0)[2]
+    Hj = oracle.Hierarchy(ops, res, 2, True, omega=1.0 / theta)
+    b = np.random.default_rng(1).standard_normal(P.n)
+    xc, xj = Hc.vmult(b), Hj.vmult(b)
+    assert np.linalg.norm(xc - xj) / np.linalg.norm(xj) < 1e-14
