@@ -60,6 +60,9 @@ def parse_args(argv=None):
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = N cubes of --cells^3 stacked along z (the default the driver runs); "
                          "strong = one --cells^3 cube row-partitioned over the N GPUs (BASELINE configs[3])")
+    ap.add_argument("--levels", type=int, default=2,
+                    help="N = 1: hierarchy depth; levels beyond the second aggregate 2x2x2 agglomerates each "
+                         "(hostsetup.build_multilevel; the reference cannot build more than two levels itself)")
     ap.add_argument("--north-star", default="auto", choices=["auto", "on", "off"],
                     help="also measure BASELINE configs[3] (512^3 cells): auto = only for the default workload")
     ap.add_argument("--north-star-cells", type=int, default=512)
@@ -84,7 +87,8 @@ def canonical_config(args, world, n, nnz, n_c):
         "workload": (f"3D Q{args.degree} {args.material} Laplace, {cx}x{cy}x{cz} cells (h=1/{args.cells}), n={n}, "
                      f"nnz={nnz}; two-level spectral AMGe, {args.block}^3-cell agglomerates x {args.neig} eigvec "
                      f"(n_c={n_c}); V(1,1) Jacobi omega=1, direct LU coarse solve, preconditioner mode; level 0 "
-                     + ("matrix-free (laplace_matrix_free)" if args.matrix_free else "assembled CSR")),
+                     + ("matrix-free (laplace_matrix_free)" if args.matrix_free else "assembled CSR")
+                     + (f"; {args.levels} levels (2x2x2 aggregation below level 1)" if args.levels > 2 else "")),
         "scaling": args.scaling,
         "units_per_step": units,
         "value_definition": ("single-GPU-sized V-cycle units per second = units_per_step x (V-cycles of the global "
@@ -121,6 +125,15 @@ def build_global(args, world):
         P = hs.LaplaceProblem.create_box(3, args.degree, cells, h, args.material)
     R = hs.build_restrictor(P, (args.block,) * 3, args.neig)
     Ac = hs.galerkin(P.A, R)
+    if args.levels > 2:   # deeper hierarchy: (operators, restrictors) lists ride along on the problem object
+        grid = tuple(-(-c // args.block) for c in cells)
+        ops, res = [P.A, Ac], [R]
+        for _ in range(args.levels - 2):
+            R2 = hs.aggregate_restrictor(grid, (2, 2, 2), args.neig)
+            res.append(R2)
+            ops.append(hs.galerkin(ops[-1], R2))
+            grid = tuple(-(-g // 2) for g in grid)
+        P.levels = (ops, res)
     return P, R, Ac, time.time() - t0
 
 
@@ -248,6 +261,10 @@ def oracle_hierarchy(P, R, Ac, matrix_free=False):
     fine = (P.n, P.A.rowptr, P.A.col, P.A.val)
     if matrix_free:
         fine = oracle.MatrixFreeLaplace(3, P.degree, P.cells, P.h, P.coef_per_q(), P.constrained)
+    if getattr(P, "levels", None):
+        ops, res = P.levels
+        return oracle.Hierarchy([fine] + [(o.n_rows, o.rowptr, o.col, o.val) for o in ops[1:]],
+                                [(r.n_rows, r.n_cols, r.rowptr, r.col, r.val) for r in res], 1, True)
     return oracle.Hierarchy([fine, (Ac.n_rows, Ac.rowptr, Ac.col, Ac.val)],
                             [(R.n_rows, R.n_cols, R.rowptr, R.col, R.val)], 1, True)
 
@@ -592,6 +609,20 @@ def build_ours(args, d, handle, dist, rank, world):
                             [d.SparseMatrixDevice.from_host(handle, R)], {"is preconditioner": True})
             mf_nq = 0 if "stencil" in M.kernel else (1 if "per-cell" in M.kernel else (args.degree + 1) ** 3)
             nbytes = algorithmic_bytes(P, R, Ac, int(np.prod(P.cells)), mf_nq)
+        elif getattr(P, "levels", None):
+            ops, res = P.levels
+            H = d.Hierarchy(handle, [d.SparseMatrixDevice.from_host(handle, o) for o in ops],
+                            [d.SparseMatrixDevice.from_host(handle, r) for r in res], {"is preconditioner": True})
+            nbytes = algorithmic_bytes(P, R, Ac)
+            # deeper levels: the dense solve moves to the last level, levels 1 .. L-2 cost a zero-guess sweep, a
+            # residual, a fused Jacobi sweep and their transfers each
+            extra = -nbytes["dense"] + 8 * ops[-1].n_rows ** 2 + 16 * ops[-1].n_rows
+            for lvl in range(1, len(ops) - 1):
+                nl, nz, rr = ops[lvl].n_rows, ops[lvl].nnz, res[lvl]
+                extra += 24 * nl + 2 * (12 * nz + 4 * (nl + 1) + 16 * nl) + 8 * nl + 16 * nl
+                extra += 2 * 12 * rr.nnz + 4 * (rr.n_rows + 1) + 4 * (nl + 1) + 8 * nl + 8 * rr.n_rows + 8 * rr.n_rows + 16 * nl
+            nbytes["vcycle"] += extra
+            nbytes["dense"] = 8 * ops[-1].n_rows ** 2 + 16 * ops[-1].n_rows
         else:
             H = d.Hierarchy.from_host(handle, P.A, R, Ac, {"is preconditioner": True})
             nbytes = algorithmic_bytes(P, R, Ac)

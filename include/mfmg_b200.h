@@ -132,6 +132,9 @@ extern "C"
   /* out-of-place form: x_out = x_in - omega D^-1 (A x_in - b); x_out must not alias x_in */
   MFMGB_API int mfmgb_jacobi_apply_oop(mfmgb_ctx *ctx, const mfmgb_jacobi *J, const mfmgb_csr *A, const double *b,
                                        const double *x_in, double *x_out);
+  /* x <- x - omega D^-1 r for a residual r = A x - b the caller formed with its own operator (user matrix-free
+   * operators behind CudaMatrixFreeOperator): the update half of cuda_smoother.cu:52-59 */
+  MFMGB_API int mfmgb_jacobi_apply_residual(mfmgb_ctx *ctx, const mfmgb_jacobi *J, const double *r, double *x);
   /* x = omega D^-1 b : the sweep when x == 0 on entry (hierarchy.hpp:253-259 then :277-279) */
   MFMGB_API int mfmgb_jacobi_apply_zero_guess(mfmgb_ctx *ctx, const mfmgb_jacobi *J, const double *b, double *x);
 

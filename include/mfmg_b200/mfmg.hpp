@@ -24,6 +24,7 @@
 #define MFMG_B200_MFMG_HPP
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <map>
 #include <memory>
@@ -224,6 +225,33 @@ class SparseMatrixDevice
   static_assert(sizeof(ScalarType) == sizeof(double), "FP64 only on this path");
 
 public:
+  // empty matrix, to be filled by reinit (sparse_matrix_device.cuh:30, the object a MeshEvaluator receives)
+  SparseMatrixDevice() = default;
+  // TAKES OWNERSHIP like the constructor below, releasing what the object held (sparse_matrix_device.templates.cuh:274-300)
+  void reinit(std::shared_ptr<CudaHandle const> handle, ScalarType *val_dev_, int *column_index_dev_, int *row_ptr_dev_,
+              unsigned int local_nnz, unsigned int n_rows, unsigned int n_cols)
+  {
+    release();
+    _handle = std::move(handle);
+    val_dev = val_dev_;
+    column_index_dev = column_index_dev_;
+    row_ptr_dev = row_ptr_dev_;
+    check_status(_handle->ctx, mfmgb_csr_adopt_device(_handle->ctx, n_rows, n_cols, local_nnz, val_dev, column_index_dev,
+                                                      row_ptr_dev, &_csr));
+  }
+  // convert_matrix semantics: copy a host CSR into this object
+  void reinit(std::shared_ptr<CudaHandle const> handle, unsigned int n_rows, unsigned int n_cols,
+              std::vector<int64_t> const &row_ptr, std::vector<int> const &column_index, std::vector<double> const &val)
+  {
+    release();
+    _handle = std::move(handle);
+    check_status(_handle->ctx, mfmgb_csr_upload(_handle->ctx, n_rows, n_cols, row_ptr.data(), column_index.data(),
+                                                val.data(), &_csr));
+    void *rp = nullptr;
+    int is64 = 0;
+    mfmgb_csr_device_arrays(_csr, &val_dev, &column_index_dev, &rp, &is64);
+    row_ptr_dev = is64 ? nullptr : static_cast<int *>(rp);
+  }
   // TAKES OWNERSHIP of the three cudaMalloc'ed arrays and frees them in the destructor
   // (sparse_matrix_device.templates.cuh:244-272)
   SparseMatrixDevice(std::shared_ptr<CudaHandle const> handle, ScalarType *val_dev_, int *column_index_dev_,
@@ -254,7 +282,7 @@ public:
     mfmgb_csr_device_arrays(_csr, &val_dev, &column_index_dev, &rp, &is64);
     row_ptr_dev = is64 ? nullptr : static_cast<int *>(rp);
   }
-  ~SparseMatrixDevice() { mfmgb_csr_destroy(_handle->ctx, _csr); }
+  ~SparseMatrixDevice() { release(); }
   SparseMatrixDevice(SparseMatrixDevice const &) = delete;
   SparseMatrixDevice &operator=(SparseMatrixDevice const &) = delete;
 
@@ -273,20 +301,90 @@ public:
   mfmgb_csr *c_handle() const { return _csr; }
   std::shared_ptr<CudaHandle const> const &handle() const { return _handle; }
 
+  // host copy of the CSR arrays (setup-time products, tests/test_utils_device.cu:221-263)
+  void copy_to_host(std::vector<int64_t> &row_ptr, std::vector<int> &column_index, std::vector<double> &val) const
+  {
+    row_ptr.resize((std::size_t)info(0) + 1);
+    column_index.resize((std::size_t)std::max<int64_t>(info(2), 1));
+    val.resize((std::size_t)std::max<int64_t>(info(2), 1));
+    check_status(_handle->ctx, mfmgb_csr_download(_handle->ctx, _csr, row_ptr.data(), column_index.data(), val.data()));
+    column_index.resize((std::size_t)info(2));
+    val.resize((std::size_t)info(2));
+  }
+
   ScalarType *val_dev = nullptr;
   int *column_index_dev = nullptr;
   int *row_ptr_dev = nullptr;
 
 private:
+  void release()
+  {
+    if (_csr)
+      mfmgb_csr_destroy(_handle->ctx, _csr);
+    _csr = nullptr;
+  }
   int64_t info(int which) const
   {
-    int64_t v[3];
-    mfmgb_csr_info(_csr, &v[0], &v[1], &v[2]);
+    int64_t v[3] = {0, 0, 0};
+    if (_csr)
+      mfmgb_csr_info(_csr, &v[0], &v[1], &v[2]);
     return v[which];
   }
   std::shared_ptr<CudaHandle const> _handle;
   mfmgb_csr *_csr = nullptr;
 };
+
+namespace internal
+{
+// C = A B on the host (Gustavson, rows of C sorted by column).  SETUP operation: like the reference's parallel path,
+// which multiplies through Trilinos on the host (include/mfmg/cuda/sparse_matrix_device.templates.cuh:417-433), the
+// Galerkin product R A R^T is formed once on the host and uploaded.
+inline std::shared_ptr<SparseMatrixDevice<double>> host_multiply(SparseMatrixDevice<double> const &a,
+                                                                 SparseMatrixDevice<double> const &b)
+{
+  ASSERT_THROW(a.n() == b.m(), "multiply: inner dimensions differ");
+  std::vector<int64_t> arp, brp;
+  std::vector<int> ac, bc;
+  std::vector<double> av, bv;
+  a.copy_to_host(arp, ac, av);
+  b.copy_to_host(brp, bc, bv);
+  unsigned int const m = a.m(), n = b.n();
+  std::vector<int64_t> crp(1, 0);
+  std::vector<int> cc;
+  std::vector<double> cv;
+  std::vector<double> acc(n, 0.);
+  std::vector<char> used(n, 0);
+  std::vector<int> cols;
+  for (unsigned int i = 0; i < m; ++i)
+  {
+    cols.clear();
+    for (int64_t ka = arp[i]; ka < arp[i + 1]; ++ka)
+    {
+      int const k = ac[(std::size_t)ka];
+      for (int64_t kb = brp[k]; kb < brp[k + 1]; ++kb)
+      {
+        int const j = bc[(std::size_t)kb];
+        if (!used[j])
+        {
+          used[j] = 1;
+          cols.push_back(j);
+        }
+        acc[j] += av[(std::size_t)ka] * bv[(std::size_t)kb];
+      }
+    }
+    std::sort(cols.begin(), cols.end());
+    for (int j : cols)
+    {
+      cc.push_back(j);
+      cv.push_back(acc[j]);
+      acc[j] = 0.;
+      used[j] = 0;
+    }
+    crp.push_back((int64_t)cc.size());
+  }
+  return std::make_shared<SparseMatrixDevice<double>>(a.handle(), m, n, crp, cc, cv);
+}
+} // namespace internal
 
 // source/cuda/cuda_matrix_operator.cu
 template <typename VectorType>
@@ -316,16 +414,21 @@ public:
       build_transpose();
     return std::make_shared<CudaMatrixOperator<vector_type>>(_transposed_matrix);
   }
-  // Setup operations: the reference computes products with cuSPARSE csrgemm (serial) or on the host through
-  // Trilinos (parallel).  Setup stays on the host path here, so these are not provided by the device library.
-  std::shared_ptr<Operator<vector_type>> multiply(std::shared_ptr<Operator<vector_type> const>) const override
+  // Setup operations (cuda_matrix_operator.cu:132-225): the reference computes products with cuSPARSE csrgemm (serial)
+  // or on the host through Trilinos (parallel).  Setup stays on the host path: host product, uploaded once.
+  std::shared_ptr<Operator<vector_type>> multiply(std::shared_ptr<Operator<vector_type> const> b) const override
   {
-    throw NotImplementedExc("CudaMatrixOperator::multiply: setup stays on the host path (mfmg_b200.hostsetup)");
+    auto rhs = std::dynamic_pointer_cast<CudaMatrixOperator<vector_type> const>(b);
+    ASSERT_THROW(rhs != nullptr, "CudaMatrixOperator::multiply needs a CudaMatrixOperator");
+    return std::make_shared<CudaMatrixOperator<vector_type>>(internal::host_multiply(*_matrix, *rhs->get_matrix()));
   }
   std::shared_ptr<Operator<vector_type>>
-  multiply_transpose(std::shared_ptr<Operator<vector_type> const>) const override
+  multiply_transpose(std::shared_ptr<Operator<vector_type> const> b) const override
   {
-    throw NotImplementedExc("CudaMatrixOperator::multiply_transpose: setup stays on the host path");
+    auto rhs = std::dynamic_pointer_cast<CudaMatrixOperator<vector_type> const>(b);
+    ASSERT_THROW(rhs != nullptr, "CudaMatrixOperator::multiply_transpose needs a CudaMatrixOperator");
+    auto bt = std::dynamic_pointer_cast<CudaMatrixOperator<vector_type>>(rhs->transpose());
+    return std::make_shared<CudaMatrixOperator<vector_type>>(internal::host_multiply(*_matrix, *bt->get_matrix()));
   }
   std::shared_ptr<vector_type> build_domain_vector() const override
   {
@@ -448,6 +551,236 @@ private:
   mfmgb_dense *_dense = nullptr;
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Mesh evaluators and the matrix-free operator slot
+//   include/mfmg/common/mesh_evaluator.hpp, include/mfmg/cuda/cuda_mesh_evaluator.cuh:25-74,
+//   include/mfmg/cuda/cuda_matrix_free_mesh_evaluator.cuh:25-104, include/mfmg/cuda/cuda_matrix_free_operator.cuh:22-77
+// The reference evaluators carry a dealii::DoFHandler and AffineConstraints; without deal.II they carry the CudaHandle
+// only, and -- because SETUP STAYS ON THE HOST PATH -- one extra hook, build_restrictor_matrix, through which the
+// restriction matrix produced by mfmg's own AMGe setup is handed over (the reference calls AMGe_device there,
+// source/cuda/cuda_hierarchy_helpers.cu:56-81).
+// ---------------------------------------------------------------------------------------------------------------
+class MeshEvaluator
+{
+public:
+  virtual ~MeshEvaluator() = default;
+  virtual int get_dim() const = 0;
+  virtual std::string get_mesh_evaluator_type() const = 0;
+};
+
+template <int dim>
+class CudaMeshEvaluator : public MeshEvaluator
+{
+public:
+  explicit CudaMeshEvaluator(std::shared_ptr<CudaHandle const> cuda_handle) : _cuda_handle(std::move(cuda_handle)) {}
+  int get_dim() const final { return dim; }
+  std::string get_mesh_evaluator_type() const override { return "CudaMeshEvaluator"; }
+  // user hook: fill the global system matrix (cuda_mesh_evaluator.cuh:44-49)
+  virtual void evaluate_global(SparseMatrixDevice<double> &) const { throw NotImplementedExc(); }
+  // user hook: local matrix of an agglomerate (cuda_mesh_evaluator.cuh:37-42) -- only the host setup needs it
+  virtual void evaluate_agglomerate(SparseMatrixDevice<double> &) const { throw NotImplementedExc(); }
+  // hand-over of the host setup's restriction matrix (n_coarse x n_fine), see the banner above
+  virtual void build_restrictor_matrix(std::shared_ptr<ParameterTree const>, SparseMatrixDevice<double> &) const
+  {
+    throw NotImplementedExc("build_restrictor_matrix: bind mfmg's host AMGe setup here");
+  }
+  std::shared_ptr<CudaHandle const> const &get_cuda_handle() const { return _cuda_handle; }
+
+protected:
+  std::shared_ptr<CudaHandle const> _cuda_handle;
+};
+
+// dealii::DiagonalMatrix<VectorType> stand-in: the inverse diagonal a matrix-free smoother uses
+class DiagonalMatrix
+{
+public:
+  explicit DiagonalMatrix(std::shared_ptr<DeviceVector> diagonal) : _diagonal(std::move(diagonal)) {}
+  DeviceVector const &get_vector() const { return *_diagonal; }
+
+private:
+  std::shared_ptr<DeviceVector> _diagonal;
+};
+
+template <int dim>
+class CudaMatrixFreeMeshEvaluator : public CudaMeshEvaluator<dim>
+{
+public:
+  using size_type = unsigned int;
+  static int constexpr _dim = dim;
+  explicit CudaMatrixFreeMeshEvaluator(std::shared_ptr<CudaHandle const> cuda_handle)
+      : CudaMeshEvaluator<dim>(std::move(cuda_handle))
+  {
+  }
+  std::string get_mesh_evaluator_type() const final { return "CudaMatrixFreeMeshEvaluator"; }
+  // the hooks of cuda_matrix_free_mesh_evaluator.cuh:47-97 (all NotImplemented in the reference)
+  virtual std::shared_ptr<DeviceVector> build_range_vector() const { throw NotImplementedExc(); }
+  virtual void matrix_free_evaluate_global(DeviceVector const & /*src*/, DeviceVector & /*dst*/) const
+  {
+    throw NotImplementedExc();
+  }
+  virtual std::shared_ptr<DiagonalMatrix> matrix_free_get_diagonal_inverse() const { throw NotImplementedExc(); }
+  virtual std::shared_ptr<DeviceVector> get_diagonal() const { throw NotImplementedExc(); }
+  // non-null when the evaluator is served by the library's own operator: the fused V-cycle then uses it directly
+  virtual mfmgb_mf const *native_operator() const { return nullptr; }
+};
+
+// The library's evaluator for the reference's matrix-free test problem (tests/laplace_matrix_free.hpp:30-199) on a
+// uniform Cartesian grid with lexicographic DoFs: fills every hook above with the hand-written sm_100a kernels.
+template <int dim>
+class LaplaceMatrixFreeMeshEvaluator : public CudaMatrixFreeMeshEvaluator<dim>
+{
+public:
+  // coef: [n_cells][(degree+1)^dim] coefficient at the quadrature points; constrained: [n_dofs] Dirichlet flags
+  LaplaceMatrixFreeMeshEvaluator(std::shared_ptr<CudaHandle const> cuda_handle, int degree, std::vector<int64_t> const &cells,
+                                 std::vector<double> const &h, std::vector<double> const &coef,
+                                 std::vector<uint8_t> const &constrained)
+      : CudaMatrixFreeMeshEvaluator<dim>(std::move(cuda_handle))
+  {
+    ASSERT_THROW((int)cells.size() == dim && (int)h.size() == dim, "LaplaceMatrixFreeMeshEvaluator: bad grid description");
+    check_status(this->_cuda_handle->ctx, mfmgb_mf_laplace_create(this->_cuda_handle->ctx, dim, degree, cells.data(), h.data(),
+                                                                  coef.data(), constrained.data(), &_mf));
+  }
+  ~LaplaceMatrixFreeMeshEvaluator() override { mfmgb_mf_destroy(this->_cuda_handle->ctx, _mf); }
+  std::shared_ptr<DeviceVector> build_range_vector() const override
+  {
+    return std::make_shared<DeviceVector>(this->_cuda_handle, (std::size_t)mfmgb_mf_size(_mf));
+  }
+  void matrix_free_evaluate_global(DeviceVector const &src, DeviceVector &dst) const override
+  {
+    check_status(this->_cuda_handle->ctx, mfmgb_mf_apply(this->_cuda_handle->ctx, _mf, src.get_values(), dst.get_values()));
+  }
+  std::shared_ptr<DeviceVector> get_diagonal() const override
+  {
+    auto d = build_range_vector();
+    check_status(this->_cuda_handle->ctx, mfmgb_mf_diagonal(this->_cuda_handle->ctx, _mf, d->get_values()));
+    return d;
+  }
+  std::shared_ptr<DiagonalMatrix> matrix_free_get_diagonal_inverse() const override
+  {
+    auto d = get_diagonal();
+    auto h = d->export_to_host();
+    for (auto &v : h)
+      v = 1. / v;
+    d->import_from_host(h);
+    return std::make_shared<DiagonalMatrix>(d);
+  }
+  mfmgb_mf const *native_operator() const override { return _mf; }
+
+private:
+  mfmgb_mf *_mf = nullptr;
+};
+
+// include/mfmg/cuda/cuda_matrix_free_operator.cuh:22-77, source/cuda/cuda_matrix_free_operator.cu:24-140
+template <int dim, typename VectorType>
+class CudaMatrixFreeOperator final : public Operator<VectorType>
+{
+public:
+  using vector_type = VectorType;
+  using size_type = std::size_t;
+  explicit CudaMatrixFreeOperator(std::shared_ptr<CudaMatrixFreeMeshEvaluator<dim>> matrix_free_mesh_evaluator)
+      : _mesh_evaluator(std::move(matrix_free_mesh_evaluator))
+  {
+  }
+  void vmult(vector_type &dst, vector_type const &src) const { _mesh_evaluator->matrix_free_evaluate_global(src, dst); }
+  void apply(vector_type const &x, vector_type &y, OperatorMode mode = OperatorMode::NO_TRANS) const override
+  {
+    if (mode != OperatorMode::NO_TRANS)
+      throw NotImplementedExc(); // cuda_matrix_free_operator.cu:62-66
+    vmult(y, x);
+  }
+  std::shared_ptr<Operator<vector_type>> transpose() const override { throw NotImplementedExc(); }
+  std::shared_ptr<Operator<vector_type>> multiply(std::shared_ptr<Operator<vector_type> const>) const override
+  {
+    throw NotImplementedExc();
+  }
+  // this * b^T column by column: the operator applied to every row of b (the restrictor), a SETUP operation like
+  // DealIIMatrixFreeOperator::multiply_transpose on the reference's host path; the result is assembled
+  std::shared_ptr<Operator<vector_type>> multiply_transpose(std::shared_ptr<Operator<vector_type> const> b) const override
+  {
+    auto r = std::dynamic_pointer_cast<CudaMatrixOperator<vector_type> const>(b);
+    ASSERT_THROW(r != nullptr, "CudaMatrixFreeOperator::multiply_transpose needs a CudaMatrixOperator");
+    auto rm = r->get_matrix();
+    std::vector<int64_t> rp;
+    std::vector<int> rc;
+    std::vector<double> rv;
+    rm->copy_to_host(rp, rc, rv);
+    unsigned int const nc = rm->m(), n = rm->n();
+    auto v = build_domain_vector(), w = build_range_vector();
+    std::vector<std::vector<std::pair<int, double>>> rows(n); // (A R^T) by row: entry (i, c)
+    std::vector<double> dense(n, 0.);
+    for (unsigned int c = 0; c < nc; ++c)
+    {
+      std::fill(dense.begin(), dense.end(), 0.);
+      for (int64_t k = rp[c]; k < rp[c + 1]; ++k)
+        dense[(std::size_t)rc[(std::size_t)k]] = rv[(std::size_t)k];
+      v->import_from_host(dense);
+      vmult(*w, *v);
+      auto col = w->export_to_host();
+      for (unsigned int i = 0; i < n; ++i)
+        if (col[i] != 0.)
+          rows[i].emplace_back((int)c, col[i]);
+    }
+    std::vector<int64_t> orp(1, 0);
+    std::vector<int> oc;
+    std::vector<double> ov;
+    for (unsigned int i = 0; i < n; ++i)
+    {
+      for (auto const &e : rows[i])
+      {
+        oc.push_back(e.first);
+        ov.push_back(e.second);
+      }
+      orp.push_back((int64_t)oc.size());
+    }
+    return std::make_shared<CudaMatrixOperator<vector_type>>(
+        std::make_shared<SparseMatrixDevice<double>>(_mesh_evaluator->get_cuda_handle(), n, nc, orp, oc, ov));
+  }
+  std::shared_ptr<vector_type> build_domain_vector() const override { return _mesh_evaluator->build_range_vector(); }
+  std::shared_ptr<vector_type> build_range_vector() const override { return _mesh_evaluator->build_range_vector(); }
+  size_type grid_complexity() const override { return build_range_vector()->size(); }
+  size_type operator_complexity() const override { throw NotImplementedExc(); } // cuda_matrix_free_operator.cu:128-133
+  std::shared_ptr<DiagonalMatrix> get_diagonal_inverse() const { return _mesh_evaluator->matrix_free_get_diagonal_inverse(); }
+  std::shared_ptr<CudaHandle const> const &get_cuda_handle() const { return _mesh_evaluator->get_cuda_handle(); }
+  std::shared_ptr<CudaMatrixFreeMeshEvaluator<dim>> const &get_mesh_evaluator() const { return _mesh_evaluator; }
+
+private:
+  std::shared_ptr<CudaMatrixFreeMeshEvaluator<dim>> _mesh_evaluator;
+};
+
+// Jacobi smoother on a matrix-free operator: x <- x - D^-1 (A x - b) from the evaluator's inverse diagonal (the
+// composition the reference's host path uses for matrix-free levels, source/dealii/dealii_matrix_free_smoother.cc:67-79,
+// with PreconditionChebyshev of degree 0 and theta = 1).  Unfused: the fused form lives in Hierarchy::apply.
+template <int dim, typename VectorType>
+class CudaMatrixFreeSmoother : public Smoother<VectorType>
+{
+public:
+  using vector_type = VectorType;
+  CudaMatrixFreeSmoother(std::shared_ptr<Operator<vector_type> const> op, std::shared_ptr<ParameterTree const> params)
+      : Smoother<vector_type>(op, params)
+  {
+    auto mf = std::dynamic_pointer_cast<CudaMatrixFreeOperator<dim, vector_type> const>(this->_operator);
+    ASSERT_THROW(mf != nullptr, "CudaMatrixFreeSmoother must be constructed from a CudaMatrixFreeOperator");
+    _inverse_diagonal = mf->get_diagonal_inverse();
+    auto diag = mf->get_mesh_evaluator()->get_diagonal();
+    auto const &ctx = diag->handle()->ctx;
+    check_status(ctx, mfmgb_jacobi_setup_diag(ctx, diag->get_values(), (int64_t)diag->size(), 1.0, &_jacobi));
+    check_status(ctx, mfmgb_ctx_synchronize(ctx));
+  }
+  ~CudaMatrixFreeSmoother() override { mfmgb_jacobi_destroy(_inverse_diagonal->get_vector().handle()->ctx, _jacobi); }
+  void apply(vector_type const &b, vector_type &x) const override
+  {
+    vector_type r(b);
+    this->_operator->apply(x, r); // r = A x
+    r.add(-1., b);                // r = A x - b
+    auto const &ctx = _inverse_diagonal->get_vector().handle()->ctx;
+    check_status(ctx, mfmgb_jacobi_apply_residual(ctx, _jacobi, r.get_values(), x.get_values())); // x -= D^-1 r
+  }
+
+private:
+  std::shared_ptr<DiagonalMatrix> _inverse_diagonal;
+  mfmgb_jacobi *_jacobi = nullptr;
+};
+
 // include/mfmg/common/level.hpp:22-76
 template <typename VectorType>
 class Level
@@ -470,19 +803,207 @@ private:
   std::shared_ptr<Solver<vector_type> const> _solver;
 };
 
-// include/mfmg/common/hierarchy.hpp:159-309.  The reference ctor runs the SETUP from a MeshEvaluator;
-// setup stays on the host path, so this ctor receives the level operators it produced (A_l, R_l) and
-// builds smoothers / coarse solver exactly as hierarchy.hpp:183-234 does.
+// dealii::TimerOutput stand-in (hierarchy.hpp:36-47): wall-clock seconds per named section
+class TimerOutput
+{
+public:
+  void enter_subsection(std::string const &section)
+  {
+    _open.emplace_back(section, std::chrono::steady_clock::now());
+  }
+  void leave_subsection()
+  {
+    if (_open.empty())
+      return;
+    auto const dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - _open.back().second).count();
+    _seconds[_open.back().first] += dt;
+    _open.pop_back();
+  }
+  std::map<std::string, double> const &get_summary_data() const { return _seconds; }
+
+private:
+  std::vector<std::pair<std::string, std::chrono::steady_clock::time_point>> _open;
+  std::map<std::string, double> _seconds;
+};
+
+inline void timer_enter_subsection(std::shared_ptr<TimerOutput> const &timer, std::string const &section)
+{
+  if (timer)
+    timer->enter_subsection(section);
+}
+inline void timer_leave_subsection(std::shared_ptr<TimerOutput> const &timer)
+{
+  if (timer)
+    timer->leave_subsection();
+}
+
+#ifndef MPI_VERSION
+// one process per GPU; without an MPI installation the communicator argument is a placeholder
+using MPI_Comm = int;
+constexpr MPI_Comm MPI_COMM_SELF = 1, MPI_COMM_WORLD = 0;
+#endif
+
+// include/mfmg/common/hierarchy_helpers.hpp:27-62
+template <typename VectorType>
+class HierarchyHelpers
+{
+public:
+  using vector_type = VectorType;
+  virtual ~HierarchyHelpers() = default;
+  virtual std::shared_ptr<Operator<vector_type>> get_global_operator(std::shared_ptr<MeshEvaluator> mesh_evaluator) = 0;
+  virtual std::shared_ptr<Operator<vector_type>> build_restrictor(MPI_Comm comm, std::shared_ptr<MeshEvaluator> mesh_evaluator,
+                                                                  std::shared_ptr<ParameterTree const> params) = 0;
+  virtual std::shared_ptr<Smoother<vector_type>> build_smoother(std::shared_ptr<Operator<vector_type> const> op,
+                                                                std::shared_ptr<ParameterTree const> params) = 0;
+  virtual std::shared_ptr<Solver<vector_type>> build_coarse_solver(std::shared_ptr<Operator<vector_type> const> op,
+                                                                   std::shared_ptr<ParameterTree const> params) = 0;
+  // hierarchy_helpers.hpp:52-57 (the matrix-free helpers override it on the host path)
+  virtual std::shared_ptr<Operator<vector_type>>
+  fast_multiply_transpose(std::shared_ptr<Operator<vector_type> const> a, std::shared_ptr<Operator<vector_type> const> r)
+  {
+    return a->multiply_transpose(r);
+  }
+};
+
+// include/mfmg/cuda/cuda_hierarchy_helpers.cuh:24-54, source/cuda/cuda_hierarchy_helpers.cu:29-121
+template <int dim, typename VectorType>
+class CudaHierarchyHelpers : public HierarchyHelpers<VectorType>
+{
+public:
+  using vector_type = VectorType;
+  explicit CudaHierarchyHelpers(std::shared_ptr<CudaHandle const> cuda_handle) : _cuda_handle(std::move(cuda_handle)) {}
+  std::shared_ptr<Operator<vector_type>> get_global_operator(std::shared_ptr<MeshEvaluator> mesh_evaluator) override
+  {
+    if (_operator == nullptr)
+    {
+      auto cuda_mesh_evaluator = std::dynamic_pointer_cast<CudaMeshEvaluator<dim>>(mesh_evaluator);
+      ASSERT_THROW(cuda_mesh_evaluator != nullptr, "CudaHierarchyHelpers needs a CudaMeshEvaluator");
+      auto mf_evaluator = std::dynamic_pointer_cast<CudaMatrixFreeMeshEvaluator<dim>>(mesh_evaluator);
+      if (mf_evaluator)
+        _operator.reset(new CudaMatrixFreeOperator<dim, vector_type>(mf_evaluator));
+      else
+      {
+        auto system_matrix = std::make_shared<SparseMatrixDevice<double>>();
+        cuda_mesh_evaluator->evaluate_global(*system_matrix); // user function fills the system matrix
+        _operator.reset(new CudaMatrixOperator<vector_type>(system_matrix));
+      }
+    }
+    return _operator;
+  }
+  std::shared_ptr<Operator<vector_type>> build_restrictor(MPI_Comm, std::shared_ptr<MeshEvaluator> mesh_evaluator,
+                                                          std::shared_ptr<ParameterTree const> params) override
+  {
+    auto cuda_mesh_evaluator = std::dynamic_pointer_cast<CudaMeshEvaluator<dim>>(mesh_evaluator);
+    ASSERT_THROW(cuda_mesh_evaluator != nullptr, "CudaHierarchyHelpers needs a CudaMeshEvaluator");
+    auto restrictor_matrix = std::make_shared<SparseMatrixDevice<double>>();
+    cuda_mesh_evaluator->build_restrictor_matrix(params, *restrictor_matrix); // the host AMGe setup's result
+    return std::make_shared<CudaMatrixOperator<vector_type>>(restrictor_matrix);
+  }
+  std::shared_ptr<Smoother<vector_type>> build_smoother(std::shared_ptr<Operator<vector_type> const> op,
+                                                        std::shared_ptr<ParameterTree const> params) override
+  {
+    if (std::dynamic_pointer_cast<CudaMatrixFreeOperator<dim, vector_type> const>(op))
+      return std::make_shared<CudaMatrixFreeSmoother<dim, vector_type>>(op, params);
+    return std::make_shared<CudaSmoother<vector_type>>(op, params);
+  }
+  std::shared_ptr<Solver<vector_type>> build_coarse_solver(std::shared_ptr<Operator<vector_type> const> op,
+                                                           std::shared_ptr<ParameterTree const> params) override
+  {
+    return std::make_shared<CudaSolver<vector_type>>(*_cuda_handle, op, params);
+  }
+
+private:
+  std::shared_ptr<CudaHandle const> _cuda_handle;
+  std::shared_ptr<Operator<vector_type>> _operator;
+};
+
+// include/mfmg/common/hierarchy.hpp:49-153: dispatch on the evaluator's type string and dimension
+template <typename VectorType>
+std::unique_ptr<HierarchyHelpers<VectorType>> create_hierarchy_helpers(std::shared_ptr<MeshEvaluator const> evaluator)
+{
+  std::unique_ptr<HierarchyHelpers<VectorType>> hierarchy_helpers;
+  std::string const evaluator_type = evaluator->get_mesh_evaluator_type();
+  if (evaluator_type == "CudaMeshEvaluator" || evaluator_type == "CudaMatrixFreeMeshEvaluator")
+  {
+    int const dim = evaluator->get_dim();
+    if (dim == 2)
+      hierarchy_helpers.reset(new CudaHierarchyHelpers<2, VectorType>(
+          std::dynamic_pointer_cast<CudaMeshEvaluator<2> const>(evaluator)->get_cuda_handle()));
+    else if (dim == 3)
+      hierarchy_helpers.reset(new CudaHierarchyHelpers<3, VectorType>(
+          std::dynamic_pointer_cast<CudaMeshEvaluator<3> const>(evaluator)->get_cuda_handle()));
+    else
+      throw NotImplementedExc();
+  }
+  else // the DealII* evaluators belong to the reference's host path
+    throw NotImplementedExc("create_hierarchy_helpers: " + evaluator_type + " is not a device evaluator");
+  return hierarchy_helpers;
+}
+
+// include/mfmg/common/hierarchy.hpp:155-315
 template <typename VectorType>
 class Hierarchy
 {
 public:
   using vector_type = VectorType;
+
+  // The reference constructor (hierarchy.hpp:159-236): setup from a MeshEvaluator, statement by statement.  The
+  // operators come from the evaluator's hooks (setup stays on the host path); smoothers, the coarse solver and the
+  // Galerkin product are built exactly where the reference builds them.
+  Hierarchy(MPI_Comm comm, std::shared_ptr<MeshEvaluator> evaluator, std::shared_ptr<ParameterTree> params = nullptr,
+            std::shared_ptr<TimerOutput> timer = nullptr)
+      : _timer(std::move(timer))
+  {
+    timer_enter_subsection(_timer, "Setup");
+    if (!params)
+      params = std::make_shared<ParameterTree>();
+    auto hierarchy_helpers = create_hierarchy_helpers<vector_type>(evaluator);
+    _is_preconditioner = params->get("is preconditioner", true);        // :168
+    _n_smoothing_steps = params->get("smoother.n_smoothing_steps", 1u); // :169
+    unsigned int const num_levels = params->get("max levels", 2u);      // :171
+    ASSERT_THROW(num_levels >= 1 && num_levels <= 2, "max levels > 2 needs one evaluator per level (hierarchy.hpp:209-210 "
+                                                     "re-uses the fine evaluator, which the reference itself marks broken)");
+    _levels.resize(num_levels);
+    for (unsigned int level_index = 0; level_index < num_levels; ++level_index)
+    {
+      auto &level_fine = _levels[level_index];
+      if (level_index == 0)
+      {
+        timer_enter_subsection(_timer, "Setup: build global operator");
+        level_fine.set_operator(hierarchy_helpers->get_global_operator(evaluator)); // :178-180
+        timer_leave_subsection(_timer);
+      }
+      if (level_index == num_levels - 1)
+      {
+        timer_enter_subsection(_timer, "Setup: build coarse solver");
+        level_fine.set_solver(hierarchy_helpers->build_coarse_solver(level_fine.get_operator(), params)); // :192-195
+        timer_leave_subsection(_timer);
+        break;
+      }
+      timer_enter_subsection(_timer, "Setup: build smoother");
+      level_fine.set_smoother(hierarchy_helpers->build_smoother(level_fine.get_operator(), params)); // :203-205
+      timer_leave_subsection(_timer);
+      auto &level_coarse = _levels[level_index + 1];
+      timer_enter_subsection(_timer, "Setup: build restrictor");
+      auto restrictor = hierarchy_helpers->build_restrictor(comm, evaluator, params); // :212-214
+      level_coarse.set_restrictor(restrictor);
+      timer_leave_subsection(_timer);
+      timer_enter_subsection(_timer, "Setup: build coarse operator");
+      auto a = level_fine.get_operator();
+      auto ap = hierarchy_helpers->fast_multiply_transpose(a, restrictor); // :222-226  A R^T
+      level_coarse.set_operator(restrictor->multiply(ap));                 // :229-231  R (A R^T)
+      timer_leave_subsection(_timer);
+    }
+    build_fused(params);
+    timer_leave_subsection(_timer);
+  }
+
+  // Setup already done on the host path: the level operators A_l and restrictors R_l are given; smoothers and the coarse
+  // solver are built exactly as hierarchy.hpp:183-234 does.
   Hierarchy(std::shared_ptr<CudaHandle const> handle,
             std::vector<std::shared_ptr<CudaMatrixOperator<vector_type>>> const &operators,
             std::vector<std::shared_ptr<CudaMatrixOperator<vector_type>>> const &restrictors,
             std::shared_ptr<ParameterTree> params = nullptr)
-      : _handle(std::move(handle))
   {
     if (!params)
       params = std::make_shared<ParameterTree>(); // (the reference dereferences a null default, hierarchy.hpp:160,168)
@@ -499,31 +1020,33 @@ public:
       if (l + 1 < num_levels)
         _levels[l].set_smoother(std::make_shared<CudaSmoother<vector_type>>(operators[l], params)); // :204
       else
-        _levels[l].set_solver(std::make_shared<CudaSolver<vector_type>>(*_handle, operators[l], params)); // :194
+        _levels[l].set_solver(std::make_shared<CudaSolver<vector_type>>(*handle, operators[l], params)); // :194
     }
-    // fused device path
-    check_status(_handle->ctx, mfmgb_hierarchy_create(_handle->ctx, (int)num_levels, (int)_n_smoothing_steps,
-                                                      _is_preconditioner ? 1 : 0, 1.0, &_fused));
-    for (unsigned int l = 0; l < num_levels; ++l)
-    {
-      check_status(_handle->ctx, mfmgb_hierarchy_set_operator(_fused, (int)l, operators[l]->get_matrix()->c_handle()));
-      if (l > 0)
-        check_status(_handle->ctx, mfmgb_hierarchy_set_restrictor(_fused, (int)l,
-                                                                  restrictors[l - 1]->get_matrix()->c_handle(), nullptr));
-    }
-    check_status(_handle->ctx, mfmgb_hierarchy_finalize(_handle->ctx, _fused));
+    build_fused(params);
+    ASSERT_THROW(_fused != nullptr, "Hierarchy: the fused device path could not be built");
   }
-  ~Hierarchy() { mfmgb_hierarchy_destroy(_handle->ctx, _fused); }
+  ~Hierarchy()
+  {
+    if (_fused)
+      mfmgb_hierarchy_destroy(_ctx, _fused);
+  }
   Hierarchy(Hierarchy const &) = delete;
 
   // hierarchy.hpp:238-244
   void vmult(vector_type &x, vector_type const &b) const { apply(b, x, 0); }
 
-  // hierarchy.hpp:246-309 -- fused kernels, preallocated workspaces, one launch sequence
+  // hierarchy.hpp:246-309 -- fused kernels, preallocated workspaces, one launch sequence.  Hierarchies whose level
+  // operators are user objects the library does not know run the same algorithm through the abstract interfaces.
   void apply(vector_type const &b, vector_type &x, int level_index = 0) const
   {
-    check_status(_handle->ctx, mfmgb_hierarchy_apply(_handle->ctx, _fused, b.get_values(), x.get_values(), level_index));
+    timer_enter_subsection(_timer, "Apply");
+    if (_fused)
+      check_status(_ctx, mfmgb_hierarchy_apply(_ctx, _fused, b.get_values(), x.get_values(), level_index));
+    else
+      apply_generic(b, x, level_index);
+    timer_leave_subsection(_timer);
   }
+  bool is_fused() const { return _fused != nullptr; }
 
   // The same algorithm written against the abstract Operator / Smoother / Solver interfaces, line for line as
   // the reference composes it (unfused C-ABI calls).  Kept to show the drop-in objects are interchangeable.
@@ -558,6 +1081,9 @@ public:
       smoother->apply(b, x);
   }
 
+  // hierarchy.hpp:311-312 (build_range_vector of the finest operator)
+  std::shared_ptr<vector_type> build_range_vector() const { return _levels[0].get_operator()->build_range_vector(); }
+
   double grid_complexity() const
   {
     double s = 0;
@@ -575,7 +1101,64 @@ public:
   mfmgb_hierarchy *c_handle() const { return _fused; }
 
 private:
-  std::shared_ptr<CudaHandle const> _handle;
+  // the fused device V-cycle needs level operators the library owns: CSR matrices, or (level 0) its matrix-free operator
+  template <int dim>
+  static mfmgb_mf const *native_mf(std::shared_ptr<Operator<vector_type> const> const &op, mfmgb_ctx *&ctx)
+  {
+    auto mf = std::dynamic_pointer_cast<CudaMatrixFreeOperator<dim, vector_type> const>(op);
+    if (!mf)
+      return nullptr;
+    ctx = mf->get_cuda_handle()->ctx;
+    return mf->get_mesh_evaluator()->native_operator();
+  }
+  void build_fused(std::shared_ptr<ParameterTree> const &params)
+  {
+    unsigned int const num_levels = (unsigned int)_levels.size();
+    std::vector<mfmgb_csr const *> ops(num_levels, nullptr), res(num_levels, nullptr);
+    mfmgb_mf const *mf0 = nullptr;
+    for (unsigned int l = 0; l < num_levels; ++l)
+    {
+      auto op = std::dynamic_pointer_cast<CudaMatrixOperator<vector_type> const>(_levels[l].get_operator());
+      if (op)
+      {
+        ops[l] = op->get_matrix()->c_handle();
+        _ctx = op->get_matrix()->handle()->ctx;
+      }
+      else if (l == 0 && ((mf0 = native_mf<3>(_levels[0].get_operator(), _ctx)) != nullptr ||
+                          (mf0 = native_mf<2>(_levels[0].get_operator(), _ctx)) != nullptr))
+        ;
+      else
+        return; // a user operator: the abstract composition serves the hierarchy
+      if (l > 0)
+      {
+        auto r = std::dynamic_pointer_cast<CudaMatrixOperator<vector_type> const>(_levels[l].get_restrictor());
+        if (!r)
+          return;
+        res[l] = r->get_matrix()->c_handle();
+      }
+    }
+    std::string smoother = params->get("smoother.type", "Jacobi");
+    std::transform(smoother.begin(), smoother.end(), smoother.begin(), ::tolower);
+    check_status(_ctx, mfmgb_hierarchy_create(_ctx, (int)num_levels, (int)_n_smoothing_steps, _is_preconditioner ? 1 : 0, 1.0,
+                                              &_fused));
+    for (unsigned int l = 0; l < num_levels; ++l)
+    {
+      if (ops[l])
+        check_status(_ctx, mfmgb_hierarchy_set_operator(_fused, (int)l, ops[l]));
+      else
+        check_status(_ctx, mfmgb_hierarchy_set_mf_operator(_fused, mf0));
+      if (l > 0)
+        check_status(_ctx, mfmgb_hierarchy_set_restrictor(_fused, (int)l, res[l], nullptr));
+    }
+    if (smoother == "chebyshev") // source/dealii/dealii_matrix_free_smoother.cc:34-60
+      check_status(_ctx, mfmgb_hierarchy_set_smoother_chebyshev(_fused, params->get("smoother.degree", 0),
+                                                                params->get("smoother.smoothing_range", 0.),
+                                                                params->get("smoother.max_eigenvalue", 1.), 8));
+    check_status(_ctx, mfmgb_hierarchy_finalize(_ctx, _fused));
+  }
+
+  std::shared_ptr<TimerOutput> _timer;
+  mfmgb_ctx *_ctx = nullptr;
   bool _is_preconditioner = true;
   unsigned int _n_smoothing_steps = 1;
   std::vector<Level<vector_type>> _levels;

@@ -83,6 +83,7 @@ SIGNATURES = {
     "mfmgb_jacobi_inv_diag": (_vp, [_vp]),
     "mfmgb_jacobi_apply": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "mfmgb_jacobi_apply_oop": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "mfmgb_jacobi_apply_residual": (_int, [_vp, _vp, _vp, _vp]),
     "mfmgb_jacobi_apply_zero_guess": (_int, [_vp, _vp, _vp, _vp]),
     "mfmgb_dense_factor": (_int, [_vp, _vp, _pp]),
     "mfmgb_dense_destroy": (_int, [_vp, _vp]),

@@ -61,6 +61,21 @@ __global__ void __launch_bounds__(kBlock)
     x[i] = zero_guess_value(dinv[i], b[i], omega);
 }
 
+// x <- x - omega D^-1 r with r = A x - b formed by the caller (operators that are not CSR matrices)
+__global__ void __launch_bounds__(kBlock)
+    residual_update_kernel(int64_t n, const double *__restrict__ dinv, const double *__restrict__ r, double omega,
+                           double *__restrict__ x)
+{
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i < n)
+  {
+    double t = __dmul_rn(dinv[i], r[i]);
+    if (omega != 1.)
+      t = __dmul_rn(omega, t);
+    x[i] = __dsub_rn(x[i], t);
+  }
+}
+
 // 16-byte aligned vectors: two entries per thread and load (24 B of traffic per entry, nothing else to hide latency)
 __global__ void __launch_bounds__(kBlock)
     zero_guess_kernel_v2(int64_t n, const double *__restrict__ dinv, const double *__restrict__ b, double omega,
@@ -179,6 +194,16 @@ extern "C"
                                               "smoother was set up for; use mfmgb_jacobi_apply_oop");
     MFMGB_CUDA(ctx, cudaMemcpyAsync(J->tmp, x, sizeof(double) * (size_t)A->n_cols, cudaMemcpyDeviceToDevice, ctx->stream));
     return mfmgb_jacobi_apply_oop(ctx, J, A, b, J->tmp, x);
+  }
+
+  MFMGB_API int mfmgb_jacobi_apply_residual(mfmgb_ctx *ctx, const mfmgb_jacobi *J, const double *r, double *x)
+  {
+    MFMGB_REQUIRE(ctx, ctx && J && r && x && r != x, "mfmgb_jacobi_apply_residual: bad arguments");
+    if (J->n == 0)
+      return MFMGB_OK;
+    residual_update_kernel<<<(unsigned)ceil_div(J->n, kBlock), kBlock, 0, ctx->stream>>>(J->n, J->dinv, r, J->omega, x);
+    MFMGB_LAUNCHED(ctx);
+    return MFMGB_OK;
   }
 
   MFMGB_API int mfmgb_jacobi_apply_zero_guess(mfmgb_ctx *ctx, const mfmgb_jacobi *J, const double *b, double *x)

@@ -2,7 +2,7 @@
 assembly, Galerkin product).  Per the north star this stays on the host and only produces the CSR
 operators that are uploaded once; nothing here is on the V-cycle hot path and nothing here is a
 fallback for it."""
-from .amge import (block_agglomerates, build_restrictor, galerkin, lowest_eigenpairs, restriction_from_local,  # noqa: F401
+from .amge import (aggregate_restrictor, block_agglomerates, build_multilevel, build_restrictor, galerkin, lowest_eigenpairs, restriction_from_local,  # noqa: F401
                    transpose)  # noqa: F401
 from .problems import (HostCSR, LaplaceProblem, assemble, boundary_mask, csr_from_dealii_sparse_matrix,  # noqa: F401
                        coefficient_table, material_value, num_threads, reference_matrices,

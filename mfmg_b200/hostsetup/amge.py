@@ -278,3 +278,48 @@ def transpose(R: HostCSR) -> HostCSR:
     t = R.to_scipy().T.tocsr()
     t.sort_indices()
     return HostCSR.from_scipy(t)
+
+
+def aggregate_restrictor(agg_grid, block, n_eigenvectors: int = 1) -> HostCSR:
+    """Restrictor of a FURTHER level ("max levels" > 2 -- which the reference itself cannot
+    build: include/mfmg/common/hierarchy.hpp:209-210 re-uses the fine evaluator).  The coarse DoFs of a structured
+    block agglomeration are numbered (agglomerate, eigenvector) with lexicographic agglomerates `agg_grid`; this groups
+    `block` agglomerates per direction and sums DoFs of equal eigenvector index (unsmoothed aggregation: entries 1).
+    Rows = (super-agglomerate, eigenvector), columns = the coarse DoFs of the level above.  Unpinned by the reference:
+    the oracle's generic multi-level cycle is the contract for the device path, convergence is reported separately."""
+    agg_grid = tuple(int(a) for a in agg_grid)
+    block = tuple(int(b) for b in block)
+    dim = len(agg_grid)
+    sup = tuple(-(-a // b) for a, b in zip(agg_grid, block))
+    idx = np.indices(agg_grid[::-1])[::-1]                 # idx[d][..., j, i] = coordinate d (x fastest in memory)
+    sup_id = np.zeros(agg_grid[::-1], dtype=np.int64)
+    stride = 1
+    for d in range(dim):
+        sup_id += (idx[d] // block[d]) * stride
+        stride *= sup[d]
+    sup_id = sup_id.reshape(-1)                            # per agglomerate, lexicographic
+    n_agg, n_sup, ne = sup_id.size, int(np.prod(sup)), n_eigenvectors
+    rows = (sup_id[:, None] * ne + np.arange(ne)[None, :]).reshape(-1)
+    cols = np.arange(n_agg * ne, dtype=np.int64)
+    import scipy.sparse as sp
+
+    m = sp.csr_matrix((np.ones(n_agg * ne), (rows, cols)), shape=(n_sup * ne, n_agg * ne))
+    m.sort_indices()
+    return HostCSR.from_scipy(m)
+
+
+def build_multilevel(problem: LaplaceProblem, block, n_eigenvectors: int, coarse_blocks, eigensolver: str = "free"):
+    """Operators [A_0, A_1, ...] and restrictors [R_1, R_2, ...] of a hierarchy with len(coarse_blocks) + 2 levels:
+    spectral AMGe from the mesh for the first transition (build_restrictor), aggregate_restrictor for the others,
+    Galerkin operators A_{l+1} = R (A_l R^T) throughout (hierarchy.hpp:225,230)."""
+    R = build_restrictor(problem, block, n_eigenvectors, eigensolver=eigensolver)
+    ops, res = [problem.A], [R]
+    ops.append(galerkin(problem.A, R))
+    grid = tuple(-(-c // b) for c, b in zip(problem.cells, block))
+    for cb in coarse_blocks:
+        R2 = aggregate_restrictor(grid, cb, n_eigenvectors)
+        assert R2.n_cols == ops[-1].n_rows
+        res.append(R2)
+        ops.append(galerkin(ops[-1], R2))
+        grid = tuple(-(-g // b) for g, b in zip(grid, cb))
+    return ops, res

@@ -298,6 +298,195 @@ int main()
       }
   }
 
+  // ---- Hierarchy(comm, MeshEvaluator, params, timer): the reference constructor (hierarchy.hpp:159-236) through
+  //      create_hierarchy_helpers / CudaHierarchyHelpers with a user CudaMeshEvaluator (matrix-based) ----
+  {
+    struct TridiagEvaluator : mfmg::CudaMeshEvaluator<2>
+    {
+      using mfmg::CudaMeshEvaluator<2>::CudaMeshEvaluator;
+      void evaluate_global(mfmg::SparseMatrixDevice<double> &m) const override
+      {
+        auto a = tridiag(255);
+        m.reinit(_cuda_handle, a.n_rows, a.n_cols, a.rp, a.col, a.val);
+      }
+      void build_restrictor_matrix(std::shared_ptr<mfmg::ParameterTree const>,
+                                   mfmg::SparseMatrixDevice<double> &m) const override
+      {
+        HostCsr r{127, 255, {0}, {}, {}};
+        for (unsigned i = 0; i < 127; ++i)
+        {
+          for (unsigned j = 0; j < 3; ++j)
+          {
+            r.col.push_back((int)(2 * i + j));
+            r.val.push_back(j == 1 ? 1. : 0.5);
+          }
+          r.rp.push_back((int64_t)r.col.size());
+        }
+        m.reinit(_cuda_handle, r.n_rows, r.n_cols, r.rp, r.col, r.val);
+      }
+    };
+    auto evaluator = std::make_shared<TridiagEvaluator>(handle);
+    auto p = std::make_shared<mfmg::ParameterTree>();
+    p->put("is preconditioner", false);
+    p->put("smoother.n_smoothing_steps", 2u);
+    auto timer = std::make_shared<mfmg::TimerOutput>();
+    mfmg::Hierarchy<V> hierarchy(mfmg::MPI_COMM_SELF, evaluator, p, timer);
+    CHECK(hierarchy.is_fused());
+    auto b = hierarchy.build_range_vector();
+    CHECK(b->size() == 255);
+    std::vector<double> bh(255), xh(255);
+    std::default_random_engine gen(11);
+    std::uniform_real_distribution<double> dist(0., 1.);
+    for (auto &v : bh)
+      v = dist(gen);
+    for (auto &v : xh)
+      v = dist(gen);
+    V x1(handle, 255), x2(handle, 255);
+    b->import_from_host(bh);
+    x1.import_from_host(xh);
+    x2.import_from_host(xh);
+    hierarchy.vmult(x1, *b);
+    hierarchy.apply_generic(*b, x2);
+    auto h1 = x1.export_to_host(), h2 = x2.export_to_host();
+    double num = 0., den = 0.;
+    for (unsigned i = 0; i < 255; ++i)
+    {
+      num += (h1[i] - h2[i]) * (h1[i] - h2[i]);
+      den += h2[i] * h2[i];
+    }
+    CHECK(std::sqrt(num / den) < 1e-13);
+    CHECK(timer->get_summary_data().count("Setup: build coarse operator") == 1);
+    CHECK(timer->get_summary_data().count("Apply") == 1);
+    // unknown evaluator types are rejected like hierarchy.hpp:102-105
+    struct HostEvaluator : mfmg::MeshEvaluator
+    {
+      int get_dim() const override { return 3; }
+      std::string get_mesh_evaluator_type() const override { return "DealIIMeshEvaluator"; }
+    };
+    bool threw = false;
+    try
+    {
+      mfmg::Hierarchy<V> h2(mfmg::MPI_COMM_SELF, std::make_shared<HostEvaluator>(), p);
+    }
+    catch (mfmg::NotImplementedExc const &)
+    {
+      threw = true;
+    }
+    CHECK(threw);
+  }
+
+  // ---- CudaMatrixFreeOperator / CudaMatrixFreeMeshEvaluator (cuda_matrix_free_operator.cuh, *_mesh_evaluator.cuh):
+  //      the library's evaluator of the reference's matrix-free Laplace problem, and a user evaluator ----
+  {
+    int const c = 12; // 12^3 cells, Q1, constant coefficient, Dirichlet on the whole boundary
+    int const nn = c + 1;
+    unsigned const n = (unsigned)(nn * nn * nn);
+    std::vector<double> coef((std::size_t)c * c * c * 8, 1.);
+    std::vector<uint8_t> constrained(n, 0);
+    for (int k = 0; k < nn; ++k)
+      for (int j = 0; j < nn; ++j)
+        for (int i = 0; i < nn; ++i)
+          if (i == 0 || j == 0 || k == 0 || i == c || j == c || k == c)
+            constrained[(std::size_t)(k * nn + j) * nn + i] = 1;
+    // piecewise-constant restrictor over 3x3x3-cell agglomerates (rows: agglomerates; unconstrained nodes only)
+    struct Evaluator : mfmg::LaplaceMatrixFreeMeshEvaluator<3>
+    {
+      using mfmg::LaplaceMatrixFreeMeshEvaluator<3>::LaplaceMatrixFreeMeshEvaluator;
+      HostCsr r;
+      void build_restrictor_matrix(std::shared_ptr<mfmg::ParameterTree const>,
+                                   mfmg::SparseMatrixDevice<double> &m) const override
+      {
+        m.reinit(_cuda_handle, r.n_rows, r.n_cols, r.rp, r.col, r.val);
+      }
+    };
+    double const hh = 1. / c;
+    auto evaluator = std::make_shared<Evaluator>(handle, 1, std::vector<int64_t>{c, c, c}, std::vector<double>{hh, hh, hh},
+                                                 coef, constrained);
+    int const na = c / 3;
+    evaluator->r = HostCsr{(unsigned)(na * na * na), n, {0}, {}, {}};
+    for (int ak = 0; ak < na; ++ak)
+      for (int aj = 0; aj < na; ++aj)
+        for (int ai = 0; ai < na; ++ai)
+        {
+          for (int k = 3 * ak; k < 3 * ak + 3; ++k)
+            for (int j = 3 * aj; j < 3 * aj + 3; ++j)
+              for (int i = 3 * ai; i < 3 * ai + 3; ++i)
+                if (!constrained[(std::size_t)(k * nn + j) * nn + i])
+                {
+                  evaluator->r.col.push_back((k * nn + j) * nn + i);
+                  evaluator->r.val.push_back(1.);
+                }
+          evaluator->r.rp.push_back((int64_t)evaluator->r.col.size());
+        }
+    mfmg::CudaMatrixFreeOperator<3, V> op(evaluator);
+    auto x = op.build_domain_vector(), y = op.build_range_vector();
+    CHECK(x->size() == n && y->size() == n && op.grid_complexity() == n);
+    *x = 1.;
+    op.apply(*x, *y);
+    // A 1 restricted to interior rows: rows whose 27 neighbours are all unconstrained sum to zero (Laplace of a constant)
+    auto yh = y->export_to_host();
+    CHECK(std::abs(yh[(std::size_t)((6 * nn + 6) * nn + 6)]) < 1e-13);
+    CHECK(yh[0] == 1.); // constrained rows act as identity
+    bool threw = false;
+    try
+    {
+      op.apply(*x, *y, mfmg::OperatorMode::TRANS);
+    }
+    catch (mfmg::NotImplementedExc const &)
+    {
+      threw = true;
+    }
+    CHECK(threw);
+    for (auto smoother : {"Jacobi", "Chebyshev"})
+    {
+      auto p = std::make_shared<mfmg::ParameterTree>();
+      p->put("is preconditioner", false);
+      p->put("smoother.type", smoother);
+      mfmg::Hierarchy<V> hierarchy(mfmg::MPI_COMM_SELF, evaluator, p);
+      CHECK(hierarchy.is_fused()); // the library's own matrix-free operator feeds the fused V-cycle
+      std::vector<double> xh(n);
+      std::default_random_engine gen(5);
+      std::uniform_real_distribution<double> dist(0., 1.);
+      for (unsigned i = 0; i < n; ++i)
+        xh[i] = constrained[i] ? 0. : dist(gen);
+      V b(handle, n), x1(handle, n), r(handle, n);
+      b = 0.;
+      x1.import_from_host(xh);
+      double prev = 0., rate = 0.;
+      for (int cycle = 0; cycle < 12; ++cycle)
+      {
+        hierarchy.vmult(x1, b);
+        op.apply(x1, r);
+        double const nrm = r.l2_norm();
+        if (cycle > 0)
+          rate = nrm / prev;
+        prev = nrm;
+      }
+      CHECK(rate > 0. && rate < 0.9); // the two-grid iteration contracts
+      if (std::string(smoother) == "Jacobi")
+      {
+        // fused == the abstract composition (CudaMatrixFreeSmoother + CudaMatrixFreeOperator + CudaSolver)
+        V x2(handle, n), x3(handle, n);
+        x2.import_from_host(xh);
+        x3.import_from_host(xh);
+        std::vector<double> bh(n);
+        for (unsigned i = 0; i < n; ++i)
+          bh[i] = constrained[i] ? 0. : dist(gen);
+        b.import_from_host(bh);
+        hierarchy.vmult(x2, b);
+        hierarchy.apply_generic(b, x3);
+        auto h2 = x2.export_to_host(), h3 = x3.export_to_host();
+        double num = 0., den = 0.;
+        for (unsigned i = 0; i < n; ++i)
+        {
+          num += (h2[i] - h3[i]) * (h2[i] - h3[i]);
+          den += h3[i] * h3[i];
+        }
+        CHECK(std::sqrt(num / den) < 1e-12);
+      }
+    }
+  }
+
   if (failures == 0)
     std::printf("test_adapter: ALL OK\n");
   return failures == 0 ? 0 : 1;

@@ -601,3 +601,35 @@ def test_chebyshev_gold_rate_on_gpu(handle):
     with pytest.raises(d.MfmgError):
         d.Hierarchy(handle, [M, d.SparseMatrixDevice.from_host(handle, Ac)],
                     [d.SparseMatrixDevice.from_host(handle, R)], {"smoother": {"type": "Gauss-Seidel"}})
+
+
+@pytest.mark.parametrize("coarse_blocks", [[(2, 2, 2)], [(2, 2, 2), (2, 2, 2)]])
+@pytest.mark.parametrize("nu,precond", [(1, True), (2, False)])
+def test_multilevel_hierarchy_vs_oracle(handle, coarse_blocks, nu, precond):
+    """True multi-level V-cycle ("max levels" > 2, which the reference cannot build itself,
+    hierarchy.hpp:209-210): 3 and 4 levels -- AMGe restrictor from the mesh, aggregation restrictors below --
+    against the oracle's recursive restatement of Hierarchy::apply: V-cycle 1e-12, PCG equal iterations / 1e-10."""
+    d = _dev()
+    from mfmg_b200 import hostsetup as hs
+
+    P = hs.LaplaceProblem.create(3, 1, 24, "discontinuous")
+    ops, res = hs.build_multilevel(P, (3, 3, 3), 2, coarse_blocks)
+    assert len(ops) == len(coarse_blocks) + 2
+    H = d.Hierarchy(handle, [d.SparseMatrixDevice.from_host(handle, o) for o in ops],
+                    [d.SparseMatrixDevice.from_host(handle, r) for r in res],
+                    {"is preconditioner": precond, "smoother": {"n_smoothing_steps": nu}})
+    Ho = oracle.Hierarchy([(o.n_rows, o.rowptr, o.col, o.val) for o in ops],
+                          [(r.n_rows, r.n_cols, r.rowptr, r.col, r.val) for r in res], nu, precond)
+    rng = np.random.default_rng(len(ops) + nu)
+    b_h, x_h = rng.standard_normal(P.n), rng.standard_normal(P.n)
+    for graph in (False, True):
+        H.use_graph(graph)
+        b, x = d.DeviceVector.from_host(handle, b_h), d.DeviceVector.from_host(handle, x_h)
+        H.vmult(x, b)
+        assert rel_err(x.to_host(), Ho.vmult(b_h, x_h)) < TOL_OP
+    if precond:
+        x0 = oracle.std_uniform01(P.n, skip=P.constrained)
+        _, it_ref, hist_ref = Ho.pcg(np.zeros(P.n), x0, 1e-8, 200)
+        xd = d.DeviceVector.from_host(handle, x0)
+        it, hist = d.solver_cg(handle, H.operators[0], xd, d.DeviceVector.from_host(handle, np.zeros(P.n)), H, 1e-8, 200)
+        assert it == it_ref and np.max(np.abs(hist - hist_ref) / hist_ref) < TOL_PCG

@@ -190,3 +190,27 @@ def test_block_agglomerates_3d_match_reference_partition():
         first_visit.setdefault(a, len(first_visit) + 1)
         got.append(first_visit[a])
     assert got == ref
+
+
+def test_multilevel_setup_and_oracle_convergence():
+    """hostsetup.build_multilevel: Galerkin operators stay symmetric, the aggregation restrictor partitions the coarse
+    DoFs, and the oracle's PCG iteration count grows by at most 2 from 2 to 4 levels (own convergence study for
+    SURVEY 8f-2; unpinned by the reference)."""
+    import oracle
+    from mfmg_b200 import hostsetup as hs
+
+    P = hs.LaplaceProblem.create(3, 1, 16, "constant")
+    its = []
+    for cbs in ([], [(2, 2, 2)], [(2, 2, 2), (2, 2, 2)]):
+        ops, res = hs.build_multilevel(P, (2, 2, 2), 1, cbs)
+        for r in res[1:]:
+            assert np.all(np.diff(r.rowptr) > 0) and np.array_equal(np.sort(r.col), np.arange(r.n_cols))
+        a = ops[-1].to_scipy()
+        assert abs(a - a.T).max() < 1e-12 * abs(a).max()
+        H = oracle.Hierarchy([(o.n_rows, o.rowptr, o.col, o.val) for o in ops],
+                             [(r.n_rows, r.n_cols, r.rowptr, r.col, r.val) for r in res], 1, True)
+        x0 = oracle.std_uniform01(P.n, skip=P.constrained)
+        _, it, _ = H.pcg(np.zeros(P.n), x0, 1e-8, 200)
+        assert it > 0
+        its.append(it)
+    assert its[2] <= its[0] + 2
