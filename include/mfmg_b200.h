@@ -146,6 +146,12 @@ extern "C"
   MFMGB_API int64_t mfmgb_dense_size(const mfmgb_dense *D);
   /* number of row interchanges the factorisation performed (diagnostic) */
   MFMGB_API int64_t mfmgb_dense_num_swaps(const mfmgb_dense *D);
+  /* how mfmgb_dense_solve applies the factorisation: 0 = one GEMV with A^-1 = U^-1 L^-1 P formed at setup (well-conditioned
+   * operators: a substitution solve would be ~n dependent steps per cycle), 1 = forward / backward substitution with the
+   * kept factors, getrs' operation order (chosen when min |u_kk| / max |u_kk| < 1e-12, returned in *pivot_ratio: the
+   * reference's own 4^3-cell gold configuration has a numerically singular coarse operator).  MFMGB_DENSE_SOLVE=
+   * substitution | inverse overrides. */
+  MFMGB_API int mfmgb_dense_solve_mode(const mfmgb_dense *D, double *pivot_ratio);
 
   /* ---- matrix-free Laplace/diffusion operator: fills the CudaMatrixFreeOperator slot
    *      (source/cuda/cuda_matrix_free_operator.cu:32-37,60-70; the operator itself is defined by

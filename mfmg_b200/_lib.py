@@ -90,6 +90,7 @@ SIGNATURES = {
     "mfmgb_dense_solve": (_int, [_vp, _vp, _vp, _vp]),
     "mfmgb_dense_size": (_i64, [_vp]),
     "mfmgb_dense_num_swaps": (_i64, [_vp]),
+    "mfmgb_dense_solve_mode": (_int, [_vp, ctypes.POINTER(_dbl)]),
     "mfmgb_mf_laplace_create": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _pp]),
     "mfmgb_mf_laplace_create_slab": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _i64, _i64, _pp]),
     "mfmgb_mf_vector_size": (_i64, [_vp]),

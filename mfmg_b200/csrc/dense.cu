@@ -14,6 +14,9 @@
 //                   Multi-GPU: every rank holds M, computes a contiguous block of rows, one all-gather.
 // No cuSOLVER / cuBLAS.  Tensor cores are not used (FP64, and the hot part is a GEMV).
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "comm.cuh"
@@ -473,6 +476,68 @@ __global__ void __launch_bounds__(256) gemv_kernel(int64_t n, const double *__re
   }
 }
 
+// diagonal of the packed factors (pivots of U)
+__global__ void __launch_bounds__(256) lu_diag_kernel(const double *__restrict__ lu, int64_t lda, int64_t n,
+                                                      double *__restrict__ diag)
+{
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n)
+    diag[i] = lu[i * lda + i];
+}
+
+// x = U^-1 L^-1 P b by substitution, in the operation order of getrs' reference implementation (the oracle's
+// orc_lu_solve: row-oriented, ascending column index, separate multiply and subtract): one thread, small systems
+__global__ void lu_subst_serial_kernel(const double *__restrict__ lu, int64_t lda, int64_t n, const int *__restrict__ perm,
+                                       const double *__restrict__ b, double *__restrict__ x)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0)
+    return;
+  for (int64_t i = 0; i < n; ++i)
+  {
+    double s = b[perm[i]];
+    const double *row = lu + i * lda;
+    for (int64_t j = 0; j < i; ++j)
+      s = __dsub_rn(s, __dmul_rn(row[j], x[j]));
+    x[i] = s;
+  }
+  for (int64_t i = n - 1; i >= 0; --i)
+  {
+    double s = x[i];
+    const double *row = lu + i * lda;
+    for (int64_t j = i + 1; j < n; ++j)
+      s = __dsub_rn(s, __dmul_rn(row[j], x[j]));
+    x[i] = __ddiv_rn(s, row[i]);
+  }
+}
+
+// the same solve, column-oriented, one CTA (larger ill-conditioned systems): every entry still receives its updates in
+// ascending k in the forward sweep; the backward sweep runs in descending k
+__global__ void __launch_bounds__(1024)
+    lu_subst_cta_kernel(const double *__restrict__ lu, int64_t lda, int64_t n, const int *__restrict__ perm,
+                        const double *__restrict__ b, double *__restrict__ x)
+{
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x)
+    x[i] = b[perm[i]];
+  __syncthreads();
+  for (int64_t k = 0; k < n; ++k)
+  {
+    const double xk = x[k];
+    for (int64_t i = k + 1 + threadIdx.x; i < n; i += blockDim.x)
+      x[i] = __dsub_rn(x[i], __dmul_rn(lu[i * lda + k], xk));
+    __syncthreads();
+  }
+  for (int64_t k = n - 1; k >= 0; --k)
+  {
+    if (threadIdx.x == 0)
+      x[k] = __ddiv_rn(x[k], lu[k * lda + k]);
+    __syncthreads();
+    const double xk = x[k];
+    for (int64_t i = threadIdx.x; i < k; i += blockDim.x)
+      x[i] = __dsub_rn(x[i], __dmul_rn(lu[i * lda + k], xk));
+    __syncthreads();
+  }
+}
+
 int launch_gemv(mfmgb_ctx *ctx, const mfmgb_dense *D, const double *b, double *out, int64_t row0, int64_t n_out)
 {
   if (n_out <= 0)
@@ -498,6 +563,15 @@ int dense_solve_async(mfmgb_ctx *ctx, const mfmgb_dense *D, const double *b, dou
     // in-place solve, or a right-hand side that is not 16-byte aligned: stage it (the GEMV reads b with 128-bit loads)
     MFMGB_CUDA(ctx, cudaMemcpyAsync(D->work0, b, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
     b = D->work0;
+  }
+  if (D->substitution && !D->distributed)
+  {
+    if (n <= 128)
+      lu_subst_serial_kernel<<<1, 32, 0, ctx->stream>>>(D->lu, D->lda, n, D->perm, b, x);
+    else
+      lu_subst_cta_kernel<<<1, 1024, 0, ctx->stream>>>(D->lu, D->lda, n, D->perm, b, x);
+    MFMGB_LAUNCHED(ctx);
+    return MFMGB_OK;
   }
   if (!D->distributed)
     return launch_gemv(ctx, D, b, x, 0, n);
@@ -644,6 +718,28 @@ int dense_factor_device(mfmgb_ctx *ctx, double *lu, int64_t n, mfmgb_dense **out
       D->num_swaps = swaps;
       MFMGB_CUDA(ctx, cudaMemcpyAsync(D->perm, perm.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
       MFMGB_CUDA(ctx, cudaStreamSynchronize(st));
+      // conditioning from the pivots: a spread of more than 12 decades keeps the factors and solves by substitution
+      {
+        std::vector<double> hdiag((size_t)n);
+        lu_diag_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(lu, lda, n, D->work0);
+        MFMGB_LAUNCHED(ctx);
+        MFMGB_CUDA(ctx, cudaMemcpyAsync(hdiag.data(), D->work0, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        MFMGB_CUDA(ctx, cudaStreamSynchronize(st));
+        double dmin = std::fabs(hdiag[0]), dmax = dmin;
+        for (double v : hdiag)
+        {
+          dmin = std::min(dmin, std::fabs(v));
+          dmax = std::max(dmax, std::fabs(v));
+        }
+        D->pivot_ratio = dmax > 0. ? dmin / dmax : 0.;
+        const char *force = getenv("MFMGB_DENSE_SOLVE"); // "substitution" / "inverse" override the automatic choice
+        D->substitution = force ? !strcmp(force, "substitution") : D->pivot_ratio < 1e-12;
+        if (D->substitution)
+        {
+          MFMGB_CUDA(ctx, cudaMalloc(&D->lu, bytes));
+          MFMGB_CUDA(ctx, cudaMemcpyAsync(D->lu, lu, bytes, cudaMemcpyDeviceToDevice, st));
+        }
+      }
       // triangular inverses by block doubling
       const int64_t nblk = ceil_div(n, NB);
       tri_diag_inverse_kernel<<<(unsigned)nblk, 32, 0, st>>>(lu, lda, n, linv, uinv);
@@ -703,6 +799,7 @@ extern "C"
     MFMGB_REQUIRE(ctx, ctx, "ctx is NULL");
     MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(D->inv);
+    cudaFree(D->lu);
     cudaFree(D->perm);
     cudaFree(D->work0);
     cudaFree(D->work1);
@@ -720,4 +817,10 @@ extern "C"
 
   MFMGB_API int64_t mfmgb_dense_size(const mfmgb_dense *D) { return D ? D->n : 0; }
   MFMGB_API int64_t mfmgb_dense_num_swaps(const mfmgb_dense *D) { return D ? D->num_swaps : 0; }
+  MFMGB_API int mfmgb_dense_solve_mode(const mfmgb_dense *D, double *pivot_ratio)
+  {
+    if (D && pivot_ratio)
+      *pivot_ratio = D->pivot_ratio;
+    return D && D->substitution ? 1 : 0;
+  }
 }

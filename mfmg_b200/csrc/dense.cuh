@@ -8,6 +8,13 @@ struct mfmgb_dense
   int64_t n = 0, lda = 0;
   double *inv = nullptr; // M = U^-1 L^-1 P (= A^-1), row-major [n][lda], padding columns zero
   int *perm = nullptr;   // composed row permutation: (P b)[i] = b[perm[i]]
+  // Factor-and-solve form (getrs: source/cuda/dealii_operator_device_helpers.cu:214) for factorisations whose pivots
+  // span more than 12 decades: the explicit inverse of a numerically singular coarse operator (the reference's own
+  // gold configuration, 4^3 cells with 2 eigenvectors per agglomerate, has cond(A_c) ~ 1e17) has entries ~1/sigma_min and
+  // its product with a consistent right-hand side cancels catastrophically, substitution does not.
+  bool substitution = false;
+  double *lu = nullptr;  // the packed factors L\U (row-major [n][lda]) when substitution is on
+  double pivot_ratio = 1.; // min |u_kk| / max |u_kk|
   double *work0 = nullptr, *work1 = nullptr;
   int64_t num_swaps = 0;
   // multi-GPU: the GEMV is split by rows across the ranks (every rank holds M and the full right-hand side);

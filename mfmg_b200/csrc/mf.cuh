@@ -21,6 +21,9 @@ struct mfmgb_mf
   // 27-point stencil z-sweep (mf_q1_sweep.cuh) serves the operator
   bool q1_stencil = false;
   double q1_const_coef = 0.;
+  // the constrained nodes of the local box are exactly its x / y faces plus (bottom_bc / top_bc) its first / last
+  // plane: the stencil kernel then computes the flags instead of loading them
+  bool q1_arith_flags = false, q1_bottom_bc = false, q1_top_bc = false;
   bool force_generic = false;     // tests: run the generic colour-phase kernel instead
   int q1_tz = 6;                  // owned node planes per CTA of mf_q1_kernel
   uint8_t *brick_flags = nullptr; // device, one byte per CTA brick: does it contain a constrained node?

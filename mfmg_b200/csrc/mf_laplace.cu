@@ -614,6 +614,37 @@ extern "C"
       }
       M->q1_stencil = stencil;
       M->q1_const_coef = coef[0];
+      if (stencil)
+      {
+        // are the flags of the WHOLE local box (vector layout [owned | ghost below | ghost above]) the box's x / y faces
+        // plus, possibly, its first / last plane?  Then the kernel computes them.
+        const int64_t nz = M->nodes[2];
+        auto vec_off = [&](int64_t g) {
+          if (g >= own_plane_begin && g < own_plane_end)
+            return (g - own_plane_begin) * pl;
+          if (g < own_plane_begin)
+            return M->n + g * pl;
+          return M->n + (own_plane_begin + (g - own_plane_end)) * pl;
+        };
+        auto interior_flag = [&](int64_t g) { return constrained[vec_off(g) + (ny / 2) * nx + nx / 2] != 0; };
+        M->q1_bottom_bc = interior_flag(0);
+        M->q1_top_bc = interior_flag(nz - 1);
+        bool arith = true;
+        for (int64_t g = 0; g < nz && arith; ++g)
+        {
+          const bool face = (g == 0 && M->q1_bottom_bc) || (g == nz - 1 && M->q1_top_bc);
+          const uint8_t *f = constrained + vec_off(g);
+          for (int64_t j = 0; j < ny && arith; ++j)
+            for (int64_t i = 0; i < nx; ++i)
+              if ((f[j * nx + i] != 0) != (face || i == 0 || i == nx - 1 || j == 0 || j == ny - 1))
+              {
+                arith = false;
+                break;
+              }
+        }
+        const char *af = getenv("MFMGB_MF_ARITH_FLAGS");
+        M->q1_arith_flags = arith && !(af && af[0] == '0');
+      }
       std::vector<double> cc((size_t)M->n_cells);
       for (int64_t c = 0; c < M->n_cells; ++c)
         cc[(size_t)c] = coef[(size_t)c * M->nq];

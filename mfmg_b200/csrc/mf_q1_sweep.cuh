@@ -23,84 +23,123 @@ namespace
 {
 constexpr int SW_TX = 32, SW_TY = 16;           // threads per CTA
 constexpr int SW_UX = SW_TX - 2, SW_UY = SW_TY - 2; // nodes a CTA emits per plane
-constexpr int SW_RING = 6;                       // x planes in flight per thread (cp.async ring in shared memory)
+constexpr int SW_RING = 4;                       // x planes in flight per thread (cp.async ring in shared memory)
 
-template <int EPI, int MINB>
+struct StencilArgs
+{
+  int64_t nx, ny, nz, pl;     // nodes of the local box, nodes per plane
+  int64_t own0, own1, n_owned; // owned planes [own0, own1) (slab layout: [owned | ghost below | ghost above])
+  int64_t g_begin, g_end;     // planes this launch emits
+  int seg_planes;
+  const uint8_t *constr;      // vector layout (read when the flags are not arithmetic)
+  int bottom_bc, top_bc;      // arithmetic flags: plane 0 / nz-1 of the local box is a Dirichlet face
+  double cax, cay, caz;
+};
+
+__device__ __forceinline__ int64_t sw_plane_offset(const StencilArgs &a, int64_t g)
+{
+  if (g >= a.own0 && g < a.own1)
+    return (g - a.own0) * a.pl;
+  if (g < a.own0)
+    return a.n_owned + g * a.pl;
+  return a.n_owned + (a.own0 + (g - a.own1)) * a.pl;
+}
+
+// (ncu of the first version, profiles/r02_ncu_full_mf_stencil_v1_raw.csv: issue slots 77 % busy, FP64 pipe and barrier
+// stalls, long-scoreboard stalls ~0 -- 236 instructions per warp and plane, most of them 64-bit index arithmetic.  This
+// version keeps running pointers: the planes of a segment are contiguous except possibly its first and its last one.)
+template <int EPI, bool ARITH, int MINB>
 __global__ void __launch_bounds__(SW_TX *SW_TY, MINB)
-    mf_q1_stencil_kernel(const Q1Params p, const double *__restrict__ x, const EpiArgs e, const int64_t g_begin,
-                         const int64_t g_end, const int seg_planes, const double cax, const double cay, const double caz)
+    mf_q1_stencil_kernel(const StencilArgs a, const double *__restrict__ x, const EpiArgs e)
 {
   __shared__ double sm_m[2][SW_TY][SW_TX], sm_d[2][SW_TY][SW_TX];
   // x of the next SW_RING planes: slot [t % SW_RING][thread] is written by this thread's own cp.async and read by this
   // thread only (x-neighbours travel by shuffle), so the ring needs no barrier -- it is an asynchronous register file
   __shared__ double xr[SW_RING][SW_TX * SW_TY];
   const int tid = threadIdx.x, tx = tid % SW_TX, ty = tid / SW_TX;
-  const int64_t gi = (int64_t)blockIdx.x * SW_UX - 1 + tx, gj = (int64_t)blockIdx.y * SW_UY - 1 + ty;
-  const bool node_ok = gi >= 0 && gi < p.nx && gj >= 0 && gj < p.ny;
+  const int gi = (int)blockIdx.x * SW_UX - 1 + tx, gj = (int)blockIdx.y * SW_UY - 1 + ty;
+  const bool node_ok = gi >= 0 && gi < (int)a.nx && gj >= 0 && gj < (int)a.ny;
   const bool emit_xy = node_ok && tx >= 1 && tx <= SW_UX && ty >= 1 && ty <= SW_UY;
-  const int64_t P0 = g_begin + (int64_t)blockIdx.z * seg_planes;
-  const int64_t P1 = P0 + seg_planes < g_end ? P0 + seg_planes : g_end;
+  const int64_t P0 = a.g_begin + (int64_t)blockIdx.z * a.seg_planes;
+  const int64_t P1 = P0 + a.seg_planes < a.g_end ? P0 + a.seg_planes : a.g_end;
   if (P0 >= P1)
     return;
-  const int64_t pl = p.nx * p.ny;
-  const int64_t node_xy = node_ok ? gj * p.nx + gi : 0;
+  const int64_t pl = a.pl;
+  const int64_t node_xy = node_ok ? (int64_t)gj * a.nx + gi : 0;
   const int tyd = ty > 0 ? ty - 1 : 0, tyu = ty < SW_TY - 1 ? ty + 1 : SW_TY - 1;
   const int n_steps = (int)(P1 - P0) + 2; // step t handles plane g = P0 - 1 + t; plane g - 1 is emitted at t >= 2
+  // planes P0 .. P1-1 are owned and contiguous; only the first (P0-1) and the last (P1) plane of the segment can be a
+  // ghost plane or lie outside the box
+  const bool ok_first = node_ok && P0 - 1 >= 0, ok_last = node_ok && P1 < a.nz;
+  const int64_t off_first = ok_first ? sw_plane_offset(a, P0 - 1) + node_xy : 0;
+  const int64_t off_last = ok_last ? sw_plane_offset(a, P1) + node_xy : 0;
+  const int64_t off_mid = (P0 - a.own0) * pl + node_xy; // plane P0 (step 1)
+  const bool edge_xy = !node_ok || gi == 0 || gi == (int)a.nx - 1 || gj == 0 || gj == (int)a.ny - 1;
 
   // asynchronous copy of this thread's node of the plane of step t into its ring slot (zero-fill outside the box);
   // exactly one commit group per step, so "all but the newest SW_RING - 1 groups done" == the plane of step t landed
+  const double *xq = x + off_mid - pl; // running pointer: plane of step t at xq + t pl for 1 <= t <= n_steps - 2
   auto request_x = [&](int t) {
     if (t < n_steps)
     {
-      const int64_t g = P0 - 1 + t;
-      const bool ok = node_ok && g >= 0 && g < p.nz;
-      cp_async_f64(&xr[t % SW_RING][tid], x + (ok ? plane_offset(p, g) + node_xy : 0), ok);
+      const bool first = t == 0, last = t == n_steps - 1;
+      const bool ok = first ? ok_first : (last ? ok_last : node_ok);
+      const double *src = first ? x + off_first : (last ? x + off_last : xq + (int64_t)t * pl);
+      cp_async_f64(&xr[t & (SW_RING - 1)][tid], ok ? src : x, ok);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  auto load_flag = [&](int64_t g) -> unsigned { // nodes outside the box read as constrained zeros
-    return node_ok && g >= 0 && g < p.nz ? (unsigned)p.constr[plane_offset(p, g) + node_xy] : 1u;
+  auto flag_of = [&](int t) -> unsigned { // constraint flag of this thread's node on the plane of step t
+    const int64_t g = P0 - 1 + t;
+    if (ARITH)
+      return (edge_xy || (g <= 0 && a.bottom_bc) || (g >= a.nz - 1 && a.top_bc) || g < 0 || g >= a.nz) ? 1u : 0u;
+    if (t >= n_steps)
+      return 1u;
+    const bool first = t == 0, last = t == n_steps - 1;
+    const bool ok = first ? ok_first : (last ? ok_last : node_ok);
+    if (!ok)
+      return 1u; // nodes outside the box read as constrained zeros
+    return a.constr[first ? off_first : (last ? off_last : off_mid + (int64_t)(t - 1) * pl)];
   };
+  static_assert((SW_RING & (SW_RING - 1)) == 0, "the ring depth is a power of two");
 #pragma unroll
   for (int t = 0; t < SW_RING - 1; ++t)
     request_x(t);
-  unsigned fa = load_flag(P0 - 1), fb = load_flag(P0); // flags of planes g and g + 1 of the current step
-  // epilogue operands: "b" slot = plane g of the current step, "a" slot = plane g - 1 (the one that is emitted).  The
-  // operands of plane P0 enter the pipeline as the "next" of step 0, like every later plane's do one step ahead.
-  double ba = 0., bb = 0., da = 0., db = 0.;
-  double pend_b = 0., pend_d = 0.;
+  unsigned fa = flag_of(0), fb = flag_of(1); // flags of the planes of steps t and t + 1
+  // epilogue operands ride one step ahead: "b" slot = plane of the current step, "a" slot = the plane that is emitted
+  const int64_t row0 = off_mid; // row of this thread's node on plane P0 (owned planes: vector offset == row)
+  double ba = 0., bb = 0., da = 0., db = 0., bn = 0., dn = 0.;
   if (emit_xy && EPI != (int)Epi::Spmv)
   {
-    const int64_t row = (P0 - p.own0) * pl + node_xy;
-    pend_b = e.b[row];
+    bn = e.b[row0];
     if (EPI == (int)Epi::Jacobi)
-      pend_d = e.dinv[row];
+      dn = e.dinv[row0];
   }
   double u_prev = 0.;
   unsigned f_prev = 1u;
   double Pm = 0., Pc = 0., Qm = 0., Qc = 0.;
+  int64_t row_emit = row0 - 2 * pl; // row emitted at step t is row_emit + t pl  (plane P0 at t = 2)
   for (int t = 0; t < n_steps; ++t)
   {
-    const int64_t g = P0 - 1 + t;
-    // ---- requests for later steps: x of step t + SW_RING - 1, flag of plane g + 2, epilogue operands of plane g + 1
+    // ---- requests for later steps: x of step t + SW_RING - 1, flag of step t + 2, epilogue operands of step t + 1
     request_x(t + SW_RING - 1);
-    const unsigned fn = g + 2 <= P1 ? load_flag(g + 2) : 1u;
-    double bn = 0., dn = 0.;
-    if (t == 0)
+    const unsigned fn = flag_of(t + 2);
+    // (operands of plane P0 were requested before the loop and enter as "next" of step 0)
+    if (t > 0)
     {
-      bn = pend_b;
-      dn = pend_d;
+      bn = 0.;
+      dn = 0.;
+      if (emit_xy && EPI != (int)Epi::Spmv && t + 1 <= n_steps - 2)
+      {
+        const int64_t row = row0 + (int64_t)t * pl; // plane of step t + 1 = P0 + t
+        bn = e.b[row];
+        if (EPI == (int)Epi::Jacobi)
+          dn = e.dinv[row];
+      }
     }
-    else if (emit_xy && EPI != (int)Epi::Spmv && g + 1 < P1)
-    {
-      const int64_t row = (g + 1 - p.own0) * pl + node_xy;
-      bn = e.b[row];
-      if (EPI == (int)Epi::Jacobi)
-        dn = e.dinv[row];
-    }
-    // ---- x stage of plane g ----
+    // ---- x stage of the plane of step t ----
     asm volatile("cp.async.wait_group %0;" ::"n"(SW_RING - 1) : "memory");
-    const double ua = xr[t % SW_RING][tid];
+    const double ua = xr[t & (SW_RING - 1)][tid];
     const double uz = fa ? 0. : ua;
     const double ul = __shfl_up_sync(0xffffffffu, uz, 1), ur = __shfl_down_sync(0xffffffffu, uz, 1);
     const double lr = ul + ur;
@@ -109,15 +148,15 @@ __global__ void __launch_bounds__(SW_TX *SW_TY, MINB)
     sm_m[buf][ty][tx] = m;
     sm_d[buf][ty][tx] = d;
     __syncthreads();
-    // ---- y stage: in-plane operators of plane g ----
+    // ---- y stage: in-plane operators ----
     const double mo = sm_m[buf][tyd][tx] + sm_m[buf][tyu][tx], dO = sm_d[buf][tyd][tx] + sm_d[buf][tyu][tx];
     const double Pn = fma(4., m, mo);
-    const double Qn = fma(cax, fma(4., d, dO), cay * fma(2., m, -mo));
-    // ---- z stage: plane g - 1 is complete ----
+    const double Qn = fma(a.cax, fma(4., d, dO), a.cay * fma(2., m, -mo));
+    // ---- z stage: the plane of step t - 1 is complete ----
     if (emit_xy && t >= 2)
     {
-      const int64_t row = (g - 1 - p.own0) * pl + node_xy;
-      const double stencil = (Qm + fma(4., Qc, Qn)) + caz * fma(2., Pc, -(Pm + Pn));
+      const int64_t row = row_emit + (int64_t)t * pl;
+      const double stencil = (Qm + fma(4., Qc, Qn)) + a.caz * fma(2., Pc, -(Pm + Pn));
       const double s = f_prev ? u_prev : stencil; // constrained rows act as identity on the raw value
       if (EPI == (int)Epi::Spmv)
         e.y[row] = s;
@@ -155,28 +194,55 @@ int launch_q1_stencil(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, const 
     return MFMGB_OK;
   const Q1Params p = make_q1_params(M);
   const int64_t tiles = ceil_div(p.nx, SW_UX) * ceil_div(p.ny, SW_UY);
-  // z segments: enough CTAs for about three per SM, each long enough that its two-plane lead-in is noise
+  // z segments (MFMGB_MF_SEGMENTS overrides): enough CTAs to fill the resident slots about twice -- the kernel is
+  // issue-bound, a second wave costs nothing and evens out the SMs -- each long enough that its lead-in is noise
   static const int env_seg = [] {
     const char *v = getenv("MFMGB_MF_SEGMENTS");
     return v && *v ? atoi(v) : 0;
   }();
-  // resident CTAs per SM: 3 (40 registers, a few spilled loop invariants) or 2 (64 registers); MFMGB_MF_MINB selects
+  // resident CTAs per SM: 3 (40 registers) or 2 (64 registers); MFMGB_MF_MINB selects
   static const int env_minb = [] {
     const char *v = getenv("MFMGB_MF_MINB");
     return v && *v ? atoi(v) : 3;
   }();
-  int64_t seg = env_seg > 0 ? env_seg : std::max<int64_t>(1, ((int64_t)ctx->num_sms * 3) / tiles);
+  int64_t seg = env_seg > 0 ? env_seg : std::max<int64_t>(1, ((int64_t)ctx->num_sms * 6) / tiles);
   seg = std::min<int64_t>(seg, std::max<int64_t>(1, (g1 - g0) / 8));
   const int seg_planes = (int)ceil_div(g1 - g0, seg);
   seg = ceil_div(g1 - g0, seg_planes);
   const double c = M->q1_const_coef;
+  StencilArgs a;
+  a.nx = p.nx;
+  a.ny = p.ny;
+  a.nz = p.nz;
+  a.pl = p.nx * p.ny;
+  a.own0 = p.own0;
+  a.own1 = p.own1;
+  a.n_owned = p.n_owned;
+  a.g_begin = g0;
+  a.g_end = g1;
+  a.seg_planes = seg_planes;
+  a.constr = p.constr;
+  a.bottom_bc = M->q1_bottom_bc ? 1 : 0;
+  a.top_bc = M->q1_top_bc ? 1 : 0;
+  a.cax = c * p.ax;
+  a.cay = c * p.ay;
+  a.caz = c * p.az;
   dim3 grid((unsigned)ceil_div(p.nx, SW_UX), (unsigned)ceil_div(p.ny, SW_UY), (unsigned)seg);
-  if (env_minb == 2)
-    mf_q1_stencil_kernel<EPI, 2><<<grid, SW_TX * SW_TY, 0, ctx->stream>>>(p, x, e, g0, g1, seg_planes, c * p.ax, c * p.ay,
-                                                                          c * p.az);
+  const int threads = SW_TX * SW_TY;
+  if (M->q1_arith_flags)
+  {
+    if (env_minb == 2)
+      mf_q1_stencil_kernel<EPI, true, 2><<<grid, threads, 0, ctx->stream>>>(a, x, e);
+    else
+      mf_q1_stencil_kernel<EPI, true, 3><<<grid, threads, 0, ctx->stream>>>(a, x, e);
+  }
   else
-    mf_q1_stencil_kernel<EPI, 3><<<grid, SW_TX * SW_TY, 0, ctx->stream>>>(p, x, e, g0, g1, seg_planes, c * p.ax, c * p.ay,
-                                                                          c * p.az);
+  {
+    if (env_minb == 2)
+      mf_q1_stencil_kernel<EPI, false, 2><<<grid, threads, 0, ctx->stream>>>(a, x, e);
+    else
+      mf_q1_stencil_kernel<EPI, false, 3><<<grid, threads, 0, ctx->stream>>>(a, x, e);
+  }
   MFMGB_LAUNCHED(ctx);
   return MFMGB_OK;
 }

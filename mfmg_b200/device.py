@@ -402,6 +402,13 @@ class CudaSolver:
     def num_swaps(self) -> int:
         return int(self.handle.lib.mfmgb_dense_num_swaps(self.ptr))
 
+    @property
+    def solve_mode(self):
+        """("inverse" | "substitution", min |u_kk| / max |u_kk|)"""
+        r = ctypes.c_double()
+        m = self.handle.lib.mfmgb_dense_solve_mode(self.ptr, ctypes.byref(r))
+        return ("substitution" if m else "inverse"), r.value
+
     def __del__(self):
         try:
             if getattr(self, "ptr", None) and getattr(self.handle, "ctx", None):
