@@ -221,7 +221,16 @@ bool csr_uses_tile_kernel(const mfmgb_csr *A)
   if (env_kernel >= 0)
     return env_kernel == 1;
   // automatic: the TMA ring pays off on long streams; tiny operators stay on the direct-load kernel
-  return A->n_rows >= 32768 && A->nnz >= 8 * A->n_rows;
+  // (MFMGB_TILE_MIN_ROWS / MFMGB_TILE_MIN_ROW_NNZ move the thresholds: measurement aid)
+  static const int64_t min_rows = [] {
+    const char *v = getenv("MFMGB_TILE_MIN_ROWS");
+    return v && *v ? atoll(v) : (int64_t)32768;
+  }();
+  static const int64_t min_row_nnz = [] {
+    const char *v = getenv("MFMGB_TILE_MIN_ROW_NNZ");
+    return v && *v ? atoll(v) : (int64_t)8;
+  }();
+  return A->n_rows >= min_rows && A->nnz >= min_row_nnz * A->n_rows;
 }
 
 int csr_apply(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args, int64_t row_begin,
