@@ -52,10 +52,16 @@ template <int EPI, bool ARITH, int MINB>
 __global__ void __launch_bounds__(SW_TX *SW_TY, MINB)
     mf_q1_stencil_kernel(const StencilArgs a, const double *__restrict__ x, const EpiArgs e)
 {
-  __shared__ double sm_m[2][SW_TY][SW_TX], sm_d[2][SW_TY][SW_TX];
-  // x of the next SW_RING planes: slot [t % SW_RING][thread] is written by this thread's own cp.async and read by this
-  // thread only (x-neighbours travel by shuffle), so the ring needs no barrier -- it is an asynchronous register file
-  __shared__ double xr[SW_RING][SW_TX * SW_TY];
+  constexpr int NT = SW_TX * SW_TY;
+  extern __shared__ __align__(16) double sw_smem[];
+  double(*sm_m)[SW_TY][SW_TX] = reinterpret_cast<double(*)[SW_TY][SW_TX]>(sw_smem);               // [2][TY][TX]
+  double(*sm_d)[SW_TY][SW_TX] = reinterpret_cast<double(*)[SW_TY][SW_TX]>(sw_smem + 2 * NT);      // [2][TY][TX]
+  // rings SW_RING planes deep: slot [t % SW_RING][thread] is written by this thread's own cp.async and read by this
+  // thread only (x-neighbours travel by shuffle), so they need no barrier -- asynchronous register files for x and
+  // for the epilogue operands b and D^-1
+  double(*xr)[NT] = reinterpret_cast<double(*)[NT]>(sw_smem + 4 * NT);                            // [RING][NT]
+  double(*br)[NT] = reinterpret_cast<double(*)[NT]>(sw_smem + (4 + SW_RING) * NT);                // [RING][NT]
+  double(*dr)[NT] = reinterpret_cast<double(*)[NT]>(sw_smem + (4 + 2 * SW_RING) * NT);            // [RING][NT]
   const int tid = threadIdx.x, tx = tid % SW_TX, ty = tid / SW_TX;
   const int gi = (int)blockIdx.x * SW_UX - 1 + tx, gj = (int)blockIdx.y * SW_UY - 1 + ty;
   const bool node_ok = gi >= 0 && gi < (int)a.nx && gj >= 0 && gj < (int)a.ny;
@@ -79,6 +85,8 @@ __global__ void __launch_bounds__(SW_TX *SW_TY, MINB)
   // asynchronous copy of this thread's node of the plane of step t into its ring slot (zero-fill outside the box);
   // exactly one commit group per step, so "all but the newest SW_RING - 1 groups done" == the plane of step t landed
   const double *xq = x + off_mid - pl; // running pointer: plane of step t at xq + t pl for 1 <= t <= n_steps - 2
+  const int64_t row0 = off_mid;        // row of this thread's node on plane P0 (owned planes: vector offset == row)
+  // group t = x of step t + the epilogue operands of the plane that step t emits (plane P0 + t - 2)
   auto request_x = [&](int t) {
     if (t < n_steps)
     {
@@ -86,6 +94,13 @@ __global__ void __launch_bounds__(SW_TX *SW_TY, MINB)
       const bool ok = first ? ok_first : (last ? ok_last : node_ok);
       const double *src = first ? x + off_first : (last ? x + off_last : xq + (int64_t)t * pl);
       cp_async_f64(&xr[t & (SW_RING - 1)][tid], ok ? src : x, ok);
+      if (EPI != (int)Epi::Spmv && emit_xy && t >= 2)
+      {
+        const int64_t row = row0 + (int64_t)(t - 2) * pl;
+        cp_async_f64(&br[t & (SW_RING - 1)][tid], e.b + row, true);
+        if (EPI == (int)Epi::Jacobi)
+          cp_async_f64(&dr[t & (SW_RING - 1)][tid], e.dinv + row, true);
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -106,37 +121,15 @@ __global__ void __launch_bounds__(SW_TX *SW_TY, MINB)
   for (int t = 0; t < SW_RING - 1; ++t)
     request_x(t);
   unsigned fa = flag_of(0), fb = flag_of(1); // flags of the planes of steps t and t + 1
-  // epilogue operands ride one step ahead: "b" slot = plane of the current step, "a" slot = the plane that is emitted
-  const int64_t row0 = off_mid; // row of this thread's node on plane P0 (owned planes: vector offset == row)
-  double ba = 0., bb = 0., da = 0., db = 0., bn = 0., dn = 0.;
-  if (emit_xy && EPI != (int)Epi::Spmv)
-  {
-    bn = e.b[row0];
-    if (EPI == (int)Epi::Jacobi)
-      dn = e.dinv[row0];
-  }
   double u_prev = 0.;
   unsigned f_prev = 1u;
   double Pm = 0., Pc = 0., Qm = 0., Qc = 0.;
-  int64_t row_emit = row0 - 2 * pl; // row emitted at step t is row_emit + t pl  (plane P0 at t = 2)
+  const int64_t row_emit = row0 - 2 * pl; // row emitted at step t is row_emit + t pl  (plane P0 at t = 2)
   for (int t = 0; t < n_steps; ++t)
   {
-    // ---- requests for later steps: x of step t + SW_RING - 1, flag of step t + 2, epilogue operands of step t + 1
+    // ---- requests for later steps: x and epilogue operands of step t + SW_RING - 1, flag of step t + 2
     request_x(t + SW_RING - 1);
     const unsigned fn = flag_of(t + 2);
-    // (operands of plane P0 were requested before the loop and enter as "next" of step 0)
-    if (t > 0)
-    {
-      bn = 0.;
-      dn = 0.;
-      if (emit_xy && EPI != (int)Epi::Spmv && t + 1 <= n_steps - 2)
-      {
-        const int64_t row = row0 + (int64_t)t * pl; // plane of step t + 1 = P0 + t
-        bn = e.b[row];
-        if (EPI == (int)Epi::Jacobi)
-          dn = e.dinv[row];
-      }
-    }
     // ---- x stage of the plane of step t ----
     asm volatile("cp.async.wait_group %0;" ::"n"(SW_RING - 1) : "memory");
     const double ua = xr[t & (SW_RING - 1)][tid];
@@ -161,11 +154,11 @@ __global__ void __launch_bounds__(SW_TX *SW_TY, MINB)
       if (EPI == (int)Epi::Spmv)
         e.y[row] = s;
       else if (EPI == (int)Epi::Resid)
-        e.y[row] = __dsub_rn(s, ba);
+        e.y[row] = __dsub_rn(s, br[t & (SW_RING - 1)][tid]);
       else
       {
-        const double r = __dsub_rn(s, ba);
-        double tt = __dmul_rn(da, r);
+        const double r = __dsub_rn(s, br[t & (SW_RING - 1)][tid]);
+        double tt = __dmul_rn(dr[t & (SW_RING - 1)][tid], r);
         if (e.omega != 1.)
           tt = __dmul_rn(e.omega, tt);
         e.y[row] = __dsub_rn(e.xin == x ? u_prev : e.xin[row], tt);
@@ -176,10 +169,6 @@ __global__ void __launch_bounds__(SW_TX *SW_TY, MINB)
     f_prev = fa;
     fa = fb;
     fb = fn;
-    ba = bb;
-    da = db;
-    bb = bn;
-    db = dn;
     Pm = Pc;
     Pc = Pn;
     Qm = Qc;
@@ -200,12 +189,12 @@ int launch_q1_stencil(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, const 
     const char *v = getenv("MFMGB_MF_SEGMENTS");
     return v && *v ? atoi(v) : 0;
   }();
-  // resident CTAs per SM: 3 (40 registers) or 2 (64 registers); MFMGB_MF_MINB selects
+  // resident CTAs per SM: 2 (64 registers, no spills: measured faster) or 3 (40 registers); MFMGB_MF_MINB selects
   static const int env_minb = [] {
     const char *v = getenv("MFMGB_MF_MINB");
-    return v && *v ? atoi(v) : 3;
+    return v && *v ? atoi(v) : 2;
   }();
-  int64_t seg = env_seg > 0 ? env_seg : std::max<int64_t>(1, ((int64_t)ctx->num_sms * 6) / tiles);
+  int64_t seg = env_seg > 0 ? env_seg : std::max<int64_t>(1, ((int64_t)ctx->num_sms * 7) / tiles);
   seg = std::min<int64_t>(seg, std::max<int64_t>(1, (g1 - g0) / 8));
   const int seg_planes = (int)ceil_div(g1 - g0, seg);
   seg = ceil_div(g1 - g0, seg_planes);
@@ -229,22 +218,23 @@ int launch_q1_stencil(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, const 
   a.caz = c * p.az;
   dim3 grid((unsigned)ceil_div(p.nx, SW_UX), (unsigned)ceil_div(p.ny, SW_UY), (unsigned)seg);
   const int threads = SW_TX * SW_TY;
+  // shared memory: the two stage buffers, the x ring, and the b / D^-1 rings of the fused epilogues
+  const int n_rings = EPI == (int)Epi::Spmv ? 1 : (EPI == (int)Epi::Resid ? 2 : 3);
+  const size_t smem = sizeof(double) * (size_t)threads * (size_t)(4 + n_rings * SW_RING);
+  auto launch = [&](auto kernel) {
+    static unsigned long long configured = 0; // one bit per device (per instantiation: the lambda is)
+    if (!((configured >> (ctx->device & 63)) & 1ull))
+    {
+      MFMGB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(80 * 1024)));
+      configured |= 1ull << (ctx->device & 63);
+    }
+    kernel<<<grid, threads, smem, ctx->stream>>>(a, x, e);
+    MFMGB_LAUNCHED(ctx);
+    return (int)MFMGB_OK;
+  };
   if (M->q1_arith_flags)
-  {
-    if (env_minb == 2)
-      mf_q1_stencil_kernel<EPI, true, 2><<<grid, threads, 0, ctx->stream>>>(a, x, e);
-    else
-      mf_q1_stencil_kernel<EPI, true, 3><<<grid, threads, 0, ctx->stream>>>(a, x, e);
-  }
-  else
-  {
-    if (env_minb == 2)
-      mf_q1_stencil_kernel<EPI, false, 2><<<grid, threads, 0, ctx->stream>>>(a, x, e);
-    else
-      mf_q1_stencil_kernel<EPI, false, 3><<<grid, threads, 0, ctx->stream>>>(a, x, e);
-  }
-  MFMGB_LAUNCHED(ctx);
-  return MFMGB_OK;
+    return env_minb == 3 ? launch(mf_q1_stencil_kernel<EPI, true, 3>) : launch(mf_q1_stencil_kernel<EPI, true, 2>);
+  return env_minb == 3 ? launch(mf_q1_stencil_kernel<EPI, false, 3>) : launch(mf_q1_stencil_kernel<EPI, false, 2>);
 }
 
 int dispatch_q1_stencil(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, Epi epi, const EpiArgs &e, int64_t g0,
