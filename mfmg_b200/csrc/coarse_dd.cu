@@ -55,29 +55,24 @@ struct DdRhsArgs
   double *t;
 };
 
-// this rank's contribution to the separator right-hand side:
+// this rank's contribution to the separator right-hand side, one WARP per entry (the row of A_SI is read by the 32
+// lanes at once: a thread-per-row loop exposed one L2 round trip per non-zero, ~25 us for 27-entry rows):
 // t[k] = (k adjacent ? -(A_SI y)[k - adj_begin] : 0) + (k in own separator ? b_c[sep_index[k]] : 0)
 //        + (k in the separator below ? g_below[k - adj_begin] : 0)   [this rank's share of R r on those rows]
 template <typename OffT>
-__device__ __forceinline__ double dd_rhs_value(const DdRhsArgs &a, int64_t k)
+__device__ __forceinline__ double dd_rhs_value_warp(const DdRhsArgs &a, int64_t k, int lane)
 {
-  double v = 0.;
+  double s = 0.;
   if (k >= a.adj_begin && k < a.adj_begin + a.n_adj)
   {
     const OffT *rp = static_cast<const OffT *>(a.si_rowptr);
     const int64_t r = k - a.adj_begin;
-    double s0 = 0., s1 = 0.;
-    OffT j = rp[r];
     const OffT je = rp[r + 1];
-    for (; j + 1 < je; j += 2)
-    {
-      s0 = fma(a.si_val[j], a.y[a.si_col[j]], s0);
-      s1 = fma(a.si_val[j + 1], a.y[a.si_col[j + 1]], s1);
-    }
-    if (j < je)
-      s0 = fma(a.si_val[j], a.y[a.si_col[j]], s0);
-    v = -(s0 + s1);
+    for (OffT j = rp[r] + lane; j < je; j += 32)
+      s = fma(a.si_val[j], a.y[a.si_col[j]], s);
   }
+  s = subwarp_sum<32>(s); // fixed tree
+  double v = -s;
   if (k >= a.own_begin && k < a.own_begin + a.own_n)
     v += a.b_c[a.sep_index[k]];
   if (a.g_below && k >= a.adj_begin && k < a.adj_begin + a.n_below)
@@ -90,8 +85,13 @@ __device__ __forceinline__ double dd_rhs_value(const DdRhsArgs &a, int64_t k)
 template <typename OffT>
 __global__ void __launch_bounds__(1024) dd_rhs_allreduce_kernel(const DdRhsArgs a, const PeerAllreduceArgs pa)
 {
-  for (int64_t k = threadIdx.x; k < a.n_S; k += blockDim.x)
-    a.t[k] = dd_rhs_value<OffT>(a, k);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  for (int64_t k = warp; k < a.n_S; k += n_warps)
+  {
+    const double v = dd_rhs_value_warp<OffT>(a, k, lane);
+    if (lane == 0)
+      a.t[k] = v;
+  }
   __syncthreads();
   peer_allreduce_cta(a.t, (int)a.n_S, pa);
 }
@@ -100,9 +100,14 @@ __global__ void __launch_bounds__(1024) dd_rhs_allreduce_kernel(const DdRhsArgs 
 template <typename OffT>
 __global__ void __launch_bounds__(256) dd_rhs_kernel(const DdRhsArgs a)
 {
-  const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t k = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (k < a.n_S)
-    a.t[k] = dd_rhs_value<OffT>(a, k);
+  {
+    const double v = dd_rhs_value_warp<OffT>(a, k, lane);
+    if (lane == 0)
+      a.t[k] = v;
+  }
 }
 
 // blocks [0, interior_blocks): x_I[i] = y[i] - sum_j E[i][j] xs[j]   (one warp per row, fixed shuffle tree)
@@ -194,9 +199,9 @@ int coarse_dd_solve_async(mfmgb_ctx *ctx, const mfmgb_coarse_dd *d, const double
     else
     {
       if (d->A_SI->off64)
-        dd_rhs_kernel<int64_t><<<(unsigned)ceil_div(d->n_S, 256), 256, 0, st>>>(a);
+        dd_rhs_kernel<int64_t><<<(unsigned)ceil_div(d->n_S, 8), 256, 0, st>>>(a);
       else
-        dd_rhs_kernel<int32_t><<<(unsigned)ceil_div(d->n_S, 256), 256, 0, st>>>(a);
+        dd_rhs_kernel<int32_t><<<(unsigned)ceil_div(d->n_S, 8), 256, 0, st>>>(a);
       MFMGB_LAUNCHED(ctx);
       MFMGB_CHECK(allreduce_sum(ctx, d->t, (int)d->n_S));
     }

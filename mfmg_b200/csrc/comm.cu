@@ -289,6 +289,31 @@ int peer_error(mfmgb_ctx *ctx)
   return c && c->peer.err_host ? *c->peer.err_host : 0;
 }
 
+static PushArgs make_push_args(const mfmgb_comm *c, const mfmgb_halo *h, const double *v)
+{
+  PushArgs a;
+  a.links = h->links;
+  a.n_links = h->n_neighbors;
+  a.nranks = c->nranks;
+  a.rank = c->rank;
+  a.send_idx = h->contiguous ? nullptr : h->send_idx;
+  a.v = v;
+  a.base = c->peer.base_dev;
+  a.box_off = h->box_off;
+  a.flag_off = h->flag_off;
+  a.box_cap = (long long)h->box_cap;
+  a.seq = h->seq;
+  a.done = h->done;
+  return a;
+}
+static unsigned push_grid(const mfmgb_halo *h)
+{
+  int64_t widest = 1;
+  for (int k = 0; k < h->n_neighbors; ++k)
+    widest = std::max(widest, h->send_cnt[k]);
+  return (unsigned)std::min<int64_t>(32, ceil_div(widest, 256 * 4));
+}
+
 int halo_start(mfmgb_ctx *ctx, const mfmgb_halo *h, double *v)
 {
   mfmgb_comm *c = ctx_comm(ctx);
@@ -299,24 +324,7 @@ int halo_start(mfmgb_ctx *ctx, const mfmgb_halo *h, double *v)
   if (h->peer)
   {
     // our own kernel stores the boundary entries into the neighbours' mailboxes over NVLink and raises their flags
-    PushArgs a;
-    a.links = h->links;
-    a.n_links = h->n_neighbors;
-    a.nranks = c->nranks;
-    a.rank = c->rank;
-    a.send_idx = h->contiguous ? nullptr : h->send_idx;
-    a.v = v;
-    a.base = c->peer.base_dev;
-    a.box_off = h->box_off;
-    a.flag_off = h->flag_off;
-    a.box_cap = (long long)h->box_cap;
-    a.seq = h->seq;
-    a.done = h->done;
-    int64_t widest = 1;
-    for (int k = 0; k < h->n_neighbors; ++k)
-      widest = std::max(widest, h->send_cnt[k]);
-    const unsigned grid = (unsigned)std::min<int64_t>(32, ceil_div(widest, 256 * 4));
-    halo_push_kernel<<<grid, 256, 0, c->stream>>>(a);
+    halo_push_kernel<<<push_grid(h), 256, 0, c->stream>>>(make_push_args(c, h, v));
     ctx->launches++;
     MFMGB_CUDA(ctx, cudaGetLastError());
     MFMGB_CUDA(ctx, cudaEventRecord(c->ev_done, c->stream));
@@ -343,6 +351,44 @@ int halo_start(mfmgb_ctx *ctx, const mfmgb_halo *h, double *v)
   MFMGB_NCCL(ctx, ncclGroupEnd());
   MFMGB_CUDA(ctx, cudaEventRecord(c->ev_done, c->stream));
   return MFMGB_OK;
+}
+
+bool halo_can_fuse(mfmgb_ctx *ctx, const mfmgb_halo *h)
+{
+  static const bool enabled = [] {
+    const char *v = getenv("MFMGB_HALO_FUSED");
+    return !(v && v[0] == '0');
+  }();
+  mfmgb_comm *c = ctx_comm(ctx);
+  return enabled && c && h->peer && c->peer.enabled;
+}
+
+int halo_push_inline(mfmgb_ctx *ctx, const mfmgb_halo *h, const double *v)
+{
+  mfmgb_comm *c = ctx_comm(ctx);
+  halo_push_kernel<<<push_grid(h), 256, 0, ctx->stream>>>(make_push_args(c, h, v));
+  MFMGB_LAUNCHED(ctx);
+  return MFMGB_OK;
+}
+
+void halo_ghost_args(mfmgb_ctx *ctx, const mfmgb_halo *h, int64_t blo, int64_t bhi, GhostArgs *g)
+{
+  mfmgb_comm *c = ctx_comm(ctx);
+  g->enabled = 1;
+  g->n_links = h->n_neighbors;
+  g->nranks = c->nranks;
+  g->n_owned = (long long)h->n_owned;
+  g->blo = (long long)blo;
+  g->bhi = (long long)bhi;
+  g->local = c->peer.local;
+  g->box_off = h->box_off;
+  g->flag_off = h->flag_off;
+  g->box_cap = (long long)h->box_cap;
+  g->links = h->ghost_links;
+  g->seq = h->seq;
+  g->done = h->done;
+  g->timeout_ns = c->peer.timeout_ns;
+  g->err = c->peer.err_dev;
 }
 
 int halo_wait(mfmgb_ctx *ctx, const mfmgb_halo *h, double *v)
@@ -585,6 +631,11 @@ extern "C"
                               (long long)h->recv_cnt[(size_t)k]};
         MFMGB_CUDA(ctx, cudaMalloc(&h->links, sizeof(mfmgb_halo::Link) * links.size()));
         MFMGB_CUDA(ctx, cudaMemcpy(h->links, links.data(), sizeof(mfmgb_halo::Link) * links.size(), cudaMemcpyHostToDevice));
+        std::vector<GhostLink> gl(links.size());
+        for (int k = 0; k < n_neighbors; ++k)
+          gl[(size_t)k] = {h->ranks[(size_t)k], (long long)h->recv_off[(size_t)k], (long long)h->recv_cnt[(size_t)k]};
+        MFMGB_CUDA(ctx, cudaMalloc(&h->ghost_links, sizeof(GhostLink) * gl.size()));
+        MFMGB_CUDA(ctx, cudaMemcpy(h->ghost_links, gl.data(), sizeof(GhostLink) * gl.size(), cudaMemcpyHostToDevice));
         MFMGB_CUDA(ctx, cudaMalloc(&h->seq, sizeof(unsigned long long) * 2));
         MFMGB_CUDA(ctx, cudaMemset(h->seq, 0, sizeof(unsigned long long) * 2));
         MFMGB_CUDA(ctx, cudaMalloc(&h->done, sizeof(unsigned int) * 2));
@@ -604,6 +655,7 @@ extern "C"
     cudaFree(h->send_idx);
     cudaFree(h->sendbuf);
     cudaFree(h->links);
+    cudaFree(h->ghost_links);
     cudaFree(h->seq);
     cudaFree(h->done);
     delete h;

@@ -3,6 +3,7 @@
 #include <nccl.h>
 
 #include "common.cuh"
+#include "csr.cuh"
 
 // Peer-memory window (NVLink / NVSwitch): one cudaMalloc'ed block per rank, exported with CUDA IPC and mapped by every
 // other rank of the node at mfmgb_comm_init.  Sub-allocations are SYMMETRIC -- every rank performs the same sequence
@@ -58,6 +59,7 @@ struct mfmgb_halo
     long long send_off, send_cnt, send_first, recv_off, recv_cnt;
   };
   Link *links = nullptr;
+  mfmgb::GhostLink *ghost_links = nullptr;  // device [n_neighbors]: the same links as the fused consumer kernel reads them
   unsigned int *done = nullptr;      // device [2]: CTA completion counters of the push / wait kernels
 };
 
@@ -77,6 +79,11 @@ mfmgb_comm *ctx_comm(mfmgb_ctx *ctx);
 // stream so far); halo_wait makes the compute stream wait for it.
 int halo_start(mfmgb_ctx *ctx, const mfmgb_halo *h, double *v);
 int halo_wait(mfmgb_ctx *ctx, const mfmgb_halo *h, double *v);
+// fused form for levels served by the tile kernel over peer memory: the push kernel runs on the COMPUTE stream right
+// after the producer of v (no fork / join), and the consumer kernel waits for the flags itself (GhostArgs, csr.cuh)
+bool halo_can_fuse(mfmgb_ctx *ctx, const mfmgb_halo *h);
+int halo_push_inline(mfmgb_ctx *ctx, const mfmgb_halo *h, const double *v);
+void halo_ghost_args(mfmgb_ctx *ctx, const mfmgb_halo *h, int64_t blo, int64_t bhi, GhostArgs *g);
 // in-stream (compute stream) sum over ranks of n doubles: one kernel over peer memory when the window is mapped and
 // n fits a slot (every rank sums the contributions in rank order: identical bits on all ranks), else ncclAllReduce
 int allreduce_sum(mfmgb_ctx *ctx, double *dev, int n);

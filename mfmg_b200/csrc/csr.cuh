@@ -36,6 +36,31 @@ enum class Epi : int
   Sub = 3     // y = y - A x                       (hierarchy.hpp:297-302)
 };
 
+// Ghost columns served straight from the NVLink mailbox of a row-partitioned level (comm.cu): the tile kernel waits --
+// inside the kernel, right before its first tile that references ghost columns -- for the neighbours' flags of the
+// current exchange and then gathers ghost entries from the mailbox itself.  No wait kernel, no copy into the ghost
+// tail, no second launch for the boundary rows: one launch per operator application, like on one GPU.
+struct GhostLink
+{
+  int rank;
+  long long recv_off, recv_cnt; // position of this neighbour's entries in the ghost tail
+};
+struct GhostArgs
+{
+  int enabled = 0;
+  int n_links = 0, nranks = 1;
+  long long n_owned = 0;
+  long long blo = 0, bhi = 0;          // rows [blo, bhi) reference owned columns only
+  const unsigned char *local = nullptr; // this rank's peer window
+  size_t box_off = 0, flag_off = 0;    // mailboxes [2][nranks][box_cap] doubles, flags [2][nranks] uint64
+  long long box_cap = 0;
+  const GhostLink *links = nullptr;    // device
+  unsigned long long *seq = nullptr;   // device [2]: [1] = exchanges consumed so far
+  unsigned int *done = nullptr;        // device [2]: [1] = consumer-warp completion counter
+  unsigned long long timeout_ns = 0;
+  int *err = nullptr;
+};
+
 struct EpiArgs
 {
   double *y = nullptr;
@@ -54,7 +79,10 @@ int csr_apply_vec(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, 
 int choose_lanes(int64_t n_rows, int64_t nnz);
 // tile-streamed variant (csr_tile.cu): same contract as csr_apply; requires A->tile_ok
 int csr_apply_tile(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args, int64_t row_begin,
-                   int64_t row_end, int64_t row_begin2 = 0, int64_t row_end2 = 0);
+                   int64_t row_end, int64_t row_begin2 = 0, int64_t row_end2 = 0, const GhostArgs *ghost = nullptr);
+// all rows of a partitioned level in ONE launch, ghost columns from the mailbox; false when the tile kernel cannot
+// serve every row of A (then the caller takes the interior / wait / boundary path)
+bool csr_can_fuse_ghost(const mfmgb_csr *A);
 // two disjoint row ranges (the boundary blocks of a partitioned level): one launch with the tile kernel
 int csr_apply2(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args, int64_t r0, int64_t r1,
                int64_t q0, int64_t q1);

@@ -19,6 +19,7 @@
 #include <mutex>
 
 #include "csr.cuh"
+#include "peer.cuh"
 
 using namespace mfmgb;
 
@@ -99,8 +100,8 @@ __host__ __device__ constexpr size_t tile_stage_bytes(int cap)
   return round_up_sz((size_t)cap * 12 + (size_t)(kConsumerWarps * 32 / LPR + 4) * sizeof(OffT), 128);
 }
 
-template <int LPR, int EPI, typename OffT>
-__global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArgs<OffT> a, const EpiArgs e)
+template <int LPR, int EPI, typename OffT, bool GHOST>
+__global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArgs<OffT> a, const EpiArgs e, const GhostArgs g)
 {
   constexpr int RPT = kConsumerWarps * 32 / LPR; // rows per tile
   constexpr int RP_ELEMS = RPT + 4;              // staged row offsets (a multiple of 4 => 16-byte multiple)
@@ -170,12 +171,29 @@ __global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArg
   const int sub = lane % LPR;
   int s = 0;
   uint32_t ph = 0;
+  // partitioned level served in one launch: exchange number and mailbox of this exchange (see GhostArgs)
+  const unsigned long long xs = GHOST ? g.seq[1] + 1 : 0;
+  const double *gbox = GHOST ? reinterpret_cast<const double *>(g.local + g.box_off) +
+                                       (size_t)(xs & 1ull) * (size_t)g.nranks * (size_t)g.box_cap
+                                 : nullptr;
+  bool ghosts_ready = false;
   for (int64_t i = t_begin; i < t_end; ++i)
   {
     const int64_t t = tile_of(i);
     const int64_t row = t * RPT + lr;
     const bool active = i < a.n_tiles1 ? (row >= a.row_begin && row < a.row_end) : (row >= a.row_begin2 && row < a.row_end2);
     const bool writer = active && sub == 0;
+    // a tile whose rows may reference ghost columns: wait (once per warp) for every neighbour's flag of this exchange
+    const bool tile_ghost = GHOST && (t * RPT < g.blo || (t + 1) * RPT > g.bhi);
+    if (tile_ghost && !ghosts_ready)
+    {
+      if (lane < g.n_links)
+        wait_flag(reinterpret_cast<const unsigned long long *>(g.local + g.flag_off) +
+                      ((size_t)(xs & 1ull) * (size_t)g.nranks + (size_t)g.links[lane].rank),
+                  xs, g.timeout_ns, g.err);
+      __syncwarp();
+      ghosts_ready = true;
+    }
     // epilogue operands are requested before the wait so that their latency overlaps it
     double eb = 0., ed = 0., ex = 0.;
     if (writer)
@@ -216,9 +234,31 @@ __global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArg
           kk[u] = min(k + u * LPR, ke - 1);
           c[u] = scol[kk[u]];
         }
+        if (!tile_ghost)
+        {
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-          xv[u] = __ldg(a.x + c[u]);
+          for (int u = 0; u < kUnroll; ++u)
+            xv[u] = __ldg(a.x + c[u]);
+        }
+        else
+        {
+          // ghost columns come straight from the mailbox the neighbour's push kernel filled over NVLink (L2 loads:
+          // the lines were written by a peer during this kernel)
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u)
+          {
+            const long long gc = (long long)c[u] - g.n_owned;
+            if (gc < 0)
+              xv[u] = __ldg(a.x + c[u]);
+            else
+            {
+              int l = 0;
+              while (l + 1 < g.n_links && gc >= g.links[l + 1].recv_off)
+                ++l;
+              xv[u] = __ldcg(gbox + (size_t)g.links[l].rank * (size_t)g.box_cap + (size_t)(gc - g.links[l].recv_off));
+            }
+          }
+        }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u)
           v[u] = sval[kk[u]];
@@ -261,6 +301,17 @@ __global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArg
       ph ^= 1u;
     }
   }
+  // exchange bookkeeping: the last consumer warp of the grid advances the count of consumed exchanges (every warp
+  // read it before it could finish, so all of them saw the same exchange number)
+  if (GHOST && lane == 0)
+  {
+    const unsigned int prev = atomicAdd(&g.done[1], 1u);
+    if (prev == gridDim.x * (unsigned)kConsumerWarps - 1u)
+    {
+      g.done[1] = 0;
+      g.seq[1] = xs;
+    }
+  }
 }
 
 int env_int(const char *name, int dflt)
@@ -269,9 +320,51 @@ int env_int(const char *name, int dflt)
   return v && *v ? atoi(v) : dflt;
 }
 
+template <int LPR, int EPI, typename OffT, bool GHOST>
+int launch_tile_kernel(mfmgb_ctx *ctx, const mfmgb_csr *A, const TileArgs<OffT> &a, const EpiArgs &e, const GhostArgs &g,
+                       size_t smem)
+{
+  // per instantiation: opt in to large dynamic shared memory once, and ask how many CTAs are really co-resident
+  // (registers can allow fewer than the planned number; the grid must not spill into a second wave)
+  // (cached per device: the attribute is a per-device property, and one process may hold contexts on several devices)
+  constexpr int kMaxDevices = 64;
+  struct PerDevice
+  {
+    bool attr_set = false;
+    size_t occ_smem = 0;
+    int occ_ctas = 0;
+  };
+  static PerDevice cache[kMaxDevices];
+  static std::mutex cache_mutex;
+  int occ_ctas = 0;
+  {
+    std::lock_guard<std::mutex> lock(cache_mutex);
+    PerDevice &pd = cache[ctx->device % kMaxDevices];
+    if (!pd.attr_set)
+    {
+      MFMGB_CUDA(ctx, cudaFuncSetAttribute(csr_tile_kernel<LPR, EPI, OffT, GHOST>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+      pd.attr_set = true;
+    }
+    if (pd.occ_smem != smem)
+    {
+      MFMGB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pd.occ_ctas, csr_tile_kernel<LPR, EPI, OffT, GHOST>,
+                                                                    kTileThreads, smem));
+      pd.occ_smem = smem;
+    }
+    occ_ctas = pd.occ_ctas;
+  }
+  if (occ_ctas < 1)
+    return fail(ctx, MFMGB_ERR_CUDA, "csr_tile_kernel: %zu bytes of shared memory do not fit an SM", smem);
+  const int64_t grid = std::min<int64_t>(a.n_tiles, (int64_t)ctx->num_sms * std::min(A->tile_ctas, occ_ctas));
+  csr_tile_kernel<LPR, EPI, OffT, GHOST><<<(unsigned)grid, kTileThreads, smem, ctx->stream>>>(a, e, g);
+  MFMGB_LAUNCHED(ctx);
+  return MFMGB_OK;
+}
+
 template <int LPR, int EPI, typename OffT>
 int launch_tile(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArgs &e, int64_t r0, int64_t r1,
-                int64_t q0, int64_t q1)
+                int64_t q0, int64_t q1, const GhostArgs &g)
 {
   constexpr int RPT = kConsumerWarps * 32 / LPR;
   if (r1 <= r0) // (an empty first range: the second one takes its place)
@@ -301,77 +394,46 @@ int launch_tile(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiAr
   const size_t smem = (size_t)a.stages * tile_stage_bytes<LPR, OffT>(a.cap) + (size_t)a.stages * 16;
   // per instantiation: opt in to large dynamic shared memory once, and ask how many CTAs are really co-resident
   // (registers can allow fewer than the planned number; the grid must not spill into a second wave)
-  // (cached per device: the attribute is a per-device property, and one process may hold contexts on several devices)
-  constexpr int kMaxDevices = 64;
-  struct PerDevice
-  {
-    bool attr_set = false;
-    size_t occ_smem = 0;
-    int occ_ctas = 0;
-  };
-  static PerDevice cache[kMaxDevices];
-  static std::mutex cache_mutex;
-  int occ_ctas = 0;
-  {
-    std::lock_guard<std::mutex> lock(cache_mutex);
-    PerDevice &pd = cache[ctx->device % kMaxDevices];
-    if (!pd.attr_set)
-    {
-      MFMGB_CUDA(ctx, cudaFuncSetAttribute(csr_tile_kernel<LPR, EPI, OffT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)(227 * 1024)));
-      pd.attr_set = true;
-    }
-    if (pd.occ_smem != smem)
-    {
-      MFMGB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pd.occ_ctas, csr_tile_kernel<LPR, EPI, OffT>,
-                                                                    kTileThreads, smem));
-      pd.occ_smem = smem;
-    }
-    occ_ctas = pd.occ_ctas;
-  }
-  if (occ_ctas < 1)
-    return fail(ctx, MFMGB_ERR_CUDA, "csr_tile_kernel: %zu bytes of shared memory do not fit an SM", smem);
-  const int64_t grid = std::min<int64_t>(a.n_tiles, (int64_t)ctx->num_sms * std::min(A->tile_ctas, occ_ctas));
-  csr_tile_kernel<LPR, EPI, OffT><<<(unsigned)grid, kTileThreads, smem, ctx->stream>>>(a, e);
-  MFMGB_LAUNCHED(ctx);
-  return MFMGB_OK;
+  if (g.enabled)
+    return launch_tile_kernel<LPR, EPI, OffT, true>(ctx, A, a, e, g, smem);
+  return launch_tile_kernel<LPR, EPI, OffT, false>(ctx, A, a, e, g, smem);
 }
 
 template <int EPI, typename OffT>
 int dispatch_lanes(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArgs &e, int64_t r0, int64_t r1,
-                   int64_t q0, int64_t q1)
+                   int64_t q0, int64_t q1, const GhostArgs &g)
 {
   switch (A->lanes)
   {
   case 1:
-    return launch_tile<1, EPI, OffT>(ctx, A, x, e, r0, r1, q0, q1);
+    return launch_tile<1, EPI, OffT>(ctx, A, x, e, r0, r1, q0, q1, g);
   case 2:
-    return launch_tile<2, EPI, OffT>(ctx, A, x, e, r0, r1, q0, q1);
+    return launch_tile<2, EPI, OffT>(ctx, A, x, e, r0, r1, q0, q1, g);
   case 4:
-    return launch_tile<4, EPI, OffT>(ctx, A, x, e, r0, r1, q0, q1);
+    return launch_tile<4, EPI, OffT>(ctx, A, x, e, r0, r1, q0, q1, g);
   case 8:
-    return launch_tile<8, EPI, OffT>(ctx, A, x, e, r0, r1, q0, q1);
+    return launch_tile<8, EPI, OffT>(ctx, A, x, e, r0, r1, q0, q1, g);
   case 16:
-    return launch_tile<16, EPI, OffT>(ctx, A, x, e, r0, r1, q0, q1);
+    return launch_tile<16, EPI, OffT>(ctx, A, x, e, r0, r1, q0, q1, g);
   default:
-    return launch_tile<32, EPI, OffT>(ctx, A, x, e, r0, r1, q0, q1);
+    return launch_tile<32, EPI, OffT>(ctx, A, x, e, r0, r1, q0, q1, g);
   }
 }
 
 template <typename OffT>
 int dispatch_epi(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &e, int64_t r0, int64_t r1,
-                 int64_t q0, int64_t q1)
+                 int64_t q0, int64_t q1, const GhostArgs &g)
 {
   switch (epi)
   {
   case Epi::Spmv:
-    return dispatch_lanes<(int)Epi::Spmv, OffT>(ctx, A, x, e, r0, r1, q0, q1);
+    return dispatch_lanes<(int)Epi::Spmv, OffT>(ctx, A, x, e, r0, r1, q0, q1, g);
   case Epi::Resid:
-    return dispatch_lanes<(int)Epi::Resid, OffT>(ctx, A, x, e, r0, r1, q0, q1);
+    return dispatch_lanes<(int)Epi::Resid, OffT>(ctx, A, x, e, r0, r1, q0, q1, g);
   case Epi::Jacobi:
-    return dispatch_lanes<(int)Epi::Jacobi, OffT>(ctx, A, x, e, r0, r1, q0, q1);
+    return dispatch_lanes<(int)Epi::Jacobi, OffT>(ctx, A, x, e, r0, r1, q0, q1, g);
   default:
-    return dispatch_lanes<(int)Epi::Sub, OffT>(ctx, A, x, e, r0, r1, q0, q1);
+    return dispatch_lanes<(int)Epi::Sub, OffT>(ctx, A, x, e, r0, r1, q0, q1, g);
   }
 }
 
@@ -492,9 +554,16 @@ int csr_measure_tiles(mfmgb_ctx *ctx, mfmgb_csr *A)
   return MFMGB_OK;
 }
 
-int csr_apply_tile(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args, int64_t row_begin,
-                   int64_t row_end, int64_t row_begin2, int64_t row_end2)
+bool csr_can_fuse_ghost(const mfmgb_csr *A)
 {
+  return csr_uses_tile_kernel(A) && A->tile_rows[tile_cap_slot(A->lanes)] >= A->n_rows;
+}
+
+int csr_apply_tile(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi, const EpiArgs &args, int64_t row_begin,
+                   int64_t row_end, int64_t row_begin2, int64_t row_end2, const GhostArgs *ghost)
+{
+  const GhostArgs no_ghost;
+  const GhostArgs &g = ghost ? *ghost : no_ghost;
   // adopted arrays: rows past the last servable tile go to the direct-load kernel (same summation order)
   const int64_t lim = A->tile_rows[tile_cap_slot(A->lanes)];
   if (row_end > lim || row_end2 > lim)
@@ -510,7 +579,7 @@ int csr_apply_tile(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, Epi epi,
       return MFMGB_OK;
   }
   if (A->off64)
-    return dispatch_epi<int64_t>(ctx, A, x, epi, args, row_begin, row_end, row_begin2, row_end2);
-  return dispatch_epi<int32_t>(ctx, A, x, epi, args, row_begin, row_end, row_begin2, row_end2);
+    return dispatch_epi<int64_t>(ctx, A, x, epi, args, row_begin, row_end, row_begin2, row_end2, g);
+  return dispatch_epi<int32_t>(ctx, A, x, epi, args, row_begin, row_end, row_begin2, row_end2, g);
 }
 } // namespace mfmgb

@@ -125,6 +125,19 @@ int level_apply_A(mfmgb_ctx *ctx, const mfmgb_level &l, double *x, Epi epi, cons
     const char *v = getenv("MFMGB_HALO_OVERLAP");
     return !(v && v[0] == '0');
   }();
+  if (halo_can_fuse(ctx, l.halo) && csr_can_fuse_ghost(l.A))
+  {
+    // ONE launch per application, like on one GPU: the push kernel stores this rank's boundary entries into the
+    // neighbours' mailboxes from the compute stream; the tile kernel computes all rows, waits for the neighbours'
+    // flags inside the kernel right before its first boundary tile, and gathers ghost columns from the mailbox
+    MFMGB_CHECK(halo_push_inline(ctx, l.halo, x));
+    prof_mark(ctx, "A push boundary plane(s) to the neighbours (NVLink)");
+    GhostArgs g;
+    halo_ghost_args(ctx, l.halo, l.blo, l.bhi, &g);
+    MFMGB_CHECK(csr_apply_tile(ctx, l.A, x, epi, e, 0, l.n, 0, 0, &g));
+    prof_mark(ctx, "A all rows, ghost columns from the mailbox (fused wait)");
+    return MFMGB_OK;
+  }
   MFMGB_CHECK(halo_start(ctx, l.halo, x));
   if (!overlap)
   {
