@@ -67,10 +67,12 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const PushArgs a)
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < l.send_cnt; i += (long long)gridDim.x * 256)
       dst[i] = a.send_idx ? a.v[a.send_idx[l.send_off + i]] : a.v[l.send_first + i];
   }
-  __threadfence_system();
+  // one system fence per CTA (thread 0, after the barrier that orders the CTA's remote stores before it), not one per
+  // thread: every fence waits for the NVLink write acknowledgements of its SM
   __syncthreads();
   if (threadIdx.x == 0)
   {
+    __threadfence_system();
     const unsigned int prev = atomicAdd(&a.done[0], 1u);
     if (prev == gridDim.x - 1)
     {
@@ -389,6 +391,15 @@ void halo_ghost_args(mfmgb_ctx *ctx, const mfmgb_halo *h, int64_t blo, int64_t b
   g->done = h->done;
   g->timeout_ns = c->peer.timeout_ns;
   g->err = c->peer.err_dev;
+  // push half inside the consumer kernel (MFMGB_HALO_PUSH_IN_KERNEL=0: separate push kernel on the compute stream)
+  static const bool push_in_kernel = [] {
+    const char *v = getenv("MFMGB_HALO_PUSH_IN_KERNEL");
+    return !(v && v[0] == '0');
+  }();
+  g->n_push_ctas = push_in_kernel ? 16 : 0;
+  g->rank = c->rank;
+  g->base = c->peer.base_dev;
+  g->send_idx = h->contiguous ? nullptr : h->send_idx;
 }
 
 int halo_wait(mfmgb_ctx *ctx, const mfmgb_halo *h, double *v)
@@ -633,7 +644,9 @@ extern "C"
         MFMGB_CUDA(ctx, cudaMemcpy(h->links, links.data(), sizeof(mfmgb_halo::Link) * links.size(), cudaMemcpyHostToDevice));
         std::vector<GhostLink> gl(links.size());
         for (int k = 0; k < n_neighbors; ++k)
-          gl[(size_t)k] = {h->ranks[(size_t)k], (long long)h->recv_off[(size_t)k], (long long)h->recv_cnt[(size_t)k]};
+          gl[(size_t)k] = {h->ranks[(size_t)k],          (long long)h->recv_off[(size_t)k],
+                           (long long)h->recv_cnt[(size_t)k], (long long)h->send_off[(size_t)k],
+                           (long long)h->send_cnt[(size_t)k], (long long)h->send_first[(size_t)k]};
         MFMGB_CUDA(ctx, cudaMalloc(&h->ghost_links, sizeof(GhostLink) * gl.size()));
         MFMGB_CUDA(ctx, cudaMemcpy(h->ghost_links, gl.data(), sizeof(GhostLink) * gl.size(), cudaMemcpyHostToDevice));
         MFMGB_CUDA(ctx, cudaMalloc(&h->seq, sizeof(unsigned long long) * 2));

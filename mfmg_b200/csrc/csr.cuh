@@ -44,6 +44,7 @@ struct GhostLink
 {
   int rank;
   long long recv_off, recv_cnt; // position of this neighbour's entries in the ghost tail
+  long long send_off, send_cnt, send_first; // entries this rank sends to it (index list offset / contiguous start)
 };
 struct GhostArgs
 {
@@ -59,6 +60,12 @@ struct GhostArgs
   unsigned int *done = nullptr;        // device [2]: [1] = consumer-warp completion counter
   unsigned long long timeout_ns = 0;
   int *err = nullptr;
+  // push half of the exchange, done by the first n_push_ctas CTAs of the SAME kernel before they start on their tiles:
+  // this rank's boundary entries of x -> the neighbours' mailboxes (remote stores), then the neighbours' flags
+  int n_push_ctas = 0;
+  int rank = 0;
+  unsigned char *const *base = nullptr; // device: mapped windows of all ranks
+  const int32_t *send_idx = nullptr;    // device: concatenated send lists (NULL: contiguous ranges)
 };
 
 struct EpiArgs

@@ -100,6 +100,73 @@ __host__ __device__ constexpr size_t tile_stage_bytes(int cap)
   return round_up_sz((size_t)cap * 12 + (size_t)(kConsumerWarps * 32 / LPR + 4) * sizeof(OffT), 128);
 }
 
+// dot product of one row's staged entries [k0, ke) (stride LPR) with x; GHOST: columns >= n_owned are read from the
+// NVLink mailbox of the current exchange instead of the vector's ghost tail
+template <int LPR, bool GHOST>
+__device__ __forceinline__ double tile_row_sum(const double *__restrict__ sval, const int *__restrict__ scol,
+                                               const double *__restrict__ x, int k, const int ke, const GhostArgs &g,
+                                               const double *__restrict__ gbox)
+{
+  double s0 = 0., s1 = 0.;
+  // kUnroll gathers of x in flight per lane (the gather latency under load is what the consumers wait on);
+  // even multiples of LPR go to s0, odd ones to s1, ascending: the vector-CSR kernel's summation order
+  for (; k < ke; k += kUnroll * LPR)
+  {
+    // No predicated memory operation in this block: lanes past the row end re-read the row's last entry and
+    // get their product zeroed afterwards.  (With predicated loads ptxas paired every gather with its FMA --
+    // one gather in flight per lane; unconditional, the kUnroll gathers issue back to back.)
+    int kk[kUnroll], c[kUnroll];
+    double v[kUnroll], xv[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+    {
+      kk[u] = min(k + u * LPR, ke - 1);
+      c[u] = scol[kk[u]];
+    }
+    if (!GHOST)
+    {
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        xv[u] = __ldg(x + c[u]);
+    }
+    else
+    {
+      // pointer select first, then unconditional loads (L2: the mailbox lines were written by a peer during this kernel)
+      const double *px[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+      {
+        const long long gc = (long long)c[u] - g.n_owned;
+        px[u] = x + c[u];
+        if (gc >= 0)
+        {
+          int l = 0;
+          while (l + 1 < g.n_links && gc >= g.links[l + 1].recv_off)
+            ++l;
+          px[u] = gbox + (size_t)g.links[l].rank * (size_t)g.box_cap + (size_t)(gc - g.links[l].recv_off);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        xv[u] = __ldcg(px[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      v[u] = sval[kk[u]];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (k + u * LPR >= ke)
+        v[u] = 0., xv[u] = 0.;
+#pragma unroll
+    for (int u = 0; u < kUnroll; u += 2)
+    {
+      s0 = fma(v[u], xv[u], s0);
+      s1 = fma(v[u + 1], xv[u + 1], s1);
+    }
+  }
+  return s0 + s1;
+}
+
 template <int LPR, int EPI, typename OffT, bool GHOST>
 __global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArgs<OffT> a, const EpiArgs e, const GhostArgs g)
 {
@@ -121,6 +188,40 @@ __global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArg
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
+  if (GHOST && (int)blockIdx.x < g.n_push_ctas)
+  {
+    // ---- fused exchange, push half: the first CTAs store this rank's boundary entries of x into the neighbours'
+    // mailboxes over NVLink (every CTA a slice of every send list), the last of them to finish raises the flags.
+    // Pushes never wait, and all CTAs of this single-wave grid are resident: the neighbour's kernel, which waits for
+    // these flags at its boundary tiles, cannot be starved by anything this rank does.
+    const unsigned long long ps = g.seq[0] + 1;
+    const size_t pslot = ((size_t)(ps & 1ull) * (size_t)g.nranks + (size_t)g.rank) * (size_t)g.box_cap;
+    for (int k = 0; k < g.n_links; ++k)
+    {
+      const GhostLink l = g.links[k];
+      double *dst = reinterpret_cast<double *>(g.base[l.rank] + g.box_off) + pslot;
+      const long long chunk = (l.send_cnt + g.n_push_ctas - 1) / g.n_push_ctas;
+      const long long lo = (long long)blockIdx.x * chunk, hi = lo + chunk < l.send_cnt ? lo + chunk : l.send_cnt;
+      for (long long i = lo + threadIdx.x; i < hi; i += kTileThreads)
+        dst[i] = g.send_idx ? a.x[g.send_idx[l.send_off + i]] : a.x[l.send_first + i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      __threadfence_system();
+      const unsigned int prev = atomicAdd(&g.done[0], 1u);
+      if (prev == (unsigned)g.n_push_ctas - 1u)
+      {
+        g.done[0] = 0;
+        __threadfence_system();
+        for (int k = 0; k < g.n_links; ++k)
+          st_release_sys(reinterpret_cast<unsigned long long *>(g.base[g.links[k].rank] + g.flag_off) +
+                             ((ps & 1ull) * (unsigned long long)g.nranks + (unsigned long long)g.rank),
+                         ps);
+        g.seq[0] = ps;
+      }
+    }
+  }
   // this CTA's contiguous run of tile slots; slot -> tile (two row ranges may share one launch)
   const int64_t tpc = (a.n_tiles + gridDim.x - 1) / gridDim.x;
   const int64_t t_begin = (int64_t)blockIdx.x * tpc;
@@ -213,71 +314,20 @@ __global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArg
     const double *sval = reinterpret_cast<const double *>(st);
     const int *scol = reinterpret_cast<const int *>(st + (size_t)a.cap * 8);
     const OffT *srp = reinterpret_cast<const OffT *>(st + (size_t)a.cap * 12);
-    double s0 = 0., s1 = 0.;
+    double rs = 0.;
     if (active)
     {
       const OffT base = srp[0] & ~(OffT)3;
-      int k = (int)(srp[lr] - base) + sub;
-      const int ke = (int)(srp[lr + 1] - base);
-      // kUnroll gathers of x in flight per lane (the gather latency under load is what the consumers wait on);
-      // even multiples of LPR go to s0, odd ones to s1, ascending: the vector-CSR kernel's summation order
-      for (; k < ke; k += kUnroll * LPR)
-      {
-        // No predicated memory operation in this block: lanes past the row end re-read the row's last entry and
-        // get their product zeroed afterwards.  (With predicated loads ptxas paired every gather with its FMA --
-        // one gather in flight per lane; unconditional, the kUnroll gathers issue back to back.)
-        int kk[kUnroll], c[kUnroll];
-        double v[kUnroll], xv[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-        {
-          kk[u] = min(k + u * LPR, ke - 1);
-          c[u] = scol[kk[u]];
-        }
-        if (!tile_ghost)
-        {
-#pragma unroll
-          for (int u = 0; u < kUnroll; ++u)
-            xv[u] = __ldg(a.x + c[u]);
-        }
-        else
-        {
-          // ghost columns come straight from the mailbox the neighbour's push kernel filled over NVLink (L2 loads:
-          // the lines were written by a peer during this kernel)
-#pragma unroll
-          for (int u = 0; u < kUnroll; ++u)
-          {
-            const long long gc = (long long)c[u] - g.n_owned;
-            if (gc < 0)
-              xv[u] = __ldg(a.x + c[u]);
-            else
-            {
-              int l = 0;
-              while (l + 1 < g.n_links && gc >= g.links[l + 1].recv_off)
-                ++l;
-              xv[u] = __ldcg(gbox + (size_t)g.links[l].rank * (size_t)g.box_cap + (size_t)(gc - g.links[l].recv_off));
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-          v[u] = sval[kk[u]];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-          if (k + u * LPR >= ke)
-            v[u] = 0., xv[u] = 0.;
-#pragma unroll
-        for (int u = 0; u < kUnroll; u += 2)
-        {
-          s0 = fma(v[u], xv[u], s0);
-          s1 = fma(v[u + 1], xv[u + 1], s1);
-        }
-      }
+      const int k0 = (int)(srp[lr] - base) + sub, ke = (int)(srp[lr + 1] - base);
+      // (two separate instantiations: the ghost form must not touch the register allocation and the load scheduling
+      // of the form that serves 98 % of the tiles)
+      rs = tile_ghost ? tile_row_sum<LPR, true>(sval, scol, a.x, k0, ke, g, gbox)
+                      : tile_row_sum<LPR, false>(sval, scol, a.x, k0, ke, g, gbox);
     }
     __syncwarp();
     if (lane == 0)
       mbar_arrive(empty + s); // every lane of this warp has its col/val in registers: the stage may be refilled
-    const double sum = subwarp_sum<LPR>(s0 + s1);
+    const double sum = subwarp_sum<LPR>(rs);
     if (writer)
     {
       if (EPI == (int)Epi::Spmv)
@@ -357,7 +407,9 @@ int launch_tile_kernel(mfmgb_ctx *ctx, const mfmgb_csr *A, const TileArgs<OffT> 
   if (occ_ctas < 1)
     return fail(ctx, MFMGB_ERR_CUDA, "csr_tile_kernel: %zu bytes of shared memory do not fit an SM", smem);
   const int64_t grid = std::min<int64_t>(a.n_tiles, (int64_t)ctx->num_sms * std::min(A->tile_ctas, occ_ctas));
-  csr_tile_kernel<LPR, EPI, OffT, GHOST><<<(unsigned)grid, kTileThreads, smem, ctx->stream>>>(a, e, g);
+  GhostArgs gg = g;
+  gg.n_push_ctas = (int)std::min<int64_t>(gg.n_push_ctas, grid);
+  csr_tile_kernel<LPR, EPI, OffT, GHOST><<<(unsigned)grid, kTileThreads, smem, ctx->stream>>>(a, e, gg);
   MFMGB_LAUNCHED(ctx);
   return MFMGB_OK;
 }

@@ -127,15 +127,19 @@ int level_apply_A(mfmgb_ctx *ctx, const mfmgb_level &l, double *x, Epi epi, cons
   }();
   if (halo_can_fuse(ctx, l.halo) && csr_can_fuse_ghost(l.A))
   {
-    // ONE launch per application, like on one GPU: the push kernel stores this rank's boundary entries into the
-    // neighbours' mailboxes from the compute stream; the tile kernel computes all rows, waits for the neighbours'
-    // flags inside the kernel right before its first boundary tile, and gathers ghost columns from the mailbox
-    MFMGB_CHECK(halo_push_inline(ctx, l.halo, x));
-    prof_mark(ctx, "A push boundary plane(s) to the neighbours (NVLink)");
+    // ONE launch per application, like on one GPU -- the fused compute + exchange kernel: its first CTAs store this
+    // rank's boundary entries into the neighbours' mailboxes over NVLink and raise their flags, all CTAs compute rows,
+    // those that reach a boundary tile wait for the neighbours' flags inside the kernel and gather the ghost columns
+    // straight from the mailbox
     GhostArgs g;
     halo_ghost_args(ctx, l.halo, l.blo, l.bhi, &g);
+    if (g.n_push_ctas == 0)
+    {
+      MFMGB_CHECK(halo_push_inline(ctx, l.halo, x));
+      prof_mark(ctx, "A push boundary plane(s) to the neighbours (NVLink)");
+    }
     MFMGB_CHECK(csr_apply_tile(ctx, l.A, x, epi, e, 0, l.n, 0, 0, &g));
-    prof_mark(ctx, "A all rows, ghost columns from the mailbox (fused wait)");
+    prof_mark(ctx, "A all rows: push + in-kernel wait + ghost columns from the mailbox (one launch)");
     return MFMGB_OK;
   }
   MFMGB_CHECK(halo_start(ctx, l.halo, x));
