@@ -81,16 +81,49 @@ __device__ __forceinline__ double dd_rhs_value_warp(const DdRhsArgs &a, int64_t 
 }
 
 // ONE CTA: the local contributions, then the sum over the ranks through NVLink peer memory (peer.cuh) -- the SpMV with
-// A_SI, the right-hand-side assembly and the all-reduce of the reference solve's Schur step in a single launch
+// A_SI, the right-hand-side assembly and the all-reduce of the reference solve's Schur step in a single launch.
+// A single CTA has little memory-level parallelism, so the SpMV is done in two flat passes instead of row by row (a
+// warp-per-row loop chained ~3 L2 round trips per row, 8 rows per warp: ~20 us): every thread forms products
+// val[j] * y[col[j]] for a strided share of ALL non-zeros into shared memory (two round trips in total), then one
+// thread per row adds its segment in ascending order.
 template <typename OffT>
-__global__ void __launch_bounds__(1024) dd_rhs_allreduce_kernel(const DdRhsArgs a, const PeerAllreduceArgs pa)
+__global__ void __launch_bounds__(1024) dd_rhs_allreduce_kernel(const DdRhsArgs a, const PeerAllreduceArgs pa, int prod_cap)
 {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-  for (int64_t k = warp; k < a.n_S; k += n_warps)
+  extern __shared__ double dd_prod[];
+  const OffT *rp = static_cast<const OffT *>(a.si_rowptr);
+  const int64_t nnz = a.n_adj > 0 ? (int64_t)rp[a.n_adj] : 0;
+  if (nnz <= prod_cap)
   {
-    const double v = dd_rhs_value_warp<OffT>(a, k, lane);
-    if (lane == 0)
+    for (int64_t j = threadIdx.x; j < nnz; j += blockDim.x)
+      dd_prod[j] = a.si_val[j] * a.y[a.si_col[j]];
+    __syncthreads();
+    for (int64_t k = threadIdx.x; k < a.n_S; k += blockDim.x)
+    {
+      double v = 0.;
+      if (k >= a.adj_begin && k < a.adj_begin + a.n_adj)
+      {
+        const int64_t r = k - a.adj_begin;
+        double s = 0.;
+        for (OffT j = rp[r]; j < rp[r + 1]; ++j)
+          s += dd_prod[j];
+        v = -s;
+      }
+      if (k >= a.own_begin && k < a.own_begin + a.own_n)
+        v += a.b_c[a.sep_index[k]];
+      if (a.g_below && k >= a.adj_begin && k < a.adj_begin + a.n_below)
+        v += a.g_below[k - a.adj_begin];
       a.t[k] = v;
+    }
+  }
+  else
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    for (int64_t k = warp; k < a.n_S; k += n_warps)
+    {
+      const double v = dd_rhs_value_warp<OffT>(a, k, lane);
+      if (lane == 0)
+        a.t[k] = v;
+    }
   }
   __syncthreads();
   peer_allreduce_cta(a.t, (int)a.n_S, pa);
@@ -190,10 +223,22 @@ int coarse_dd_solve_async(mfmgb_ctx *ctx, const mfmgb_coarse_dd *d, const double
     if (c->peer.enabled && d->n_S <= c->peer.ar_cap)
     {
       // one launch: contributions + sum over the ranks through peer memory
+      // products of all non-zeros of A_SI in shared memory when they fit (they do: a few thousand entries)
+      const int prod_cap = (int)std::min<int64_t>(std::max<int64_t>(d->A_SI->nnz, 1), 20000);
+      const size_t smem = sizeof(double) * (size_t)prod_cap;
+      static unsigned long long configured = 0; // one bit per device
+      if (!((configured >> (ctx->device & 63)) & 1ull))
+      {
+        MFMGB_CUDA(ctx, cudaFuncSetAttribute(dd_rhs_allreduce_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(160 * 1024)));
+        MFMGB_CUDA(ctx, cudaFuncSetAttribute(dd_rhs_allreduce_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(160 * 1024)));
+        configured |= 1ull << (ctx->device & 63);
+      }
       if (d->A_SI->off64)
-        dd_rhs_allreduce_kernel<int64_t><<<1, 1024, 0, st>>>(a, peer_allreduce_args(c));
+        dd_rhs_allreduce_kernel<int64_t><<<1, 1024, smem, st>>>(a, peer_allreduce_args(c), prod_cap);
       else
-        dd_rhs_allreduce_kernel<int32_t><<<1, 1024, 0, st>>>(a, peer_allreduce_args(c));
+        dd_rhs_allreduce_kernel<int32_t><<<1, 1024, smem, st>>>(a, peer_allreduce_args(c), prod_cap);
       MFMGB_LAUNCHED(ctx);
     }
     else

@@ -223,10 +223,45 @@ __global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArg
     }
   }
   // this CTA's contiguous run of tile slots; slot -> tile (two row ranges may share one launch)
-  const int64_t tpc = (a.n_tiles + gridDim.x - 1) / gridDim.x;
-  const int64_t t_begin = (int64_t)blockIdx.x * tpc;
-  const int64_t t_end = t_begin + tpc < a.n_tiles ? t_begin + tpc : a.n_tiles;
-  auto tile_of = [&](int64_t slot) { return slot < a.n_tiles1 ? a.tile_begin + slot : a.tile_begin2 + (slot - a.n_tiles1); };
+  // Plain mode: CTA b owns the contiguous slots [b tpc, (b+1) tpc) (the j+-1 neighbour lines of x are re-used from L1).
+  // Ghost mode (all rows of a partitioned level in one launch): interior tiles first, in contiguous runs as above, then
+  // the boundary tiles dealt out round-robin -- at most a few per CTA, at the END of its work.  (With the boundary
+  // tiles in their natural place the first and last CTAs held nothing else: they started only when the neighbour's
+  // flag arrived and then had a full share of tiles to do, which made the whole launch ~35 us longer.)
+  int64_t t_begin, t_end, n_first = 0, bt_lo = 0, bt_hi = 0, a_int0 = 0;
+  if (GHOST)
+  {
+    const int64_t nt = a.n_tiles;                       // tiles 0 .. nt-1 of rows [0, n_rows)
+    bt_lo = (g.blo + RPT - 1) / RPT;                    // tiles [0, bt_lo) touch rows below blo
+    bt_hi = g.bhi / RPT;                                // tiles [bt_hi, nt) touch rows from bhi on
+    if (bt_hi < bt_lo)
+      bt_hi = bt_lo;
+    const int64_t n_int = bt_hi - bt_lo, n_bnd = nt - n_int;
+    const int64_t tpc = (n_int + gridDim.x - 1) / gridDim.x;
+    const int64_t i0 = (int64_t)blockIdx.x * tpc < n_int ? (int64_t)blockIdx.x * tpc : n_int;
+    const int64_t i1 = i0 + tpc < n_int ? i0 + tpc : n_int;
+    n_first = i1 - i0;
+    const int64_t mine_bnd = n_bnd > (int64_t)blockIdx.x ? (n_bnd - 1 - (int64_t)blockIdx.x) / gridDim.x + 1 : 0;
+    t_begin = 0;
+    t_end = n_first + mine_bnd; // local slot count
+    a_int0 = i0; // first interior tile of this CTA, relative to bt_lo
+  }
+  else
+  {
+    const int64_t tpc = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+    t_begin = (int64_t)blockIdx.x * tpc;
+    t_end = t_begin + tpc < a.n_tiles ? t_begin + tpc : a.n_tiles;
+  }
+  auto tile_of = [&](int64_t slot) -> int64_t {
+    if (GHOST)
+    {
+      if (slot < n_first)
+        return bt_lo + a_int0 + slot;
+      const int64_t j = (int64_t)blockIdx.x + (slot - n_first) * (int64_t)gridDim.x; // j-th boundary tile
+      return j < bt_lo ? j : bt_hi + (j - bt_lo);
+    }
+    return slot < a.n_tiles1 ? a.tile_begin + slot : a.tile_begin2 + (slot - a.n_tiles1);
+  };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == kConsumerWarps)
@@ -282,7 +317,8 @@ __global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArg
   {
     const int64_t t = tile_of(i);
     const int64_t row = t * RPT + lr;
-    const bool active = i < a.n_tiles1 ? (row >= a.row_begin && row < a.row_end) : (row >= a.row_begin2 && row < a.row_end2);
+    const bool active = (GHOST || i < a.n_tiles1) ? (row >= a.row_begin && row < a.row_end)
+                                                  : (row >= a.row_begin2 && row < a.row_end2);
     const bool writer = active && sub == 0;
     // a tile whose rows may reference ghost columns: wait (once per warp) for every neighbour's flag of this exchange
     const bool tile_ghost = GHOST && (t * RPT < g.blo || (t + 1) * RPT > g.bhi);

@@ -538,8 +538,189 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// solve, large n: TMA-streamed GEMV.  The round-1 kernel (one CTA per row, direct 128-bit loads) reached 4.1 TB/s at
+// n_c = 4096: 4096 short-lived CTAs, each exposing its own ramp-up and a block reduction.  Here the rows of M do not
+// occupy warps while they travel: one persistent CTA per SM owns a contiguous run of rows and walks the matrix in
+// column chunks of kGemvChunk doubles; one elected producer thread streams (row, chunk) pieces into a shared-memory
+// ring with cp.async.bulk (1-D TMA, L2 evict-first) guarded by full / empty mbarriers; consumer warp w takes the
+// pieces of its rows (row mod 8 == w), multiplies them with the chunk of b held in shared memory (loaded once per
+// chunk and CTA, not once per row), reduces with a fixed shuffle tree and adds the result to the row's accumulator in
+// shared memory -- only that warp ever touches it, so the only block-wide synchronisation is one consumer barrier per
+// column chunk.  Summation order depends on sizes only: deterministic.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGemvChunk = 2048;  // doubles per piece (16 KB)
+constexpr int kGemvStages = 10;   // ring depth: one piece per consumer warp in flight + 2
+constexpr int kGemvWarps = 8;
+constexpr int kGemvThreads = (kGemvWarps + 1) * 32;
+constexpr int kGemvRowsMax = 256; // rows per CTA (accumulators in shared memory)
+
+__device__ __forceinline__ uint32_t gv_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gv_mbar_init(uint64_t *bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gv_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gv_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gv_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gv_mbar_arrive(uint64_t *bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gv_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void gv_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  uint32_t done;
+  do
+  {
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                 "selp.u32 %0, 1, 0, p;\n"
+                 "}"
+                 : "=r"(done)
+                 : "r"(gv_smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
+
+__global__ void __launch_bounds__(kGemvThreads, 1)
+    gemv_stream_kernel(int64_t n, const double *__restrict__ M, int64_t lda, const double *__restrict__ v,
+                       double *__restrict__ out, int64_t row0, int64_t n_out)
+{
+  extern __shared__ __align__(128) unsigned char gv_smem[];
+  double *ring = reinterpret_cast<double *>(gv_smem);           // [stages][chunk]
+  double *vbuf = ring + (size_t)kGemvStages * kGemvChunk;       // [2][chunk]
+  double *acc = vbuf + 2 * kGemvChunk;                          // [kGemvRowsMax]
+  uint64_t *full = reinterpret_cast<uint64_t *>(acc + kGemvRowsMax);
+  uint64_t *empty = full + kGemvStages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0)
+  {
+    for (int s = 0; s < kGemvStages; ++s)
+    {
+      gv_mbar_init(full + s, 1);
+      gv_mbar_init(empty + s, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  // this CTA's contiguous run of output slots; its valid rows (< n) are a prefix of the run, the others give 0
+  const int64_t rpc = (n_out + gridDim.x - 1) / gridDim.x;
+  const int64_t s_begin = (int64_t)blockIdx.x * rpc;
+  const int64_t s_end = s_begin + rpc < n_out ? s_begin + rpc : n_out;
+  int64_t s_valid = s_end;
+  if (row0 + s_valid > n)
+    s_valid = n - row0 > s_begin ? n - row0 : s_begin;
+  const int n_rows = (int)(s_valid > s_begin ? s_valid - s_begin : 0); // <= kGemvRowsMax
+  const int n_chunks = (int)((lda + kGemvChunk - 1) / kGemvChunk);
+  if (warp == kGemvWarps)
+  {
+    // ---- producer: pieces in (chunk, row) order ----
+    if (lane != 0)
+      return;
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    int64_t piece = 0;
+    for (int c = 0; c < n_chunks; ++c)
+    {
+      const int64_t len = lda - (int64_t)c * kGemvChunk < kGemvChunk ? lda - (int64_t)c * kGemvChunk : kGemvChunk;
+      for (int r = 0; r < n_rows; ++r, ++piece)
+      {
+        const int st = (int)(piece % kGemvStages);
+        const uint32_t ph = (uint32_t)((piece / kGemvStages) & 1);
+        gv_mbar_wait(empty + st, ph ^ 1u);
+        gv_mbar_expect_tx(full + st, (uint32_t)(len * 8));
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+            :
+            : "r"(gv_smem_u32(ring + (size_t)st * kGemvChunk)),
+              "l"(M + (row0 + s_begin + r) * lda + (int64_t)c * kGemvChunk), "r"((uint32_t)(len * 8)),
+              "r"(gv_smem_u32(full + st)), "l"(policy)
+            : "memory");
+      }
+    }
+    return;
+  }
+  // ---- consumers ----
+  const int ct = threadIdx.x; // 0 .. 255
+  for (int r = ct; r < kGemvRowsMax; r += kGemvWarps * 32)
+    acc[r] = 0.;
+  for (int c = 0; c < n_chunks; ++c)
+  {
+    const int64_t len = lda - (int64_t)c * kGemvChunk < kGemvChunk ? lda - (int64_t)c * kGemvChunk : kGemvChunk;
+    // the chunk of b for these columns (zero beyond n: the padding columns of M are zero as well)
+    double *vb = vbuf + (size_t)(c & 1) * kGemvChunk;
+    for (int j = ct; j < kGemvChunk; j += kGemvWarps * 32)
+    {
+      const int64_t col = (int64_t)c * kGemvChunk + j;
+      vb[j] = col < n ? v[col] : 0.;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kGemvWarps * 32) : "memory"); // consumers only
+    for (int r = warp; r < n_rows; r += kGemvWarps)
+    {
+      const int64_t piece = (int64_t)c * n_rows + r;
+      const int st = (int)(piece % kGemvStages);
+      const uint32_t ph = (uint32_t)((piece / kGemvStages) & 1);
+      gv_mbar_wait(full + st, ph);
+      const double *m = ring + (size_t)st * kGemvChunk;
+      double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
+      // 128-bit accesses, lane-contiguous: element pairs lane * 2 + 64 k
+#pragma unroll 8
+      for (int j = lane * 2; j < (int)len; j += 128)
+      {
+        const double2 a0 = *reinterpret_cast<const double2 *>(m + j), b0 = *reinterpret_cast<const double2 *>(vb + j);
+        s0 = fma(a0.x, b0.x, s0);
+        s1 = fma(a0.y, b0.y, s1);
+        if (j + 64 < (int)len)
+        {
+          const double2 a1 = *reinterpret_cast<const double2 *>(m + j + 64),
+                        b1 = *reinterpret_cast<const double2 *>(vb + j + 64);
+          s2 = fma(a1.x, b1.x, s2);
+          s3 = fma(a1.y, b1.y, s3);
+        }
+      }
+      __syncwarp();
+      if (lane == 0)
+        gv_mbar_arrive(empty + st); // the piece is in registers: the slot may be refilled
+      const double w = subwarp_sum<32>((s0 + s1) + (s2 + s3));
+      if (lane == 0)
+        acc[r] += w; // only this warp touches acc[r]; chunks are added in ascending order
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kGemvWarps * 32) : "memory");
+  for (int64_t slot = s_begin + ct; slot < s_end; slot += kGemvWarps * 32)
+    out[slot] = slot < s_valid ? acc[slot - s_begin] : 0.;
+}
+
+int launch_gemv_stream(mfmgb_ctx *ctx, const mfmgb_dense *D, const double *b, double *out, int64_t row0, int64_t n_out)
+{
+  const size_t smem = sizeof(double) * ((size_t)(kGemvStages + 2) * kGemvChunk + kGemvRowsMax) +
+                      sizeof(uint64_t) * 2 * kGemvStages;
+  static unsigned long long configured = 0; // one bit per device
+  if (!((configured >> (ctx->device & 63)) & 1ull))
+  {
+    MFMGB_CUDA(ctx, cudaFuncSetAttribute(gemv_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    configured |= 1ull << (ctx->device & 63);
+  }
+  // one CTA per SM; more only when a CTA would own more rows than it has accumulators for
+  const int64_t grid = std::max<int64_t>(std::min<int64_t>(n_out, ctx->num_sms), ceil_div(n_out, kGemvRowsMax));
+  gemv_stream_kernel<<<(unsigned)grid, kGemvThreads, smem, ctx->stream>>>(D->n, D->inv, D->lda, b, out, row0, n_out);
+  MFMGB_LAUNCHED(ctx);
+  return MFMGB_OK;
+}
+
 int launch_gemv(mfmgb_ctx *ctx, const mfmgb_dense *D, const double *b, double *out, int64_t row0, int64_t n_out)
 {
+  // large operators: the TMA-streamed kernel (MFMGB_GEMV_STREAM=0 keeps the direct-load kernel: measurement aid)
+  static const bool stream = [] {
+    const char *v = getenv("MFMGB_GEMV_STREAM");
+    return !(v && v[0] == '0');
+  }();
+  if (stream && D->n >= 1024 && n_out >= 256)
+    return launch_gemv_stream(ctx, D, b, out, row0, n_out);
+
   if (n_out <= 0)
     return MFMGB_OK;
   if (D->n >= 1024)
