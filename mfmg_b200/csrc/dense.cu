@@ -543,14 +543,18 @@ __global__ void __launch_bounds__(1024)
 // n_c = 4096: 4096 short-lived CTAs, each exposing its own ramp-up and a block reduction.  Here the rows of M do not
 // occupy warps while they travel: one persistent CTA per SM owns a contiguous run of rows and walks the matrix in
 // column chunks of kGemvChunk doubles; one elected producer thread streams (row, chunk) pieces into a shared-memory
-// ring with cp.async.bulk (1-D TMA, L2 evict-first) guarded by full / empty mbarriers; consumer warp w takes the
-// pieces of its rows (row mod 8 == w), multiplies them with the chunk of b held in shared memory (loaded once per
+// ring (one small ring per consumer warp) with cp.async.bulk (1-D TMA, L2 evict-first) guarded by full / empty
+// mbarriers; consumer warp w takes the pieces of its rows (row mod 8 == w), multiplies them with the chunk of b held in
+// shared memory (loaded once per
 // chunk and CTA, not once per row), reduces with a fixed shuffle tree and adds the result to the row's accumulator in
 // shared memory -- only that warp ever touches it, so the only block-wide synchronisation is one consumer barrier per
 // column chunk.  Summation order depends on sizes only: deterministic.
 // ---------------------------------------------------------------------------------------------
-constexpr int kGemvChunk = 2048;  // doubles per piece (16 KB)
-constexpr int kGemvStages = 10;   // ring depth: one piece per consumer warp in flight + 2
+constexpr int kGemvChunk = 1024;  // doubles per piece (8 KB)
+constexpr int kGemvDepth = 3;     // every consumer warp has its OWN ring of this depth (single producer, single consumer:
+                                  // with one shared ring a fast warp could wait on a slot use that is two phases ahead of
+                                  // the barrier, which mbarrier parity waits cannot tell from a completed one)
+constexpr int kGemvStages = 8 * kGemvDepth;
 constexpr int kGemvWarps = 8;
 constexpr int kGemvThreads = (kGemvWarps + 1) * 32;
 constexpr int kGemvRowsMax = 256; // rows per CTA (accumulators in shared memory)
@@ -622,29 +626,41 @@ __global__ void __launch_bounds__(kGemvThreads, 1)
       return;
     uint64_t policy;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-    int64_t piece = 0;
+    int cnt[kGemvWarps];
+#pragma unroll
+    for (int w = 0; w < kGemvWarps; ++w)
+      cnt[w] = 0;
     for (int c = 0; c < n_chunks; ++c)
     {
       const int64_t len = lda - (int64_t)c * kGemvChunk < kGemvChunk ? lda - (int64_t)c * kGemvChunk : kGemvChunk;
-      for (int r = 0; r < n_rows; ++r, ++piece)
+      for (int r0 = 0; r0 < n_rows; r0 += kGemvWarps)
       {
-        const int st = (int)(piece % kGemvStages);
-        const uint32_t ph = (uint32_t)((piece / kGemvStages) & 1);
-        gv_mbar_wait(empty + st, ph ^ 1u);
-        gv_mbar_expect_tx(full + st, (uint32_t)(len * 8));
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-            :
-            : "r"(gv_smem_u32(ring + (size_t)st * kGemvChunk)),
-              "l"(M + (row0 + s_begin + r) * lda + (int64_t)c * kGemvChunk), "r"((uint32_t)(len * 8)),
-              "r"(gv_smem_u32(full + st)), "l"(policy)
-            : "memory");
+#pragma unroll
+        for (int w = 0; w < kGemvWarps; ++w)
+        {
+          const int r = r0 + w;
+          if (r >= n_rows)
+            break;
+          const int st = w * kGemvDepth + cnt[w] % kGemvDepth;
+          const uint32_t ph = (uint32_t)((cnt[w] / kGemvDepth) & 1);
+          ++cnt[w];
+          gv_mbar_wait(empty + st, ph ^ 1u);
+          gv_mbar_expect_tx(full + st, (uint32_t)(len * 8));
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+              :
+              : "r"(gv_smem_u32(ring + (size_t)st * kGemvChunk)),
+                "l"(M + (row0 + s_begin + r) * lda + (int64_t)c * kGemvChunk), "r"((uint32_t)(len * 8)),
+                "r"(gv_smem_u32(full + st)), "l"(policy)
+              : "memory");
+        }
       }
     }
     return;
   }
   // ---- consumers ----
   const int ct = threadIdx.x; // 0 .. 255
+  int my_cnt = 0;             // pieces this warp has taken from its ring
   for (int r = ct; r < kGemvRowsMax; r += kGemvWarps * 32)
     acc[r] = 0.;
   for (int c = 0; c < n_chunks; ++c)
@@ -660,14 +676,14 @@ __global__ void __launch_bounds__(kGemvThreads, 1)
     asm volatile("bar.sync 1, %0;" ::"n"(kGemvWarps * 32) : "memory"); // consumers only
     for (int r = warp; r < n_rows; r += kGemvWarps)
     {
-      const int64_t piece = (int64_t)c * n_rows + r;
-      const int st = (int)(piece % kGemvStages);
-      const uint32_t ph = (uint32_t)((piece / kGemvStages) & 1);
+      const int st = warp * kGemvDepth + my_cnt % kGemvDepth; // this warp's own ring
+      const uint32_t ph = (uint32_t)((my_cnt / kGemvDepth) & 1);
+      ++my_cnt;
       gv_mbar_wait(full + st, ph);
       const double *m = ring + (size_t)st * kGemvChunk;
       double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
       // 128-bit accesses, lane-contiguous: element pairs lane * 2 + 64 k
-#pragma unroll 8
+#pragma unroll 4
       for (int j = lane * 2; j < (int)len; j += 128)
       {
         const double2 a0 = *reinterpret_cast<const double2 *>(m + j), b0 = *reinterpret_cast<const double2 *>(vb + j);
