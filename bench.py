@@ -640,7 +640,8 @@ def build_ours(args, d, handle, dist, rank, world):
                     parallelism="1 GPU", coarse="dense LU (explicit inverse, one GEMV per apply)")
         return H, info
 
-    handle.init_comm_from_torch()
+    if getattr(handle, "nranks", None) is None:   # (the north-star leg re-uses the communicator of the main leg)
+        handle.init_comm_from_torch()
     hs.set_num_threads(max(1, host_threads() // world))  # torchrun exports OMP_NUM_THREADS=1
 
     def gather(obj):

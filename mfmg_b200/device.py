@@ -56,6 +56,7 @@ class CudaHandle:
         check(None, rc)
         self.ctx = p
         self.device = device
+        self.nranks, self.rank = None, None   # set by init_comm*
 
     def synchronize(self) -> None:
         check(self.ctx, self.lib.mfmgb_ctx_synchronize(self.ctx))

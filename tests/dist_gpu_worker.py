@@ -43,6 +43,9 @@ def main():
             assert np.array_equal(v.to_host(), tri * pattern * (k + 1)), (rank, "allreduce", n, k)
     cases = [(3, 1, 16, 2, 2, "constant", 1), (3, 1, 24, 4, 1, "discontinuous", 2), (3, 2, 8, 2, 2, "linear", 1),
              (2, 1, 64, 2, 2, "constant", 1)]
+    if world > 4:   # every rank needs at least one agglomerate layer
+        cases = [(3, 1, 16, 2, 2, "constant", 1), (3, 1, 32, 4, 1, "discontinuous", 2), (3, 2, 16, 2, 1, "linear", 1),
+                 (2, 1, 64, 2, 2, "constant", 1)]
     # second pass: force the row-split (multi-GPU) dense coarse solve, which is normally used from n_c = 8192 on
     # coarse-solver variants: "dd" = domain-decomposed direct solve (the default for slab partitions), "split" = dense
     # inverse split by rows over the ranks, "replicated" = dense inverse on every rank
