@@ -44,6 +44,10 @@ struct mfmgb_level
   bool restrict_no_halo = false;
   const mfmgb_csr *R_below = nullptr;
   double *gb = nullptr;
+  // [R ; R_below] as ONE matrix (built at setup) writing [own coarse rows | separator-below share] into rs: one launch
+  // instead of two on every rank but the first (those ranks are the critical path into the coarse all-reduce)
+  mfmgb_csr *R_stack = nullptr;
+  double *rs = nullptr;
   // Chebyshev smoother (dealii::PreconditionChebyshev as DealIIMatrixFreeSmoother uses it): estimate and work vectors
   double cheb_lmin = 1., cheb_lmax = 1., cheb_theta = 1., cheb_delta = 0.;
   double *c_r = nullptr, *c_dst = nullptr, *c_u1 = nullptr, *c_u2 = nullptr;
@@ -411,8 +415,18 @@ int apply_level(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, 
   const int64_t n = fine.n;
   const bool x_is_zero = li > 0 || H->is_preconditioner; // hierarchy.hpp:253-259
   if (li == H->n_levels - 1) // hierarchy.hpp:261-268 (the solve overwrites x)
-    return H->dd ? coarse_dd_solve_async(ctx, H->dd, b, x, fine.restrict_no_halo ? fine.gb : nullptr)
-                 : dense_solve_async(ctx, fine.D, b, x);
+  {
+    if (!H->dd)
+      return dense_solve_async(ctx, fine.D, b, x);
+    if (fine.R_stack && b == fine.bc)
+    {
+      // the stacked restriction wrote [own rows | share below] into rs: the solver addresses its right-hand side by
+      // GLOBAL coarse index and only touches this rank's rows, so hand it rs shifted back by the rank's offset
+      mfmgb_comm *c = ctx_comm(ctx);
+      return coarse_dd_solve_async(ctx, H->dd, fine.rs - H->coarse_offsets[c->rank], x, fine.rs + fine.R->n_rows);
+    }
+    return coarse_dd_solve_async(ctx, H->dd, b, x, fine.restrict_no_halo ? fine.gb : nullptr);
+  }
 
   mfmgb_level &coarse = H->lev[li + 1];
   const int nu = H->nu;
@@ -466,12 +480,20 @@ int apply_level(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x, 
     // no exchange at all: the ghost-plane entries of R were dropped at setup; the neighbour above computes them
     // (its R_below) and they are summed by the all-reduce of the domain-decomposed coarse solve
     mfmgb_comm *c = ctx_comm(ctx);
-    e.y = coarse.bc + H->coarse_offsets[c->rank];
-    MFMGB_CHECK(csr_apply(ctx, coarse.R, fine.res, Epi::Spmv, e));
-    if (coarse.R_below)
+    if (coarse.R_stack)
     {
-      e.y = coarse.gb;
-      MFMGB_CHECK(csr_apply(ctx, coarse.R_below, fine.res, Epi::Spmv, e));
+      e.y = coarse.rs; // [own coarse rows | this rank's share of the separator rows below]
+      MFMGB_CHECK(csr_apply(ctx, coarse.R_stack, fine.res, Epi::Spmv, e));
+    }
+    else
+    {
+      e.y = coarse.bc + H->coarse_offsets[c->rank];
+      MFMGB_CHECK(csr_apply(ctx, coarse.R, fine.res, Epi::Spmv, e));
+      if (coarse.R_below)
+      {
+        e.y = coarse.gb;
+        MFMGB_CHECK(csr_apply(ctx, coarse.R_below, fine.res, Epi::Spmv, e));
+      }
     }
   }
   else if (fine.halo)
@@ -722,7 +744,39 @@ extern "C"
     l.restrict_no_halo = true;
     l.R_below = R_below;
     if (R_below)
+    {
       MFMGB_CHECK(mfmgb_vec_alloc(ctx, n_below, &l.gb));
+      const char *st = getenv("MFMGB_RESTRICT_STACK");
+      if (!(st && st[0] == '0'))
+      {
+        // stack the two restrictors (setup: download, concatenate, upload)
+        const mfmgb_csr *parts[2] = {l.R, R_below};
+        std::vector<int64_t> rp(1, 0);
+        std::vector<int32_t> col;
+        std::vector<double> val;
+        for (const mfmgb_csr *M : parts)
+        {
+          std::vector<int64_t> prp((size_t)M->n_rows + 1);
+          std::vector<int32_t> pc((size_t)std::max<int64_t>(M->nnz, 1));
+          std::vector<double> pv((size_t)std::max<int64_t>(M->nnz, 1));
+          MFMGB_CHECK(mfmgb_csr_download(ctx, M, prp.data(), pc.data(), pv.data()));
+          const int64_t base = rp.back();
+          for (int64_t i = 1; i <= M->n_rows; ++i)
+            rp.push_back(base + prp[(size_t)i]);
+          col.insert(col.end(), pc.begin(), pc.begin() + M->nnz);
+          val.insert(val.end(), pv.begin(), pv.begin() + M->nnz);
+        }
+        if (col.empty())
+        {
+          col.push_back(0);
+          val.push_back(0.);
+        }
+        MFMGB_CHECK(mfmgb_csr_upload(ctx, l.R->n_rows + n_below, l.R->n_cols, rp.data(), col.data(), val.data(), &l.R_stack));
+        l.R_stack->lanes = l.R->lanes; // same row structure: keep the restrictor's lanes-per-row choice
+        csr_plan_tile(l.R_stack);
+        MFMGB_CHECK(mfmgb_vec_alloc(ctx, l.R->n_rows + n_below, &l.rs));
+      }
+    }
     return MFMGB_OK;
   }
 
@@ -922,6 +976,9 @@ extern "C"
       cudaFree(l.bc);
       cudaFree(l.xc);
       cudaFree(l.gb);
+      cudaFree(l.rs);
+      if (l.R_stack)
+        mfmgb_csr_destroy(ctx, l.R_stack);
       cudaFree(l.c_r);
       cudaFree(l.c_dst);
       cudaFree(l.c_u1);
