@@ -208,6 +208,13 @@ extern "C"
   /* Hierarchy<Vector<double,Host>>::vmult: HOST vectors, H2D + V-cycle + D2H inside, synchronous
    * (the host-vector specialisations, source/cuda/cuda_matrix_operator.cu:51-70, cuda_smoother.cu:62-84) */
   MFMGB_API int mfmgb_vcycle_host(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b_host, double *x_host);
+  /* The same for n_rhs independent right-hand sides (preconditioner mode; block / multi-right-hand-side Krylov drivers):
+   * x_host[j] = V-cycle(b_host[j]).  Every right-hand side makes its own host -> device -> host trip; the trips are
+   * pipelined over three staging buffers -- H2D of j+1, the cycle of j and D2H of j-1 overlap (PCIe is full duplex) --
+   * so the throughput is bound by the slowest of the three stages instead of their sum.  Synchronous: all results are
+   * on the host on return.  Pointers may repeat (the same pinned buffer for several j). */
+  MFMGB_API int mfmgb_vcycle_host_batch(mfmgb_ctx *ctx, mfmgb_hierarchy *H, int n_rhs, const double *const *b_host,
+                                        double *const *x_host);
   /* one un-captured V-cycle with CUDA events between the level-0 stages (measurement aid for bench.py):
    * stage_ms[6] = pre-smoothing, residual, restriction, coarse levels (recursion), prolongation+correction,
    * post-smoothing -- the "Apply: fine levels" / "Apply: coarsest level" timer sections of hierarchy.hpp:263,271. */

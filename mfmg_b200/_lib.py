@@ -110,6 +110,7 @@ SIGNATURES = {
     "mfmgb_vcycle": (_int, [_vp, _vp, _vp, _vp]),
     "mfmgb_hierarchy_apply": (_int, [_vp, _vp, _vp, _vp, _int]),
     "mfmgb_vcycle_host": (_int, [_vp, _vp, _vp, _vp]),
+    "mfmgb_vcycle_host_batch": (_int, [_vp, _vp, _int, _vp, _vp]),
     "mfmgb_vcycle_profile": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "mfmgb_vcycle_timeline": (_int, [_vp, _vp, _vp, _vp, _int, ctypes.c_char_p, _int, _vp, _int, ctypes.POINTER(_int)]),
     "mfmgb_hierarchy_use_graph": (_int, [_vp, _int]),

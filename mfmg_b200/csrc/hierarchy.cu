@@ -69,9 +69,23 @@ struct mfmgb_hierarchy
   std::vector<mfmgb_level> lev;
   // graph replay
   bool use_graph = false;
-  cudaGraphExec_t graph_exec = nullptr;
-  const double *graph_b = nullptr;
-  double *graph_x = nullptr;
+  // instantiated cycles, keyed by the (b, x) pair they were captured with (PCG, the host-vector entry point and the
+  // pipelined batch entry point each bring their own buffers); least recently used slot is replaced
+  struct GraphSlot
+  {
+    const double *b = nullptr;
+    double *x = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t last_use = 0;
+  };
+  GraphSlot graphs[6];
+  uint64_t graph_clock = 0;
+  // pipelined host-vector batches (mfmgb_vcycle_host_batch): staging buffers, copy streams, events
+  static constexpr int kBatchBuffers = 3;
+  double *bb_dev[kBatchBuffers] = {nullptr, nullptr, nullptr}, *bx_dev[kBatchBuffers] = {nullptr, nullptr, nullptr};
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_h2d[kBatchBuffers] = {nullptr, nullptr, nullptr}, ev_comp[kBatchBuffers] = {nullptr, nullptr, nullptr},
+              ev_d2h[kBatchBuffers] = {nullptr, nullptr, nullptr};
   int launches_per_cycle = 0;
   // device staging for the *_host entry points and PCG work vectors
   double *b_dev = nullptr, *x_dev = nullptr;
@@ -94,11 +108,12 @@ constexpr int kBlock = 256;
 void drop_graph(void *h)
 {
   mfmgb_hierarchy *H = static_cast<mfmgb_hierarchy *>(h);
-  if (H->graph_exec)
-  {
-    cudaGraphExecDestroy(H->graph_exec);
-    H->graph_exec = nullptr;
-  }
+  for (auto &g : H->graphs)
+    if (g.exec)
+    {
+      cudaGraphExecDestroy(g.exec);
+      g = mfmgb_hierarchy::GraphSlot();
+    }
 }
 
 int level_apply_A(mfmgb_ctx *ctx, const mfmgb_level &l, double *x, Epi epi, const EpiArgs &e)
@@ -560,12 +575,21 @@ int run_vcycle(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x)
   }();
   if (!H->use_graph || (H->distributed && !dist_graph))
     return apply_level(ctx, H, b, x, 0);
-  if (!H->graph_exec || H->graph_b != b || H->graph_x != x)
+  mfmgb_hierarchy::GraphSlot *slot = nullptr, *victim = &H->graphs[0];
+  for (auto &g : H->graphs)
   {
-    if (H->graph_exec)
+    if (g.exec && g.b == b && g.x == x)
+      slot = &g;
+    if (!g.exec || (victim->exec && g.last_use < victim->last_use))
+      victim = &g;
+  }
+  if (!slot)
+  {
+    slot = victim;
+    if (slot->exec)
     {
-      cudaGraphExecDestroy(H->graph_exec);
-      H->graph_exec = nullptr;
+      cudaGraphExecDestroy(slot->exec);
+      slot->exec = nullptr;
     }
     cudaGraph_t graph = nullptr;
     const int64_t before = ctx->launches;
@@ -581,12 +605,13 @@ int run_vcycle(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x)
     MFMGB_CUDA(ctx, ce);
     H->launches_per_cycle = (int)(ctx->launches - before);
     ctx->launches = before;
-    MFMGB_CUDA(ctx, cudaGraphInstantiate(&H->graph_exec, graph, 0));
+    MFMGB_CUDA(ctx, cudaGraphInstantiate(&slot->exec, graph, 0));
     cudaGraphDestroy(graph);
-    H->graph_b = b;
-    H->graph_x = x;
+    slot->b = b;
+    slot->x = x;
   }
-  MFMGB_CUDA(ctx, cudaGraphLaunch(H->graph_exec, ctx->stream));
+  slot->last_use = ++H->graph_clock;
+  MFMGB_CUDA(ctx, cudaGraphLaunch(slot->exec, ctx->stream));
   ctx->launches += H->launches_per_cycle;
   return MFMGB_OK;
 }
@@ -954,8 +979,22 @@ extern "C"
       return MFMGB_OK;
     MFMGB_REQUIRE(ctx, ctx, "ctx is NULL");
     MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (H->graph_exec)
-      cudaGraphExecDestroy(H->graph_exec);
+    drop_graph(H);
+    for (int k = 0; k < mfmgb_hierarchy::kBatchBuffers; ++k)
+    {
+      cudaFree(H->bb_dev[k]);
+      cudaFree(H->bx_dev[k]);
+      if (H->ev_h2d[k])
+        cudaEventDestroy(H->ev_h2d[k]);
+      if (H->ev_comp[k])
+        cudaEventDestroy(H->ev_comp[k]);
+      if (H->ev_d2h[k])
+        cudaEventDestroy(H->ev_d2h[k]);
+    }
+    if (H->s_in)
+      cudaStreamDestroy(H->s_in);
+    if (H->s_out)
+      cudaStreamDestroy(H->s_out);
     for (size_t k = 0; k < ctx->graph_owners.size(); ++k)
       if (ctx->graph_owners[k].first == H)
       {
@@ -1106,6 +1145,59 @@ extern "C"
       MFMGB_CUDA(ctx, cudaMemcpyAsync(H->x_dev, x_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     MFMGB_CHECK(run_vcycle(ctx, H, H->b_dev, H->x_dev));
     MFMGB_CUDA(ctx, cudaMemcpyAsync(x_host, H->x_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return mfmgb_comm_check(ctx);
+  }
+
+  MFMGB_API int mfmgb_vcycle_host_batch(mfmgb_ctx *ctx, mfmgb_hierarchy *H, int n_rhs, const double *const *b_host,
+                                        double *const *x_host)
+  {
+    MFMGB_REQUIRE(ctx, ctx && H && H->finalized && n_rhs >= 0 && (n_rhs == 0 || (b_host && x_host)),
+                  "mfmgb_vcycle_host_batch: bad arguments");
+    if (!H->is_preconditioner) // solver mode reads x as well: the plain entry point, one right-hand side at a time
+    {
+      for (int j = 0; j < n_rhs; ++j)
+        MFMGB_CHECK(mfmgb_vcycle_host(ctx, H, b_host[j], x_host[j]));
+      return MFMGB_OK;
+    }
+    constexpr int NB = mfmgb_hierarchy::kBatchBuffers;
+    const int64_t n = H->lev[0].n;
+    const int64_t n_vec = mfmgb_hierarchy_vector_size(H, 0);
+    const size_t bytes = sizeof(double) * (size_t)n;
+    if (!H->s_in)
+    {
+      MFMGB_CUDA(ctx, cudaStreamCreateWithFlags(&H->s_in, cudaStreamNonBlocking));
+      MFMGB_CUDA(ctx, cudaStreamCreateWithFlags(&H->s_out, cudaStreamNonBlocking));
+      for (int k = 0; k < NB; ++k)
+      {
+        MFMGB_CHECK(mfmgb_vec_alloc(ctx, n_vec, &H->bb_dev[k]));
+        MFMGB_CHECK(mfmgb_vec_alloc(ctx, n_vec, &H->bx_dev[k]));
+        MFMGB_CUDA(ctx, cudaEventCreateWithFlags(&H->ev_h2d[k], cudaEventDisableTiming));
+        MFMGB_CUDA(ctx, cudaEventCreateWithFlags(&H->ev_comp[k], cudaEventDisableTiming));
+        MFMGB_CUDA(ctx, cudaEventCreateWithFlags(&H->ev_d2h[k], cudaEventDisableTiming));
+      }
+      MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    // Three stages in flight: H2D of right-hand side j+1 (copy stream in) || V-cycle j (compute stream) || D2H of
+    // result j-1 (copy stream out): PCIe runs full duplex, and the cycle hides behind the copies.  Every right-hand
+    // side still makes its own trip host -> device -> host.
+    for (int j = 0; j < n_rhs; ++j)
+    {
+      const int k = j % NB;
+      if (j >= NB) // buffer k is free for new input once cycle j - NB has consumed it
+        MFMGB_CUDA(ctx, cudaStreamWaitEvent(H->s_in, H->ev_comp[k], 0));
+      MFMGB_CUDA(ctx, cudaMemcpyAsync(H->bb_dev[k], b_host[j], bytes, cudaMemcpyHostToDevice, H->s_in));
+      MFMGB_CUDA(ctx, cudaEventRecord(H->ev_h2d[k], H->s_in));
+      MFMGB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, H->ev_h2d[k], 0));
+      if (j >= NB) // ... and its output buffer once result j - NB has left
+        MFMGB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, H->ev_d2h[k], 0));
+      MFMGB_CHECK(run_vcycle(ctx, H, H->bb_dev[k], H->bx_dev[k]));
+      MFMGB_CUDA(ctx, cudaEventRecord(H->ev_comp[k], ctx->stream));
+      MFMGB_CUDA(ctx, cudaStreamWaitEvent(H->s_out, H->ev_comp[k], 0));
+      MFMGB_CUDA(ctx, cudaMemcpyAsync(x_host[j], H->bx_dev[k], bytes, cudaMemcpyDeviceToHost, H->s_out));
+      MFMGB_CUDA(ctx, cudaEventRecord(H->ev_d2h[k], H->s_out));
+    }
+    MFMGB_CUDA(ctx, cudaStreamSynchronize(H->s_out));
     MFMGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return mfmgb_comm_check(ctx);
   }

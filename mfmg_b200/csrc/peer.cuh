@@ -74,13 +74,12 @@ __device__ __forceinline__ void peer_allreduce_cta(double *__restrict__ buf, int
     for (int i = threadIdx.x; i < n; i += blockDim.x)
       dst[i] = buf[i];
   }
-  // One warp-level fence, not one per thread: the barrier orders every thread's remote stores before it, and the
-  // fence + release store of the flag-writing lanes is cumulative over them.  (A system fence per thread cost ~20 us
-  // here: 32 warps each waiting for their NVLink write acknowledgements one after the other.)
+  // No fence per thread: the barrier orders every thread's remote stores before the release stores of the
+  // flag-writing lanes, and a release is cumulative over what happens-before it.  (A system fence per thread cost
+  // ~20 us here: 32 warps each waiting for their NVLink write acknowledgements one after the other.)
   __syncthreads();
   if ((int)threadIdx.x < a.nranks)
   {
-    __threadfence_system();
     st_release_sys(reinterpret_cast<unsigned long long *>(a.base[threadIdx.x] + a.flag_off) +
                        (par * (size_t)a.nranks + (size_t)a.rank),
                    s);

@@ -698,6 +698,19 @@ class Hierarchy:
         check(self.handle.ctx, self.handle.lib.mfmgb_vcycle_host(self.handle.ctx, self.ptr, ctypes.c_void_p(b_ptr),
                                                                  ctypes.c_void_p(x_ptr)))
 
+    def vmult_host_batch_ptr(self, x_ptrs, b_ptrs) -> None:
+        """x_j = V-cycle(b_j) for a batch of independent HOST vectors (addresses of pinned buffers), pipelined:
+        H2D of j+1, the cycle of j and D2H of j-1 overlap (mfmgb_vcycle_host_batch)."""
+        n = len(b_ptrs)
+        assert len(x_ptrs) == n
+        bp = (ctypes.c_void_p * n)(*[ctypes.c_void_p(p) for p in b_ptrs])
+        xp = (ctypes.c_void_p * n)(*[ctypes.c_void_p(p) for p in x_ptrs])
+        check(self.handle.ctx, self.handle.lib.mfmgb_vcycle_host_batch(self.handle.ctx, self.ptr, n, bp, xp))
+
+    def vmult_host_batch(self, xs, bs) -> None:
+        """The same for lists of float64 numpy arrays."""
+        self.vmult_host_batch_ptr([x.ctypes.data for x in xs], [b.ctypes.data for b in bs])
+
     STAGES = ("pre_smooth", "residual", "restrict", "coarse", "prolong_correct", "post_smooth")
 
     def profile(self, x: DeviceVector, b: DeviceVector) -> dict:
