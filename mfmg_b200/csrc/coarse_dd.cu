@@ -18,6 +18,13 @@
 // (own agglomerates + the layer below, a separator), so neither the right-hand side nor the solution is all-gathered.
 // Setup (once): A_II^-1 by the dense factorisation of dense.cu, E_r = A_II^-1 A_IS and A_SI E_r by GEMM, the Schur
 // matrix summed over the ranks by an all-reduce and inverted redundantly.
+//
+// Overlapped form (round 2, default over peer memory): steps 1-3 as written are a chain -- the all-reduce (latency +
+// the skew between the ranks) and the Schur GEMV sit behind the interior GEMV.  With W_r = A_SI,r A_II,r^-1 formed
+// once at setup (n_adj x n_I, dense) the separator right-hand side t = b_S - sum_r W_r b_I,r depends on the restricted
+// residual only, so  [W b_I -> all-reduce -> Schur GEMV]  runs on a second stream NEXT TO  y = A_II^-1 b_I  and the
+// two meet in the interior update.  Same block elimination, one more rounding-level reassociation ((A_SI A_II^-1) b
+// instead of A_SI (A_II^-1 b)).
 #include <algorithm>
 
 #include "comm.cuh"
@@ -39,6 +46,13 @@ struct mfmgb_coarse_dd
   int64_t ldE = 0;
   int32_t *sep_index = nullptr; // [n_S] global coarse index of every separator row
   double *y = nullptr, *t = nullptr, *xs = nullptr, *g = nullptr;
+  // overlapped form
+  bool overlap = false;
+  double *W = nullptr; // n_adj x ldW: A_SI A_II^-1
+  int64_t ldW = 0;
+  double *w = nullptr, *bI = nullptr; // W b_I; aligned copy of b_I when the caller's is not
+  unsigned int *done = nullptr;       // CTA completion counter of dd_w_rhs_allreduce_kernel
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace
@@ -129,6 +143,90 @@ __global__ void __launch_bounds__(1024) dd_rhs_allreduce_kernel(const DdRhsArgs 
   peer_allreduce_cta(a.t, (int)a.n_S, pa);
 }
 
+// Overlapped form: w = W b_I with TPR threads per row (the loop of dense.cu's gemv_kernel), and the LAST CTA to finish
+// assembles t = (own part of b_S) - w [+ share of R r below] and sums it over the ranks through peer memory -- the
+// dense product, the right-hand-side assembly and the all-reduce in one launch.
+template <int TPR>
+__global__ void __launch_bounds__(256)
+    dd_w_rhs_allreduce_kernel(int64_t n_I, const double *__restrict__ W, int64_t ldW, const double *__restrict__ bI,
+                              double *__restrict__ w, const DdRhsArgs a, const PeerAllreduceArgs pa,
+                              unsigned int *__restrict__ done)
+{
+  __shared__ double sm[8];
+  __shared__ int is_last;
+  constexpr int ROWS = 256 / TPR;
+  const int t = threadIdx.x % TPR;
+  const int64_t r = (int64_t)blockIdx.x * ROWS + threadIdx.x / TPR;
+  double s0 = 0., s1 = 0., s2 = 0., s3 = 0.;
+  if (r < a.n_adj)
+  {
+    const double2 *row2 = reinterpret_cast<const double2 *>(W + r * ldW);
+    const double2 *v2 = reinterpret_cast<const double2 *>(bI);
+    const int64_t npairs = n_I >> 1;
+    int64_t q = t;
+    for (; q + 3 * TPR < npairs; q += 4 * TPR)
+    {
+      const double2 a0 = ld_stream_f64x2(reinterpret_cast<const double *>(row2 + q));
+      const double2 a1 = ld_stream_f64x2(reinterpret_cast<const double *>(row2 + q + TPR));
+      const double2 a2 = ld_stream_f64x2(reinterpret_cast<const double *>(row2 + q + 2 * TPR));
+      const double2 a3 = ld_stream_f64x2(reinterpret_cast<const double *>(row2 + q + 3 * TPR));
+      const double2 b0 = v2[q], b1 = v2[q + TPR], b2 = v2[q + 2 * TPR], b3 = v2[q + 3 * TPR];
+      s0 = fma(a0.y, b0.y, fma(a0.x, b0.x, s0));
+      s1 = fma(a1.y, b1.y, fma(a1.x, b1.x, s1));
+      s2 = fma(a2.y, b2.y, fma(a2.x, b2.x, s2));
+      s3 = fma(a3.y, b3.y, fma(a3.x, b3.x, s3));
+    }
+    for (; q < npairs; q += TPR)
+    {
+      const double2 a0 = ld_stream_f64x2(reinterpret_cast<const double *>(row2 + q));
+      const double2 b0 = v2[q];
+      s0 = fma(a0.y, b0.y, fma(a0.x, b0.x, s0));
+    }
+    if ((n_I & 1) && t == 0)
+      s1 = fma(W[r * ldW + n_I - 1], bI[n_I - 1], s1);
+  }
+  double s = (s0 + s1) + (s2 + s3);
+  if (TPR == 256)
+  {
+    s = block_sum<256>(s, sm);
+    if (threadIdx.x == 0 && r < a.n_adj)
+      w[r] = s;
+  }
+  else
+  {
+    s = subwarp_sum<32>(s);
+    if (t == 0 && r < a.n_adj)
+      w[r] = s;
+  }
+  // completion count: the writers fence, the barrier orders them before thread 0's ticket
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    __threadfence();
+    is_last = atomicAdd(done, 1u) == gridDim.x - 1 ? 1 : 0;
+  }
+  __syncthreads();
+  if (!is_last)
+    return;
+  if (threadIdx.x == 0)
+    *done = 0; // for the next launch (graph replay)
+  __threadfence();
+  for (int64_t k = threadIdx.x; k < a.n_S; k += blockDim.x)
+  {
+    double v = 0.;
+    if (k >= a.adj_begin && k < a.adj_begin + a.n_adj)
+      v = -__ldcg(w + (k - a.adj_begin));
+    if (k >= a.own_begin && k < a.own_begin + a.own_n)
+      v += a.b_c[a.sep_index[k]];
+    if (a.g_below && k >= a.adj_begin && k < a.adj_begin + a.n_below)
+      v += a.g_below[k - a.adj_begin];
+    a.t[k] = v;
+  }
+  __syncthreads();
+  peer_allreduce_cta(a.t, (int)a.n_S, pa);
+}
+
 // the same without the reduction (NCCL transport: ncclAllReduce follows)
 template <typename OffT>
 __global__ void __launch_bounds__(256) dd_rhs_kernel(const DdRhsArgs a)
@@ -198,6 +296,57 @@ int coarse_dd_solve_async(mfmgb_ctx *ctx, const mfmgb_coarse_dd *d, const double
 {
   mfmgb_comm *c = ctx_comm(ctx);
   cudaStream_t st = ctx->stream;
+  if (d->overlap && d->n_S > 0 && c->peer.enabled && d->n_S <= c->peer.ar_cap)
+  {
+    // [W b_I -> all-reduce -> Schur GEMV] on the communication stream next to y = A_II^-1 b_I on the compute stream
+    const double *bI = b_c + d->own_begin;
+    if (d->n_I > 0 && (reinterpret_cast<uintptr_t>(bI) & 15))
+    {
+      MFMGB_CUDA(ctx, cudaMemcpyAsync(d->bI, bI, sizeof(double) * (size_t)d->n_I, cudaMemcpyDeviceToDevice, st));
+      bI = d->bI;
+    }
+    DdRhsArgs a;
+    a.n_S = d->n_S;
+    a.adj_begin = d->adj_begin;
+    a.n_adj = d->n_I > 0 ? d->n_adj : 0;
+    a.own_begin = d->own_sep_begin;
+    a.own_n = d->own_sep_n;
+    a.n_below = d->n_adj - d->own_sep_n;
+    a.si_rowptr = nullptr;
+    a.si_col = nullptr;
+    a.si_val = nullptr;
+    a.y = nullptr;
+    a.sep_index = d->sep_index;
+    a.b_c = b_c;
+    a.g_below = g_below;
+    a.t = d->t;
+    MFMGB_CUDA(ctx, cudaEventRecord(d->ev_fork, st));
+    MFMGB_CUDA(ctx, cudaStreamWaitEvent(c->stream, d->ev_fork, 0));
+    if (d->n_I >= 1024)
+      dd_w_rhs_allreduce_kernel<256><<<(unsigned)std::max<int64_t>(a.n_adj, 1), 256, 0, c->stream>>>(
+          d->n_I, d->W, d->ldW, bI, d->w, a, peer_allreduce_args(c), d->done);
+    else
+      dd_w_rhs_allreduce_kernel<32><<<(unsigned)std::max<int64_t>(ceil_div(a.n_adj, 8), 1), 256, 0, c->stream>>>(
+          d->n_I, d->W, d->ldW, bI, d->w, a, peer_allreduce_args(c), d->done);
+    MFMGB_LAUNCHED(ctx);
+    ctx->stream = c->stream; // the Schur solve follows on the same stream
+    const int rc = dense_solve_async(ctx, d->D_S, d->t, d->xs);
+    ctx->stream = st;
+    MFMGB_CHECK(rc);
+    MFMGB_CUDA(ctx, cudaEventRecord(d->ev_join, c->stream));
+    if (d->n_I > 0)
+      MFMGB_CHECK(dense_solve_async(ctx, d->D_II, bI, d->y));
+    MFMGB_CUDA(ctx, cudaStreamWaitEvent(st, d->ev_join, 0));
+    prof_mark(ctx, "coarse: y = A_II^-1 b_I  ||  W b_I + all-reduce + Schur GEMV");
+    const int interior_blocks = (int)ceil_div(d->n_I, 8);
+    const int scatter_blocks = (int)ceil_div(d->n_S, 256);
+    dd_interior_scatter_kernel<<<(unsigned)(interior_blocks + scatter_blocks), 256, 0, st>>>(
+        d->n_I, d->n_adj, d->E, d->ldE, d->xs + d->adj_begin, d->y, x_c + d->own_begin, interior_blocks, d->n_S,
+        d->sep_index, d->xs, x_c);
+    MFMGB_LAUNCHED(ctx);
+    prof_mark(ctx, "coarse: interior update + scatter");
+    return MFMGB_OK;
+  }
   // y = A_II^-1 b_I
   if (d->n_I > 0)
     MFMGB_CHECK(dense_solve_async(ctx, d->D_II, b_c + d->own_begin, d->y));
@@ -316,6 +465,9 @@ extern "C"
     // interior block: A_II^-1
     if (n_I > 0)
       MFMGB_CHECK(mfmgb_dense_factor(ctx, A_II, &d->D_II));
+    // overlapped form: over peer memory, unless MFMGB_COARSE_OVERLAP=0 (measurement aid)
+    const char *ov = getenv("MFMGB_COARSE_OVERLAP");
+    const bool want_overlap = c->peer.enabled && n_S > 0 && n_S <= c->peer.ar_cap && !(ov && ov[0] == '0');
     if (n_S > 0)
     {
       const int64_t ldS = (n_S + 3) & ~(int64_t)3;
@@ -343,6 +495,14 @@ extern "C"
         dim3 grid((unsigned)ceil_div(n_adj, 256), (unsigned)n_adj);
         dd_sub_block_kernel<<<grid, 256, 0, st>>>(n_adj, C, ldE, S, ldS, adj_begin);
         MFMGB_LAUNCHED(ctx);
+        if (want_overlap && !d->D_II->substitution)
+        {
+          // W = A_SI A_II^-1
+          d->ldW = ldI;
+          MFMGB_CUDA(ctx, cudaMalloc(&d->W, sizeof(double) * (size_t)(n_adj * ldI)));
+          MFMGB_CUDA(ctx, cudaMemsetAsync(d->W, 0, sizeof(double) * (size_t)(n_adj * ldI), st));
+          MFMGB_CHECK(dense_gemm(ctx, n_adj, n_I, n_I, Asi, ldI, d->D_II->inv, d->D_II->lda, d->W, ldI, 1., 0.));
+        }
         MFMGB_CUDA(ctx, cudaStreamSynchronize(st));
         cudaFree(Ais);
         cudaFree(Asi);
@@ -350,6 +510,22 @@ extern "C"
       }
       MFMGB_NCCL(ctx, ncclAllReduce(S, S, (size_t)(n_S * ldS), ncclDouble, ncclSum, c->nccl, st));
       MFMGB_CHECK(dense_factor_device(ctx, S, n_S, &d->D_S)); // takes ownership of S
+      // every rank must take the same branch (each form issues exactly one peer all-reduce, so mixing them would
+      // still pair up, but keep the cycle symmetric): overlap unless some rank had to keep its interior factors
+      long long veto = (want_overlap && (n_I == 0 || n_adj == 0 || d->W != nullptr)) ? 0 : 1;
+      MFMGB_CHECK(comm_agree_max(ctx, &veto));
+      d->overlap = veto == 0;
+      if (d->overlap)
+      {
+        d->D_S->direct_gemv = true; // runs next to the streamed interior GEMV: no shared-memory footprint
+        MFMGB_CUDA(ctx, cudaMalloc(&d->w, sizeof(double) * (size_t)(n_adj + 2)));
+        MFMGB_CUDA(ctx, cudaMemsetAsync(d->w, 0, sizeof(double) * (size_t)(n_adj + 2), st));
+        MFMGB_CUDA(ctx, cudaMalloc(&d->bI, sizeof(double) * (size_t)(n_I + 2)));
+        MFMGB_CUDA(ctx, cudaMalloc(&d->done, sizeof(unsigned int)));
+        MFMGB_CUDA(ctx, cudaMemsetAsync(d->done, 0, sizeof(unsigned int), st));
+        MFMGB_CUDA(ctx, cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
+        MFMGB_CUDA(ctx, cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
+      }
     }
     MFMGB_CUDA(ctx, cudaStreamSynchronize(st));
     *out = d;
@@ -365,6 +541,14 @@ extern "C"
     mfmgb_dense_destroy(ctx, d->D_II);
     mfmgb_dense_destroy(ctx, d->D_S);
     cudaFree(d->E);
+    cudaFree(d->W);
+    cudaFree(d->w);
+    cudaFree(d->bI);
+    cudaFree(d->done);
+    if (d->ev_fork)
+      cudaEventDestroy(d->ev_fork);
+    if (d->ev_join)
+      cudaEventDestroy(d->ev_join);
     cudaFree(d->sep_index);
     cudaFree(d->y);
     cudaFree(d->t);

@@ -264,6 +264,8 @@ void peer_teardown(mfmgb_comm *c)
 
 namespace mfmgb
 {
+int comm_agree_max(mfmgb_ctx *ctx, long long *value) { return agree_max(ctx, ctx_comm(ctx), value); }
+
 mfmgb_comm *ctx_comm(mfmgb_ctx *ctx)
 {
   auto it = registry().find(ctx);

@@ -92,6 +92,8 @@ int allgather_slices(mfmgb_ctx *ctx, double *full, const std::vector<int64_t> &o
 // symmetric sub-allocation of the peer window (collective: every rank calls it in the same order; the size is the
 // maximum over the ranks).  Returns MFMGB_OK and *offset, or sets *offset = (size_t)-1 when the window is full / off.
 int peer_alloc(mfmgb_ctx *ctx, size_t bytes, size_t *offset);
+// collective max over the ranks of one 64-bit value (setup time; synchronises)
+int comm_agree_max(mfmgb_ctx *ctx, long long *value);
 // non-zero when a kernel of this context gave up waiting for a peer (checked at synchronisation points)
 int peer_error(mfmgb_ctx *ctx);
 } // namespace mfmgb

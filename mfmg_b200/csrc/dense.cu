@@ -734,7 +734,7 @@ int launch_gemv(mfmgb_ctx *ctx, const mfmgb_dense *D, const double *b, double *o
     const char *v = getenv("MFMGB_GEMV_STREAM");
     return !(v && v[0] == '0');
   }();
-  if (stream && D->n >= 1024 && n_out >= 256)
+  if (stream && !D->direct_gemv && D->n >= 1024 && n_out >= 256)
     return launch_gemv_stream(ctx, D, b, out, row0, n_out);
 
   if (n_out <= 0)

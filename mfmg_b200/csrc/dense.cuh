@@ -15,6 +15,7 @@ struct mfmgb_dense
   bool substitution = false;
   double *lu = nullptr;  // the packed factors L\U (row-major [n][lda]) when substitution is on
   double pivot_ratio = 1.; // min |u_kk| / max |u_kk|
+  bool direct_gemv = false; // always the direct-load GEMV (no shared-memory ring): for solves that run NEXT TO another kernel
   double *work0 = nullptr, *work1 = nullptr;
   int64_t num_swaps = 0;
   // multi-GPU: the GEMV is split by rows across the ranks (every rank holds M and the full right-hand side);

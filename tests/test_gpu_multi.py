@@ -16,7 +16,7 @@ def _n_gpus():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kernel,transport", [("auto", "peer"), ("tile", "peer"), ("tile", "peer_unfused"),
-                                              ("auto", "nccl")])
+                                              ("tile", "peer_serial_coarse"), ("auto", "nccl")])
 @pytest.mark.parametrize("world", [2, 4])
 def test_partitioned_hierarchy_on_gpus(world, kernel, transport):
     if _n_gpus() < world:
@@ -28,8 +28,11 @@ def test_partitioned_hierarchy_on_gpus(world, kernel, transport):
     # into peer memory over NVLink by our own kernels, "nccl": the NCCL send/recv + all-reduce path
     # "peer_unfused": the interior rows / wait kernel / boundary rows form instead of the one-launch form in which
     # the tile kernel waits for the neighbours' flags itself and gathers ghost columns from the mailbox
+    # "peer_serial_coarse": the domain-decomposed coarse solve as a chain (GEMV, all-reduce, Schur GEMV) instead of the
+    # default two-stream form  y = A_II^-1 b_I  ||  [W b_I -> all-reduce -> Schur GEMV]
     env = dict(os.environ, MFMGB_CSR_KERNEL=kernel, MFMGB_PEER="0" if transport == "nccl" else "1",
-               MFMGB_HALO_FUSED="0" if transport == "peer_unfused" else "1")
+               MFMGB_HALO_FUSED="0" if transport == "peer_unfused" else "1",
+               MFMGB_COARSE_OVERLAP="0" if transport == "peer_serial_coarse" else "1")
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, env=env)
     out_dir = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(out_dir):   # keep the worker's log as evidence (copied to profiles/ by the builder)
