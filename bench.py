@@ -67,6 +67,10 @@ def parse_args(argv=None):
                     help="also measure BASELINE configs[3] (512^3 cells): auto = only for the default workload")
     ap.add_argument("--north-star-cells", type=int, default=512)
     ap.add_argument("--north-star-timeout", type=float, default=480.0)
+    ap.add_argument("--other-configs", default="auto", choices=["auto", "on", "off"],
+                    help="N = 1: also measure BASELINE configs[2] (Q2) and configs[4] (matrix-free fine level) in child "
+                         "processes and report them under 'other_configs': auto = only for the default workload")
+    ap.add_argument("--other-configs-timeout", type=float, default=200.0)
     return ap.parse_args(argv)
 
 
@@ -744,6 +748,46 @@ def north_star_subprocess(args):
     return summarise_north_star(line, time.time() - t0)
 
 
+OTHER_CONFIGS = (
+    ("cfg2", "BASELINE configs[2]: 3D Q2 discontinuous diffusion, 100^3 cells",
+     ["--cells", "100", "--degree", "2", "--block", "10", "--material", "discontinuous"]),
+    ("cfg4", "BASELINE configs[4]: matrix-free Q1 fine level, 256^3 cells, assembled R / A_c",
+     ["--cells", "256", "--block", "16", "--matrix-free"]),
+)
+
+
+def other_configs_subprocess(args):
+    """N = 1: the two remaining single-GPU configurations of BASELINE.json, each in a bounded child process (host setup,
+    upload, 20 timed cycles, size-independent parity properties; their oracle parity lives in tests/ and profiles/)."""
+    out = {}
+    for key, desc, flags in OTHER_CONFIGS:
+        cmd = [sys.executable, os.path.abspath(__file__)] + flags + [
+            "--steps", "20", "--warmup", "3", "--repeats", "3", "--no-cpu-baseline", "--parity", "props",
+            "--north-star", "off", "--other-configs", "off"]
+        t0 = time.time()
+        try:
+            res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                                 timeout=args.other_configs_timeout)
+        except subprocess.TimeoutExpired:
+            out[key] = {"config": desc, "skipped": f"did not finish within {args.other_configs_timeout:.0f} s"}
+            continue
+        if res.returncode != 0:
+            out[key] = {"config": desc, "skipped": f"child exited {res.returncode}: {res.stderr[-300:]}"}
+            continue
+        try:
+            line = json.loads(res.stdout.strip().splitlines()[-1])
+        except (ValueError, IndexError):
+            out[key] = {"config": desc, "skipped": "child printed no JSON line"}
+            continue
+        out[key] = {"config": desc + " -- " + line["config"]["workload"], "vcycles_per_s": line["value"],
+                    "ms_per_step": line["ms_per_step"], "timing": line.get("timing"),
+                    "vcycle_roofline": line["vcycle_roofline"], "roofline": line["roofline"],
+                    "timeline_in_graph_ms": line.get("timeline_in_graph_ms"), "parity": line.get("parity"),
+                    "e2e": {k: line["e2e"][k] for k in ("value", "unit", "ms_per_step") if k in line["e2e"]},
+                    "clocks": line["clocks"], "wall_s": time.time() - t0}
+    return out
+
+
 def summarise_north_star(line, wall_s):
     return {"config": "BASELINE configs[3]: " + line["config"]["workload"], "n_gpus": line["n_gpus"],
             "scaling": "strong", "vcycles_per_s": line["value"], "ms_per_step": line["ms_per_step"],
@@ -895,6 +939,16 @@ def run_ours(args):
             ns = north_star_in_process(args, d, handle, stream, dist, rank, world, local_rank)
         if rank == 0:
             out["north_star"] = ns
+    want_other = world == 1 and (args.other_configs == "on" or (args.other_configs == "auto" and default_workload))
+    if want_other:
+        if not want_ns:
+            del H
+            Ho = None
+            info["global_ops"] = gops = None
+            import gc
+
+            gc.collect()
+        out["other_configs"] = other_configs_subprocess(args)
     if rank == 0:
         _emit(json.dumps(out))
     if dist is not None:

@@ -131,6 +131,8 @@ SIGNATURES = {
     "mfmgb_hierarchy_set_halo": (_int, [_vp, _int, _vp, _i64, _i64]),
     "mfmgb_hierarchy_set_coarse_offsets": (_int, [_vp, _vp, _int]),
     "mfmgb_hierarchy_vector_size": (_i64, [_vp, _int]),
+    "mfmgb_tunable_set": (_int, [ctypes.c_char_p, ctypes.c_longlong]),
+    "mfmgb_tunable_get": (ctypes.c_longlong, [ctypes.c_char_p]),
     "mfmgb_coarse_dd_create": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _pp]),
     "mfmgb_coarse_dd_destroy": (_int, [_vp, _vp]),
     "mfmgb_coarse_dd_solve": (_int, [_vp, _vp, _vp, _vp]),

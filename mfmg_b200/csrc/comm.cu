@@ -17,9 +17,11 @@
 // No kernel of a rank ever waits for something a LATER kernel of the same rank produces, and pushes never wait:
 // every wait is satisfied by work the peer issues unconditionally (no deadlock across GPUs).
 #include <algorithm>
+#include <cctype>
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <string>
 
 #include "comm.cuh"
 #include "peer.cuh"
@@ -375,6 +377,45 @@ int halo_push_inline(mfmgb_ctx *ctx, const mfmgb_halo *h, const double *v)
   return MFMGB_OK;
 }
 
+// process-wide launch parameters of the exchange kernels (mfmgb_tunable_set: measurement aid; defaults from the
+// environment variables MFMGB_<NAME IN CAPITALS>)
+struct Tunable
+{
+  const char *name;
+  long long value;
+  bool init;
+};
+static Tunable g_tunables[] = {
+    {"halo_push_ctas", 16, false},   // CTAs of the fused A-kernel that store the boundary plane(s) into the neighbours
+    {"halo_push_penalty", 2, false}, // interior tiles such a CTA is spared
+};
+
+static Tunable *find_tunable(const char *name)
+{
+  for (Tunable &t : g_tunables)
+    if (name && strcmp(t.name, name) == 0)
+    {
+      if (!t.init)
+      {
+        std::string env = std::string("MFMGB_") + t.name;
+        for (char &ch : env)
+          ch = (char)toupper((unsigned char)ch);
+        const char *v = getenv(env.c_str());
+        if (v && *v)
+          t.value = atoll(v);
+        t.init = true;
+      }
+      return &t;
+    }
+  return nullptr;
+}
+
+long long tunable(const char *name)
+{
+  Tunable *t = find_tunable(name);
+  return t ? t->value : 0;
+}
+
 void halo_ghost_args(mfmgb_ctx *ctx, const mfmgb_halo *h, int64_t blo, int64_t bhi, GhostArgs *g)
 {
   mfmgb_comm *c = ctx_comm(ctx);
@@ -398,7 +439,8 @@ void halo_ghost_args(mfmgb_ctx *ctx, const mfmgb_halo *h, int64_t blo, int64_t b
     const char *v = getenv("MFMGB_HALO_PUSH_IN_KERNEL");
     return !(v && v[0] == '0');
   }();
-  g->n_push_ctas = push_in_kernel ? 16 : 0;
+  g->n_push_ctas = push_in_kernel ? (int)tunable("halo_push_ctas") : 0;
+  g->push_penalty = (int)tunable("halo_push_penalty");
   g->rank = c->rank;
   g->base = c->peer.base_dev;
   g->send_idx = h->contiguous ? nullptr : h->send_idx;
@@ -688,5 +730,23 @@ extern "C"
   {
     MFMGB_REQUIRE(ctx, ctx && dev && n >= 0, "mfmgb_allreduce_sum: bad arguments");
     return allreduce_sum(ctx, dev, n);
+  }
+}
+
+extern "C"
+{
+  MFMGB_API int mfmgb_tunable_set(const char *name, long long value)
+  {
+    mfmgb::Tunable *t = mfmgb::find_tunable(name);
+    if (!t)
+      return MFMGB_ERR_INVALID;
+    t->value = value;
+    return MFMGB_OK;
+  }
+
+  MFMGB_API long long mfmgb_tunable_get(const char *name)
+  {
+    mfmgb::Tunable *t = mfmgb::find_tunable(name);
+    return t ? t->value : -1;
   }
 }

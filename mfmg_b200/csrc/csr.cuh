@@ -63,6 +63,7 @@ struct GhostArgs
   // push half of the exchange, done by the first n_push_ctas CTAs of the SAME kernel before they start on their tiles:
   // this rank's boundary entries of x -> the neighbours' mailboxes (remote stores), then the neighbours' flags
   int n_push_ctas = 0;
+  int push_penalty = 0; // interior tiles a pushing CTA is spared (its stores + system fence cost about that much)
   int rank = 0;
   unsigned char *const *base = nullptr; // device: mapped windows of all ranks
   const int32_t *send_idx = nullptr;    // device: concatenated send lists (NULL: contiguous ranges)

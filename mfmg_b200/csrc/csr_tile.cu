@@ -29,7 +29,11 @@ namespace
 {
 constexpr int kConsumerWarps = 8;
 constexpr int kTileThreads = (kConsumerWarps + 1) * 32;
-constexpr int kUnroll = 8;
+constexpr int kUnroll = 8;      // gathers in flight per lane (rows served by <= 4 lanes)
+constexpr int kUnrollLong = 16; // ... by >= 8 lanes (long rows: Q2 stencils have up to 125 entries; shared memory limits such
+                                // kernels to 2 CTAs per SM, so registers are free and one gather round covers a row)
+template <int LPR> constexpr int unroll_of() { return LPR >= 8 ? kUnrollLong : kUnroll; }
+template <int LPR> constexpr int min_ctas_of() { return LPR >= 8 ? 2 : 4; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -102,23 +106,23 @@ __host__ __device__ constexpr size_t tile_stage_bytes(int cap)
 
 // dot product of one row's staged entries [k0, ke) (stride LPR) with x; GHOST: columns >= n_owned are read from the
 // NVLink mailbox of the current exchange instead of the vector's ghost tail
-template <int LPR, bool GHOST>
+template <int LPR, bool GHOST, int UNR = unroll_of<LPR>()>
 __device__ __forceinline__ double tile_row_sum(const double *__restrict__ sval, const int *__restrict__ scol,
                                                const double *__restrict__ x, int k, const int ke, const GhostArgs &g,
                                                const double *__restrict__ gbox)
 {
   double s0 = 0., s1 = 0.;
-  // kUnroll gathers of x in flight per lane (the gather latency under load is what the consumers wait on);
+  // UNR gathers of x in flight per lane (the gather latency under load is what the consumers wait on);
   // even multiples of LPR go to s0, odd ones to s1, ascending: the vector-CSR kernel's summation order
-  for (; k < ke; k += kUnroll * LPR)
+  for (; k < ke; k += UNR * LPR)
   {
     // No predicated memory operation in this block: lanes past the row end re-read the row's last entry and
     // get their product zeroed afterwards.  (With predicated loads ptxas paired every gather with its FMA --
-    // one gather in flight per lane; unconditional, the kUnroll gathers issue back to back.)
-    int kk[kUnroll], c[kUnroll];
-    double v[kUnroll], xv[kUnroll];
+    // one gather in flight per lane; unconditional, the UNR gathers issue back to back.)
+    int kk[UNR], c[UNR];
+    double v[UNR], xv[UNR];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
+    for (int u = 0; u < UNR; ++u)
     {
       kk[u] = min(k + u * LPR, ke - 1);
       c[u] = scol[kk[u]];
@@ -126,15 +130,15 @@ __device__ __forceinline__ double tile_row_sum(const double *__restrict__ sval, 
     if (!GHOST)
     {
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u)
+      for (int u = 0; u < UNR; ++u)
         xv[u] = __ldg(x + c[u]);
     }
     else
     {
       // pointer select first, then unconditional loads (L2: the mailbox lines were written by a peer during this kernel)
-      const double *px[kUnroll];
+      const double *px[UNR];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u)
+      for (int u = 0; u < UNR; ++u)
       {
         const long long gc = (long long)c[u] - g.n_owned;
         px[u] = x + c[u];
@@ -147,18 +151,18 @@ __device__ __forceinline__ double tile_row_sum(const double *__restrict__ sval, 
         }
       }
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u)
+      for (int u = 0; u < UNR; ++u)
         xv[u] = __ldcg(px[u]);
     }
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
+    for (int u = 0; u < UNR; ++u)
       v[u] = sval[kk[u]];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
+    for (int u = 0; u < UNR; ++u)
       if (k + u * LPR >= ke)
         v[u] = 0., xv[u] = 0.;
 #pragma unroll
-    for (int u = 0; u < kUnroll; u += 2)
+    for (int u = 0; u < UNR; u += 2)
     {
       s0 = fma(v[u], xv[u], s0);
       s1 = fma(v[u + 1], xv[u + 1], s1);
@@ -168,7 +172,7 @@ __device__ __forceinline__ double tile_row_sum(const double *__restrict__ sval, 
 }
 
 template <int LPR, int EPI, typename OffT, bool GHOST>
-__global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArgs<OffT> a, const EpiArgs e, const GhostArgs g)
+__global__ void __launch_bounds__(kTileThreads, min_ctas_of<LPR>()) csr_tile_kernel(const TileArgs<OffT> a, const EpiArgs e, const GhostArgs g)
 {
   constexpr int RPT = kConsumerWarps * 32 / LPR; // rows per tile
   constexpr int RP_ELEMS = RPT + 4;              // staged row offsets (a multiple of 4 => 16-byte multiple)
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArg
   // the boundary tiles dealt out round-robin -- at most a few per CTA, at the END of its work.  (With the boundary
   // tiles in their natural place the first and last CTAs held nothing else: they started only when the neighbour's
   // flag arrived and then had a full share of tiles to do, which made the whole launch ~35 us longer.)
-  int64_t t_begin, t_end, n_first = 0, bt_lo = 0, bt_hi = 0, a_int0 = 0;
+  int64_t t_begin, t_end, n_first = 0, bt_lo = 0, bt_hi = 0, a_int0 = 0, bnd0 = 0;
   if (GHOST)
   {
     const int64_t nt = a.n_tiles;                       // tiles 0 .. nt-1 of rows [0, n_rows)
@@ -237,11 +241,17 @@ __global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArg
     if (bt_hi < bt_lo)
       bt_hi = bt_lo;
     const int64_t n_int = bt_hi - bt_lo, n_bnd = nt - n_int;
-    const int64_t tpc = (n_int + gridDim.x - 1) / gridDim.x;
-    const int64_t i0 = (int64_t)blockIdx.x * tpc < n_int ? (int64_t)blockIdx.x * tpc : n_int;
-    const int64_t i1 = i0 + tpc < n_int ? i0 + tpc : n_int;
+    const int64_t G = gridDim.x, P = g.n_push_ctas < (int)gridDim.x ? g.n_push_ctas : 0, pen = P > 0 ? g.push_penalty : 0;
+    // interior tiles: contiguous runs; the P pushing CTAs get `pen` tiles fewer than the others
+    const int64_t tpc = (n_int + P * pen + G - 1) / G, q = tpc > pen ? tpc - pen : 0;
+    int64_t i0 = (int64_t)blockIdx.x < P ? (int64_t)blockIdx.x * q : P * q + ((int64_t)blockIdx.x - P) * tpc;
+    int64_t i1 = i0 + ((int64_t)blockIdx.x < P ? q : tpc);
+    i0 = i0 < n_int ? i0 : n_int;
+    i1 = i1 < n_int ? i1 : n_int;
     n_first = i1 - i0;
-    const int64_t mine_bnd = n_bnd > (int64_t)blockIdx.x ? (n_bnd - 1 - (int64_t)blockIdx.x) / gridDim.x + 1 : 0;
+    // boundary tiles: round-robin over the CTAs, starting behind the pushing ones
+    bnd0 = ((int64_t)blockIdx.x - P + G) % G;
+    const int64_t mine_bnd = n_bnd > bnd0 ? (n_bnd - 1 - bnd0) / G + 1 : 0;
     t_begin = 0;
     t_end = n_first + mine_bnd; // local slot count
     a_int0 = i0; // first interior tile of this CTA, relative to bt_lo
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArg
     {
       if (slot < n_first)
         return bt_lo + a_int0 + slot;
-      const int64_t j = (int64_t)blockIdx.x + (slot - n_first) * (int64_t)gridDim.x; // j-th boundary tile
+      const int64_t j = bnd0 + (slot - n_first) * (int64_t)gridDim.x; // j-th boundary tile
       return j < bt_lo ? j : bt_hi + (j - bt_lo);
     }
     return slot < a.n_tiles1 ? a.tile_begin + slot : a.tile_begin2 + (slot - a.n_tiles1);
@@ -387,15 +397,20 @@ __global__ void __launch_bounds__(kTileThreads, 4) csr_tile_kernel(const TileArg
       ph ^= 1u;
     }
   }
-  // exchange bookkeeping: the last consumer warp of the grid advances the count of consumed exchanges (every warp
-  // read it before it could finish, so all of them saw the same exchange number)
-  if (GHOST && lane == 0)
+  // exchange bookkeeping: the last CTA of the grid advances the count of consumed exchanges (every consumer warp read
+  // it before it could finish, so all of them saw the same exchange number); one atomic per CTA, behind a barrier of
+  // the consumer warps (the producer warp has left)
+  if (GHOST)
   {
-    const unsigned int prev = atomicAdd(&g.done[1], 1u);
-    if (prev == gridDim.x * (unsigned)kConsumerWarps - 1u)
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+    if (threadIdx.x == 0)
     {
-      g.done[1] = 0;
-      g.seq[1] = xs;
+      const unsigned int prev = atomicAdd(&g.done[1], 1u);
+      if (prev == gridDim.x - 1u)
+      {
+        g.done[1] = 0;
+        g.seq[1] = xs;
+      }
     }
   }
 }

@@ -45,3 +45,4 @@ alg = 16 * n + (0 if "stencil" in M.kernel else 8 * ncells * (1 if "per-cell" in
 flops = ncells * 2 * (16 * (degree + 1) ** 4 + 40)
 print(json.dumps({"cells": cells, "degree": degree, "n": n, "ms": ms, "alg_bytes": alg, "gbs": alg / ms / 1e6,
                   "approx_tflops": flops / ms / 1e9}))
+
