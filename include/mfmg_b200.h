@@ -210,7 +210,7 @@ extern "C"
   MFMGB_API int mfmgb_vcycle_host(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b_host, double *x_host);
   /* The same for n_rhs independent right-hand sides (preconditioner mode; block / multi-right-hand-side Krylov drivers):
    * x_host[j] = V-cycle(b_host[j]).  Every right-hand side makes its own host -> device -> host trip; the trips are
-   * pipelined over three staging buffers -- H2D of j+1, the cycle of j and D2H of j-1 overlap (PCIe is full duplex) --
+   * pipelined over four staging buffers -- H2D of j+1, the cycle of j and D2H of j-1 overlap (PCIe is full duplex) --
    * so the throughput is bound by the slowest of the three stages instead of their sum.  Synchronous: all results are
    * on the host on return.  Pointers may repeat (the same pinned buffer for several j). */
   MFMGB_API int mfmgb_vcycle_host_batch(mfmgb_ctx *ctx, mfmgb_hierarchy *H, int n_rhs, const double *const *b_host,

@@ -95,6 +95,66 @@ __global__ void __launch_bounds__(kBlock)
     epilogue<EPI>(e, g, row, s);
 }
 
+// one THREAD per row, RPT rows per thread in flight: operators with one or two entries per row (the prolongation P = R^T:
+// 1.2 - 1.4 entries per row).  With one row per thread the kernel is a chain of three dependent loads (row offsets ->
+// column / value -> x gather) and runs at occupancy x latency: 17 M rows in 0.133 ms = 4.4 TB/s at cfg4.  Here the loads
+// of RPT rows are issued together, unconditionally (clamped indices; a predicated load is paired with its use by ptxas,
+// DESIGN.md section 4), so RPT chains overlap.  Summation order of csr_vec_kernel<1> (even entries -> s0, odd -> s1):
+// identical bits.
+template <int EPI, typename OffT, int RPT>
+__global__ void __launch_bounds__(kBlock)
+    csr_short_kernel(int64_t row_begin, int64_t n_rows, const OffT *__restrict__ rowptr, const int *__restrict__ col,
+                     const double *__restrict__ val, const double *__restrict__ x, EpiArgs e)
+{
+  const int64_t base = row_begin + (int64_t)blockIdx.x * (kBlock * RPT) + threadIdx.x;
+  OffT k0[RPT], k1[RPT];
+  EpiRegs g[RPT];
+#pragma unroll
+  for (int j = 0; j < RPT; ++j)
+  {
+    const int64_t row = base + (int64_t)j * kBlock;
+    const int64_t rc = row < n_rows ? row : n_rows - 1;
+    k0[j] = rowptr[rc];
+    k1[j] = rowptr[rc + 1];
+    g[j] = epilogue_load<EPI>(e, rc);
+  }
+  int c[RPT];
+  double v[RPT], xv[RPT], s0[RPT], s1[RPT];
+#pragma unroll
+  for (int j = 0; j < RPT; ++j)
+  {
+    const OffT k = k0[j] < k1[j] ? k0[j] : (OffT)0; // empty row: entry 0 of the matrix (read, not used)
+    c[j] = col[k];
+    v[j] = val[k];
+  }
+#pragma unroll
+  for (int j = 0; j < RPT; ++j)
+    xv[j] = __ldg(x + c[j]);
+#pragma unroll
+  for (int j = 0; j < RPT; ++j)
+  {
+    s0[j] = k0[j] < k1[j] ? fma(v[j], xv[j], 0.) : 0.;
+    s1[j] = 0.;
+  }
+#pragma unroll
+  for (int j = 0; j < RPT; ++j)
+    for (OffT k = k0[j] + 1; k < k1[j]; ++k)
+    {
+      const double p = val[k], q = __ldg(x + col[k]);
+      if ((k - k0[j]) & 1)
+        s1[j] = fma(p, q, s1[j]);
+      else
+        s0[j] = fma(p, q, s0[j]);
+    }
+#pragma unroll
+  for (int j = 0; j < RPT; ++j)
+  {
+    const int64_t row = base + (int64_t)j * kBlock;
+    if (row < n_rows)
+      epilogue<EPI>(e, g[j], row, s0[j] + s1[j]);
+  }
+}
+
 // one CTA per row: rows of thousands of entries (restrictors of large agglomerates: 17^3 = 4913, 21^3 = 9261) in
 // matrices with too few rows to fill the GPU with one warp per row.  4 gathers in flight per thread, fixed block tree.
 template <int EPI, typename OffT>
@@ -153,11 +213,31 @@ int launch_vec(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArg
 }
 
 template <int EPI, typename OffT>
+int launch_short(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArgs &e, int64_t r0, int64_t r1)
+{
+  constexpr int RPT = 4;
+  const int64_t nb = ceil_div(r1 - r0, (int64_t)kBlock * RPT);
+  if (nb <= 0)
+    return MFMGB_OK;
+  csr_short_kernel<EPI, OffT, RPT><<<(unsigned)nb, kBlock, 0, ctx->stream>>>(r0, r1, (const OffT *)A->rowptr, A->col,
+                                                                             A->val, x, e);
+  MFMGB_LAUNCHED(ctx);
+  return MFMGB_OK;
+}
+
+template <int EPI, typename OffT>
 int dispatch_lanes(mfmgb_ctx *ctx, const mfmgb_csr *A, const double *x, const EpiArgs &e, int64_t r0, int64_t r1)
 {
+  // MFMGB_CSR_SHORT=0: one row per thread for lanes == 1 (measurement aid)
+  static const bool short_rows = [] {
+    const char *v = getenv("MFMGB_CSR_SHORT");
+    return !(v && v[0] == '0');
+  }();
   switch (A->lanes)
   {
   case 1:
+    if (short_rows && A->nnz > 0 && r1 - r0 >= 4096)
+      return launch_short<EPI, OffT>(ctx, A, x, e, r0, r1);
     return launch_vec<1, EPI, OffT>(ctx, A, x, e, r0, r1);
   case 2:
     return launch_vec<2, EPI, OffT>(ctx, A, x, e, r0, r1);

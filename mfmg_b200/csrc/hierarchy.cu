@@ -81,11 +81,10 @@ struct mfmgb_hierarchy
   GraphSlot graphs[6];
   uint64_t graph_clock = 0;
   // pipelined host-vector batches (mfmgb_vcycle_host_batch): staging buffers, copy streams, events
-  static constexpr int kBatchBuffers = 3;
-  double *bb_dev[kBatchBuffers] = {nullptr, nullptr, nullptr}, *bx_dev[kBatchBuffers] = {nullptr, nullptr, nullptr};
+  static constexpr int kBatchBuffers = 4; // one more than the three stages: slack for jitter between the copies and the cycle
+  double *bb_dev[kBatchBuffers] = {}, *bx_dev[kBatchBuffers] = {};
   cudaStream_t s_in = nullptr, s_out = nullptr;
-  cudaEvent_t ev_h2d[kBatchBuffers] = {nullptr, nullptr, nullptr}, ev_comp[kBatchBuffers] = {nullptr, nullptr, nullptr},
-              ev_d2h[kBatchBuffers] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_h2d[kBatchBuffers] = {}, ev_comp[kBatchBuffers] = {}, ev_d2h[kBatchBuffers] = {};
   int launches_per_cycle = 0;
   // device staging for the *_host entry points and PCG work vectors
   double *b_dev = nullptr, *x_dev = nullptr;

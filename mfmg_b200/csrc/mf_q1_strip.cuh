@@ -303,8 +303,9 @@ int launch_q1_stencil3(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, const
     const char *v = getenv("MFMGB_MF_SEGMENTS");
     return v && *v ? atoi(v) : 0;
   }();
-  // two resident CTAs per SM; about two waves of CTAs, each segment long enough that its two lead-in planes are noise
-  int64_t seg = env_seg > 0 ? env_seg : std::max<int64_t>(1, ((int64_t)ctx->num_sms * 4 + tiles / 2) / tiles);
+  // two resident CTAs per SM; about four waves of CTAs (measured at 257^2 x 257: 6 segments 0.080 ms, 8: 0.072, 12:
+  // 0.072 -- many short sweeps balance the SMs better than the two lead-in planes of a segment cost)
+  int64_t seg = env_seg > 0 ? env_seg : std::max<int64_t>(1, ((int64_t)ctx->num_sms * 8 + tiles / 2) / tiles);
   seg = std::min<int64_t>(seg, std::max<int64_t>(1, (g1 - g0) / 8));
   const int seg_planes = (int)ceil_div(g1 - g0, seg);
   seg = ceil_div(g1 - g0, seg_planes);
@@ -327,6 +328,8 @@ int launch_q1_stencil3(mfmgb_ctx *ctx, const mfmgb_mf *M, const double *x, const
   a.cay = c * p.ay;
   a.caz = c * p.az;
   dim3 grid((unsigned)ceil_div(p.nx, S3_UX), (unsigned)ceil_div(p.ny, S3_UY), (unsigned)seg);
+  // ring depth = planes in flight per thread.  (Deeper rings -- 8 / 6 / 4 -- were measured SLOWER: 0.083 vs 0.072 ms per
+  // apply, fused forms +30 %: ncu shows barrier and dependency waits, not memory latency, as what is left)
   constexpr int RING = EPI == (int)Epi::Jacobi ? 3 : 4;
   constexpr int n_rings = EPI == (int)Epi::Spmv ? 1 : (EPI == (int)Epi::Resid ? 2 : 3);
   const size_t smem = sizeof(double) * ((size_t)2 * 2 * 2 * (S3_NS + 1) * 32 + (size_t)n_rings * RING * S3_R * S3_NT);
