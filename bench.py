@@ -948,7 +948,10 @@ def run_ours(args):
             import gc
 
             gc.collect()
-        out["other_configs"] = other_configs_subprocess(args)
+        try:
+            out["other_configs"] = other_configs_subprocess(args)
+        except Exception as exc:  # never lose the main line to a secondary leg
+            out["other_configs"] = {"skipped": f"{type(exc).__name__}: {exc}"}
     if rank == 0:
         _emit(json.dumps(out))
     if dist is not None:

@@ -306,7 +306,7 @@ extern "C"
   MFMGB_API int64_t mfmgb_hierarchy_vector_size(const mfmgb_hierarchy *H, int level);
   /* Process-wide launch parameters of the exchange kernels (measurement aid; results do not depend on them):
    * "halo_push_ctas" (16): CTAs of the fused compute + exchange A-kernel that store the boundary plane(s) into the
-   * neighbours' mailboxes; "halo_push_penalty" (2): interior tiles such a CTA is spared.  Defaults can also be given
+   * neighbours' mailboxes; "halo_push_penalty" (0): interior tiles such a CTA is spared.  Defaults can also be given
    * as MFMGB_HALO_PUSH_CTAS / MFMGB_HALO_PUSH_PENALTY.  A change applies to launches (and graph captures) made after it.
    * set: MFMGB_ERR_INVALID for an unknown name; get: -1 for an unknown name. */
   MFMGB_API int mfmgb_tunable_set(const char *name, long long value);

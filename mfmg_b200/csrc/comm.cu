@@ -387,7 +387,7 @@ struct Tunable
 };
 static Tunable g_tunables[] = {
     {"halo_push_ctas", 16, false},   // CTAs of the fused A-kernel that store the boundary plane(s) into the neighbours
-    {"halo_push_penalty", 2, false}, // interior tiles such a CTA is spared
+    {"halo_push_penalty", 0, false}, // interior tiles such a CTA is spared (measured: no effect, profiles/r02_probe_weak_n2_push_params.txt)
 };
 
 static Tunable *find_tunable(const char *name)

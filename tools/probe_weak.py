@@ -62,8 +62,8 @@ def run(setting):
 
 
 settings = [{"halo_push_ctas": 16, "halo_push_penalty": 0}]
-for ctas in (4, 16, 64, 148):
-    for pen in (2, 4, 8):
+for ctas in (8, 16, 32, 64):
+    for pen in (2, 4, 6):
         settings.append({"halo_push_ctas": ctas, "halo_push_penalty": pen})
 settings.append({"halo_push_ctas": 16, "halo_push_penalty": 0})
 ref = None
