@@ -15,7 +15,11 @@ LIB = os.path.join(ROOT, "mfmg_b200", "csrc", "libmfmg_b200.so")
 KERNELS = [
     ("csr_tile_kernel<4,Jacobi,int32,GHOST=false> (the A-kernel of cfg1)", r"csr_tile_kernelILi4ELi2EiLb0E"),
     ("csr_tile_kernel<4,Jacobi,int32,GHOST=true> (fused compute + NVLink exchange form)", r"csr_tile_kernelILi4ELi2EiLb1E"),
-    ("mf_q1_stencil_kernel<Jacobi, arithmetic flags, 2 CTAs/SM>", r"mf_q1_stencil_kernelILi2ELb1ELi2E"),
+    ("mf_q1_stencil3_kernel<Jacobi, arithmetic flags, ring 3, in place> (strip form, default)", r"mf_q1_stencil3_kernelILi2ELb1ELi3ELb1E"),
+    ("mf_q1_stencil3_kernel<Spmv, arithmetic flags, ring 4>", r"mf_q1_stencil3_kernelILi0ELb1ELi4ELb1E"),
+    ("mf_q1_stencil_kernel<Jacobi, arithmetic flags, 2 CTAs/SM> (one node per thread, form 1)", r"mf_q1_stencil_kernelILi2ELb1ELi2E"),
+    ("csr_short_kernel<Sub, int32, 4 rows per thread> (prolongation)", r"csr_short_kernelILi3EiLi4E"),
+    ("csr_tile_kernel<8,Jacobi,int32,GHOST=false> (Q2 rows: 16 gathers in flight per lane)", r"csr_tile_kernelILi8ELi2EiLb0E"),
     ("gemv_stream_kernel", r"gemv_stream_kernel"),
     ("halo_push_kernel", r"halo_push_kernel"),
     ("halo_wait_kernel", r"halo_wait_kernel"),
