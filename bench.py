@@ -933,10 +933,13 @@ def run_ours(args):
         import gc
 
         gc.collect()
-        if world == 1:
-            ns = north_star_subprocess(args)
-        else:
-            ns = north_star_in_process(args, d, handle, stream, dist, rank, world, local_rank)
+        try:
+            if world == 1:
+                ns = north_star_subprocess(args)
+            else:
+                ns = north_star_in_process(args, d, handle, stream, dist, rank, world, local_rank)
+        except Exception as exc:  # never lose the main line to a secondary leg
+            ns = {"skipped": f"{type(exc).__name__}: {exc}"}
         if rank == 0:
             out["north_star"] = ns
     want_other = world == 1 and (args.other_configs == "on" or (args.other_configs == "auto" and default_workload))
