@@ -298,6 +298,10 @@ public:
     check_status(_handle->ctx, mfmgb_spmv(_handle->ctx, _csr, src.get_values(), dst.get_values()));
   }
 
+  // C = (*this) * B; C's previous content is released (sparse_matrix_device.templates.cuh:373-433; the reference uses
+  // cusparseDcsrgemm on one rank and Trilinos on the host in parallel).  Setup operation, formed on the host here.
+  void mmult(SparseMatrixDevice<ScalarType> &C, SparseMatrixDevice<ScalarType> const &B) const;
+
   mfmgb_csr *c_handle() const { return _csr; }
   std::shared_ptr<CudaHandle const> const &handle() const { return _handle; }
 
@@ -339,8 +343,8 @@ namespace internal
 // C = A B on the host (Gustavson, rows of C sorted by column).  SETUP operation: like the reference's parallel path,
 // which multiplies through Trilinos on the host (include/mfmg/cuda/sparse_matrix_device.templates.cuh:417-433), the
 // Galerkin product R A R^T is formed once on the host and uploaded.
-inline std::shared_ptr<SparseMatrixDevice<double>> host_multiply(SparseMatrixDevice<double> const &a,
-                                                                 SparseMatrixDevice<double> const &b)
+inline void host_multiply_arrays(SparseMatrixDevice<double> const &a, SparseMatrixDevice<double> const &b,
+                                 std::vector<int64_t> &crp, std::vector<int> &cc, std::vector<double> &cv)
 {
   ASSERT_THROW(a.n() == b.m(), "multiply: inner dimensions differ");
   std::vector<int64_t> arp, brp;
@@ -349,9 +353,9 @@ inline std::shared_ptr<SparseMatrixDevice<double>> host_multiply(SparseMatrixDev
   a.copy_to_host(arp, ac, av);
   b.copy_to_host(brp, bc, bv);
   unsigned int const m = a.m(), n = b.n();
-  std::vector<int64_t> crp(1, 0);
-  std::vector<int> cc;
-  std::vector<double> cv;
+  crp.assign(1, 0);
+  cc.clear();
+  cv.clear();
   std::vector<double> acc(n, 0.);
   std::vector<char> used(n, 0);
   std::vector<int> cols;
@@ -382,9 +386,29 @@ inline std::shared_ptr<SparseMatrixDevice<double>> host_multiply(SparseMatrixDev
     }
     crp.push_back((int64_t)cc.size());
   }
-  return std::make_shared<SparseMatrixDevice<double>>(a.handle(), m, n, crp, cc, cv);
+}
+
+inline std::shared_ptr<SparseMatrixDevice<double>> host_multiply(SparseMatrixDevice<double> const &a,
+                                                                 SparseMatrixDevice<double> const &b)
+{
+  std::vector<int64_t> crp;
+  std::vector<int> cc;
+  std::vector<double> cv;
+  host_multiply_arrays(a, b, crp, cc, cv);
+  return std::make_shared<SparseMatrixDevice<double>>(a.handle(), a.m(), b.n(), crp, cc, cv);
 }
 } // namespace internal
+
+template <typename ScalarType>
+void SparseMatrixDevice<ScalarType>::mmult(SparseMatrixDevice<ScalarType> &C,
+                                           SparseMatrixDevice<ScalarType> const &B) const
+{
+  std::vector<int64_t> crp;
+  std::vector<int> cc;
+  std::vector<double> cv;
+  internal::host_multiply_arrays(*this, B, crp, cc, cv);
+  C.reinit(_handle, m(), B.n(), crp, cc, cv);
+}
 
 // source/cuda/cuda_matrix_operator.cu
 template <typename VectorType>

@@ -4,6 +4,7 @@
 //   tests/test_sparse_matrix_device_operator.cu   30x39 banded matrix, apply / transpose, exact
 //   Hierarchy::apply (fused) == the same algorithm composed from the abstract objects == dense host algebra
 // Build: g++ -std=c++17 -Iinclude tests/cpp/test_adapter.cpp -Lmfmg_b200/csrc -lmfmg_b200 (+rpath).  Needs a GPU to run.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <random>
@@ -127,6 +128,72 @@ int main()
     for (double v : y.export_to_host())
       CHECK(v == 0.25);
   } // (the destructor frees the three adopted arrays)
+
+  // ---- SparseMatrixDevice::mmult (tests/test_sparse_matrix_device.cu:242-361): 30 x 30, five random columns per row
+  //      from std::default_random_engine(i) plus the diagonal, A(i,j) = i + j, B(i,j) = i - j, C = A B against the
+  //      dense product ----
+  {
+    unsigned const size = 30;
+    HostCsr a{size, size, {0}, {}, {}}, b{size, size, {0}, {}, {}};
+    std::vector<std::vector<double>> Ad(size, std::vector<double>(size, 0.)), Bd = Ad;
+    for (unsigned i = 0; i < size; ++i)
+    {
+      std::vector<unsigned> indices;
+      std::default_random_engine generator(i);
+      std::uniform_int_distribution<int> distribution(0, size - 1);
+      for (unsigned j = 0; j < 5; ++j)
+        indices.push_back((unsigned)distribution(generator));
+      indices.push_back(i);
+      std::sort(indices.begin(), indices.end());
+      indices.erase(std::unique(indices.begin(), indices.end()), indices.end());
+      for (unsigned j : indices)
+      {
+        a.col.push_back((int)j);
+        a.val.push_back((double)(i + j));
+        b.col.push_back((int)j);
+        b.val.push_back((double)i - (double)j);
+        Ad[i][j] = (double)(i + j);
+        Bd[i][j] = (double)i - (double)j;
+      }
+      a.rp.push_back((int64_t)a.col.size());
+      b.rp.push_back((int64_t)b.col.size());
+    }
+    mfmg::SparseMatrixDevice<double> A_dev(handle, size, size, a.rp, a.col, a.val);
+    mfmg::SparseMatrixDevice<double> B_dev(handle, size, size, b.rp, b.col, b.val);
+    mfmg::SparseMatrixDevice<double> C_dev(handle, size, size, b.rp, b.col, b.val); // overwritten, like the reference's
+    A_dev.mmult(C_dev, B_dev);
+    CHECK(C_dev.m() == size && C_dev.n() == size);
+    std::vector<int64_t> crp;
+    std::vector<int> cc;
+    std::vector<double> cv;
+    C_dev.copy_to_host(crp, cc, cv);
+    std::vector<std::vector<double>> Cd(size, std::vector<double>(size, 0.)), Cgot = Cd;
+    for (unsigned i = 0; i < size; ++i)
+      for (unsigned k = 0; k < size; ++k)
+        for (unsigned j = 0; j < size; ++j)
+          Cd[i][j] += Ad[i][k] * Bd[k][j];
+    for (unsigned i = 0; i < size; ++i)
+      for (int64_t k = crp[i]; k < crp[i + 1]; ++k)
+      {
+        CHECK(k == crp[i] || cc[(std::size_t)k - 1] < cc[(std::size_t)k]); // ascending columns, no duplicates
+        Cgot[i][(unsigned)cc[(std::size_t)k]] = cv[(std::size_t)k];
+      }
+    for (unsigned i = 0; i < size; ++i)
+      for (unsigned j = 0; j < size; ++j)
+        CHECK(std::abs(Cgot[i][j] - Cd[i][j]) <= 1e-12 * (std::abs(Cd[i][j]) + 1.));
+    // and the product acts like A (B x)
+    std::vector<double> xh(size);
+    for (unsigned i = 0; i < size; ++i)
+      xh[i] = 1. + 0.1 * i;
+    V x(handle, size), t(handle, size), y1(handle, size), y2(handle, size);
+    x.import_from_host(xh);
+    B_dev.vmult(t, x);
+    A_dev.vmult(y1, t);
+    C_dev.vmult(y2, x);
+    auto h1 = y1.export_to_host(), h2 = y2.export_to_host();
+    for (unsigned i = 0; i < size; ++i)
+      CHECK(std::abs(h1[i] - h2[i]) <= 1e-10 * (std::abs(h1[i]) + 1.));
+  }
 
   // ---- direct solver ----
   {
