@@ -426,6 +426,7 @@ extern "C"
                                        const mfmgb_csr *A_IS, const mfmgb_csr *A_SI, const mfmgb_csr *A_SS,
                                        const int32_t *sep_index, mfmgb_coarse_dd **out)
   {
+    NvtxRange nvtx_range("mfmgb: coarse solver setup (domain-decomposed)");
     MFMGB_REQUIRE(ctx, ctx && out && A_II && A_IS && A_SI && A_SS && (n_S == 0 || sep_index),
                   "mfmgb_coarse_dd_create: bad arguments");
     mfmgb_comm *c = ctx_comm(ctx);

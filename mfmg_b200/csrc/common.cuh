@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h> // header-only NVTX 3: ranges are no-ops unless a tool (nsys, ncu) is attached
 
 #include <cstdarg>
 #include <cstdint>
@@ -101,6 +102,16 @@ inline int fail(mfmgb_ctx *ctx, int code, const char *fmt, ...)
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // marks the END of the piece called `name` on the compute stream (no-op unless a timeline is being taken)
+// NVTX range over a host entry point -- the counterpart of the reference's timer sections (hierarchy.hpp:36-47, 241, 263,
+// 271: "Setup", "Apply", per-level sections), visible in nsys / ncu timelines
+struct NvtxRange
+{
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+  NvtxRange &operator=(const NvtxRange &) = delete;
+};
+
 inline void prof_mark(mfmgb_ctx *ctx, const char *name)
 {
   if (!ctx->prof_on)

@@ -421,6 +421,7 @@ extern "C"
   MFMGB_API int mfmgb_csr_upload(mfmgb_ctx *ctx, int64_t n_rows, int64_t n_cols, const int64_t *rowptr,
                                  const int32_t *col, const double *val, mfmgb_csr **out)
   {
+    NvtxRange nvtx_range("mfmgb: operator upload");
     return upload_impl<int64_t>(ctx, n_rows, n_cols, rowptr, col, val, out);
   }
 

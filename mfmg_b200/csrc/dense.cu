@@ -979,6 +979,7 @@ extern "C"
 {
   MFMGB_API int mfmgb_dense_factor(mfmgb_ctx *ctx, const mfmgb_csr *A, mfmgb_dense **out)
   {
+    NvtxRange nvtx_range("mfmgb: coarse solver setup (dense LU)");
     MFMGB_REQUIRE(ctx, ctx && A && out, "mfmgb_dense_factor: bad arguments");
     MFMGB_REQUIRE(ctx, A->n_rows == A->n_cols, "mfmgb_dense_factor: the matrix is not square");
     *out = nullptr;

@@ -858,6 +858,7 @@ extern "C"
 
   MFMGB_API int mfmgb_hierarchy_finalize(mfmgb_ctx *ctx, mfmgb_hierarchy *H)
   {
+    NvtxRange nvtx_range("mfmgb: hierarchy setup (finalize)");
     MFMGB_REQUIRE(ctx, ctx && H && !H->finalized, "mfmgb_hierarchy_finalize: bad arguments");
     for (int li = 0; li < H->n_levels; ++li)
     {
@@ -1054,6 +1055,7 @@ extern "C"
 
   MFMGB_API int mfmgb_vcycle(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b, double *x)
   {
+    NvtxRange nvtx_range("mfmgb: V-cycle apply");
     MFMGB_REQUIRE(ctx, ctx && H && H->finalized && b && x, "mfmgb_vcycle: bad arguments");
     MFMGB_REQUIRE(ctx, b != x, "mfmgb_vcycle: b and x must not alias");
     return run_vcycle(ctx, H, b, x);
@@ -1135,6 +1137,7 @@ extern "C"
 
   MFMGB_API int mfmgb_vcycle_host(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const double *b_host, double *x_host)
   {
+    NvtxRange nvtx_range("mfmgb: V-cycle apply (host vectors)");
     MFMGB_REQUIRE(ctx, ctx && H && H->finalized && b_host && x_host, "mfmgb_vcycle_host: bad arguments");
     const int64_t n = H->lev[0].n;
     MFMGB_CHECK(ensure_host_staging(ctx, H, n));
@@ -1151,6 +1154,7 @@ extern "C"
   MFMGB_API int mfmgb_vcycle_host_batch(mfmgb_ctx *ctx, mfmgb_hierarchy *H, int n_rhs, const double *const *b_host,
                                         double *const *x_host)
   {
+    NvtxRange nvtx_range("mfmgb: V-cycle apply (host vector batch)");
     MFMGB_REQUIRE(ctx, ctx && H && H->finalized && n_rhs >= 0 && (n_rhs == 0 || (b_host && x_host)),
                   "mfmgb_vcycle_host_batch: bad arguments");
     if (!H->is_preconditioner) // solver mode reads x as well: the plain entry point, one right-hand side at a time
@@ -1204,6 +1208,7 @@ extern "C"
   MFMGB_API int mfmgb_pcg(mfmgb_ctx *ctx, mfmgb_hierarchy *H, const mfmgb_csr *A, const double *b, double *x, double tol,
                           int max_it, int *iterations, double *res_hist_host)
   {
+    NvtxRange nvtx_range("mfmgb: PCG solve");
     MFMGB_REQUIRE(ctx, ctx && b && x && iterations && max_it >= 0, "mfmgb_pcg: bad arguments");
     MFMGB_REQUIRE(ctx, H || A, "mfmgb_pcg: need a hierarchy or a matrix");
     MFMGB_REQUIRE(ctx, !H || H->finalized, "mfmgb_pcg: hierarchy not finalized");

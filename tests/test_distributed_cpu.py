@@ -269,3 +269,63 @@ def test_rows_restricted():
     ref = np.zeros((10, 40))
     ref[2:8, :12] = M.toarray()[3:9, 10:22]
     assert (sub.n_rows, sub.n_cols) == (10, 40) and np.array_equal(sub.to_scipy().toarray(), ref)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_distributed_mv_kat_halo_plan(world):
+    """The reference's distributed SpMV KAT (tests/test_sparse_matrix_device.cu:116-223) on the host-side plan: 10 rows
+    per rank, five columns per row drawn from std::default_random_engine(local row) over ALL global columns (so every
+    rank is every other rank's neighbour), value i + j with set() semantics, x = local index.  The reference
+    all-gathers the source vector (sparse_matrix_device.templates.cuh:104-138); here the rows are renumbered
+    [owned | ghost] and only the listed entries travel.  Checked: ghost order == send-list order for every pair of
+    ranks, and local SpMV on [owned | received] == the global product, bit for bit."""
+    import oracle
+    from mfmg_b200.hostsetup.partition import _localise, wire_send_lists
+    from mfmg_b200.hostsetup.problems import HostCSR
+
+    n_local = 10
+    size = world * n_local
+    rowptr, col, val = [0], [], []
+    for r in range(world):
+        for i in range(n_local):
+            cols = oracle.std_uniform_int(5, 0, size - 1, seed=i)
+            entries = {}
+            for j, c in enumerate(cols):
+                entries[int(c)] = float(i + j)          # set(): the last value written to an entry stays
+            for c in sorted(entries):
+                col.append(c)
+                val.append(entries[c])
+            rowptr.append(len(col))
+    A = HostCSR(size, size, np.array(rowptr, dtype=np.int64), np.array(col, dtype=np.int32), np.array(val))
+    x = (np.arange(size) % n_local).astype(np.float64)      # vector.local_element(i) = i on every rank
+    y_ref = oracle.spmv(size, A.rowptr, A.col, A.val, x)
+    assert np.array_equal(y_ref, A.to_scipy() @ x)
+    offsets = np.arange(world + 1) * n_local
+    ghosts, locals_ = [], []
+    for r in range(world):
+        rb, re_ = int(offsets[r]), int(offsets[r + 1])
+        c = A.col[A.rowptr[rb]:A.rowptr[re_]].astype(np.int64)
+        g = np.unique(c[(c < rb) | (c >= re_)])
+        ghosts.append(g)
+        locals_.append(_localise(A, slice(rb, re_), rb, re_, g))
+    n_pairs = 0
+    for r in range(world):
+        rb, re_ = int(offsets[r]), int(offsets[r + 1])
+        v = np.full(n_local + len(ghosts[r]), np.nan)
+        v[:n_local] = x[rb:re_]
+        owner = np.searchsorted(offsets, ghosts[r], side="right") - 1
+        off = 0
+        for q in np.unique(owner):
+            cnt = int(np.sum(owner == q))
+            nb, send_idx = wire_send_lists(ghosts, offsets, int(q))       # what rank q sends, per destination
+            sent = x[offsets[q]:offsets[q + 1]][send_idx[nb.index(r)]]     # ... to rank r, in q's send order
+            assert len(sent) == cnt
+            v[n_local + off:n_local + off + cnt] = sent                    # lands in r's ghost slots in ghost order
+            off += cnt
+            n_pairs += 1
+        assert off == len(ghosts[r]) and not np.isnan(v).any()
+        assert np.array_equal(v[n_local:], x[ghosts[r]])
+        L = locals_[r]
+        y_loc = oracle.spmv(L.n_rows, L.rowptr, L.col, L.val, v)
+        assert np.array_equal(y_loc, y_ref[rb:re_])
+    assert n_pairs >= world    # the random columns make (nearly) every rank a neighbour of every other
