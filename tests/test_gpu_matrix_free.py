@@ -153,15 +153,19 @@ def test_generic_kernel_still_serves_3d_q1(handle, monkeypatch):
     assert rel_err(y1.to_host(), y2.to_host()) < 1e-13
 
 
+@pytest.mark.parametrize("arith_flags", ["1", "0"])
 @pytest.mark.parametrize("mat", ["constant"])
-def test_stencil_sweep_equals_cell_kernel_and_fused_epilogues(handle, monkeypatch, mat):
+def test_stencil_sweep_equals_cell_kernel_and_fused_epilogues(handle, monkeypatch, mat, arith_flags):
     """The constant-coefficient stencil z-sweep against the per-cell kernel of the same operator (MFMGB_MF_STENCIL=0),
-    and its fused residual / Jacobi epilogues against their unfused definitions."""
+    and its fused residual / Jacobi epilogues against their unfused definitions; with the constraint flags computed
+    from the box geometry (default when the constrained set is exactly the box faces) and loaded from the flag array
+    (MFMGB_MF_ARITH_FLAGS=0: the form every other constrained set gets)."""
     import ctypes
 
     from mfmg_b200 import device as d
     from mfmg_b200 import hostsetup as hs
 
+    monkeypatch.setenv("MFMGB_MF_ARITH_FLAGS", arith_flags)
     P = hs.LaplaceProblem.create_box(3, 1, (45, 31, 23), (0.02, 0.03, 0.05), mat)
     fast = _mf(handle, P)
     monkeypatch.setenv("MFMGB_MF_STENCIL", "0")
