@@ -217,6 +217,41 @@ public:
   virtual size_type operator_complexity() const = 0;
 };
 
+#ifndef MPI_VERSION
+// one process per GPU; without an MPI installation the communicator argument is a placeholder
+using MPI_Comm = int;
+constexpr MPI_Comm MPI_COMM_SELF = 1, MPI_COMM_WORLD = 0;
+#endif
+
+// The part of dealii::IndexSet the reference's SparseMatrixDevice constructor reads: a contiguous range of locally owned
+// indices inside a global index space (sparse_matrix_device.templates.cuh:244-272 uses n_elements() and size()).
+class IndexSet
+{
+public:
+  using size_type = std::size_t;
+  IndexSet() = default;
+  explicit IndexSet(size_type size) : _size(size) {}
+  void set_size(size_type size) { _size = size; }
+  void add_range(size_type begin, size_type end)
+  {
+    ASSERT_THROW(begin <= end && end <= _size, "IndexSet::add_range: range outside the index space");
+    ASSERT_THROW(_begin == _end || begin == _end, "IndexSet: only one contiguous range (one row block per rank)");
+    if (_begin == _end)
+      _begin = begin;
+    _end = end;
+  }
+  void add_index(size_type index) { add_range(index, index + 1); }
+  void compress() const {}
+  size_type size() const { return _size; }
+  size_type n_elements() const { return _end - _begin; }
+  size_type nth_index_in_set(size_type n) const { return _begin + n; }
+  bool is_element(size_type i) const { return i >= _begin && i < _end; }
+  bool is_contiguous() const { return true; }
+
+private:
+  size_type _size = 0, _begin = 0, _end = 0;
+};
+
 // include/mfmg/cuda/sparse_matrix_device.cuh:28-104.  The reference's ctor takes an MPI_Comm and two
 // dealii::IndexSet; without deal.II the (local) sizes are passed directly.
 template <typename ScalarType>
@@ -261,6 +296,24 @@ public:
     check_status(_handle->ctx, mfmgb_csr_adopt_device(_handle->ctx, n_rows, n_cols, local_nnz, val_dev,
                                                       column_index_dev, row_ptr_dev, &_csr));
   }
+  // the reference's own argument list (sparse_matrix_device.cuh:37-47): communicator + range / domain index sets, the
+  // cuSPARSE handle replaced by the CudaHandle that owns the mfmgb context.  One rank owning every row is served here;
+  // row-partitioned operators go through the halo-plan entry points of the C ABI (mfmgb_halo_create,
+  // mfmgb_hierarchy_set_halo), where the column indices are LOCAL [owned | ghost].
+  SparseMatrixDevice(MPI_Comm comm, ScalarType *val_dev_, int *column_index_dev_, int *row_ptr_dev_,
+                     unsigned int local_nnz, IndexSet const &range_indexset, IndexSet const &domain_indexset,
+                     std::shared_ptr<CudaHandle const> handle)
+      : val_dev(val_dev_), column_index_dev(column_index_dev_), row_ptr_dev(row_ptr_dev_), _handle(std::move(handle)),
+        _comm(comm)
+  {
+    ASSERT_THROW(range_indexset.n_elements() == range_indexset.size(),
+                 "SparseMatrixDevice(MPI_Comm, ...): a rank that owns a row block only -- use the partitioned C ABI");
+    check_status(_handle->ctx,
+                 mfmgb_csr_adopt_device(_handle->ctx, (int64_t)range_indexset.n_elements(),
+                                        (int64_t)domain_indexset.size(), local_nnz, val_dev, column_index_dev,
+                                        row_ptr_dev, &_csr));
+  }
+  MPI_Comm get_mpi_communicator() const { return _comm; }
   // convert_matrix semantics (source/cuda/utils.cu:39-168): copy a host CSR to the device
   SparseMatrixDevice(std::shared_ptr<CudaHandle const> handle, unsigned int n_rows, unsigned int n_cols,
                      std::vector<int64_t> const &row_ptr, std::vector<int> const &column_index,
@@ -336,6 +389,7 @@ private:
   }
   std::shared_ptr<CudaHandle const> _handle;
   mfmgb_csr *_csr = nullptr;
+  MPI_Comm _comm = MPI_COMM_SELF;
 };
 
 namespace internal
@@ -860,12 +914,6 @@ inline void timer_leave_subsection(std::shared_ptr<TimerOutput> const &timer)
   if (timer)
     timer->leave_subsection();
 }
-
-#ifndef MPI_VERSION
-// one process per GPU; without an MPI installation the communicator argument is a placeholder
-using MPI_Comm = int;
-constexpr MPI_Comm MPI_COMM_SELF = 1, MPI_COMM_WORLD = 0;
-#endif
 
 // include/mfmg/common/hierarchy_helpers.hpp:27-62
 template <typename VectorType>

@@ -13,6 +13,13 @@
 
 using V = mfmg::DeviceVector;
 
+// the reference's own constructor argument list (sparse_matrix_device.cuh:37-47) is accepted as written
+#include <type_traits>
+static_assert(std::is_constructible<mfmg::SparseMatrixDevice<double>, mfmg::MPI_Comm, double *, int *, int *, unsigned int,
+                                    mfmg::IndexSet const &, mfmg::IndexSet const &,
+                                    std::shared_ptr<mfmg::CudaHandle const>>::value,
+              "SparseMatrixDevice(MPI_Comm, val, col, rowptr, local_nnz, range, domain, handle)");
+
 static int failures = 0;
 #define CHECK(cond)                                                                                 \
   do                                                                                                \
