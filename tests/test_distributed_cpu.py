@@ -231,6 +231,23 @@ def test_coarse_dd_plan_block_elimination(world, cells, block, ne):
         a0, na = pl["adj_begin"], pl["A_IS"].n_cols
         x[pl["own_begin"]:pl["own_begin"] + pl["n_I"]] = y - Er @ xs[a0:a0 + na]
     assert np.linalg.norm(x - x_ref) <= 1e-12 * np.linalg.norm(x_ref)
+    # the two-stream form of csrc/coarse_dd.cu: W = A_SI A_II^-1 formed at setup, so the separator right-hand side
+    # t = b_S - sum_r W_r b_I,r needs the restricted residual only (it runs NEXT TO y = A_II^-1 b_I on the device)
+    t2 = np.zeros(n_S)
+    for pl, Mi in zip(plans, Minv):
+        W = pl["A_SI"].to_scipy().toarray() @ Mi
+        a0, na = pl["adj_begin"], pl["A_IS"].n_cols
+        t2[a0:a0 + na] -= W @ b[pl["own_begin"]:pl["own_begin"] + pl["n_I"]]
+        o0, on = pl["own_sep_begin"], pl["own_sep_n"]
+        t2[o0:o0 + on] += b[sep[o0:o0 + on]]
+    assert np.linalg.norm(t2 - t) <= 1e-13 * np.linalg.norm(t)
+    xs2 = np.linalg.solve(S, t2)
+    x2 = np.zeros(n_c)
+    x2[sep] = xs2
+    for pl, y, Er in zip(plans, ys, E):
+        a0, na = pl["adj_begin"], pl["A_IS"].n_cols
+        x2[pl["own_begin"]:pl["own_begin"] + pl["n_I"]] = y - Er @ xs2[a0:a0 + na]
+    assert np.linalg.norm(x2 - x_ref) <= 1e-12 * np.linalg.norm(x_ref)
     for p, pl in zip(parts, plans):
         assert np.all(np.isin(p.P.col, pl["valid_cols"]))
 
